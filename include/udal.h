@@ -1,0 +1,256 @@
+/* libudal - C ABI of the B200-native uncertainty-sampling / post-processing hot path.
+ *
+ * Drop-in boundary for ONE path of continental/uncertainty-detection-autolabeling:
+ *   BiFPN features -> T x class/box(+sigma) heads -> anchor decode with exact moment propagation
+ *   -> MC mean/std -> top-k | max-reduce -> NMS -> detections.
+ *
+ * The reference has no FFI of its own (pure Python on TensorFlow); each entry point below cites
+ * the reference function(s) (file:line under the reference's src/) whose arithmetic it replaces.
+ * The Python mirror of the reference's modules (postprocess.py / anchors.py / nms_np.py /
+ * utils_box.py / utils_extra.py) binds these symbols with ctypes; INTEGRATION.md shows the stub a
+ * reference maintainer would add.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no framework types.  "device pointer" = CUDA global memory
+ *     on the context's device (a DLPack / __cuda_array_interface__ data pointer passes as is).
+ *   - every function returns 0 on success, a negative udal_status otherwise;
+ *     udal_last_error() returns a thread-local message for the last failure.
+ *   - all work is enqueued on the context's stream; functions return without synchronising
+ *     unless stated.  One context per GPU, one host thread per context.
+ *   - the library never frees caller memory and keeps no global state.
+ *   - tensors are C-contiguous fp32, NHWC, levels ordered min_level..max_level.
+ */
+#ifndef UDAL_H_
+#define UDAL_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define UDAL_MAX_LEVELS 8
+#define UDAL_ABI_VERSION 1
+
+typedef enum {
+  UDAL_OK = 0,
+  UDAL_ERR_INVALID = -1, /* bad argument / unsupported configuration (Python: ValueError) */
+  UDAL_ERR_CUDA = -2,    /* CUDA runtime failure (Python: RuntimeError)                    */
+  UDAL_ERR_STATE = -3,   /* call order (weights / anchors not set)                          */
+  UDAL_ERR_NOMEM = -4
+} udal_status;
+
+/* decode method, reference utils_box.py:105-276 (decode_uncert) */
+enum { UDAL_DECODE_LNORM = 0, UDAL_DECODE_NFLOW = 1, UDAL_DECODE_FALSEDEC = 2 };
+/* NMS method, reference postprocess.py:373-388 */
+enum { UDAL_NMS_HARD = 0, UDAL_NMS_GAUSSIAN = 1 };
+/* head-GEMM arithmetic */
+enum { UDAL_HEADS_FP32 = 0, UDAL_HEADS_BF16_TC = 1 };
+enum { UDAL_HEAD_CLASS = 0, UDAL_HEAD_BOX = 1 };
+
+/* The hot-path slice of the reference's params dict (hparams_config.py:183-370) plus geometry. */
+typedef struct {
+  int32_t abi_version;              /* UDAL_ABI_VERSION */
+  int32_t device;                   /* CUDA ordinal */
+  int32_t image_h, image_w;         /* utils.parse_image_size(params["image_size"]) */
+  int32_t num_levels;               /* max_level - min_level + 1 */
+  int32_t level_h[UDAL_MAX_LEVELS]; /* utils.get_feat_sizes(...)[min_level..max_level] */
+  int32_t level_w[UDAL_MAX_LEVELS];
+  int32_t anchors_per_loc;          /* A = num_scales * len(aspect_ratios) */
+  int32_t num_classes;              /* C */
+  int32_t num_filters;              /* F = fpn_num_filters */
+  int32_t repeats;                  /* R = box_class_repeats */
+  int32_t mc_samples;               /* T = mc_dropoutsamp */
+  int32_t loss_attenuation;         /* box head emits 8A channels (4A box | 4A sigma) */
+  int32_t cls_mc;                   /* bool(mc_classheadrate or mc_dropoutrate) */
+  int32_t box_mc;                   /* bool(mc_boxheadrate or mc_dropoutrate) */
+  float rate_class, rate_box;       /* SpatialDropout2D rates of the two heads */
+  int32_t decode_method;            /* UDAL_DECODE_* */
+  int32_t nms_method;               /* UDAL_NMS_* */
+  float nms_iou_thresh;             /* after the reference's defaulting (postprocess.py:380-386) */
+  float nms_score_thresh;           /* -INFINITY allowed */
+  float nms_sigma_tf;               /* soft_nms_sigma passed to TF = sigma / 2; 0 for hard */
+  int32_t nms_variant_old;          /* 0: TF >= 2.4 kernel semantics (pinned 2.10), 1: TF <= 2.3 */
+  int32_t max_nms_inputs;           /* 0: max-reduce (serving), >0: top-k (eval) */
+  int32_t max_output_size;          /* detections per image (100) */
+  int32_t heads_mode;               /* UDAL_HEADS_* */
+  int32_t prefilter_k;              /* global soft-NMS candidate pre-filter (0 = library default) */
+  float inv_keep_class, inv_keep_box; /* fp32(1 / (1 - rate)) computed in double by the host, as TF does */
+  int32_t reserved[5];
+} udal_config;
+
+typedef struct udal_ctx udal_ctx;
+
+const char* udal_last_error(void);
+int udal_abi_version(void);
+
+/* ---- context, memory, stream ------------------------------------------------------------ */
+int udal_create(const udal_config* cfg, udal_ctx** out);
+int udal_destroy(udal_ctx* ctx);
+/* use an external CUDA stream (cudaStream_t as void*); NULL restores the context's own stream */
+int udal_set_stream(udal_ctx* ctx, void* cuda_stream);
+int udal_sync(udal_ctx* ctx);
+int udal_malloc(udal_ctx* ctx, size_t bytes, void** dev_ptr);
+int udal_free(udal_ctx* ctx, void* dev_ptr);
+int udal_host_alloc(size_t bytes, void** pinned_ptr);
+int udal_host_free(void* pinned_ptr);
+int udal_memcpy_h2d(udal_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes);
+int udal_memcpy_d2h(udal_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes);
+int udal_memcpy_d2d(udal_ctx* ctx, void* dst_dev, const void* src_dev, size_t bytes);
+int udal_memset(udal_ctx* ctx, void* dst_dev, int value, size_t bytes);
+/* CUDA-event stopwatch on the context's stream (bench.py) */
+int udal_timer_start(udal_ctx* ctx);
+int udal_timer_stop(udal_ctx* ctx, float* elapsed_ms); /* synchronises */
+int udal_device_count(int* count);
+int udal_num_anchors(const udal_ctx* ctx, int64_t* n);
+/* kernels this context has launched since creation (bench.py "gpu_launches") */
+int udal_launch_count(const udal_ctx* ctx, int64_t* n);
+
+/* ---- anchors ---------------------------------------------------------------------------- */
+/* anchors.py:158-215 (Anchors._generate_boxes): the host mirror builds the float64 table the way
+ * the reference does and uploads its float32 cast, [N,4] = (ymin, xmin, ymax, xmax). */
+int udal_set_anchors(udal_ctx* ctx, const float* anchors_host, int64_t num_anchors);
+
+/* ---- head sampler ----------------------------------------------------------------------- */
+/* efficientdet_keras.py:353-513 (ClassNet), 516-692 (BoxNet); host pointers, copied.
+ *   dw   [R][3][3][F]      depthwise kernels of the tower (shared over levels)
+ *   pw   [R][F][F]         pointwise kernels   bias [R][F]
+ *   bn_* [R][L][F]         per (repeat, level) gamma / beta / moving mean / moving variance
+ *   dwp  [3][3][F], pwp [F][Cout], bp [Cout]   the predict layer (Cout = A*C or 4A / 8A)   */
+int udal_set_head_weights(udal_ctx* ctx, int head, const float* dw, const float* pw,
+                          const float* bias, const float* bn_gamma, const float* bn_beta,
+                          const float* bn_mean, const float* bn_var, const float* dwp,
+                          const float* pwp, const float* bp);
+
+/* efficientdet_keras.py:979-1050 (MC loop) + utils_extra.py:201-217 (stack_mcpred), starting at
+ * the BiFPN outputs.  feats[l]: device [B,H_l,W_l,F].  keep_masks: device uint8
+ * [T,2,L,R,B,F] (1 = keep) or NULL to draw them in-kernel from Philox4x32-10 keyed by
+ * (seed; t, head, level, repeat, b, f).  cls_out[l]: device [T,B,H_l,W_l,A*C];
+ * box_out[l]: device [T,B,H_l,W_l,4A|8A].  A head without MC dropout writes T identical
+ * samples only when T-stacking was requested by cfg (cls_mc / box_mc), else [B,...]. */
+int udal_heads_sample(udal_ctx* ctx, const float* const* feats, int batch,
+                      const uint8_t* keep_masks, uint64_t seed, float* const* cls_out,
+                      float* const* box_out);
+
+/* ---- pre-NMS: MC moments + decode ------------------------------------------------------- */
+/* Per-anchor outputs of the serving variant (max_nms_inputs == 0), all device pointers;
+ * any pointer may be NULL to skip that output.
+ *   utils_extra.py:220-244 (get_mcuncert)  -> mean_logits, std_logits  [B,N,C]
+ *   utils_box.py:105-276 (decode_uncert) / anchors.py:41-75 + postprocess.py:297-331
+ *                                          -> boxes, albox, mcbox     [B,N,4]
+ *   postprocess.py:123-135, 284            -> scores = sigmoid(max_c), classes = argmax_c [B,N] */
+typedef struct {
+  float* mean_logits;
+  float* std_logits;
+  float* boxes;
+  float* albox;
+  float* mcbox;
+  float* scores;
+  int32_t* classes;
+} udal_prenms_out;
+
+/* cls[l]: device [T,B,H,W,A*C] if cfg.cls_mc else [B,H,W,A*C]; box[l]: device
+ * [T,B,H,W,4A|8A] if cfg.box_mc else [B,H,W,4A|8A].  postprocess.py:144-339 (pre_nms) without
+ * top-k. */
+int udal_decode_moments(udal_ctx* ctx, const float* const* cls, const float* const* box,
+                        int batch, const udal_prenms_out* out);
+
+/* postprocess.py:90-121 (topk_class_boxes, max_nms_inputs > 0): k largest of values[B,M] in
+ * canonical order (value descending, index ascending).  idx_out [B,k] int32, val_out [B,k]. */
+int udal_topk(udal_ctx* ctx, const float* values, int batch, int64_t m, int k, int32_t* idx_out,
+              float* val_out);
+
+/* pre_nms with top-k (postprocess.py:212-282, 297-331): mean logits -> top-k -> gather ->
+ * decode -> moments on the k selected (anchor, class) pairs.  Outputs device [B,k,...]. */
+typedef struct {
+  float* mean_logits; /* [B,N,C]  classes_multi (un-gathered, postprocess.py:210-211) */
+  int32_t* topk_idx;  /* [B,k]    flat index into N*C */
+  float* boxes;       /* [B,k,4] */
+  float* albox;       /* [B,k,4] or NULL */
+  float* mcbox;       /* [B,k,4] or NULL */
+  float* mcclass;     /* [B,k]   std of the selected logit, or NULL */
+  float* scores;      /* [B,k] */
+  int32_t* classes;   /* [B,k] */
+} udal_prenms_topk_out;
+int udal_prenms_topk(udal_ctx* ctx, const float* const* cls, const float* const* box, int batch,
+                     const udal_prenms_topk_out* out);
+
+/* ---- NMS -------------------------------------------------------------------------------- */
+/* tf.raw_ops.NonMaxSuppressionV5 as called at postprocess.py:392-400, batched over independent
+ * segments: boxes [S,n,4], scores [S,n] (device).  Thresholds come from cfg.  sel_idx [S,max_out]
+ * int32 and sel_scores [S,max_out] are zero padded, valid [S] int32. */
+int udal_nms_v5(udal_ctx* ctx, const float* boxes, const float* scores, int segments, int n,
+                int32_t* sel_idx, float* sel_scores, int32_t* valid);
+
+/* ---- fused post-processing -------------------------------------------------------------- */
+/* postprocess.py:472-621 (postprocess_global), serving variant.  image_scales: device [B] or
+ * NULL.  Outputs (device): boxes [B,max_out,4*(1+has_al+has_mc)] = box|albox|mcbox,
+ * scores [B,max_out], classes [B,max_out,1+C*has_mcclass] = class|mcclass-std, valid [B] int32,
+ * logits [B,max_out,C]. */
+typedef struct {
+  float* boxes;
+  float* scores;
+  float* classes;
+  int32_t* valid;
+  float* logits;
+} udal_detections;
+int udal_postprocess_global(udal_ctx* ctx, const float* const* cls, const float* const* box,
+                            int batch, const float* image_scales, const udal_detections* out);
+
+/* postprocess.py:719-740 (postprocess_per_class), eval variant (cfg.max_nms_inputs > 0).
+ * Outputs: boxes [B,max_out,4], scores, classes [B,max_out], valid [B], logits [B,max_out,C].
+ * strict_reference != 0 reproduces the reference's logits chain (postprocess.py:659-666). */
+int udal_postprocess_per_class(udal_ctx* ctx, const float* const* cls, const float* const* box,
+                               int batch, const float* image_scales, int strict_reference,
+                               const udal_detections* out);
+
+/* postprocess.py:624-716 (per_class_nms) on already decoded candidates: boxes [B,K,4], scores
+ * [B,K], classes [B,K] int32 in the candidate order the reference would pass (top-k order).
+ * logits: [B,logit_rows,C] or NULL.  strict_reference != 0: the reference's logits chain; else
+ * logits rows are taken at the candidate position. */
+int udal_per_class_nms(udal_ctx* ctx, const float* boxes, const float* scores,
+                       const int32_t* classes, int batch, int k, const float* image_scales,
+                       const float* logits, int64_t logit_rows, int strict_reference,
+                       const udal_detections* out);
+
+/* postprocess.py:743-785 (generate_detections_from_nms_output): rows
+ * [id, x1, y1, x2, y2, score, class, logits...] from [B,mo,box_stride] boxes (first 4 columns
+ * ymin,xmin,ymax,xmax), scores [B,mo], classes [B,mo*class_stride] (first column), image ids [B],
+ * original widths [B] (flip only), logits [B,mo,nlogits] or NULL.  out [B,mo,7+nlogits]. */
+int udal_format_detections(udal_ctx* ctx, const float* boxes, int box_stride, const float* scores,
+                           const float* classes, int class_stride, const float* image_ids,
+                           const float* widths, int flip, const float* logits, int nlogits,
+                           int batch, int max_out, float* out);
+/* postprocess.py:874-887 (transform_detections): [id,x1,y1,x2,y2,score,class,...] ->
+ * [id,x,y,w,h,score,class]; in [rows,in_cols], out [rows,7]. */
+int udal_transform_detections(udal_ctx* ctx, const float* in, int64_t rows, int in_cols, float* out);
+
+/* layout helpers used by the Python mirror (device pointers):
+ * out[r] = a[r] ++ b[r] for r < rows (tf.concat on the last axis) */
+int udal_concat_channels(udal_ctx* ctx, const float* a, int ca, const float* b, int cb,
+                         int64_t rows, float* out);
+/* out[b][j][:] = src[b][idx[b][j]][:] (tf.gather / gather_nd batch_dims=1); rows out of range
+ * read as zero (TF GPU rule).  mode 0: 32-bit copy; mode 1: int32 -> float32(value + 1)
+ * (CLASS_OFFSET, postprocess.py:403). */
+int udal_gather_rows(udal_ctx* ctx, const void* src, int batch, int64_t n_rows, int width,
+                     const int32_t* idx, int m, int mode, void* out);
+
+/* heads + post-processing in one call: feats -> detections (variant by cfg.max_nms_inputs). */
+int udal_run(udal_ctx* ctx, const float* const* feats, int batch, const uint8_t* keep_masks,
+             uint64_t seed, const float* image_scales, const udal_detections* out);
+
+/* bytes of device scratch the context currently holds (grows on demand, never shrinks) */
+int udal_scratch_bytes(const udal_ctx* ctx, size_t* bytes);
+
+/* ---- nms_np family ---------------------------------------------------------------------- */
+/* nms_np.py:30-220 on the device: dets [n,5] = (x1,y1,x2,y2,score) host pointer in, kept rows
+ * out in selection order; method: 0 hard, 1 diou, 2 linear, 3 gaussian.  Returns the number of
+ * kept rows in *num_kept (synchronises). */
+int udal_nms_np(udal_ctx* ctx, const float* dets_host, int n, int method, float iou_thresh,
+                float sigma, float score_thresh, float* kept_host, int32_t* num_kept);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UDAL_H_ */

@@ -1,0 +1,125 @@
+"""CPU checks of the drop-in boundary: the C-ABI library loads and exports every symbol that
+include/udal.h declares, the ctypes struct mirrors the C struct, host logic behaves like the
+reference.  No compute calls - there is no GPU here."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_symbols():
+    text = open(os.path.join(ROOT, "include", "udal.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(udal_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    import udal_b200 as u
+    lib = ctypes.CDLL(u._lib.LIB_PATH)
+    syms = _header_symbols()
+    assert len(syms) >= 30
+    for s in syms:
+        assert hasattr(lib, s), "libudal.so does not export %s" % s
+    # and the binding table covers the header one to one
+    assert sorted(u._lib.SIGNATURES) == syms
+
+
+def test_config_struct_matches_c_layout(tmp_path):
+    import udal_b200 as u
+    src = tmp_path / "sz.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "udal.h"\nint main(){printf("%zu %zu %zu %zu\\n", sizeof(udal_config),'
+                   ' offsetof(udal_config, anchors_per_loc), offsetof(udal_config, nms_score_thresh), offsetof(udal_config, inv_keep_box));return 0;}\n')
+    exe = tmp_path / "sz"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    size, o1, o2, o3 = map(int, subprocess.check_output([str(exe)]).split())
+    C = u._lib.Config
+    assert ctypes.sizeof(C) == size
+    assert C.anchors_per_loc.offset == o1 and C.nms_score_thresh.offset == o2 and C.inv_keep_box.offset == o3
+
+
+def test_header_compiles_as_plain_c(tmp_path):
+    src = tmp_path / "t.c"
+    src.write_text('#include "udal.h"\nint main(void){return UDAL_ABI_VERSION - 1;}\n')
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           "-c", str(src), "-o", str(tmp_path / "t.o")])
+
+
+def test_no_gpu_fails_loudly_not_silently():
+    import udal_b200 as u
+    if u._lib.device_count() > 0:
+        pytest.skip("GPU present")
+    p = u.hparams_config.get_detection_config("efficientdet-d0", image_size=64, num_classes=3,
+                                              enable_softmax=True)
+    cls = [np.zeros((1, 8 >> i or 1, 8 >> i or 1, 27), np.float32) for i in range(5)]
+    with pytest.raises((RuntimeError, ValueError)):
+        u.postprocess.postprocess_global(p, cls, cls)
+
+
+def test_missing_library_is_an_import_error(tmp_path):
+    code = ("import sys; sys.path.insert(0, %r)\n"
+            "import importlib\n"
+            "m = importlib.import_module('uncertainty-detection-autolabeling_b200._lib')\n"
+            "m.LIB_PATH = %r; m._lib = None\n"
+            "try:\n    m.load()\nexcept ImportError as e:\n    print('IMPORT_ERROR'); sys.exit(0)\nsys.exit(1)\n"
+            % (ROOT, str(tmp_path / "nope.so")))
+    out = subprocess.check_output([sys.executable, "-c", code], env=dict(os.environ, PYTHONPATH=ROOT))
+    assert b"IMPORT_ERROR" in out
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "uncertainty-detection-autolabeling_b200")
+    bad = re.compile(r"^\s*(import\s+oracle|from\s+oracle|from\s+\.+oracle|#\s*include\s*[\"<].*oracle)|liboracle|oracle/_build", re.M)
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert not bad.search(text), f
+
+
+def test_host_helpers_match_reference_semantics():
+    import udal_b200 as u
+    assert u.utils.parse_image_size("1024x512") == (512, 1024)
+    assert u.utils.parse_image_size(512) == (512, 512)
+    assert u.utils.parse_image_size((3, 4)) == (3, 4)
+    with pytest.raises(ValueError):
+        u.utils.parse_image_size(1.5)
+    fs = u.utils.get_feat_sizes((720, 1280), 7)
+    assert [(f["height"], f["width"]) for f in fs[3:]] == [(90, 160), (45, 80), (23, 40), (12, 20), (6, 10)]
+    assert u.postprocess.to_list({"b": 2, "a": 1}) == [1, 2]
+    assert u.postprocess.to_list((1, 2)) == [1, 2]
+    assert u.postprocess.to_list(3) is None
+    with pytest.raises(ValueError, match="invalid nms method"):
+        u.engine.nms_thresholds(dict(method="bogus", iou_thresh=None, score_thresh=None, sigma=None))
+    assert u.engine.nms_thresholds(dict(method="gaussian", iou_thresh=None, score_thresh=0.0, sigma=None)) == (1, 0.25, 0.5, 0.001)
+    assert u.engine.nms_thresholds(dict(method="hard", iou_thresh=None, score_thresh=None, sigma=None))[1:] == (0.0, 0.5, float("-inf"))
+
+
+def test_anchor_table_matches_golden():
+    import udal_b200 as u
+    from tests.helpers import load_golden
+    g = load_golden("anchors")
+    for tag, size in (("512", 512), ("384x1280", (384, 1280)), ("720x1280", (720, 1280)), ("768", 768),
+                      ("str1024x512", "1024x512"), ("64x96", (64, 96))):
+        a = u.anchors.Anchors(3, 7, 3, [1.0, 2.0, 0.5], 4.0, size)
+        assert a.boxes.shape[0] == int(g[tag + "_n"])
+        np.testing.assert_array_equal(a.boxes[g[tag + "_rows"]], g[tag + "_vals"])
+        np.testing.assert_array_equal(a.boxes.astype(np.float64).sum(0), g[tag + "_sum64"])
+        assert a.get_anchors_per_location() == 9
+    np.testing.assert_array_equal(
+        u.anchors.Anchors(3, 5, 2, [1.0, [1.4, 0.7]], [4.0, 3.0, 5.0], 128).boxes, g["custom_128"])
+
+
+def test_philox_reference_vector():
+    # Random123 known answer: philox4x32-10, counter = key = 0
+    import udal_b200 as u
+    m = u.heads.philox_keep_masks((1, 2, 1, 1, 1, 4), 0.0, 0.0, 0)
+    assert m.shape == (1, 2, 1, 1, 1, 4) and m.dtype == np.uint8 and m.all()
+    # statistical sanity of the uniform stream
+    k = u.heads.philox_keep_masks((8, 2, 5, 3, 4, 64), 0.05, 0.3, 1234)
+    assert abs(k[:, 0].mean() - 0.95) < 0.01 and abs(k[:, 1].mean() - 0.7) < 0.01

@@ -1,0 +1,348 @@
+"""GPU parity: the CUDA path (through the C ABI / the Python mirror) against the CPU oracle and
+the committed golden fixtures.  Bar: bit-exact for index / integer outputs, rtol 1e-4 for fp32
+(plus an atol of a few box ulps where the reference itself cancels, SURVEY hard part 1)."""
+import copy
+import ctypes
+
+import numpy as np
+import pytest
+
+from oracle import nms_ref, ref_np
+from tests.helpers import (golden_inputs, golden_params, load_golden, random_boxes, synth_head_outputs)
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-4
+BOX_ATOL = 2e-4  # ~ 4 ulp of a 512 px coordinate
+
+
+@pytest.fixture(scope="module")
+def u():
+    import udal_b200
+    assert udal_b200._lib.device_count() > 0
+    return udal_b200
+
+
+A_CASES = ["A_mcla_gauss", "A_mcla_hard", "A_la_only", "A_mc_only", "A_plain", "A_mcla_falsedec"]
+B_CASES = ["B_mcla_gauss", "B_mcla_hard", "B_plain_hard"]
+
+
+# ---------------------------------------------------------------------------------------------
+# golden fixtures (made by executing the reference's own source, tests/golden/make_golden.py)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", A_CASES + B_CASES)
+def test_extract_uncertainties_vs_golden(u, name):
+    g = load_golden("post_" + name)
+    params = golden_params(g)
+    cls, box = golden_inputs(g)
+    boxes, uncerts, scores, classes, multi = u.postprocess.extract_uncertainties(copy.deepcopy(params), cls, box)
+    np.testing.assert_allclose(boxes, g["pre_boxes"], rtol=RTOL, atol=BOX_ATOL)
+    np.testing.assert_allclose(scores, g["pre_scores"], rtol=1e-6)
+    np.testing.assert_array_equal(classes, g["pre_classes"])
+    np.testing.assert_array_equal(multi, g["pre_multi"])
+    for i in range(3):
+        key = "pre_unc%d" % i
+        if key in g.files:
+            # std of T fp32 boxes: the reference's own cancellation floor is a few box ulps
+            np.testing.assert_allclose(uncerts[i], g[key], rtol=RTOL, atol=BOX_ATOL if i == 2 else 1e-6)
+        else:
+            assert uncerts is None or uncerts[i] is None
+    # the decode is expected to be bit-exact in all but a vanishing fraction of values
+    assert np.mean(boxes != g["pre_boxes"]) < 1e-3
+
+
+@pytest.mark.parametrize("name", A_CASES)
+def test_postprocess_global_vs_golden(u, name):
+    g = load_golden("post_" + name)
+    params = golden_params(g)
+    cls, box = golden_inputs(g)
+    out = u.postprocess.postprocess_global(copy.deepcopy(params), cls, box, g["scales"])
+    n_out = len([k for k in g.files if k.startswith("out")])
+    assert len(out) == n_out
+    np.testing.assert_array_equal(out[3], g["out3"])                      # valid_len
+    cls_col = out[2][..., 0] if out[2].ndim == 3 else out[2]
+    ref_cls = g["out2"][..., 0] if g["out2"].ndim == 3 else g["out2"]
+    np.testing.assert_array_equal(cls_col, ref_cls)                        # classes => same keep indices
+    np.testing.assert_allclose(out[1], g["out1"], rtol=1e-6, atol=1e-7)    # (soft-decayed) scores
+    np.testing.assert_allclose(out[0], g["out0"], rtol=RTOL, atol=BOX_ATOL)
+    np.testing.assert_allclose(out[2], g["out2"], rtol=RTOL, atol=1e-6)
+    np.testing.assert_array_equal(out[4], g["out4"])                       # logits rows (gathered means)
+
+
+@pytest.mark.parametrize("name", B_CASES)
+def test_postprocess_per_class_vs_golden(u, name):
+    g = load_golden("post_" + name)
+    params = golden_params(g)
+    cls, box = golden_inputs(g)
+    out = u.postprocess.postprocess_per_class(copy.deepcopy(params), cls, box, g["scales"])
+    np.testing.assert_array_equal(out[3], g["out3"])
+    np.testing.assert_array_equal(out[2], g["out2"])
+    np.testing.assert_allclose(out[1], g["out1"], rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(out[0], g["out0"], rtol=RTOL, atol=BOX_ATOL)
+    np.testing.assert_array_equal(out[4], g["out4"])  # strict reference logits chain
+    ids = np.arange(cls[0].shape[-4]).astype(np.float32) + 7
+    det = u.postprocess.generate_detections(copy.deepcopy(params), cls, box, g["scales"], ids)
+    np.testing.assert_allclose(det, g["det"], rtol=RTOL, atol=BOX_ATOL)
+    det_f = u.postprocess.generate_detections(copy.deepcopy(params), cls, box, g["scales"], ids, flip=True)
+    np.testing.assert_allclose(det_f, g["det_flip"], rtol=RTOL, atol=BOX_ATOL)
+    np.testing.assert_array_equal(u.postprocess.transform_detections(g["det"]), g["det_xywh"])
+
+
+def test_per_class_correct_logits_flag(u):
+    g = load_golden("post_B_mcla_gauss")
+    params = dict(golden_params(g), strict_reference=False)
+    cls, box = golden_inputs(g)
+    out = u.postprocess.postprocess_per_class(copy.deepcopy(params), cls, box, g["scales"])
+    # non-strict: logits of a detection = mean logits of ITS anchor; its class column must then
+    # hold the (sigmoid^-1 of the) selected score for hard NMS, or at least be the anchor's row
+    pre = ref_np.extract_uncertainties(copy.deepcopy(dict(params, strict_reference=True)), cls, box)
+    multi = pre[4]
+    for b in range(out[0].shape[0]):
+        for j in range(int(out[3][b])):
+            row = out[4][b, j]
+            # the row must be one of the image's mean-logit rows
+            assert np.any(np.all(multi[b] == row[None], axis=1))
+            c = int(out[2][b, j]) - 1
+            if params["nms_configs"]["method"] == "hard":
+                assert ref_np.sigmoid(row[c:c + 1])[0] == out[1][b, j]
+
+
+@pytest.mark.parametrize("method", ["l-norm", "n-flow", "falsedec"])
+def test_decode_uncert_vs_golden(u, method):
+    g = load_golden("decode")
+    c, s = u.utils_box.decode_uncert(g["t"], g["sigma"], g["anchors"], method=method)
+    ref_c, ref_s = ref_np.decode_uncert(g["t"], g["sigma"], g["anchors"], method=method)
+    key = method if method != "n-flow" else "l-norm"
+    np.testing.assert_allclose(c, g["box_" + key], rtol=1e-6, atol=1e-5)
+    np.testing.assert_allclose(s, g["std_" + key], rtol=1e-6)
+    assert np.mean(c != ref_c) < 1e-3 and np.mean(s != ref_s) < 1e-3
+    c, s = u.utils_box.decode_uncert(g["ka_t"], g["ka_s"], g["ka_a"])
+    np.testing.assert_array_equal(c, g["ka_box"])
+    np.testing.assert_array_equal(s, g["ka_std"])
+    np.testing.assert_allclose(u.anchors.decode_box_outputs(g["t"], g["anchors"]), g["plain"], rtol=1e-6, atol=1e-5)
+    with pytest.raises(ValueError):
+        u.utils_box.decode_uncert(g["t"], g["sigma"], g["anchors"], method="sample")
+
+
+def test_get_mcuncert_vs_golden(u):
+    g = load_golden("mcuncert")
+    mean, std = u.utils_extra.get_mcuncert([g["in%d" % i] for i in range(5)])
+    for i in range(5):
+        np.testing.assert_array_equal(mean[i], g["mean%d" % i])
+        np.testing.assert_array_equal(std[i], g["std%d" % i])
+
+
+# ---------------------------------------------------------------------------------------------
+# top-k
+# ---------------------------------------------------------------------------------------------
+def _engine(u, **kw):
+    p = u.hparams_config.get_detection_config("efficientdet-d0", image_size=64, num_classes=3,
+                                              enable_softmax=True, **kw)
+    return u.engine.get_engine(p)
+
+
+@pytest.mark.parametrize("m,k,batch", [(1000, 1, 1), (1000, 1000, 2), (5000, 300, 3), (343728, 5000, 2),
+                                       (1729800, 5000, 1), (70000, 8192, 1)])
+def test_topk_vs_oracle(u, m, k, batch):
+    rng = np.random.default_rng(m + k)
+    v = rng.normal(-4.6, 2.0, (batch, m)).astype(np.float32)
+    v[0, :: max(m // 37, 1)] = v[0, 0]  # exact ties across the row
+    if m > 10:
+        v[0, 5] = 0.0
+        v[0, 6] = -0.0
+    eng = _engine(u)
+    val, idx = eng.topk(v, k)
+    rv, ri = ref_np.top_k(v, k)
+    np.testing.assert_array_equal(idx.numpy(), ri)
+    np.testing.assert_array_equal(val.numpy(), rv + np.float32(0.0))
+
+
+def test_topk_degenerate_inputs_use_the_fallback(u):
+    eng = _engine(u)
+    cap = ctypes.c_int.in_dll(eng.lib, "udal_topk_cand_cap_override")
+    rng = np.random.default_rng(0)
+    try:
+        cap.value = 64  # force the candidate buffer to overflow
+        for v in (np.zeros((2, 20000), np.float32),
+                  np.repeat(rng.normal(size=(1, 40)).astype(np.float32), 500, axis=1),
+                  rng.normal(size=(2, 30000)).astype(np.float32)):
+            val, idx = eng.topk(v, 777)
+            rv, ri = ref_np.top_k(v, 777)
+            np.testing.assert_array_equal(idx.numpy(), ri)
+            np.testing.assert_array_equal(val.numpy(), rv)
+    finally:
+        cap.value = 0
+    v = np.full((1, 300000), 1.5, np.float32)  # one huge tie with the default buffer
+    val, idx = eng.topk(v, 5000)
+    np.testing.assert_array_equal(idx.numpy(), np.arange(5000, dtype=np.int32)[None])
+
+
+def test_topk_argument_errors(u):
+    eng = _engine(u)
+    with pytest.raises(ValueError):
+        eng.topk(np.zeros((1, 10), np.float32), 11)
+    with pytest.raises(ValueError):
+        eng.topk(np.zeros((1, 100000), np.float32), 9000)
+
+
+# ---------------------------------------------------------------------------------------------
+# NMS (TF NonMaxSuppressionV5 semantics)
+# ---------------------------------------------------------------------------------------------
+def _nms_engine(u, method, variant="new", prefilter=0, score_thresh=0.0, iou=None, sigma=None, max_out=100):
+    p = u.hparams_config.get_detection_config(
+        "efficientdet-d0", image_size=64, num_classes=3, enable_softmax=True, tf_nms_variant=variant,
+        nms_prefilter_k=prefilter,
+        nms_configs=dict(method=method, score_thresh=score_thresh, iou_thresh=iou, sigma=sigma,
+                         max_output_size=max_out))
+    return u.engine.get_engine(p), p
+
+
+@pytest.mark.parametrize("method", ["hard", "gaussian"])
+@pytest.mark.parametrize("variant", ["new", "old"])
+@pytest.mark.parametrize("n,extent,prefilter", [(0, 300, 0), (1, 300, 0), (50, 100, 0), (700, 200, 0),
+                                                (5000, 400, 0), (49104, 512, 0), (3000, 60, 64),
+                                                (3000, 300, 16)])
+def test_nms_v5_vs_oracle(u, method, variant, n, extent, prefilter):
+    eng, p = _nms_engine(u, method, variant, prefilter)
+    rng = np.random.default_rng(n + prefilter)
+    S = 3
+    boxes = np.stack([random_boxes(rng, n, extent) for _ in range(S)]) if n else np.zeros((S, 0, 4), np.float32)
+    scores = rng.uniform(0, 1, (S, n)).astype(np.float32)
+    if n >= 50:
+        boxes[0, 3] = boxes[0, 2]
+        boxes[0, 4, 2:] = boxes[0, 4, :2]
+        scores[0, 5] = scores[0, 6]
+        scores[1, :25] = 0.75  # block of ties
+    sigma_tf, iou_thr, thr, max_out = ref_np.nms_thresholds(p["nms_configs"])
+    idx, sc, valid = eng.nms_v5(boxes, scores) if n else (None, None, None)
+    if n == 0:
+        idx, sc, valid = eng.nms_v5(np.zeros((S, 0, 4), np.float32), np.zeros((S, 0), np.float32))
+    idx, sc, valid = idx.numpy(), sc.numpy(), valid.numpy()
+    for s in range(S):
+        ri, rs, rv = nms_ref.non_max_suppression_v5(boxes[s], scores[s], max_out, iou_thr, thr, sigma_tf,
+                                                    True, variant)
+        assert valid[s] == rv
+        np.testing.assert_array_equal(idx[s], ri)
+        np.testing.assert_array_equal(sc[s], rs)
+
+
+def test_nms_mirror_padded_and_unpadded(u):
+    eng, p = _nms_engine(u, "gaussian")
+    rng = np.random.default_rng(5)
+    n = 400
+    boxes, scores = random_boxes(rng, n, 150), rng.uniform(0, 1, n).astype(np.float32)
+    classes = rng.integers(0, 3, n).astype(np.int32)
+    multi = rng.normal(size=(n, 3)).astype(np.float32)
+    u1 = rng.normal(size=(n, 3)).astype(np.float32)
+    u2 = rng.normal(size=(n, 4)).astype(np.float32)
+    for padded in (True, False):
+        got = u.postprocess.nms(p, boxes, scores, classes, padded, multiclass=multi, uncerts1=u1,
+                                uncerts2=u2, uncerts3=u2)
+        ref = ref_np.nms(p, boxes, scores, classes, padded, multiclass=multi, uncerts1=u1, uncerts2=u2,
+                         uncerts3=u2)
+        assert len(got) == len(ref) == 8
+        for a, b in zip(got, ref):
+            np.testing.assert_array_equal(np.asarray(a), np.asarray(b))
+    with pytest.raises(ValueError, match="invalid nms method"):
+        bad = copy.deepcopy(p)
+        bad["nms_configs"]["method"] = "linear"
+        u.postprocess.nms(bad, boxes, scores, classes, True)
+
+
+def test_per_class_nms_mirror_vs_oracle(u):
+    for method in ("hard", "gaussian"):
+        eng, p = _nms_engine(u, method)
+        rng = np.random.default_rng(8)
+        B, K = 2, 600
+        boxes = np.stack([random_boxes(rng, K, 120) for _ in range(B)])
+        scores = -np.sort(-rng.uniform(0, 1, (B, K)).astype(np.float32), axis=1)
+        classes = rng.integers(0, 3, (B, K)).astype(np.int32)
+        classes[1][classes[1] == 1] = 2  # an empty class
+        scales = np.float32([1.0, 2.0])
+        logits = rng.normal(size=(B, 774, 3)).astype(np.float32)
+        got = u.postprocess.per_class_nms(p, boxes, scores, classes, scales, logits)
+        ref = ref_np.per_class_nms(p, boxes, scores, classes, scales, logits, strict_reference=True)
+        for a, b in zip(got, ref):
+            np.testing.assert_array_equal(a, b)
+        got = u.postprocess.per_class_nms(p, boxes, scores, classes, None, None)
+        ref = ref_np.per_class_nms(p, boxes, scores, classes, None, None)
+        assert len(got) == len(ref) == 4
+        for a, b in zip(got, ref):
+            np.testing.assert_array_equal(a, b)
+
+
+# ---------------------------------------------------------------------------------------------
+# random configurations against the oracle (not only the golden ones)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("C,T,batch,size,method", [(7, 10, 2, (64, 96), "gaussian"), (8, 1, 1, 64, "hard"),
+                                                   (10, 30, 1, 64, "gaussian"), (90, 4, 2, 64, "hard"),
+                                                   (3, 40, 1, 64, "gaussian")])
+def test_postprocess_global_vs_oracle_random(u, C, T, batch, size, method):
+    p = u.hparams_config.get_detection_config(
+        "efficientdet-d0", image_size=size, num_classes=C, enable_softmax=True, loss_attenuation=True,
+        mc_dropout=True, mc_classheadrate=0.05, mc_boxheadrate=0.05, mc_dropoutsamp=T,
+        nms_configs=dict(method=method))
+    cls, box = synth_head_outputs(p, batch, seed=C * 100 + T)
+    scales = np.linspace(1, 2, batch).astype(np.float32)
+    got = u.postprocess.postprocess_global(p, cls, box, scales)
+    ref = ref_np.postprocess_global(copy.deepcopy(p), cls, box, scales)
+    np.testing.assert_array_equal(got[3], ref[3])
+    np.testing.assert_array_equal(got[2][..., 0], ref[2][..., 0])
+    np.testing.assert_allclose(got[1], ref[1], rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(got[0], ref[0], rtol=RTOL, atol=BOX_ATOL)
+    np.testing.assert_allclose(got[2], ref[2], rtol=RTOL, atol=1e-6)
+    np.testing.assert_array_equal(got[4], ref[4])
+
+
+@pytest.mark.parametrize("C,T,batch,k,method", [(7, 10, 2, 500, "gaussian"), (10, 3, 1, 5000, "hard"),
+                                                (90, 2, 1, 2000, "gaussian")])
+def test_postprocess_per_class_vs_oracle_random(u, C, T, batch, k, method):
+    p = u.hparams_config.get_detection_config(
+        "efficientdet-d0", image_size=(64, 96), num_classes=C, enable_softmax=True, loss_attenuation=True,
+        mc_dropout=True, mc_classheadrate=0.05, mc_boxheadrate=0.05, mc_dropoutsamp=T,
+        nms_configs=dict(method=method, max_nms_inputs=k))
+    cls, box = synth_head_outputs(p, batch, seed=C + T + k)
+    scales = np.linspace(1, 2, batch).astype(np.float32)
+    got = u.postprocess.postprocess_per_class(p, cls, box, scales)
+    ref = ref_np.postprocess_per_class(copy.deepcopy(p), cls, box, scales, strict_reference=True)
+    np.testing.assert_array_equal(got[3], ref[3])
+    np.testing.assert_array_equal(got[2], ref[2])
+    np.testing.assert_allclose(got[1], ref[1], rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(got[0], ref[0], rtol=RTOL, atol=BOX_ATOL)
+    np.testing.assert_array_equal(got[4], ref[4])
+
+
+def test_device_arrays_in_device_arrays_out_and_dlpack(u):
+    import torch
+    g = load_golden("post_A_mcla_gauss")
+    params = golden_params(g)
+    cls, box = golden_inputs(g)
+    tcls = [torch.from_numpy(c).cuda() for c in cls]
+    tbox = [torch.from_numpy(b).cuda() for b in box]
+    torch.cuda.synchronize()
+    out = u.postprocess.postprocess_global(copy.deepcopy(params), tcls, tbox, g["scales"])
+    assert all(isinstance(o, u.device.DeviceArray) for o in out)
+    back = torch.from_dlpack(out[0])  # zero-copy export
+    assert back.is_cuda and tuple(back.shape) == g["out0"].shape
+    np.testing.assert_allclose(back.cpu().numpy(), g["out0"], rtol=RTOL, atol=BOX_ATOL)
+    t2 = torch.as_tensor(out[1], device="cuda")  # __cuda_array_interface__
+    np.testing.assert_allclose(t2.cpu().numpy(), g["out1"], rtol=1e-6, atol=1e-7)
+
+
+def test_error_behaviour_matches_reference(u):
+    g = load_golden("post_A_mcla_gauss")
+    params = golden_params(g)
+    cls, box = golden_inputs(g)
+    bad = copy.deepcopy(params)
+    bad["nms_configs"]["method"] = "bogus"
+    with pytest.raises(ValueError, match="invalid nms method"):
+        u.postprocess.postprocess_global(bad, cls, box)
+    no_soft = dict(copy.deepcopy(params), enable_softmax=False)
+    assert u.postprocess.extract_uncertainties(no_soft, cls, box) is None
+    with pytest.raises(TypeError):
+        u.postprocess.postprocess_global(no_soft, cls, box)
+    with pytest.raises(ValueError):
+        u.postprocess.postprocess_global(params, cls[:4], box[:4])
+    one = dict(copy.deepcopy(params), mc_dropoutsamp=1)
+    with pytest.raises(ValueError):  # T == 1 is only defined for batch 1 (postprocess.py:180-203)
+        u.postprocess.postprocess_global(one, [c[:1] for c in cls], [b[:1] for b in box])

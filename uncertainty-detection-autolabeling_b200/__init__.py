@@ -1,0 +1,20 @@
+"""udal-b200: B200-native (sm_100a) uncertainty sampling + post-processing for EfficientDet
+auto-labeling - the hot path of continental/uncertainty-detection-autolabeling behind the
+reference's own Python entry points.
+
+    import importlib; udal = importlib.import_module("uncertainty-detection-autolabeling_b200")
+    (or ``import udal_b200`` - the alias module at the repository root)
+
+Modules mirror the reference: ``postprocess``, ``anchors``, ``nms_np``, ``utils_box``,
+``utils_extra``, ``hparams_config``, ``utils``; ``heads`` and ``scheduler`` are the new entry
+points for the head sampler and the multi-GPU image scheduler.  Everything computes on the GPU
+through ``libudal.so``; importing fails loudly when the library is missing (no CPU fallback).
+"""
+from . import _lib
+
+_lib.load()  # fail loudly at import time if the CUDA library is missing
+
+from . import anchors, device, engine, heads, hparams_config, nms_np, postprocess, scheduler, utils, utils_box, utils_extra  # noqa: E402,F401
+
+__all__ = ["anchors", "device", "engine", "heads", "hparams_config", "nms_np", "postprocess",
+           "scheduler", "utils", "utils_box", "utils_extra"]

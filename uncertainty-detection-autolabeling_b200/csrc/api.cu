@@ -1,0 +1,261 @@
+// Context, memory and thin public wrappers of libudal (see include/udal.h).
+#include <stdarg.h>
+
+#include <algorithm>
+
+#include "udal_common.cuh"
+
+static thread_local char g_err[1024] = "";
+
+void udal_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int udal_cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
+  udal_set_error("CUDA error %d (%s) at %s:%d in %s", (int)e, cudaGetErrorString(e), file, line, what);
+  return e == cudaErrorMemoryAllocation ? UDAL_ERR_NOMEM : UDAL_ERR_CUDA;
+}
+
+int udal_scratch_get(udal_ctx* ctx, int slot, size_t bytes, void** out) {
+  udal_scratch& s = ctx->scratch[slot];
+  if (bytes == 0) bytes = 16;
+  if (s.bytes < bytes) {
+    if (s.ptr) {
+      // the old block may still be in use by enqueued work
+      UDAL_CUDA(cudaStreamSynchronize(ctx->stream));
+      UDAL_CUDA(cudaFree(s.ptr));
+      s.ptr = nullptr;
+      s.bytes = 0;
+    }
+    size_t want = bytes + bytes / 4;
+    want = (want + 255) & ~(size_t)255;
+    UDAL_CUDA(cudaMalloc(&s.ptr, want));
+    s.bytes = want;
+  }
+  *out = s.ptr;
+  return UDAL_OK;
+}
+
+extern "C" {
+
+const char* udal_last_error(void) { return g_err; }
+int udal_abi_version(void) { return UDAL_ABI_VERSION; }
+
+int udal_device_count(int* count) {
+  UDAL_REQUIRE(count, "NULL count");
+  UDAL_CUDA(cudaGetDeviceCount(count));
+  return UDAL_OK;
+}
+
+int udal_create(const udal_config* cfg, udal_ctx** out) {
+  UDAL_REQUIRE(cfg && out, "udal_create: NULL argument");
+  UDAL_REQUIRE(cfg->abi_version == UDAL_ABI_VERSION, "udal_create: ABI version %d, library is %d",
+               cfg->abi_version, UDAL_ABI_VERSION);
+  UDAL_REQUIRE(cfg->num_levels >= 1 && cfg->num_levels <= UDAL_MAX_LEVELS, "num_levels %d outside [1,%d]",
+               cfg->num_levels, UDAL_MAX_LEVELS);
+  UDAL_REQUIRE(cfg->anchors_per_loc >= 1 && cfg->anchors_per_loc <= 64, "anchors_per_loc %d unsupported",
+               cfg->anchors_per_loc);
+  UDAL_REQUIRE(cfg->num_classes >= 1 && cfg->num_classes <= 1024, "num_classes %d unsupported", cfg->num_classes);
+  UDAL_REQUIRE(cfg->mc_samples >= 1 && cfg->mc_samples <= 4096, "mc_samples %d unsupported", cfg->mc_samples);
+  UDAL_REQUIRE(cfg->max_output_size >= 1 && cfg->max_output_size <= 2048, "max_output_size %d unsupported",
+               cfg->max_output_size);
+  UDAL_REQUIRE(cfg->decode_method >= UDAL_DECODE_LNORM && cfg->decode_method <= UDAL_DECODE_FALSEDEC,
+               "decode method %d unsupported (the 'sample' method draws from tfp and is not offered)",
+               cfg->decode_method);
+  UDAL_REQUIRE(cfg->nms_method == UDAL_NMS_HARD || cfg->nms_method == UDAL_NMS_GAUSSIAN,
+               "Inference has invalid nms method %d", cfg->nms_method);
+  UDAL_REQUIRE(cfg->max_nms_inputs >= 0 && cfg->max_nms_inputs <= 8192, "max_nms_inputs %d outside [0,8192]",
+               cfg->max_nms_inputs);
+  for (int l = 0; l < cfg->num_levels; ++l)
+    UDAL_REQUIRE(cfg->level_h[l] > 0 && cfg->level_w[l] > 0, "level %d has an empty feature map", l);
+  int ndev = 0;
+  UDAL_CUDA(cudaGetDeviceCount(&ndev));
+  UDAL_REQUIRE(cfg->device >= 0 && cfg->device < ndev, "device %d not present (%d visible)", cfg->device, ndev);
+  UDAL_CUDA(cudaSetDevice(cfg->device));
+  udal_ctx* ctx = new udal_ctx();
+  ctx->cfg = *cfg;
+  int64_t off = 0;
+  for (int l = 0; l <= UDAL_MAX_LEVELS; ++l) {
+    ctx->level_pix_off[l] = off;
+    if (l < cfg->num_levels) off += (int64_t)cfg->level_h[l] * cfg->level_w[l];
+  }
+  ctx->num_pixels = off;
+  ctx->num_anchors = off * cfg->anchors_per_loc;
+  cudaError_t e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev_start);
+  if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev_stop);
+  if (e != cudaSuccess) {
+    delete ctx;
+    return udal_cuda_fail(e, "stream/event creation", __FILE__, __LINE__);
+  }
+  ctx->stream = ctx->own_stream;
+  *out = ctx;
+  return UDAL_OK;
+}
+
+static void free_head(udal_head_weights_dev& h) {
+  cudaFree(h.dw);
+  cudaFree(h.pw);
+  cudaFree(h.bias);
+  cudaFree(h.bn_scale);
+  cudaFree(h.bn_shift);
+  cudaFree(h.dwp);
+  cudaFree(h.pwp);
+  cudaFree(h.bp);
+  cudaFree(h.pw_bf16);
+  cudaFree(h.pwp_bf16);
+  cudaFree(h.fold_bias);
+  h = udal_head_weights_dev();
+}
+
+int udal_destroy(udal_ctx* ctx) {
+  if (!ctx) return UDAL_OK;
+  cudaSetDevice(ctx->cfg.device);
+  cudaStreamSynchronize(ctx->stream);
+  for (auto& s : ctx->scratch) cudaFree(s.ptr);
+  for (void* p : ctx->user_allocs) cudaFree(p);
+  cudaFree(ctx->anchors);
+  free_head(ctx->heads[0]);
+  free_head(ctx->heads[1]);
+  cudaEventDestroy(ctx->ev_start);
+  cudaEventDestroy(ctx->ev_stop);
+  cudaStreamDestroy(ctx->own_stream);
+  delete ctx;
+  return UDAL_OK;
+}
+
+int udal_set_stream(udal_ctx* ctx, void* cuda_stream) {
+  UDAL_REQUIRE(ctx, "NULL ctx");
+  ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+  return UDAL_OK;
+}
+
+int udal_sync(udal_ctx* ctx) {
+  UDAL_REQUIRE(ctx, "NULL ctx");
+  UDAL_CUDA(cudaStreamSynchronize(ctx->stream));
+  return UDAL_OK;
+}
+
+int udal_malloc(udal_ctx* ctx, size_t bytes, void** dev_ptr) {
+  UDAL_REQUIRE(ctx && dev_ptr, "NULL argument");
+  UDAL_CUDA(cudaSetDevice(ctx->cfg.device));
+  void* p = nullptr;
+  UDAL_CUDA(cudaMalloc(&p, bytes ? bytes : 16));
+  ctx->user_allocs.push_back(p);
+  *dev_ptr = p;
+  return UDAL_OK;
+}
+
+int udal_free(udal_ctx* ctx, void* dev_ptr) {
+  UDAL_REQUIRE(ctx, "NULL ctx");
+  if (!dev_ptr) return UDAL_OK;
+  auto it = std::find(ctx->user_allocs.begin(), ctx->user_allocs.end(), dev_ptr);
+  UDAL_REQUIRE(it != ctx->user_allocs.end(), "udal_free: pointer was not allocated by this context");
+  ctx->user_allocs.erase(it);
+  UDAL_CUDA(cudaStreamSynchronize(ctx->stream));
+  UDAL_CUDA(cudaFree(dev_ptr));
+  return UDAL_OK;
+}
+
+int udal_host_alloc(size_t bytes, void** pinned_ptr) {
+  UDAL_REQUIRE(pinned_ptr, "NULL argument");
+  UDAL_CUDA(cudaHostAlloc(pinned_ptr, bytes ? bytes : 16, cudaHostAllocDefault));
+  return UDAL_OK;
+}
+
+int udal_host_free(void* pinned_ptr) {
+  if (pinned_ptr) UDAL_CUDA(cudaFreeHost(pinned_ptr));
+  return UDAL_OK;
+}
+
+int udal_memcpy_h2d(udal_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes) {
+  UDAL_REQUIRE(ctx && (bytes == 0 || (dst_dev && src_host)), "NULL argument");
+  if (bytes) UDAL_CUDA(cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  return UDAL_OK;
+}
+
+int udal_memcpy_d2h(udal_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes) {
+  UDAL_REQUIRE(ctx && (bytes == 0 || (dst_host && src_dev)), "NULL argument");
+  if (bytes) UDAL_CUDA(cudaMemcpyAsync(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  return UDAL_OK;
+}
+
+int udal_memcpy_d2d(udal_ctx* ctx, void* dst_dev, const void* src_dev, size_t bytes) {
+  UDAL_REQUIRE(ctx && (bytes == 0 || (dst_dev && src_dev)), "NULL argument");
+  if (bytes) UDAL_CUDA(cudaMemcpyAsync(dst_dev, src_dev, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+  return UDAL_OK;
+}
+
+int udal_memset(udal_ctx* ctx, void* dst_dev, int value, size_t bytes) {
+  UDAL_REQUIRE(ctx && (bytes == 0 || dst_dev), "NULL argument");
+  if (bytes) UDAL_CUDA(cudaMemsetAsync(dst_dev, value, bytes, ctx->stream));
+  return UDAL_OK;
+}
+
+int udal_timer_start(udal_ctx* ctx) {
+  UDAL_REQUIRE(ctx, "NULL ctx");
+  UDAL_CUDA(cudaEventRecord(ctx->ev_start, ctx->stream));
+  return UDAL_OK;
+}
+
+int udal_timer_stop(udal_ctx* ctx, float* elapsed_ms) {
+  UDAL_REQUIRE(ctx && elapsed_ms, "NULL argument");
+  UDAL_CUDA(cudaEventRecord(ctx->ev_stop, ctx->stream));
+  UDAL_CUDA(cudaEventSynchronize(ctx->ev_stop));
+  UDAL_CUDA(cudaEventElapsedTime(elapsed_ms, ctx->ev_start, ctx->ev_stop));
+  return UDAL_OK;
+}
+
+int udal_num_anchors(const udal_ctx* ctx, int64_t* n) {
+  UDAL_REQUIRE(ctx && n, "NULL argument");
+  *n = ctx->num_anchors;
+  return UDAL_OK;
+}
+
+int udal_launch_count(const udal_ctx* ctx, int64_t* n) {
+  UDAL_REQUIRE(ctx && n, "NULL argument");
+  *n = ctx->launches;
+  return UDAL_OK;
+}
+
+int udal_scratch_bytes(const udal_ctx* ctx, size_t* bytes) {
+  UDAL_REQUIRE(ctx && bytes, "NULL argument");
+  size_t t = 0;
+  for (const auto& s : ctx->scratch) t += s.bytes;
+  *bytes = t;
+  return UDAL_OK;
+}
+
+int udal_set_anchors(udal_ctx* ctx, const float* anchors_host, int64_t num_anchors) {
+  UDAL_REQUIRE(ctx && anchors_host, "NULL argument");
+  UDAL_REQUIRE(num_anchors == ctx->num_anchors, "anchor table has %lld rows, the level geometry gives %lld",
+               (long long)num_anchors, (long long)ctx->num_anchors);
+  if (!ctx->anchors) UDAL_CUDA(cudaMalloc(&ctx->anchors, (size_t)num_anchors * 16));
+  // pageable source: the copy is staged before the call returns
+  UDAL_CUDA(cudaMemcpyAsync(ctx->anchors, anchors_host, (size_t)num_anchors * 16, cudaMemcpyHostToDevice, ctx->stream));
+  UDAL_CUDA(cudaStreamSynchronize(ctx->stream));
+  ctx->anchors_set = true;
+  return UDAL_OK;
+}
+
+int udal_decode_moments(udal_ctx* ctx, const float* const* cls, const float* const* box, int batch,
+                        const udal_prenms_out* out) {
+  UDAL_REQUIRE(ctx && cls && box && out, "NULL argument");
+  return udal_launch_decode_moments(ctx, cls, box, batch, out);
+}
+
+int udal_topk(udal_ctx* ctx, const float* values, int batch, int64_t m, int k, int32_t* idx_out, float* val_out) {
+  UDAL_REQUIRE(ctx, "NULL ctx");
+  return udal_launch_topk(ctx, values, batch, m, k, idx_out, val_out);
+}
+
+int udal_nms_v5(udal_ctx* ctx, const float* boxes, const float* scores, int segments, int n, int32_t* sel_idx,
+                float* sel_scores, int32_t* valid) {
+  UDAL_REQUIRE(ctx && boxes && scores && sel_idx && sel_scores && valid, "NULL argument");
+  return udal_launch_nms_v5(ctx, boxes, scores, segments, n, sel_idx, sel_scores, valid);
+}
+
+}  // extern "C"

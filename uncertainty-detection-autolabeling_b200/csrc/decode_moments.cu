@@ -1,0 +1,568 @@
+// K2: MC moments of the class logits + anchor decode with exact moment propagation + MC moments
+// of the decoded boxes, one pass over HBM.
+//
+// Replaces (reference src/): utils_extra.py:220-244 get_mcuncert, postprocess.py:75-87
+// merge_class_box_level_outputs, postprocess.py:123-135 max-reduce, postprocess.py:284 sigmoid,
+// utils_box.py:105-276 decode_uncert, anchors.py:41-75 decode_box_outputs and the MC reductions
+// of postprocess.py:297-331.
+//
+// Arithmetic contract (bit-for-bit what oracle/ref_np.py does, up to the last-ulp behaviour of
+// exp): decode in fp64 from fp32 inputs with separately rounded mul/add, results rounded to fp32;
+// MC mean = sequential fp32 sum in sample order / T; MC std = two-pass population std in fp32.
+#include "udal_common.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+
+struct DecodeParams {
+  udal_level_ptrs cls;
+  udal_level_ptrs box;
+  udal_level_geom geom;
+  int tile_off[UDAL_MAX_LEVELS + 1];  // prefix of tiles per level
+  int tile_px;                         // pixels per tile
+  int batch, A, C, BC;                 // BC = box channels (4A or 8A)
+  int Tc, Tb;                          // samples on the class / box inputs (1 = no MC axis)
+  int cls_mc, box_mc, la, method;
+  const float* anchors;                // [N,4]
+  int64_t N;
+  udal_prenms_out out;
+};
+
+__device__ __forceinline__ float seq_mean(const float* v, int T) {
+  float acc = v[0];
+  for (int t = 1; t < T; ++t) acc = __fadd_rn(acc, v[t]);
+  return __fdiv_rn(acc, (float)T);
+}
+
+template <int TMAX>
+__device__ __forceinline__ void moments_reg(const float (&v)[TMAX], int T, float& mean, float& sd) {
+  float acc = v[0];
+#pragma unroll
+  for (int t = 1; t < TMAX; ++t)
+    if (t < T) acc = __fadd_rn(acc, v[t]);
+  const float fT = (float)T;
+  mean = __fdiv_rn(acc, fT);
+  float d0 = __fsub_rn(v[0], mean);
+  float s = __fmul_rn(d0, d0);
+#pragma unroll
+  for (int t = 1; t < TMAX; ++t)
+    if (t < T) {
+      float d = __fsub_rn(v[t], mean);
+      s = __fadd_rn(s, __fmul_rn(d, d));
+    }
+  sd = __fsqrt_rn(__fdiv_rn(s, fT));
+}
+
+// decode one (anchor, sample).  t = (ty,tx,th,tw), sg = sigma (std) or unused.
+struct Decoded {
+  float box[4];
+  float sd[4];
+};
+
+__device__ __forceinline__ Decoded decode_la(const float4 a, const float4 t, const float4 sg, int method) {
+  // utils_box.py:125-160 / 186-266, fp64
+  const double a0 = a.x, a1 = a.y, a2 = a.z, a3 = a.w;
+  const double yca = __dmul_rn(__dadd_rn(a0, a2), 0.5);
+  const double xca = __dmul_rn(__dadd_rn(a1, a3), 0.5);
+  const double ha = __dsub_rn(a2, a0);
+  const double wa = __dsub_rn(a3, a1);
+  const double ty = t.x, tx = t.y, th = t.z, tw = t.w;
+  const double vy = __dmul_rn((double)sg.x, (double)sg.x);
+  const double vx = __dmul_rn((double)sg.y, (double)sg.y);
+  const double vh = __dmul_rn((double)sg.z, (double)sg.z);
+  const double vw = __dmul_rn((double)sg.w, (double)sg.w);
+  const double yc = __dadd_rn(__dmul_rn(ty, ha), yca);
+  const double xc = __dadd_rn(__dmul_rn(tx, wa), xca);
+  Decoded r;
+  if (method == UDAL_DECODE_FALSEDEC) {
+    const double w = __dmul_rn(exp(tw), wa);
+    const double h = __dmul_rn(exp(th), ha);
+    const double hh = __dmul_rn(h, 0.5), hw = __dmul_rn(w, 0.5);
+    r.box[0] = (float)__dsub_rn(yc, hh);
+    r.box[1] = (float)__dsub_rn(xc, hw);
+    r.box[2] = (float)__dadd_rn(yc, hh);
+    r.box[3] = (float)__dadd_rn(xc, hw);
+    const double dw = __dmul_rn(exp(vw), wa);
+    const double dh = __dmul_rn(exp(vh), ha);
+    const double dyc = __dadd_rn(__dmul_rn(vy, ha), yca);
+    const double dxc = __dadd_rn(__dmul_rn(vx, wa), xca);
+    const double dhh = __dmul_rn(dh, 0.5), dhw = __dmul_rn(dw, 0.5);
+    r.sd[0] = (float)sqrt(fabs(__dsub_rn(dyc, dhh)));
+    r.sd[1] = (float)sqrt(fabs(__dsub_rn(dxc, dhw)));
+    r.sd[2] = (float)sqrt(__dadd_rn(dyc, dhh));
+    r.sd[3] = (float)sqrt(__dadd_rn(dxc, dhw));
+    return r;
+  }
+  // l-norm (and n-flow, whose tfp closed forms are the same expressions)
+  const double ew = exp(__dadd_rn(tw, __dmul_rn(vw, 0.5)));
+  const double eh = exp(__dadd_rn(th, __dmul_rn(vh, 0.5)));
+  const double w = __dmul_rn(ew, wa);
+  const double h = __dmul_rn(eh, ha);
+  const double hh = __dmul_rn(h, 0.5), hw = __dmul_rn(w, 0.5);
+  r.box[0] = (float)__dsub_rn(yc, hh);
+  r.box[1] = (float)__dsub_rn(xc, hw);
+  r.box[2] = (float)__dadd_rn(yc, hh);
+  r.box[3] = (float)__dadd_rn(xc, hw);
+  double dw, dh, dyc, dxc;
+  if (method == UDAL_DECODE_NFLOW) {
+    // tfp: Normal->Scale->Shift stddev = |scale * sd|; LogNormal variance -> Scale
+    const double sy = sqrt(vy), sx = sqrt(vx), sh = sqrt(vh), sw = sqrt(vw);
+    const double q = fabs(__dmul_rn(ha, sy)), p = fabs(__dmul_rn(wa, sx));
+    dyc = __dmul_rn(q, q);
+    dxc = __dmul_rn(p, p);
+    const double sh2 = __dmul_rn(sh, sh), sw2 = __dmul_rn(sw, sw);
+    const double lh = __dmul_rn(__dsub_rn(exp(sh2), 1.0), exp(__dadd_rn(__dmul_rn(2.0, th), sh2)));
+    const double lw = __dmul_rn(__dsub_rn(exp(sw2), 1.0), exp(__dadd_rn(__dmul_rn(2.0, tw), sw2)));
+    const double qh = fabs(__dmul_rn(ha, sqrt(lh))), qw = fabs(__dmul_rn(wa, sqrt(lw)));
+    dh = __dmul_rn(qh, qh);
+    dw = __dmul_rn(qw, qw);
+  } else {
+    dw = __dmul_rn(__dmul_rn(__dsub_rn(exp(vw), 1.0), exp(__dadd_rn(__dmul_rn(2.0, tw), vw))),
+                   __dmul_rn(wa, wa));
+    dh = __dmul_rn(__dmul_rn(__dsub_rn(exp(vh), 1.0), exp(__dadd_rn(__dmul_rn(2.0, th), vh))),
+                   __dmul_rn(ha, ha));
+    dyc = __dmul_rn(vy, __dmul_rn(ha, ha));
+    dxc = __dmul_rn(vx, __dmul_rn(wa, wa));
+  }
+  const float sdy = (float)sqrt(__dadd_rn(dyc, __dmul_rn(dh, 0.25)));
+  const float sdx = (float)sqrt(__dadd_rn(dxc, __dmul_rn(dw, 0.25)));
+  r.sd[0] = sdy;
+  r.sd[1] = sdx;
+  r.sd[2] = sdy;
+  r.sd[3] = sdx;
+  return r;
+}
+
+__device__ __forceinline__ void decode_plain(const float4 a, const float4 t, float (&box)[4]) {
+  // anchors.py:41-75, fp32
+  const float yca = __fmul_rn(__fadd_rn(a.x, a.z), 0.5f);
+  const float xca = __fmul_rn(__fadd_rn(a.y, a.w), 0.5f);
+  const float ha = __fsub_rn(a.z, a.x);
+  const float wa = __fsub_rn(a.w, a.y);
+  const float w = __fmul_rn(expf(t.w), wa);
+  const float h = __fmul_rn(expf(t.z), ha);
+  const float yc = __fadd_rn(__fmul_rn(t.x, ha), yca);
+  const float xc = __fadd_rn(__fmul_rn(t.y, wa), xca);
+  const float hh = __fmul_rn(h, 0.5f), hw = __fmul_rn(w, 0.5f);
+  box[0] = __fsub_rn(yc, hh);
+  box[1] = __fsub_rn(xc, hw);
+  box[2] = __fadd_rn(yc, hh);
+  box[3] = __fadd_rn(xc, hw);
+}
+
+__device__ __forceinline__ float sigmoid_ref(float x) {
+  // oracle: fp32(1 / (1 + exp(-fp64(x))))
+  return (float)(1.0 / (1.0 + exp(-(double)x)));
+}
+
+__device__ __forceinline__ int find_level(const int* off, int nl, int v) {
+  int l = 0;
+#pragma unroll
+  for (int i = 1; i < UDAL_MAX_LEVELS; ++i)
+    if (i < nl && v >= off[i]) l = i;
+  return l;
+}
+
+// -------------------------------------------------------------------------------------------
+// logits: elementwise MC mean / std over a contiguous run of `count` floats.
+// src(t) = base + t * t_stride; dst offsets are shared by mean/std.
+// -------------------------------------------------------------------------------------------
+template <int TMAX>
+__device__ __forceinline__ void logits_run(const float* __restrict__ base, size_t t_stride, int T,
+                                           int count, float* __restrict__ mean_out,
+                                           float* __restrict__ std_out, float* smem_mean, int tid,
+                                           int nthreads) {
+  for (int e = tid; e < count; e += nthreads) {
+    float mean, sd;
+    if (TMAX == 0) {
+      // many samples: two passes over global memory (second pass hits L1/L2)
+      float acc = __ldg(base + e);
+      for (int t = 1; t < T; ++t) acc = __fadd_rn(acc, __ldg(base + (size_t)t * t_stride + e));
+      mean = __fdiv_rn(acc, (float)T);
+      float s = 0.f;
+      for (int t = 0; t < T; ++t) {
+        float d = __fsub_rn(__ldg(base + (size_t)t * t_stride + e), mean);
+        s = t == 0 ? __fmul_rn(d, d) : __fadd_rn(s, __fmul_rn(d, d));
+      }
+      sd = __fsqrt_rn(__fdiv_rn(s, (float)T));
+    } else {
+      float v[TMAX == 0 ? 1 : TMAX];
+#pragma unroll
+      for (int t = 0; t < TMAX; ++t)
+        if (t < T) v[t] = __ldg(base + (size_t)t * t_stride + e);
+      moments_reg<(TMAX == 0 ? 1 : TMAX)>(v, T, mean, sd);
+    }
+    if (mean_out) mean_out[e] = mean;
+    if (std_out) std_out[e] = sd;
+    if (smem_mean) smem_mean[e] = mean;
+  }
+}
+
+template <int TMAX>
+__global__ void __launch_bounds__(kThreads) decode_moments_kernel(const DecodeParams p) {
+  extern __shared__ float smem_mean[];  // [tile anchors * C]
+  const int b = blockIdx.y;
+  const int tile = blockIdx.x;
+  const int l = find_level(p.tile_off, p.geom.num_levels, tile);
+  const int hw = p.geom.h[l] * p.geom.w[l];
+  const int p0 = (tile - p.tile_off[l]) * p.tile_px;
+  const int npx = min(p.tile_px, hw - p0);
+  const int A = p.A, C = p.C;
+  const int64_t anchor0 = (int64_t)A * (p.geom.pix_off[l] + p0);  // first global anchor of the tile
+
+  // ---- phase 1: class logits (elementwise) ------------------------------------------------
+  {
+    const int count = npx * A * C;
+    const size_t plane = (size_t)hw * A * C;
+    const float* base = p.cls.p[l] + ((size_t)b * hw + p0) * A * C;
+    const size_t t_stride = (size_t)p.batch * plane;
+    float* mo = p.out.mean_logits ? p.out.mean_logits + ((size_t)b * p.N + anchor0) * C : nullptr;
+    float* so = (p.out.std_logits && p.cls_mc) ? p.out.std_logits + ((size_t)b * p.N + anchor0) * C : nullptr;
+    logits_run<TMAX>(base, t_stride, p.Tc, count, mo, so, smem_mean, threadIdx.x, kThreads);
+  }
+  __syncthreads();
+
+  // ---- phase 2: one thread per anchor -----------------------------------------------------
+  for (int i = threadIdx.x; i < npx * A; i += kThreads) {
+    const int px = p0 + i / A;
+    const int a = i - (i / A) * A;
+    const int64_t n = anchor0 + i;
+    const float4 anc = __ldg(reinterpret_cast<const float4*>(p.anchors) + n);
+    const size_t plane = (size_t)hw * p.BC;
+    const float* bb = p.box.p[l] + ((size_t)b * hw + px) * p.BC + a * 4;
+    const size_t t_stride = (size_t)p.batch * plane;
+    const int T = p.Tb;
+    float mb[4], sdb[4], alb[4];
+    if (TMAX != 0) {
+      constexpr int TM = TMAX == 0 ? 1 : TMAX;
+      float bx[4][TM];
+      float al[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int t = 0; t < TM; ++t)
+        if (t < T) {
+          const float4 tt = __ldg(reinterpret_cast<const float4*>(bb + (size_t)t * t_stride));
+          if (p.la) {
+            const float4 sg = __ldg(reinterpret_cast<const float4*>(bb + (size_t)t * t_stride + 4 * A));
+            const Decoded d = decode_la(anc, tt, sg, p.method);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              bx[k][t] = d.box[k];
+              al[k] = t == 0 ? d.sd[k] : __fadd_rn(al[k], d.sd[k]);
+            }
+          } else {
+            float d[4];
+            decode_plain(anc, tt, d);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) bx[k][t] = d[k];
+          }
+        }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (p.box_mc) {
+          moments_reg<TM>(bx[k], T, mb[k], sdb[k]);
+          alb[k] = __fdiv_rn(al[k], (float)T);
+        } else {
+          mb[k] = bx[k][0];
+          sdb[k] = 0.f;
+          alb[k] = al[k];
+        }
+      }
+    } else {
+      // many samples: decode twice (sum pass, deviation pass)
+      float sum[4] = {0, 0, 0, 0}, al[4] = {0, 0, 0, 0};
+      for (int t = 0; t < T; ++t) {
+        const float4 tt = __ldg(reinterpret_cast<const float4*>(bb + (size_t)t * t_stride));
+        float d[4];
+        if (p.la) {
+          const float4 sg = __ldg(reinterpret_cast<const float4*>(bb + (size_t)t * t_stride + 4 * A));
+          const Decoded dd = decode_la(anc, tt, sg, p.method);
+          for (int k = 0; k < 4; ++k) {
+            d[k] = dd.box[k];
+            al[k] = t == 0 ? dd.sd[k] : __fadd_rn(al[k], dd.sd[k]);
+          }
+        } else {
+          decode_plain(anc, tt, d);
+        }
+        for (int k = 0; k < 4; ++k) sum[k] = t == 0 ? d[k] : __fadd_rn(sum[k], d[k]);
+      }
+      float ss[4] = {0, 0, 0, 0};
+      for (int k = 0; k < 4; ++k) mb[k] = p.box_mc ? __fdiv_rn(sum[k], (float)T) : sum[k];
+      for (int t = 0; t < T && p.box_mc; ++t) {
+        const float4 tt = __ldg(reinterpret_cast<const float4*>(bb + (size_t)t * t_stride));
+        float d[4];
+        if (p.la) {
+          const float4 sg = __ldg(reinterpret_cast<const float4*>(bb + (size_t)t * t_stride + 4 * A));
+          const Decoded dd = decode_la(anc, tt, sg, p.method);
+          for (int k = 0; k < 4; ++k) d[k] = dd.box[k];
+        } else {
+          decode_plain(anc, tt, d);
+        }
+        for (int k = 0; k < 4; ++k) {
+          const float dv = __fsub_rn(d[k], mb[k]);
+          ss[k] = t == 0 ? __fmul_rn(dv, dv) : __fadd_rn(ss[k], __fmul_rn(dv, dv));
+        }
+      }
+      for (int k = 0; k < 4; ++k) {
+        sdb[k] = p.box_mc ? __fsqrt_rn(__fdiv_rn(ss[k], (float)T)) : 0.f;
+        alb[k] = p.box_mc ? __fdiv_rn(al[k], (float)T) : al[k];
+      }
+    }
+    const size_t o = (size_t)b * p.N + n;
+    if (p.out.boxes) reinterpret_cast<float4*>(p.out.boxes)[o] = make_float4(mb[0], mb[1], mb[2], mb[3]);
+    if (p.out.albox && p.la) reinterpret_cast<float4*>(p.out.albox)[o] = make_float4(alb[0], alb[1], alb[2], alb[3]);
+    if (p.out.mcbox && p.box_mc) reinterpret_cast<float4*>(p.out.mcbox)[o] = make_float4(sdb[0], sdb[1], sdb[2], sdb[3]);
+    if (p.out.scores || p.out.classes) {
+      const float* ml = smem_mean + (size_t)i * C;
+      float best = ml[0];
+      int arg = 0;
+      for (int c = 1; c < C; ++c) {
+        const float v = ml[c];
+        if (v > best) {
+          best = v;
+          arg = c;
+        }
+      }
+      if (p.out.scores) p.out.scores[o] = sigmoid_ref(best);
+      if (p.out.classes) p.out.classes[o] = arg;
+    }
+  }
+}
+
+// logits only (eval variant): mean / std of every (anchor, class) logit
+template <int TMAX>
+__global__ void __launch_bounds__(kThreads) logit_moments_kernel(const DecodeParams p) {
+  const int b = blockIdx.y;
+  const int tile = blockIdx.x;
+  const int l = find_level(p.tile_off, p.geom.num_levels, tile);
+  const int hw = p.geom.h[l] * p.geom.w[l];
+  const int p0 = (tile - p.tile_off[l]) * p.tile_px;
+  const int npx = min(p.tile_px, hw - p0);
+  const int A = p.A, C = p.C;
+  const int64_t anchor0 = (int64_t)A * (p.geom.pix_off[l] + p0);
+  const int count = npx * A * C;
+  const size_t plane = (size_t)hw * A * C;
+  const float* base = p.cls.p[l] + ((size_t)b * hw + p0) * A * C;
+  float* mo = p.out.mean_logits ? p.out.mean_logits + ((size_t)b * p.N + anchor0) * C : nullptr;
+  float* so = (p.out.std_logits && p.cls_mc) ? p.out.std_logits + ((size_t)b * p.N + anchor0) * C : nullptr;
+  logits_run<TMAX>(base, (size_t)p.batch * plane, p.Tc, count, mo, so, nullptr, threadIdx.x, kThreads);
+}
+
+struct GatherParams {
+  udal_level_ptrs box;
+  udal_level_geom geom;
+  int batch, A, C, BC, Tb, box_mc, la, method, k;
+  const float* anchors;
+  int64_t N;
+  const int32_t* topk_idx;
+  const float* topk_val;
+  const float* std_logits;  // [B,N,C] or null
+  udal_prenms_topk_out out;
+};
+
+// decode + moments on the k gathered (anchor, class) rows of each image
+__global__ void __launch_bounds__(kThreads) decode_gather_kernel(const GatherParams p) {
+  const int b = blockIdx.y;
+  const int j = blockIdx.x * kThreads + threadIdx.x;
+  if (j >= p.k) return;
+  const size_t o = (size_t)b * p.k + j;
+  const int32_t flat = p.topk_idx[o];
+  const int n = flat / p.C;
+  const int c = flat - n * p.C;
+  const int gp = n / p.A;
+  const int a = n - gp * p.A;
+  const int l = find_level(p.geom.pix_off, p.geom.num_levels, gp);
+  const int px = gp - p.geom.pix_off[l];
+  const int hw = p.geom.h[l] * p.geom.w[l];
+  const float4 anc = __ldg(reinterpret_cast<const float4*>(p.anchors) + n);
+  const float* bb = p.box.p[l] + ((size_t)b * hw + px) * p.BC + a * 4;
+  const size_t t_stride = (size_t)p.batch * hw * p.BC;
+  const int T = p.Tb;
+  float sum[4] = {0, 0, 0, 0}, al[4] = {0, 0, 0, 0}, mb[4], ss[4] = {0, 0, 0, 0};
+  for (int pass = 0; pass < (p.box_mc ? 2 : 1); ++pass) {
+    for (int t = 0; t < T; ++t) {
+      const float4 tt = __ldg(reinterpret_cast<const float4*>(bb + (size_t)t * t_stride));
+      float d[4];
+      if (p.la) {
+        const float4 sg = __ldg(reinterpret_cast<const float4*>(bb + (size_t)t * t_stride + 4 * p.A));
+        const Decoded dd = decode_la(anc, tt, sg, p.method);
+        for (int q = 0; q < 4; ++q) {
+          d[q] = dd.box[q];
+          if (pass == 0) al[q] = t == 0 ? dd.sd[q] : __fadd_rn(al[q], dd.sd[q]);
+        }
+      } else {
+        decode_plain(anc, tt, d);
+      }
+      for (int q = 0; q < 4; ++q) {
+        if (pass == 0) {
+          sum[q] = t == 0 ? d[q] : __fadd_rn(sum[q], d[q]);
+        } else {
+          const float dv = __fsub_rn(d[q], mb[q]);
+          ss[q] = t == 0 ? __fmul_rn(dv, dv) : __fadd_rn(ss[q], __fmul_rn(dv, dv));
+        }
+      }
+    }
+    if (pass == 0)
+      for (int q = 0; q < 4; ++q) mb[q] = p.box_mc ? __fdiv_rn(sum[q], (float)T) : sum[q];
+  }
+  if (p.out.boxes) reinterpret_cast<float4*>(p.out.boxes)[o] = make_float4(mb[0], mb[1], mb[2], mb[3]);
+  if (p.out.albox && p.la) {
+    float4 v;
+    v.x = p.box_mc ? __fdiv_rn(al[0], (float)T) : al[0];
+    v.y = p.box_mc ? __fdiv_rn(al[1], (float)T) : al[1];
+    v.z = p.box_mc ? __fdiv_rn(al[2], (float)T) : al[2];
+    v.w = p.box_mc ? __fdiv_rn(al[3], (float)T) : al[3];
+    reinterpret_cast<float4*>(p.out.albox)[o] = v;
+  }
+  if (p.out.mcbox && p.box_mc) {
+    float4 v;
+    v.x = __fsqrt_rn(__fdiv_rn(ss[0], (float)T));
+    v.y = __fsqrt_rn(__fdiv_rn(ss[1], (float)T));
+    v.z = __fsqrt_rn(__fdiv_rn(ss[2], (float)T));
+    v.w = __fsqrt_rn(__fdiv_rn(ss[3], (float)T));
+    reinterpret_cast<float4*>(p.out.mcbox)[o] = v;
+  }
+  if (p.out.scores) p.out.scores[o] = sigmoid_ref(p.topk_val[o]);
+  if (p.out.classes) p.out.classes[o] = c;
+  if (p.out.mcclass && p.std_logits) p.out.mcclass[o] = p.std_logits[(size_t)b * p.N * p.C + flat];
+}
+
+int fill_params(udal_ctx* ctx, const float* const* cls, const float* const* box, int batch,
+                DecodeParams& p, int* total_tiles, size_t* smem) {
+  const udal_config& c = ctx->cfg;
+  UDAL_REQUIRE(ctx->anchors_set, "anchors not set (call udal_set_anchors)");
+  UDAL_REQUIRE(batch > 0, "batch must be positive");
+  p.geom = udal_geom(ctx);
+  p.batch = batch;
+  p.A = c.anchors_per_loc;
+  p.C = c.num_classes;
+  p.BC = udal_box_channels(ctx);
+  p.cls_mc = c.cls_mc;
+  p.box_mc = c.box_mc;
+  p.Tc = c.cls_mc ? c.mc_samples : 1;
+  p.Tb = c.box_mc ? c.mc_samples : 1;
+  p.la = c.loss_attenuation;
+  p.method = c.decode_method;
+  p.anchors = ctx->anchors;
+  p.N = ctx->num_anchors;
+  int tile_px = kThreads / p.A;
+  const int cap = 12288 / (p.A * p.C);
+  if (tile_px > cap) tile_px = cap;
+  if (tile_px < 1) tile_px = 1;
+  p.tile_px = tile_px;
+  int off = 0;
+  for (int l = 0; l < UDAL_MAX_LEVELS + 1; ++l) {
+    p.tile_off[l] = off;
+    if (l < c.num_levels) {
+      const int hw = c.level_h[l] * c.level_w[l];
+      off += (hw + tile_px - 1) / tile_px;
+    }
+  }
+  *total_tiles = off;
+  *smem = (size_t)tile_px * p.A * p.C * sizeof(float);
+  for (int l = 0; l < UDAL_MAX_LEVELS; ++l) {
+    p.cls.p[l] = (cls && l < c.num_levels) ? cls[l] : nullptr;
+    p.box.p[l] = (box && l < c.num_levels) ? box[l] : nullptr;
+    if (l < c.num_levels) {
+      if (cls) UDAL_REQUIRE(cls[l] != nullptr, "cls level %d is NULL", l);
+      if (box) {
+        UDAL_REQUIRE(box[l] != nullptr, "box level %d is NULL", l);
+        UDAL_REQUIRE(((uintptr_t)box[l] & 15) == 0, "box level %d must be 16-byte aligned", l);
+      }
+    }
+  }
+  return UDAL_OK;
+}
+
+int pick_tmax(int T) {
+  if (T <= 1) return 1;
+  if (T <= 4) return 4;
+  if (T <= 10) return 10;
+  if (T <= 16) return 16;
+  if (T <= 32) return 32;
+  return 0;
+}
+
+}  // namespace
+
+int udal_launch_decode_moments(udal_ctx* ctx, const float* const* cls, const float* const* box,
+                               int batch, const udal_prenms_out* out) {
+  DecodeParams p;
+  int tiles;
+  size_t smem;
+  UDAL_TRY(fill_params(ctx, cls, box, batch, p, &tiles, &smem));
+  p.out = *out;
+  const int T = p.Tc > p.Tb ? p.Tc : p.Tb;
+  dim3 grid(tiles, batch);
+#define LAUNCH(TM)                                                                      \
+  decode_moments_kernel<TM><<<grid, kThreads, smem, ctx->stream>>>(p);                  \
+  break;
+  switch (pick_tmax(T)) {
+    case 1: LAUNCH(1)
+    case 4: LAUNCH(4)
+    case 10: LAUNCH(10)
+    case 16: LAUNCH(16)
+    case 32: LAUNCH(32)
+    default: LAUNCH(0)
+  }
+#undef LAUNCH
+  UDAL_CHECK_LAUNCH(ctx);
+  return UDAL_OK;
+}
+
+int udal_launch_logit_moments(udal_ctx* ctx, const float* const* cls, int batch, float* mean_logits,
+                              float* std_logits) {
+  DecodeParams p;
+  int tiles;
+  size_t smem;
+  UDAL_TRY(fill_params(ctx, cls, nullptr, batch, p, &tiles, &smem));
+  memset(&p.out, 0, sizeof(p.out));
+  p.out.mean_logits = mean_logits;
+  p.out.std_logits = std_logits;
+  dim3 grid(tiles, batch);
+#define LAUNCH(TM)                                                        \
+  logit_moments_kernel<TM><<<grid, kThreads, 0, ctx->stream>>>(p);        \
+  break;
+  switch (pick_tmax(p.Tc)) {
+    case 1: LAUNCH(1)
+    case 4: LAUNCH(4)
+    case 10: LAUNCH(10)
+    case 16: LAUNCH(16)
+    case 32: LAUNCH(32)
+    default: LAUNCH(0)
+  }
+#undef LAUNCH
+  UDAL_CHECK_LAUNCH(ctx);
+  return UDAL_OK;
+}
+
+int udal_launch_decode_gather(udal_ctx* ctx, const float* const* box, int batch, int k,
+                              const int32_t* topk_idx, const float* topk_val, const float* std_logits,
+                              const udal_prenms_topk_out* out) {
+  DecodeParams dp;
+  int tiles;
+  size_t smem;
+  UDAL_TRY(fill_params(ctx, nullptr, box, batch, dp, &tiles, &smem));
+  GatherParams p;
+  p.box = dp.box;
+  p.geom = dp.geom;
+  p.batch = batch;
+  p.A = dp.A;
+  p.C = dp.C;
+  p.BC = dp.BC;
+  p.Tb = dp.Tb;
+  p.box_mc = dp.box_mc;
+  p.la = dp.la;
+  p.method = dp.method;
+  p.k = k;
+  p.anchors = dp.anchors;
+  p.N = dp.N;
+  p.topk_idx = topk_idx;
+  p.topk_val = topk_val;
+  p.std_logits = std_logits;
+  p.out = *out;
+  dim3 grid((k + kThreads - 1) / kThreads, batch);
+  decode_gather_kernel<<<grid, kThreads, 0, ctx->stream>>>(p);
+  UDAL_CHECK_LAUNCH(ctx);
+  return UDAL_OK;
+}

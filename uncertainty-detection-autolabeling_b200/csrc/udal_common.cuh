@@ -1,0 +1,170 @@
+// Internal definitions shared by the libudal translation units (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "udal.h"
+
+#define UDAL_NUM_SMS 148
+
+struct udal_head_weights_dev {
+  bool set = false;
+  int cout = 0;
+  float* dw = nullptr;    // [R][9][F]
+  float* pw = nullptr;    // [R][F][F]
+  float* bias = nullptr;  // [R][F]
+  float* bn_scale = nullptr;  // [R][L][F]  gamma * rsqrt(var + eps)
+  float* bn_shift = nullptr;  // [R][L][F]  beta - mean * scale
+  float* dwp = nullptr;   // [9][F]
+  float* pwp = nullptr;   // [F][cout]
+  float* bp = nullptr;    // [cout]
+  // bf16 tensor-core mode: per (repeat, level) folded pointwise weights, K-major
+  void* pw_bf16 = nullptr;
+  void* pwp_bf16 = nullptr;
+  float* fold_bias = nullptr;
+};
+
+struct udal_scratch {
+  void* ptr = nullptr;
+  size_t bytes = 0;
+};
+
+struct udal_ctx {
+  udal_config cfg;
+  cudaStream_t own_stream = nullptr;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
+  int64_t num_anchors = 0;      // N
+  int64_t num_pixels = 0;       // P
+  int64_t level_pix_off[UDAL_MAX_LEVELS + 1];  // prefix of H_l*W_l
+  float* anchors = nullptr;     // device [N,4]
+  bool anchors_set = false;
+  udal_head_weights_dev heads[2];
+  int64_t launches = 0;
+  // named scratch slots, grown on demand
+  udal_scratch scratch[20];
+  std::vector<void*> user_allocs;
+};
+
+enum {
+  SCR_TOPK_HIST = 0,
+  SCR_TOPK_CAND,
+  SCR_TOPK_META,
+  SCR_PRE_A,
+  SCR_PRE_B,
+  SCR_NMS_A,
+  SCR_NMS_B,
+  SCR_HEADS_A,
+  SCR_HEADS_B,
+  SCR_HEADS_C,
+  SCR_MISC,
+  SCR_LEVEL_PTRS,
+  SCR_POST_A,
+  SCR_POST_B,
+  SCR_POST_C,
+  SCR_POST_D,
+  SCR_POST_C2,
+};
+
+void udal_set_error(const char* fmt, ...);
+int udal_cuda_fail(cudaError_t e, const char* what, const char* file, int line);
+int udal_scratch_get(udal_ctx* ctx, int slot, size_t bytes, void** out);
+
+#define UDAL_CUDA(call)                                                      \
+  do {                                                                       \
+    cudaError_t e__ = (call);                                                \
+    if (e__ != cudaSuccess) return udal_cuda_fail(e__, #call, __FILE__, __LINE__); \
+  } while (0)
+
+#define UDAL_CHECK_LAUNCH(ctx)                    \
+  do {                                            \
+    (ctx)->launches++;                            \
+    UDAL_CUDA(cudaGetLastError());                \
+  } while (0)
+
+#define UDAL_REQUIRE(cond, ...)        \
+  do {                                 \
+    if (!(cond)) {                     \
+      udal_set_error(__VA_ARGS__);     \
+      return UDAL_ERR_INVALID;         \
+    }                                  \
+  } while (0)
+
+#define UDAL_TRY(call)            \
+  do {                            \
+    int s__ = (call);             \
+    if (s__ != UDAL_OK) return s__; \
+  } while (0)
+
+// level pointer tables passed to kernels by value
+struct udal_level_ptrs {
+  const float* p[UDAL_MAX_LEVELS];
+};
+struct udal_level_geom {
+  int num_levels;
+  int h[UDAL_MAX_LEVELS];
+  int w[UDAL_MAX_LEVELS];
+  int pix_off[UDAL_MAX_LEVELS + 1];  // prefix sums of h*w
+};
+
+static inline udal_level_geom udal_geom(const udal_ctx* ctx) {
+  udal_level_geom g;
+  g.num_levels = ctx->cfg.num_levels;
+  for (int l = 0; l < UDAL_MAX_LEVELS; ++l) {
+    g.h[l] = l < g.num_levels ? ctx->cfg.level_h[l] : 0;
+    g.w[l] = l < g.num_levels ? ctx->cfg.level_w[l] : 0;
+  }
+  for (int l = 0; l <= UDAL_MAX_LEVELS; ++l) g.pix_off[l] = (int)ctx->level_pix_off[l < g.num_levels ? l : g.num_levels];
+  return g;
+}
+
+static inline int udal_box_channels(const udal_ctx* ctx) {
+  return 4 * ctx->cfg.anchors_per_loc * (ctx->cfg.loss_attenuation ? 2 : 1);
+}
+
+// orderable key: larger float <=> larger unsigned
+__host__ __device__ static inline uint32_t udal_float_key(float f) {
+#ifdef __CUDA_ARCH__
+  uint32_t u = __float_as_uint(f);
+#else
+  uint32_t u;
+  memcpy(&u, &f, 4);
+#endif
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__host__ __device__ static inline float udal_key_float(uint32_t k) {
+  uint32_t u = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k;
+#ifdef __CUDA_ARCH__
+  return __uint_as_float(u);
+#else
+  float f;
+  memcpy(&f, &u, 4);
+  return f;
+#endif
+}
+
+// internal entry points (defined across translation units)
+int udal_launch_decode_moments(udal_ctx* ctx, const float* const* cls, const float* const* box,
+                               int batch, const udal_prenms_out* out);
+int udal_launch_logit_moments(udal_ctx* ctx, const float* const* cls, int batch, float* mean_logits,
+                              float* std_logits);
+int udal_launch_decode_gather(udal_ctx* ctx, const float* const* box, int batch, int k,
+                              const int32_t* topk_idx, const float* topk_val, const float* std_logits,
+                              const udal_prenms_topk_out* out);
+int udal_launch_topk(udal_ctx* ctx, const float* values, int batch, int64_t m, int k,
+                     int32_t* idx_out, float* val_out);
+int udal_launch_nms_v5(udal_ctx* ctx, const float* boxes, const float* scores, int segments, int n,
+                       int32_t* sel_idx, float* sel_scores, int32_t* valid);
+int udal_nms_sorted(udal_ctx* ctx, const float* boxes, const float* scores, const int32_t* cand_idx,
+                    const int32_t* seg_start, const int32_t* seg_count, const float* next_score,
+                    int next_stride, int segments, int seg_n, int segs_per_image, int64_t img_stride,
+                    int64_t total_cand, int32_t* sel_row, int32_t* sel_rank, float* sel_scores,
+                    int32_t* valid, int32_t* flag);
+int udal_nms_full(udal_ctx* ctx, const float* boxes, const float* scores, int segments, int n,
+                  const int32_t* flag, int32_t* sel_row, float* sel_scores, int32_t* valid);
+int udal_nms_prefilter_k(const udal_ctx* ctx, int n);

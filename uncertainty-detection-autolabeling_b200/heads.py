@@ -1,0 +1,70 @@
+"""Head sampler: the EfficientDet class / box(+sigma) towers x T MC-dropout samples, starting at
+the BiFPN outputs (reference efficientdet_keras.py:353-692 ClassNet/BoxNet, 979-1050 MC loop).
+
+Valid replacement for the reference's MC loop when dropout is head-only (mc_dropoutrate == 0, the
+configuration every shipped inference YAML uses): the backbone/BiFPN are then deterministic and
+their output is identical for all T passes.  With backbone dropout the features differ
+per pass, which this entry point does not model - it raises.
+"""
+import numpy as np
+
+from . import device
+from . import engine as _engine
+
+
+class HeadSampler:
+    def __init__(self, params, weights, device_id=None, heads_mode=None):
+        if params.get("mc_dropout") and params.get("mc_dropoutrate"):
+            raise ValueError("mc_dropoutrate > 0 (backbone MC dropout) changes the BiFPN features per "
+                             "sample; the head sampler starts at the BiFPN outputs (head-only dropout)")
+        self.params = params
+        self.engine = _engine.get_engine(params, device_id, heads_mode)
+        self.engine.set_head_weights(weights)
+
+    def __call__(self, fpn_feats, masks=None, seed=0):
+        """fpn_feats: list[L] of [B,H_l,W_l,F].  Returns (cls_outputs, box_outputs) with the
+        structure of EfficientDetNet.call: list[L] of [T,B,H,W,A*C] and [T,B,H,W,8A] (no leading T
+        for a head without MC dropout).  ``masks`` [T,2,L,R,B,F] uint8 injects keep masks (parity
+        runs); otherwise Philox4x32-10 masks are drawn on the device from ``seed``."""
+        host = not any(isinstance(x, device.DeviceArray) or hasattr(x, "__cuda_array_interface__") for x in fpn_feats)
+        cls, box = self.engine.heads_sample(list(fpn_feats), masks, seed)
+        if host:
+            cls = [c.copy_to_host(sync=False) for c in cls]
+            box = [b.copy_to_host(sync=False) for b in box]
+            self.engine.ctx.sync()
+        return cls, box
+
+    def detect(self, fpn_feats, image_scales=None, masks=None, seed=0):
+        """features -> detections in one device call (udal_run); tuple like postprocess_*."""
+        host = not any(isinstance(x, device.DeviceArray) or hasattr(x, "__cuda_array_interface__") for x in fpn_feats)
+        bufs = self.engine.run(list(fpn_feats), image_scales, masks, seed)
+        out = [bufs["boxes"], bufs["scores"], bufs["classes"], bufs["valid"], bufs["logits"]]
+        if host:
+            out = [o.copy_to_host(sync=False) for o in out]
+            self.engine.ctx.sync()
+        return tuple(out)
+
+
+def philox_keep_masks(shape, rate_class, rate_box, seed):
+    """NumPy restatement of the in-kernel Philox4x32-10 keep masks (counter = flat index // 4,
+    key = seed; u = (x >> 8) * 2^-24; keep = u >= rate).  shape = (T,2,L,R,B,F)."""
+    total = int(np.prod(shape))
+    g = np.arange((total + 3) // 4, dtype=np.uint64)
+    c = [g & np.uint64(0xFFFFFFFF), g >> np.uint64(32), np.zeros_like(g), np.zeros_like(g)]
+    k0 = np.uint64(seed & 0xFFFFFFFF)
+    k1 = np.uint64((seed >> 32) & 0xFFFFFFFF)
+    m0, m1 = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57)
+    mask = np.uint64(0xFFFFFFFF)
+    for _ in range(10):
+        p0, p1 = m0 * c[0], m1 * c[2]
+        hi0, lo0, hi1, lo1 = p0 >> np.uint64(32), p0 & mask, p1 >> np.uint64(32), p1 & mask
+        c = [hi1 ^ c[1] ^ k0, lo1, hi0 ^ c[3] ^ k1, lo0]
+        k0 = (k0 + np.uint64(0x9E3779B9)) & mask
+        k1 = (k1 + np.uint64(0xBB67AE85)) & mask
+    words = np.stack(c, axis=1).reshape(-1)[:total]
+    u = (words >> np.uint64(8)).astype(np.float32) * np.float32(1.0 / 16777216.0)
+    u = u.reshape(shape)
+    keep = np.empty(shape, np.uint8)
+    keep[:, 0] = u[:, 0] >= np.float32(rate_class)
+    keep[:, 1] = u[:, 1] >= np.float32(rate_box)
+    return keep
