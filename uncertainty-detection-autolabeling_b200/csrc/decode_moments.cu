@@ -140,8 +140,9 @@ __device__ __forceinline__ void decode_plain(const float4 a, const float4 t, flo
   const float xca = __fmul_rn(__fadd_rn(a.y, a.w), 0.5f);
   const float ha = __fsub_rn(a.z, a.x);
   const float wa = __fsub_rn(a.w, a.y);
-  const float w = __fmul_rn(expf(t.w), wa);
-  const float h = __fmul_rn(expf(t.z), ha);
+  // fp32 exp of the reference (Eigen / NumPy, < 1 ulp): the correctly rounded value is the closest match
+  const float w = __fmul_rn((float)exp((double)t.w), wa);
+  const float h = __fmul_rn((float)exp((double)t.z), ha);
   const float yc = __fadd_rn(__fmul_rn(t.x, ha), yca);
   const float xc = __fadd_rn(__fmul_rn(t.y, wa), xca);
   const float hh = __fmul_rn(h, 0.5f), hw = __fmul_rn(w, 0.5f);

@@ -69,11 +69,32 @@ class Context:
         _lib.check(self.lib.udal_create(ctypes.byref(cfg), ctypes.byref(h)))
         self.handle = h
         self.device = cfg.device
+        self._pool = {}  # nbytes -> [device pointers]: stream-ordered reuse, no cudaMalloc per call
 
     def close(self):
         if getattr(self, "handle", None):
-            self.lib.udal_destroy(self.handle)
+            self._pool.clear()
+            self.lib.udal_destroy(self.handle)  # frees every allocation of the context
             self.handle = None
+
+    def _alloc(self, nbytes):
+        free = self._pool.get(nbytes)
+        if free:
+            return free.pop()
+        p = ctypes.c_void_p()
+        _lib.check(self.lib.udal_malloc(self.handle, nbytes, ctypes.byref(p)))
+        return p.value
+
+    def _release(self, ptr, nbytes):
+        # all work of a context is ordered on one stream, so a released block can be handed out again
+        self._pool.setdefault(nbytes, []).append(ptr)
+
+    def trim(self):
+        """Return pooled blocks to the driver."""
+        for ptrs in self._pool.values():
+            for p in ptrs:
+                self.lib.udal_free(self.handle, ctypes.c_void_p(p))
+        self._pool.clear()
 
     def __del__(self):
         try:
@@ -158,15 +179,13 @@ class DeviceArray:
         self._owned = ptr is None
         self._base = base
         if ptr is None:
-            p = ctypes.c_void_p()
-            _lib.check(ctx.lib.udal_malloc(ctx.handle, self.nbytes, ctypes.byref(p)))
-            ptr = p.value
+            ptr = ctx._alloc(self.nbytes)
         self.ptr = ptr
 
     def __del__(self):
         try:
             if self._owned and self.ptr and self.ctx.handle:
-                self.ctx.lib.udal_free(self.ctx.handle, ctypes.c_void_p(self.ptr))
+                self.ctx._release(self.ptr, self.nbytes)
             self.ptr = None
         except Exception:
             pass
