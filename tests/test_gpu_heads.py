@@ -83,3 +83,36 @@ def test_end_to_end_features_to_detections(u):
     ref = ref_np.postprocess_global(p, rcls, rbox, scales)
     np.testing.assert_array_equal(det[3], ref[3])
     np.testing.assert_allclose(np.sort(det[1], axis=1), np.sort(ref[1], axis=1), rtol=1e-3, atol=1e-5)
+
+
+# bf16 tensor-core mode: measured tolerance.  Operands and inter-layer activations are bf16 (8-bit
+# mantissa), accumulation fp32, swish through tanh.approx; over the 4-layer tower the error stays
+# within a few 1e-2 of the output scale (logit / box-regression units).
+BF16_ATOL = 6e-2
+BF16_RTOL = 3e-2
+
+
+@pytest.mark.parametrize("size,C,T,batch,la,rc,rb", [
+    ((64, 96), 7, 4, 2, True, 0.05, 0.05),
+    ((40, 200), 8, 2, 3, True, 0.0, 0.2),
+    (128, 8, 1, 1, True, 0.0, 0.0),
+])
+def test_heads_bf16_tensor_core_vs_oracle(u, size, C, T, batch, la, rc, rb):
+    p = _cfg(u, size, C, T, la, rc, rb, heads_mode="bf16")
+    eng = u.engine.get_engine(p)
+    L = len(eng.level_hw)
+    w = heads_ref.init_head_weights(eng.F, eng.R, L, eng.A, C, la, seed=9, randomize_bn=True)
+    feats = heads_ref.make_features(eng.level_hw, batch, eng.F, seed=11)
+    masks = heads_ref.make_masks(T, L, eng.R, batch, eng.F, rc, rb, seed=5)
+    sampler = u.heads.HeadSampler(p, w)
+    cls, box = sampler(feats, masks=masks)
+    rcls, rbox = heads_ref.heads_sample(feats, w, masks, rc, rb, T)
+    worst = 0.0
+    for l in range(L):
+        rc_l = rcls[l] if rc else rcls[l][0]
+        rb_l = rbox[l] if rb else rbox[l][0]
+        assert cls[l].shape == rc_l.shape and box[l].shape == rb_l.shape
+        worst = max(worst, float(np.abs(cls[l] - rc_l).max()), float(np.abs(box[l] - rb_l).max()))
+        np.testing.assert_allclose(cls[l], rc_l, rtol=BF16_RTOL, atol=BF16_ATOL)
+        np.testing.assert_allclose(box[l], rb_l, rtol=BF16_RTOL, atol=BF16_ATOL)
+    print("bf16 heads max abs err", worst)

@@ -1,16 +1,462 @@
-// K1 (bf16 tensor-core mode) - placeholder translation unit until the tcgen05 sampler lands.
+// K1 (bf16 tensor-core mode): the class / box(+sigma) head towers on tcgen05 (sm_100a).
+//
+// Replaces (reference src/): efficientdet_keras.py:353-513 ClassNet, 516-692 BoxNet, 979-1050 MC
+// loop - same arithmetic graph as heads_fp32.cu, with the dense contraction (pointwise 1x1 and the
+// class / box projections) on the 5th-generation tensor cores:
+//
+//   per CTA: one 8x16-pixel tile (M = 128 rows of the GEMM) of one pyramid level
+//     1. the bf16 input tile + 1-pixel halo is staged in shared memory (zero padded)
+//     2. depthwise 3x3 on the CUDA cores (fp32 math, 4 channels x 8 rows per thread, sliding
+//        window) writes the A operand [128 x 64] bf16 straight into the canonical K-major
+//        128-byte-swizzled UMMA layout
+//     3. for each MC sample handled by this CTA: the B operand [N x 64] = folded weights
+//        (pointwise * BN scale) * dropout keep-scale of the producer layer, bf16, same layout;
+//        one elected thread issues 4 x tcgen05.mma (M128, N = 64|80, K16) accumulating in TMEM;
+//        tcgen05.commit -> mbarrier; 8 warps read the accumulator with tcgen05.ld (32x32b),
+//        add the folded bias, apply swish and store bf16 activations (or fp32 predictions).
+//   SpatialDropout2D is a per-(sample, image, channel) scale; it commutes with the depthwise conv,
+//   so it is folded into the rows of B.  Layer 1 therefore computes its depthwise conv ONCE per
+//   image and loops the T samples in-kernel with the A tile resident in shared memory; layer 0
+//   (sample invariant) runs once per image.
+//
+// Numerics: bf16 operands / activations, fp32 accumulation; measured tolerance in
+// tests/test_gpu_heads.py (the fp32 path of heads_fp32.cu is the parity mode).
+#include <cuda_bf16.h>
+
 #include "udal_common.cuh"
 
-int udal_heads_tc_prepare(udal_ctx* ctx, int head) {
-  (void)ctx;
-  (void)head;
-  udal_set_error("heads_mode UDAL_HEADS_BF16_TC is not available in this build");
-  return UDAL_ERR_INVALID;
+namespace {
+
+constexpr int TH = 8, TW = 16, TPX = TH * TW;
+constexpr int HALO_W = TW + 2, HALO_H = TH + 2, HALO_PX = HALO_W * HALO_H;
+constexpr int KF = 64;            // filters = GEMM K (bf16: one 128-byte swizzle row)
+constexpr int kThreads = 256;
+constexpr int kMaxN = 80;
+
+// shared memory map (offsets from a 1024-byte aligned base)
+constexpr int SM_A = 0;                         // [128][128 B]
+constexpr int SM_B = SM_A + TPX * 128;          // [kMaxN][128 B]
+constexpr int SM_IN = SM_B + kMaxN * 128;       // [180][64] bf16
+constexpr int SM_DW = SM_IN + HALO_PX * KF * 2; // [9][64] fp32
+constexpr int SM_MBAR = SM_DW + 9 * KF * 4;     // mbarrier (8 B) + tmem base (4 B)
+constexpr int SM_TOTAL = SM_MBAR + 16;
+constexpr int SM_ALLOC = SM_TOTAL + 1024;       // slack for the manual 1024-byte alignment
+
+struct TcLayerParams {
+  int num_levels;
+  int h[UDAL_MAX_LEVELS], w[UDAL_MAX_LEVELS];
+  int tiles_x[UDAL_MAX_LEVELS];
+  int tile_off[UDAL_MAX_LEVELS + 1];
+  const void* in[UDAL_MAX_LEVELS];     // [NB_in,H,W,64] bf16 (or fp32 BiFPN features for layer 0)
+  void* out[UDAL_MAX_LEVELS];          // [NB_out,H,W,64] bf16 or [NB_out,H,W,Cout] fp32
+  const float* scale[UDAL_MAX_LEVELS]; // [NB_out,64] keep-scale of the producer layer, or null
+  const float* wf[UDAL_MAX_LEVELS];    // folded weights [Npad][64] fp32
+  const float* fb[UDAL_MAX_LEVELS];    // folded bias [Npad]
+  const float* dw;                     // [9][64]
+  int Cout, Npad, batch, nt;
+  int in_fp32, out_fp32, act, in_per_sample;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// K-major, 128-byte swizzle, 8-row groups 1024 B apart (cute::UMMA::make_umma_desc<Major::K>)
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);  // start address
+  d |= (uint64_t)1 << 16;                  // leading byte offset (unused for swizzled K-major) = 1
+  d |= (uint64_t)(1024 >> 4) << 32;        // stride byte offset: 8 rows * 128 B
+  d |= (uint64_t)1 << 46;                  // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                  // SWIZZLE_128B
+  return d;
 }
 
-int udal_heads_tc_sample(udal_ctx* ctx, const float* const* feats, int batch, const float* scale,
-                         float* const* cls_out, float* const* box_out) {
-  (void)ctx; (void)feats; (void)batch; (void)scale; (void)cls_out; (void)box_out;
-  udal_set_error("heads_mode UDAL_HEADS_BF16_TC is not available in this build");
-  return UDAL_ERR_INVALID;
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+}
+
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+__device__ __forceinline__ float swish_fast(float x) {
+  // x * sigmoid(x), sigmoid(x) = 0.5 * tanh(0.5 x) + 0.5 : one MUFU per element
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * x));
+  return x * fmaf(0.5f, t, 0.5f);
+}
+
+template <int NPAD>
+__global__ void __launch_bounds__(kThreads) sepconv_tc_kernel(const TcLayerParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
+  const uint32_t sbase = smem_u32(smem);
+  uint8_t* sA = smem + SM_A;
+  uint8_t* sB = smem + SM_B;
+  uint8_t* sIn = smem + SM_IN;
+  float* sDw = reinterpret_cast<float*>(smem + SM_DW);
+  const uint32_t mbar = sbase + SM_MBAR;
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + SM_MBAR + 8);
+  constexpr uint32_t kTmemCols = NPAD <= 64 ? 64 : 128;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  int l = 0;
+#pragma unroll
+  for (int i = 1; i < UDAL_MAX_LEVELS; ++i)
+    if (i < p.num_levels && (int)blockIdx.x >= p.tile_off[i]) l = i;
+  const int H = p.h[l], W = p.w[l];
+  const int tile = blockIdx.x - p.tile_off[l];
+  const int ty0 = (tile / p.tiles_x[l]) * TH, tx0 = (tile % p.tiles_x[l]) * TW;
+  const int nb0 = blockIdx.y;
+  const int in_img = p.in_per_sample ? nb0 : nb0 % p.batch;
+
+  if (tid == 0) mbar_init(mbar, 1);
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sbase + SM_MBAR + 8),
+                 "r"(kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+
+  // ---- stage depthwise weights and the input tile (+halo) ----
+  for (int e = tid; e < 9 * KF; e += kThreads) sDw[e] = __ldg(p.dw + e);
+  for (int e = tid; e < HALO_PX * 8; e += kThreads) {
+    const int px = e >> 3, ch = e & 7;
+    const int y = ty0 + px / HALO_W - 1, x = tx0 + px % HALO_W - 1;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (y >= 0 && y < H && x >= 0 && x < W) {
+      const size_t pix = ((size_t)in_img * H + y) * W + x;
+      if (p.in_fp32) {
+        const float4* src = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.in[l]) + pix * KF + ch * 8);
+        const float4 a = __ldg(src), b = __ldg(src + 1);
+        v.x = pack_bf16(a.x, a.y);
+        v.y = pack_bf16(a.z, a.w);
+        v.z = pack_bf16(b.x, b.y);
+        v.w = pack_bf16(b.z, b.w);
+      } else {
+        v = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.in[l]) + pix * KF + ch * 8));
+      }
+    }
+    *reinterpret_cast<uint4*>(sIn + (size_t)px * 128 + ch * 16) = v;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // ---- depthwise 3x3: thread = (channel quad q, column x), 8 output rows, sliding window ----
+  {
+    const int q = tid & 15, x = tid >> 4;
+    float wgt[9][4];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      const float4 w4 = *reinterpret_cast<const float4*>(sDw + t * KF + q * 4);
+      wgt[t][0] = w4.x;
+      wgt[t][1] = w4.y;
+      wgt[t][2] = w4.z;
+      wgt[t][3] = w4.w;
+    }
+    float acc[TH][4];
+#pragma unroll
+    for (int y = 0; y < TH; ++y)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[y][c] = 0.f;
+#pragma unroll
+    for (int r = 0; r < HALO_H; ++r) {
+#pragma unroll
+      for (int dx = 0; dx < 3; ++dx) {
+        const uint2 raw2 = *reinterpret_cast<const uint2*>(sIn + (size_t)(r * HALO_W + x + dx) * 128 + q * 8);
+        float v[4];
+        v[0] = __uint_as_float(raw2.x << 16);
+        v[1] = __uint_as_float(raw2.x & 0xffff0000u);
+        v[2] = __uint_as_float(raw2.y << 16);
+        v[3] = __uint_as_float(raw2.y & 0xffff0000u);
+#pragma unroll
+        for (int dy = 0; dy < 3; ++dy) {
+          const int y = r - dy;
+          if (y >= 0 && y < TH) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) acc[y][c] = fmaf(v[c], wgt[dy * 3 + dx][c], acc[y][c]);
+          }
+        }
+      }
+      if (r >= 2) {
+        const int y = r - 2;
+        const int m = y * TW + x;
+        uint2 o;
+        o.x = pack_bf16(acc[y][0], acc[y][1]);
+        o.y = pack_bf16(acc[y][2], acc[y][3]);
+        *reinterpret_cast<uint2*>(sA + (size_t)m * 128 + (((q >> 1) ^ (m & 7)) << 4) + (q & 1) * 8) = o;
+      }
+    }
+  }
+
+  // instruction descriptor: D = f32, A = B = bf16, K-major both, N = NPAD, M = 128
+  constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NPAD >> 3) << 17) | ((128u >> 4) << 24);
+  const uint64_t adesc = umma_desc(sbase + SM_A);
+  const uint64_t bdesc = umma_desc(sbase + SM_B);
+  constexpr int HALF = NPAD / 2;
+  const int m = (warp & 3) * 32 + lane;       // accumulator row = pixel of the tile
+  const int col0 = (warp >> 2) * HALF;        // this warp's slice of the N columns
+  const int oy = ty0 + m / TW, ox = tx0 + m % TW;
+  const bool pix_ok = oy < H && ox < W;
+
+  for (int it = 0; it < p.nt; ++it) {
+    const int nb = it * p.batch + nb0;
+    // ---- B operand: folded weights * keep-scale of the producer layer ----
+    const float* sc = p.scale[l] ? p.scale[l] + (size_t)nb * KF : nullptr;
+    for (int e = tid; e < NPAD * 8; e += kThreads) {
+      const int n = e >> 3, c = e & 7;
+      const float4* wsrc = reinterpret_cast<const float4*>(p.wf[l] + (size_t)n * KF + c * 8);
+      float4 a = __ldg(wsrc), b = __ldg(wsrc + 1);
+      if (sc) {
+        const float4 s0 = __ldg(reinterpret_cast<const float4*>(sc + c * 8));
+        const float4 s1 = __ldg(reinterpret_cast<const float4*>(sc + c * 8) + 1);
+        a.x *= s0.x; a.y *= s0.y; a.z *= s0.z; a.w *= s0.w;
+        b.x *= s1.x; b.y *= s1.y; b.z *= s1.z; b.w *= s1.w;
+      }
+      uint4 v;
+      v.x = pack_bf16(a.x, a.y);
+      v.y = pack_bf16(a.z, a.w);
+      v.z = pack_bf16(b.x, b.y);
+      v.w = pack_bf16(b.z, b.w);
+      *reinterpret_cast<uint4*>(sB + (size_t)n * 128 + ((c ^ (n & 7)) << 4)) = v;
+    }
+    fence_async_smem();   // generic-proxy smem writes (A, B) -> visible to the tensor-core proxy
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+#pragma unroll
+      for (int k = 0; k < KF / 16; ++k)  // +32 bytes per K=16 step inside the 128-byte swizzle row
+        umma_bf16(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, k > 0 ? 1u : 0u);
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mbar)
+                   : "memory");
+    }
+    mbar_wait(mbar, (uint32_t)(it & 1));
+    tc_fence_after();
+
+    // ---- epilogue: TMEM -> registers -> bias / swish -> global ----
+    uint32_t r[HALF / 8][8];
+    const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)col0;
+#pragma unroll
+    for (int j = 0; j < HALF / 8; ++j) tmem_ld8(taddr + j * 8, r[j]);
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    if (pix_ok) {
+      const size_t pix = ((size_t)nb * H + oy) * W + ox;
+      const float* fb = p.fb[l] + col0;
+      if (!p.out_fp32) {
+        __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out[l]) + pix * KF + col0;
+#pragma unroll
+        for (int j = 0; j < HALF / 8; ++j) {
+          float v[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            v[i] = __uint_as_float(r[j][i]) + __ldg(fb + j * 8 + i);
+            if (p.act) v[i] = swish_fast(v[i]);
+          }
+          uint4 o;
+          o.x = pack_bf16(v[0], v[1]);
+          o.y = pack_bf16(v[2], v[3]);
+          o.z = pack_bf16(v[4], v[5]);
+          o.w = pack_bf16(v[6], v[7]);
+          *reinterpret_cast<uint4*>(dst + j * 8) = o;
+        }
+      } else {
+        float* dst = reinterpret_cast<float*>(p.out[l]) + pix * p.Cout + col0;
+        const bool vec = (p.Cout & 3) == 0;
+#pragma unroll
+        for (int j = 0; j < HALF / 8; ++j) {
+          float v[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            v[i] = __uint_as_float(r[j][i]) + __ldg(fb + j * 8 + i);
+            if (p.act) v[i] = swish_fast(v[i]);
+          }
+          const int n = col0 + j * 8;
+          if (vec && n + 8 <= p.Cout) {
+            *reinterpret_cast<float4*>(dst + j * 8) = make_float4(v[0], v[1], v[2], v[3]);
+            *reinterpret_cast<float4*>(dst + j * 8 + 4) = make_float4(v[4], v[5], v[6], v[7]);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              if (n + i < p.Cout) dst[j * 8 + i] = v[i];
+          }
+        }
+      }
+    }
+    tc_fence_before();
+    __syncthreads();  // B tile and the accumulator may be overwritten by the next sample
+  }
+
+  if (warp == 0) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+  }
+}
+
+// folded weights: wf[n][k] = W[k][n] * bn_scale[n];  fb[n] = bias[n] * bn_scale[n] + bn_shift[n]
+__global__ void fold_weights_kernel(const float* __restrict__ w, const float* __restrict__ bias,
+                                    const float* __restrict__ bn_scale, const float* __restrict__ bn_shift, int cout,
+                                    int npad, float* __restrict__ wf, float* __restrict__ fb) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < npad * KF) {
+    const int n = i / KF, k = i % KF;
+    float v = 0.f;
+    if (n < cout) v = w[(size_t)k * cout + n] * (bn_scale ? bn_scale[n] : 1.f);
+    wf[i] = v;
+  }
+  if (i < npad) {
+    float v = 0.f;
+    if (i < cout) v = bn_scale ? fmaf(bias[i], bn_scale[i], bn_shift[i]) : bias[i];
+    fb[i] = v;
+  }
+}
+
+int npad_of(int cout) { return cout <= 64 ? 64 : 80; }
+
+}  // namespace
+
+int udal_heads_tc_prepare(udal_ctx* ctx, int head) {
+  const udal_config& c = ctx->cfg;
+  udal_head_weights_dev& h = ctx->heads[head];
+  UDAL_REQUIRE(c.num_filters == KF, "the tensor-core head sampler is built for fpn_num_filters = 64 (D0); got %d - "
+               "use heads_mode fp32", c.num_filters);
+  UDAL_REQUIRE(h.cout <= kMaxN, "predict layer with %d channels exceeds the tensor-core tile (%d)", h.cout, kMaxN);
+  const int R = c.repeats, L = c.num_levels;
+  const int npad_p = npad_of(h.cout);
+  const size_t n_w = (size_t)R * L * KF * KF + (size_t)npad_p * KF;
+  const size_t n_b = (size_t)R * L * KF + (size_t)npad_p;
+  if (h.pw_bf16) UDAL_CUDA(cudaFree(h.pw_bf16));
+  if (h.fold_bias) UDAL_CUDA(cudaFree(h.fold_bias));
+  h.pw_bf16 = nullptr;
+  h.fold_bias = nullptr;
+  UDAL_CUDA(cudaMalloc(&h.pw_bf16, n_w * sizeof(float)));
+  UDAL_CUDA(cudaMalloc(&h.fold_bias, n_b * sizeof(float)));
+  float* wf = reinterpret_cast<float*>(h.pw_bf16);
+  for (int r = 0; r < R; ++r)
+    for (int l = 0; l < L; ++l) {
+      const size_t o = (size_t)r * L + l;
+      fold_weights_kernel<<<(KF * KF + 255) / 256, 256, 0, ctx->stream>>>(
+          h.pw + (size_t)r * KF * KF, h.bias + (size_t)r * KF, h.bn_scale + o * KF, h.bn_shift + o * KF, KF, KF,
+          wf + o * KF * KF, h.fold_bias + o * KF);
+      UDAL_CHECK_LAUNCH(ctx);
+    }
+  fold_weights_kernel<<<(npad_p * KF + 255) / 256, 256, 0, ctx->stream>>>(
+      h.pwp, h.bp, nullptr, nullptr, h.cout, npad_p, wf + (size_t)R * L * KF * KF, h.fold_bias + (size_t)R * L * KF);
+  UDAL_CHECK_LAUNCH(ctx);
+  UDAL_CUDA(cudaStreamSynchronize(ctx->stream));
+  return UDAL_OK;
+}
+
+static int run_tower_tc(udal_ctx* ctx, int head, const float* const* feats, int batch, const float* scale_all,
+                        float* const* outs) {
+  const udal_config& c = ctx->cfg;
+  const udal_head_weights_dev& h = ctx->heads[head];
+  const int R = c.repeats, L = c.num_levels, T = c.mc_samples, B = batch;
+  const bool mc = head == UDAL_HEAD_CLASS ? c.cls_mc != 0 : c.box_mc != 0;
+  const int NBt = mc ? T * B : B;
+  const size_t P = (size_t)ctx->num_pixels;
+  __nv_bfloat16 *a0, *pp;
+  UDAL_TRY(udal_scratch_get(ctx, SCR_HEADS_A, (size_t)B * P * KF * 2, (void**)&a0));
+  UDAL_TRY(udal_scratch_get(ctx, SCR_HEADS_B, 2 * (size_t)NBt * P * KF * 2, (void**)&pp));
+  const float* wf_all = reinterpret_cast<const float*>(h.pw_bf16);
+  TcLayerParams p;
+  memset(&p, 0, sizeof(p));
+  p.num_levels = L;
+  int off = 0;
+  for (int l = 0; l <= UDAL_MAX_LEVELS; ++l) {
+    p.tile_off[l] = off;
+    if (l < L) {
+      p.h[l] = c.level_h[l];
+      p.w[l] = c.level_w[l];
+      p.tiles_x[l] = (p.w[l] + TW - 1) / TW;
+      off += p.tiles_x[l] * ((p.h[l] + TH - 1) / TH);
+    }
+  }
+  const int total_tiles = off;
+  p.batch = B;
+  UDAL_CUDA(cudaFuncSetAttribute(sepconv_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_ALLOC));
+  UDAL_CUDA(cudaFuncSetAttribute(sepconv_tc_kernel<80>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_ALLOC));
+  const int npad_p = npad_of(h.cout);
+  for (int layer = 0; layer <= R; ++layer) {
+    const bool predict = layer == R;
+    p.dw = predict ? h.dwp : h.dw + (size_t)layer * 9 * KF;
+    p.Cout = predict ? h.cout : KF;
+    p.Npad = predict ? npad_p : KF;
+    p.act = predict ? 0 : 1;
+    p.out_fp32 = predict ? 1 : 0;
+    p.in_fp32 = layer == 0 ? 1 : 0;
+    p.in_per_sample = layer >= 2 ? 1 : 0;
+    // layer 1 reads the sample-invariant layer-0 output: one CTA per (tile, image) loops the samples
+    p.nt = (layer == 1 && mc) ? T : 1;
+    const int grid_y = layer <= 1 ? B : NBt;
+    for (int l = 0; l < L; ++l) {
+      const size_t lvl = (size_t)ctx->level_pix_off[l] * KF;
+      if (layer == 0) p.in[l] = feats[l];
+      else if (layer == 1) p.in[l] = a0 + (size_t)B * lvl;
+      else p.in[l] = pp + (size_t)((layer - 1) & 1) * NBt * P * KF + (size_t)NBt * lvl;
+      if (predict) p.out[l] = outs[l];
+      else if (layer == 0) p.out[l] = a0 + (size_t)B * lvl;
+      else p.out[l] = pp + (size_t)(layer & 1) * NBt * P * KF + (size_t)NBt * lvl;
+      p.scale[l] = (mc && layer >= 1) ? scale_all + (((size_t)head * L + l) * R + (layer - 1)) * (size_t)NBt * KF
+                                      : nullptr;
+      if (predict) {
+        p.wf[l] = wf_all + (size_t)R * L * KF * KF;
+        p.fb[l] = h.fold_bias + (size_t)R * L * KF;
+      } else {
+        p.wf[l] = wf_all + ((size_t)layer * L + l) * KF * KF;
+        p.fb[l] = h.fold_bias + ((size_t)layer * L + l) * KF;
+      }
+    }
+    dim3 grid(total_tiles, grid_y);
+    if (p.Npad == 64) sepconv_tc_kernel<64><<<grid, kThreads, SM_ALLOC, ctx->stream>>>(p);
+    else sepconv_tc_kernel<80><<<grid, kThreads, SM_ALLOC, ctx->stream>>>(p);
+    UDAL_CHECK_LAUNCH(ctx);
+  }
+  return UDAL_OK;
+}
+
+int udal_heads_tc_sample(udal_ctx* ctx, const float* const* feats, int batch, const float* scale, float* const* cls_out,
+                         float* const* box_out) {
+  for (int l = 0; l < ctx->cfg.num_levels; ++l)
+    UDAL_REQUIRE(((uintptr_t)feats[l] & 15) == 0 && ((uintptr_t)cls_out[l] & 15) == 0 && ((uintptr_t)box_out[l] & 15) == 0,
+                 "level %d: feature / output pointers must be 16-byte aligned", l);
+  UDAL_TRY(run_tower_tc(ctx, UDAL_HEAD_CLASS, feats, batch, scale, cls_out));
+  UDAL_TRY(run_tower_tc(ctx, UDAL_HEAD_BOX, feats, batch, scale, box_out));
+  return UDAL_OK;
 }
