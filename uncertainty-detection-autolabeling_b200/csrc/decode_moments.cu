@@ -152,6 +152,58 @@ __device__ __forceinline__ void decode_plain(const float4 a, const float4 t, flo
   box[3] = __fadd_rn(xc, hw);
 }
 
+// One axis (y: ty/th, x: tx/tw) of decode_la - the two axes are independent, so the fused kernel
+// gives each axis of an anchor its own thread (twice the parallelism, half the registers).
+// exp(2 t + v) of utils_box.py:151-152 is taken as exp(t + v/2)^2: both are within 1 ulp(fp64) of
+// the true value and round to the same fp32 result except in ~1e-8 of the cases.
+__device__ __forceinline__ void decode_axis_la(int method, float a_lo_f, float a_hi_f, float t_c_f, float t_s_f,
+                                               float s_c_f, float s_s_f, float& lo, float& hi, float& sd_lo,
+                                               float& sd_hi) {
+  const double a_lo = a_lo_f, a_hi = a_hi_f, t_c = t_c_f, t_s = t_s_f;
+  const double ca = __dmul_rn(__dadd_rn(a_lo, a_hi), 0.5);
+  const double sa = __dsub_rn(a_hi, a_lo);
+  const double vc = __dmul_rn((double)s_c_f, (double)s_c_f);
+  const double vs = __dmul_rn((double)s_s_f, (double)s_s_f);
+  const double c = __dadd_rn(__dmul_rn(t_c, sa), ca);
+  if (method == UDAL_DECODE_FALSEDEC) {
+    const double half = __dmul_rn(__dmul_rn(exp(t_s), sa), 0.5);
+    lo = (float)__dsub_rn(c, half);
+    hi = (float)__dadd_rn(c, half);
+    const double dhalf = __dmul_rn(__dmul_rn(exp(vs), sa), 0.5);
+    const double dc = __dadd_rn(__dmul_rn(vc, sa), ca);
+    sd_lo = (float)sqrt(fabs(__dsub_rn(dc, dhalf)));
+    sd_hi = (float)sqrt(__dadd_rn(dc, dhalf));
+    return;
+  }
+  const double e = exp(__dadd_rn(t_s, __dmul_rn(vs, 0.5)));
+  const double half = __dmul_rn(__dmul_rn(e, sa), 0.5);
+  lo = (float)__dsub_rn(c, half);
+  hi = (float)__dadd_rn(c, half);
+  double var_c, var_s;
+  if (method == UDAL_DECODE_NFLOW) {
+    const double q = fabs(__dmul_rn(sa, sqrt(vc)));
+    var_c = __dmul_rn(q, q);
+    const double ss = sqrt(vs);
+    const double ss2 = __dmul_rn(ss, ss);
+    const double lv = __dmul_rn(__dsub_rn(exp(ss2), 1.0), exp(__dadd_rn(__dmul_rn(2.0, t_s), ss2)));
+    const double qs = fabs(__dmul_rn(sa, sqrt(lv)));
+    var_s = __dmul_rn(qs, qs);
+  } else {
+    var_s = __dmul_rn(__dmul_rn(__dsub_rn(exp(vs), 1.0), __dmul_rn(e, e)), __dmul_rn(sa, sa));
+    var_c = __dmul_rn(vc, __dmul_rn(sa, sa));
+  }
+  sd_lo = sd_hi = (float)sqrt(__dadd_rn(var_c, __dmul_rn(var_s, 0.25)));
+}
+
+__device__ __forceinline__ void decode_axis_plain(float a_lo, float a_hi, float t_c, float t_s, float& lo, float& hi) {
+  const float ca = __fmul_rn(__fadd_rn(a_lo, a_hi), 0.5f);
+  const float sa = __fsub_rn(a_hi, a_lo);
+  const float half = __fmul_rn(__fmul_rn((float)exp((double)t_s), sa), 0.5f);
+  const float c = __fadd_rn(__fmul_rn(t_c, sa), ca);
+  lo = __fsub_rn(c, half);
+  hi = __fadd_rn(c, half);
+}
+
 __device__ __forceinline__ float sigmoid_ref(float x) {
   // oracle: fp32(1 / (1 + exp(-fp64(x))))
   return (float)(1.0 / (1.0 + exp(-(double)x)));
@@ -201,7 +253,7 @@ __device__ __forceinline__ void logits_run(const float* __restrict__ base, size_
 }
 
 template <int TMAX>
-__global__ void __launch_bounds__(kThreads) decode_moments_kernel(const DecodeParams p) {
+__global__ void __launch_bounds__(kThreads, (TMAX == 0 || TMAX > 16) ? 1 : 3) decode_moments_kernel(const DecodeParams p) {
   extern __shared__ float smem_mean[];  // [tile anchors * C]
   const int b = blockIdx.y;
   const int tile = blockIdx.x;
@@ -224,108 +276,115 @@ __global__ void __launch_bounds__(kThreads) decode_moments_kernel(const DecodePa
   }
   __syncthreads();
 
-  // ---- phase 2: one thread per anchor -----------------------------------------------------
-  for (int i = threadIdx.x; i < npx * A; i += kThreads) {
-    const int px = p0 + i / A;
-    const int a = i - (i / A) * A;
-    const int64_t n = anchor0 + i;
+  // ---- phase 2: one thread per (anchor, axis): even lanes decode y (ymin, ymax), odd lanes x ----
+  const int axis = threadIdx.x & 1;
+  for (int i0 = 0; i0 < npx * A; i0 += kThreads / 2) {
+    const int i = i0 + (threadIdx.x >> 1);
+    const bool live = i < npx * A;
+    const int ii = live ? i : 0;
+    const int px = p0 + ii / A;
+    const int a = ii - (ii / A) * A;
+    const int64_t n = anchor0 + ii;
     const float4 anc = __ldg(reinterpret_cast<const float4*>(p.anchors) + n);
+    const float a_lo = axis ? anc.y : anc.x, a_hi = axis ? anc.w : anc.z;
     const size_t plane = (size_t)hw * p.BC;
     const float* bb = p.box.p[l] + ((size_t)b * hw + px) * p.BC + a * 4;
     const size_t t_stride = (size_t)p.batch * plane;
     const int T = p.Tb;
-    float mb[4], sdb[4], alb[4];
+    float m_lo, m_hi, sd_lo = 0.f, sd_hi = 0.f, al_lo = 0.f, al_hi = 0.f;
     if (TMAX != 0) {
       constexpr int TM = TMAX == 0 ? 1 : TMAX;
-      float bx[4][TM];
-      float al[4] = {0.f, 0.f, 0.f, 0.f};
+      float lo[TM], hi[TM];
 #pragma unroll
       for (int t = 0; t < TM; ++t)
         if (t < T) {
           const float4 tt = __ldg(reinterpret_cast<const float4*>(bb + (size_t)t * t_stride));
+          const float t_c = axis ? tt.y : tt.x, t_s = axis ? tt.w : tt.z;
           if (p.la) {
             const float4 sg = __ldg(reinterpret_cast<const float4*>(bb + (size_t)t * t_stride + 4 * A));
-            const Decoded d = decode_la(anc, tt, sg, p.method);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              bx[k][t] = d.box[k];
-              al[k] = t == 0 ? d.sd[k] : __fadd_rn(al[k], d.sd[k]);
-            }
+            float s_lo, s_hi;
+            decode_axis_la(p.method, a_lo, a_hi, t_c, t_s, axis ? sg.y : sg.x, axis ? sg.w : sg.z, lo[t], hi[t],
+                           s_lo, s_hi);
+            al_lo = t == 0 ? s_lo : __fadd_rn(al_lo, s_lo);
+            al_hi = t == 0 ? s_hi : __fadd_rn(al_hi, s_hi);
           } else {
-            float d[4];
-            decode_plain(anc, tt, d);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) bx[k][t] = d[k];
+            decode_axis_plain(a_lo, a_hi, t_c, t_s, lo[t], hi[t]);
           }
         }
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        if (p.box_mc) {
-          moments_reg<TM>(bx[k], T, mb[k], sdb[k]);
-          alb[k] = __fdiv_rn(al[k], (float)T);
-        } else {
-          mb[k] = bx[k][0];
-          sdb[k] = 0.f;
-          alb[k] = al[k];
-        }
+      if (p.box_mc) {
+        moments_reg<TM>(lo, T, m_lo, sd_lo);
+        moments_reg<TM>(hi, T, m_hi, sd_hi);
+        al_lo = __fdiv_rn(al_lo, (float)T);
+        al_hi = __fdiv_rn(al_hi, (float)T);
+      } else {
+        m_lo = lo[0];
+        m_hi = hi[0];
       }
     } else {
       // many samples: decode twice (sum pass, deviation pass)
-      float sum[4] = {0, 0, 0, 0}, al[4] = {0, 0, 0, 0};
-      for (int t = 0; t < T; ++t) {
-        const float4 tt = __ldg(reinterpret_cast<const float4*>(bb + (size_t)t * t_stride));
-        float d[4];
-        if (p.la) {
-          const float4 sg = __ldg(reinterpret_cast<const float4*>(bb + (size_t)t * t_stride + 4 * A));
-          const Decoded dd = decode_la(anc, tt, sg, p.method);
-          for (int k = 0; k < 4; ++k) {
-            d[k] = dd.box[k];
-            al[k] = t == 0 ? dd.sd[k] : __fadd_rn(al[k], dd.sd[k]);
+      float s_lo_sum = 0.f, s_hi_sum = 0.f, q_lo = 0.f, q_hi = 0.f;
+      m_lo = m_hi = 0.f;
+      for (int pass = 0; pass < (p.box_mc ? 2 : 1); ++pass) {
+        for (int t = 0; t < T; ++t) {
+          const float4 tt = __ldg(reinterpret_cast<const float4*>(bb + (size_t)t * t_stride));
+          const float t_c = axis ? tt.y : tt.x, t_s = axis ? tt.w : tt.z;
+          float lo, hi, s_lo = 0.f, s_hi = 0.f;
+          if (p.la) {
+            const float4 sg = __ldg(reinterpret_cast<const float4*>(bb + (size_t)t * t_stride + 4 * A));
+            decode_axis_la(p.method, a_lo, a_hi, t_c, t_s, axis ? sg.y : sg.x, axis ? sg.w : sg.z, lo, hi, s_lo, s_hi);
+          } else {
+            decode_axis_plain(a_lo, a_hi, t_c, t_s, lo, hi);
           }
-        } else {
-          decode_plain(anc, tt, d);
+          if (pass == 0) {
+            s_lo_sum = t == 0 ? lo : __fadd_rn(s_lo_sum, lo);
+            s_hi_sum = t == 0 ? hi : __fadd_rn(s_hi_sum, hi);
+            al_lo = t == 0 ? s_lo : __fadd_rn(al_lo, s_lo);
+            al_hi = t == 0 ? s_hi : __fadd_rn(al_hi, s_hi);
+          } else {
+            const float d0 = __fsub_rn(lo, m_lo), d1 = __fsub_rn(hi, m_hi);
+            q_lo = t == 0 ? __fmul_rn(d0, d0) : __fadd_rn(q_lo, __fmul_rn(d0, d0));
+            q_hi = t == 0 ? __fmul_rn(d1, d1) : __fadd_rn(q_hi, __fmul_rn(d1, d1));
+          }
         }
-        for (int k = 0; k < 4; ++k) sum[k] = t == 0 ? d[k] : __fadd_rn(sum[k], d[k]);
-      }
-      float ss[4] = {0, 0, 0, 0};
-      for (int k = 0; k < 4; ++k) mb[k] = p.box_mc ? __fdiv_rn(sum[k], (float)T) : sum[k];
-      for (int t = 0; t < T && p.box_mc; ++t) {
-        const float4 tt = __ldg(reinterpret_cast<const float4*>(bb + (size_t)t * t_stride));
-        float d[4];
-        if (p.la) {
-          const float4 sg = __ldg(reinterpret_cast<const float4*>(bb + (size_t)t * t_stride + 4 * A));
-          const Decoded dd = decode_la(anc, tt, sg, p.method);
-          for (int k = 0; k < 4; ++k) d[k] = dd.box[k];
-        } else {
-          decode_plain(anc, tt, d);
-        }
-        for (int k = 0; k < 4; ++k) {
-          const float dv = __fsub_rn(d[k], mb[k]);
-          ss[k] = t == 0 ? __fmul_rn(dv, dv) : __fadd_rn(ss[k], __fmul_rn(dv, dv));
+        if (pass == 0) {
+          m_lo = p.box_mc ? __fdiv_rn(s_lo_sum, (float)T) : s_lo_sum;
+          m_hi = p.box_mc ? __fdiv_rn(s_hi_sum, (float)T) : s_hi_sum;
         }
       }
-      for (int k = 0; k < 4; ++k) {
-        sdb[k] = p.box_mc ? __fsqrt_rn(__fdiv_rn(ss[k], (float)T)) : 0.f;
-        alb[k] = p.box_mc ? __fdiv_rn(al[k], (float)T) : al[k];
+      if (p.box_mc) {
+        sd_lo = __fsqrt_rn(__fdiv_rn(q_lo, (float)T));
+        sd_hi = __fsqrt_rn(__fdiv_rn(q_hi, (float)T));
+        al_lo = __fdiv_rn(al_lo, (float)T);
+        al_hi = __fdiv_rn(al_hi, (float)T);
       }
     }
+    // pair exchange: the y lane assembles (ymin, xmin, ymax, xmax) rows
+    const float o_m_lo = __shfl_xor_sync(0xffffffffu, m_lo, 1), o_m_hi = __shfl_xor_sync(0xffffffffu, m_hi, 1);
+    const float o_sd_lo = __shfl_xor_sync(0xffffffffu, sd_lo, 1), o_sd_hi = __shfl_xor_sync(0xffffffffu, sd_hi, 1);
+    const float o_al_lo = __shfl_xor_sync(0xffffffffu, al_lo, 1), o_al_hi = __shfl_xor_sync(0xffffffffu, al_hi, 1);
+    if (!live) continue;
     const size_t o = (size_t)b * p.N + n;
-    if (p.out.boxes) reinterpret_cast<float4*>(p.out.boxes)[o] = make_float4(mb[0], mb[1], mb[2], mb[3]);
-    if (p.out.albox && p.la) reinterpret_cast<float4*>(p.out.albox)[o] = make_float4(alb[0], alb[1], alb[2], alb[3]);
-    if (p.out.mcbox && p.box_mc) reinterpret_cast<float4*>(p.out.mcbox)[o] = make_float4(sdb[0], sdb[1], sdb[2], sdb[3]);
-    if (p.out.scores || p.out.classes) {
-      const float* ml = smem_mean + (size_t)i * C;
-      float best = ml[0];
-      int arg = 0;
-      for (int c = 1; c < C; ++c) {
-        const float v = ml[c];
-        if (v > best) {
-          best = v;
-          arg = c;
+    if (axis == 0) {
+      if (p.out.boxes) reinterpret_cast<float4*>(p.out.boxes)[o] = make_float4(m_lo, o_m_lo, m_hi, o_m_hi);
+      if (p.out.mcbox && p.box_mc)
+        reinterpret_cast<float4*>(p.out.mcbox)[o] = make_float4(sd_lo, o_sd_lo, sd_hi, o_sd_hi);
+    } else {
+      if (p.out.albox && p.la)
+        reinterpret_cast<float4*>(p.out.albox)[o] = make_float4(o_al_lo, al_lo, o_al_hi, al_hi);
+      if (p.out.scores || p.out.classes) {
+        const float* ml = smem_mean + (size_t)ii * C;
+        float best = ml[0];
+        int arg = 0;
+        for (int c = 1; c < C; ++c) {
+          const float v = ml[c];
+          if (v > best) {
+            best = v;
+            arg = c;
+          }
         }
+        if (p.out.scores) p.out.scores[o] = sigmoid_ref(best);
+        if (p.out.classes) p.out.classes[o] = arg;
       }
-      if (p.out.scores) p.out.scores[o] = sigmoid_ref(best);
-      if (p.out.classes) p.out.classes[o] = arg;
     }
   }
 }
@@ -446,7 +505,7 @@ int fill_params(udal_ctx* ctx, const float* const* cls, const float* const* box,
   p.method = c.decode_method;
   p.anchors = ctx->anchors;
   p.N = ctx->num_anchors;
-  int tile_px = kThreads / p.A;
+  int tile_px = (kThreads / 2) / p.A;  // two threads (y axis, x axis) per anchor
   const int cap = 12288 / (p.A * p.C);
   if (tile_px > cap) tile_px = cap;
   if (tile_px < 1) tile_px = 1;

@@ -38,7 +38,8 @@ constexpr int SM_A = 0;                         // [128][128 B]
 constexpr int SM_B = SM_A + TPX * 128;          // [kMaxN][128 B]
 constexpr int SM_IN = SM_B + kMaxN * 128;       // [180][64] bf16
 constexpr int SM_DW = SM_IN + HALO_PX * KF * 2; // [9][64] fp32
-constexpr int SM_MBAR = SM_DW + 9 * KF * 4;     // mbarrier (8 B) + tmem base (4 B)
+constexpr int SM_FB = SM_DW + 9 * KF * 4;       // [kMaxN] fp32 folded bias
+constexpr int SM_MBAR = SM_FB + kMaxN * 4;      // mbarrier (8 B) + tmem base (4 B)
 constexpr int SM_TOTAL = SM_MBAR + 16;
 constexpr int SM_ALLOC = SM_TOTAL + 1024;       // slack for the manual 1024-byte alignment
 
@@ -120,7 +121,7 @@ __device__ __forceinline__ float swish_fast(float x) {
 }
 
 template <int NPAD>
-__global__ void __launch_bounds__(kThreads) sepconv_tc_kernel(const TcLayerParams p) {
+__global__ void __launch_bounds__(kThreads, NPAD <= 64 ? 3 : 2) sepconv_tc_kernel(const TcLayerParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
@@ -129,6 +130,7 @@ __global__ void __launch_bounds__(kThreads) sepconv_tc_kernel(const TcLayerParam
   uint8_t* sB = smem + SM_B;
   uint8_t* sIn = smem + SM_IN;
   float* sDw = reinterpret_cast<float*>(smem + SM_DW);
+  float* sFb = reinterpret_cast<float*>(smem + SM_FB);
   const uint32_t mbar = sbase + SM_MBAR;
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + SM_MBAR + 8);
   constexpr uint32_t kTmemCols = NPAD <= 64 ? 64 : 128;
@@ -152,26 +154,46 @@ __global__ void __launch_bounds__(kThreads) sepconv_tc_kernel(const TcLayerParam
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
 
-  // ---- stage depthwise weights and the input tile (+halo) ----
+  // ---- stage depthwise weights, folded bias and the input tile (+halo) ----
   for (int e = tid; e < 9 * KF; e += kThreads) sDw[e] = __ldg(p.dw + e);
-  for (int e = tid; e < HALO_PX * 8; e += kThreads) {
-    const int px = e >> 3, ch = e & 7;
-    const int y = ty0 + px / HALO_W - 1, x = tx0 + px % HALO_W - 1;
-    uint4 v = make_uint4(0u, 0u, 0u, 0u);
-    if (y >= 0 && y < H && x >= 0 && x < W) {
-      const size_t pix = ((size_t)in_img * H + y) * W + x;
-      if (p.in_fp32) {
-        const float4* src = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.in[l]) + pix * KF + ch * 8);
+  if (tid < NPAD) sFb[tid] = __ldg(p.fb[l] + tid);
+  if (p.in_fp32) {
+    const float* src0 = reinterpret_cast<const float*>(p.in[l]) + (size_t)in_img * H * W * KF;
+    for (int e = tid; e < HALO_PX * 8; e += kThreads) {
+      const int px = e >> 3, ch = e & 7;
+      const int hy = px / HALO_W;
+      const int y = ty0 + hy - 1, x = tx0 + (px - hy * HALO_W) - 1;
+      uint4 v = make_uint4(0u, 0u, 0u, 0u);
+      if (y >= 0 && y < H && x >= 0 && x < W) {
+        const float4* src = reinterpret_cast<const float4*>(src0 + ((size_t)y * W + x) * KF + ch * 8);
         const float4 a = __ldg(src), b = __ldg(src + 1);
         v.x = pack_bf16(a.x, a.y);
         v.y = pack_bf16(a.z, a.w);
         v.z = pack_bf16(b.x, b.y);
         v.w = pack_bf16(b.z, b.w);
-      } else {
-        v = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.in[l]) + pix * KF + ch * 8));
+      }
+      *reinterpret_cast<uint4*>(sIn + (size_t)px * 128 + ch * 16) = v;
+    }
+  } else {
+    // bf16 activations: 16-byte cp.async straight into shared memory, zero-filled outside the image
+    const __nv_bfloat16* src0 = reinterpret_cast<const __nv_bfloat16*>(p.in[l]) + (size_t)in_img * H * W * KF;
+    const uint32_t dst0 = sbase + SM_IN;
+#pragma unroll
+    for (int i = 0; i < (HALO_PX * 8 + kThreads - 1) / kThreads; ++i) {
+      const int e = tid + i * kThreads;
+      if (e < HALO_PX * 8) {
+        const int px = e >> 3, ch = e & 7;
+        const int hy = px / HALO_W;
+        const int y = ty0 + hy - 1, x = tx0 + (px - hy * HALO_W) - 1;
+        const bool ok = y >= 0 && y < H && x >= 0 && x < W;
+        const __nv_bfloat16* src = ok ? src0 + ((size_t)y * W + x) * KF + ch * 8 : src0;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst0 + (uint32_t)e * 16u), "l"(src),
+                     "r"(ok ? 16 : 0)
+                     : "memory");
       }
     }
-    *reinterpret_cast<uint4*>(sIn + (size_t)px * 128 + ch * 16) = v;
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
   }
   tc_fence_before();
   __syncthreads();
@@ -278,7 +300,7 @@ __global__ void __launch_bounds__(kThreads) sepconv_tc_kernel(const TcLayerParam
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
     if (pix_ok) {
       const size_t pix = ((size_t)nb * H + oy) * W + ox;
-      const float* fb = p.fb[l] + col0;
+      const float* fb = sFb + col0;
       if (!p.out_fp32) {
         __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out[l]) + pix * KF + col0;
 #pragma unroll
@@ -286,7 +308,7 @@ __global__ void __launch_bounds__(kThreads) sepconv_tc_kernel(const TcLayerParam
           float v[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            v[i] = __uint_as_float(r[j][i]) + __ldg(fb + j * 8 + i);
+            v[i] = __uint_as_float(r[j][i]) + fb[j * 8 + i];
             if (p.act) v[i] = swish_fast(v[i]);
           }
           uint4 o;
@@ -304,7 +326,7 @@ __global__ void __launch_bounds__(kThreads) sepconv_tc_kernel(const TcLayerParam
           float v[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            v[i] = __uint_as_float(r[j][i]) + __ldg(fb + j * 8 + i);
+            v[i] = __uint_as_float(r[j][i]) + fb[j * 8 + i];
             if (p.act) v[i] = swish_fast(v[i]);
           }
           const int n = col0 + j * 8;
