@@ -21,6 +21,7 @@ struct DecodeParams {
   udal_level_geom geom;
   int tile_off[UDAL_MAX_LEVELS + 1];  // prefix of tiles per level
   int tile_px;                         // pixels per tile
+  int stage_off;                       // float offset of the sample staging area in dynamic smem
   int batch, A, C, BC;                 // BC = box channels (4A or 8A)
   int Tc, Tb;                          // samples on the class / box inputs (1 = no MC axis)
   int cls_mc, box_mc, la, method;
@@ -152,13 +153,113 @@ __device__ __forceinline__ void decode_plain(const float4 a, const float4 t, flo
   box[3] = __fadd_rn(xc, hw);
 }
 
+// ---- fp64 exp / sqrt tuned for this kernel ---------------------------------------------------
+// The decode needs fp64 results that round to the same fp32 value as the reference's libm: a
+// relative error of ~1e-15 is as good as 0.5 ulp for that purpose (mismatch probability ~
+// error / 2^-24).  exp(x) = 2^k * 2^(j/64) * exp(r), |r| <= ln2/128, degree-5 polynomial (truncation
+// 3.5e-17), 64-entry table in shared memory; sqrt by rsqrt.approx + two Newton corrections.
+// Arguments outside the fast range fall back to the CUDA math library.
+__constant__ double kExp2Table[64] = {
+    1.0,
+    1.0108892860517005,
+    1.0218971486541166,
+    1.0330248790212284,
+    1.0442737824274138,
+    1.0556451783605572,
+    1.0671404006768237,
+    1.0787607977571199,
+    1.0905077326652577,
+    1.102382583307841,
+    1.1143867425958924,
+    1.1265216186082418,
+    1.1387886347566916,
+    1.1511892299529827,
+    1.1637248587775775,
+    1.1763969916502812,
+    1.189207115002721,
+    1.202156731452703,
+    1.215247359980469,
+    1.22848053610687,
+    1.241857812073484,
+    1.255380757024691,
+    1.2690509571917332,
+    1.2828700160787783,
+    1.2968395546510096,
+    1.3109612115247644,
+    1.3252366431597413,
+    1.339667524053303,
+    1.3542555469368927,
+    1.3690024229745905,
+    1.383909881963832,
+    1.3989796725383112,
+    1.4142135623730951,
+    1.42961333839197,
+    1.4451808069770467,
+    1.460917794180647,
+    1.4768261459394993,
+    1.4929077282912648,
+    1.5091644275934228,
+    1.5255981507445384,
+    1.5422108254079407,
+    1.559004400237837,
+    1.5759808451078865,
+    1.593142151342267,
+    1.6104903319492543,
+    1.6280274218573478,
+    1.645755478153965,
+    1.6636765803267364,
+    1.681792830507429,
+    1.7001063537185235,
+    1.718619298122478,
+    1.7373338352737062,
+    1.7562521603732995,
+    1.7753764925265212,
+    1.7947090750031072,
+    1.8142521755003989,
+    1.8340080864093424,
+    1.8539791250833855,
+    1.8741676341103,
+    1.8945759815869656,
+    1.9152065613971474,
+    1.9360617934922943,
+    1.9571441241754002,
+    1.978456026387951};
+
+__device__ __noinline__ double exp_slow(double x) { return exp(x); }
+__device__ __noinline__ double sqrt_slow(double x) { return sqrt(x); }
+
+__device__ __forceinline__ double exp_fast(double x, const double* tbl) {
+  if (!(fabs(x) < 690.0)) return exp_slow(x);
+  const double n = rint(x * 92.33248261689366);
+  double r = fma(n, -0.010830424696248286, x);
+  r = fma(n, -8.59050471673183e-16, r);
+  double p = fma(r, 1.0 / 120.0, 1.0 / 24.0);
+  p = fma(p, r, 1.0 / 6.0);
+  p = fma(p, r, 0.5);
+  p = fma(p, r, 1.0);
+  p = fma(p, r, 1.0);
+  const int ni = (int)n;
+  const double v = tbl[ni & 63] * p;
+  return __longlong_as_double(__double_as_longlong(v) + ((long long)(ni >> 6) << 52));
+}
+
+__device__ __forceinline__ double sqrt_fast(double x) {
+  if (!(x > 1e-290 && x < 1e290)) return sqrt_slow(x);
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  y = fma(y * 0.5, fma(-x * y, y, 1.0), y);  // Newton step on 1/sqrt(x)
+  double s = x * y;
+  s = fma(fma(-s, s, x), y * 0.5, s);        // correction of sqrt(x)
+  return s;
+}
+
 // One axis (y: ty/th, x: tx/tw) of decode_la - the two axes are independent, so the fused kernel
 // gives each axis of an anchor its own thread (twice the parallelism, half the registers).
 // exp(2 t + v) of utils_box.py:151-152 is taken as exp(t + v/2)^2: both are within 1 ulp(fp64) of
 // the true value and round to the same fp32 result except in ~1e-8 of the cases.
-__device__ __forceinline__ void decode_axis_la(int method, float a_lo_f, float a_hi_f, float t_c_f, float t_s_f,
-                                               float s_c_f, float s_s_f, float& lo, float& hi, float& sd_lo,
-                                               float& sd_hi) {
+__device__ __forceinline__ void decode_axis_la(int method, const double* tbl, float a_lo_f, float a_hi_f,
+                                               float t_c_f, float t_s_f, float s_c_f, float s_s_f, float& lo,
+                                               float& hi, float& sd_lo, float& sd_hi) {
   const double a_lo = a_lo_f, a_hi = a_hi_f, t_c = t_c_f, t_s = t_s_f;
   const double ca = __dmul_rn(__dadd_rn(a_lo, a_hi), 0.5);
   const double sa = __dsub_rn(a_hi, a_lo);
@@ -166,16 +267,16 @@ __device__ __forceinline__ void decode_axis_la(int method, float a_lo_f, float a
   const double vs = __dmul_rn((double)s_s_f, (double)s_s_f);
   const double c = __dadd_rn(__dmul_rn(t_c, sa), ca);
   if (method == UDAL_DECODE_FALSEDEC) {
-    const double half = __dmul_rn(__dmul_rn(exp(t_s), sa), 0.5);
+    const double half = __dmul_rn(__dmul_rn(exp_fast(t_s, tbl), sa), 0.5);
     lo = (float)__dsub_rn(c, half);
     hi = (float)__dadd_rn(c, half);
-    const double dhalf = __dmul_rn(__dmul_rn(exp(vs), sa), 0.5);
+    const double dhalf = __dmul_rn(__dmul_rn(exp_fast(vs, tbl), sa), 0.5);
     const double dc = __dadd_rn(__dmul_rn(vc, sa), ca);
     sd_lo = (float)sqrt(fabs(__dsub_rn(dc, dhalf)));
     sd_hi = (float)sqrt(__dadd_rn(dc, dhalf));
     return;
   }
-  const double e = exp(__dadd_rn(t_s, __dmul_rn(vs, 0.5)));
+  const double e = exp_fast(__dadd_rn(t_s, __dmul_rn(vs, 0.5)), tbl);
   const double half = __dmul_rn(__dmul_rn(e, sa), 0.5);
   lo = (float)__dsub_rn(c, half);
   hi = (float)__dadd_rn(c, half);
@@ -189,10 +290,10 @@ __device__ __forceinline__ void decode_axis_la(int method, float a_lo_f, float a
     const double qs = fabs(__dmul_rn(sa, sqrt(lv)));
     var_s = __dmul_rn(qs, qs);
   } else {
-    var_s = __dmul_rn(__dmul_rn(__dsub_rn(exp(vs), 1.0), __dmul_rn(e, e)), __dmul_rn(sa, sa));
+    var_s = __dmul_rn(__dmul_rn(__dsub_rn(exp_fast(vs, tbl), 1.0), __dmul_rn(e, e)), __dmul_rn(sa, sa));
     var_c = __dmul_rn(vc, __dmul_rn(sa, sa));
   }
-  sd_lo = sd_hi = (float)sqrt(__dadd_rn(var_c, __dmul_rn(var_s, 0.25)));
+  sd_lo = sd_hi = (float)sqrt_fast(__dadd_rn(var_c, __dmul_rn(var_s, 0.25)));
 }
 
 __device__ __forceinline__ void decode_axis_plain(float a_lo, float a_hi, float t_c, float t_s, float& lo, float& hi) {
@@ -226,35 +327,63 @@ __device__ __forceinline__ void logits_run(const float* __restrict__ base, size_
                                            int count, float* __restrict__ mean_out,
                                            float* __restrict__ std_out, float* smem_mean, int tid,
                                            int nthreads) {
-  for (int e = tid; e < count; e += nthreads) {
-    float mean, sd;
-    if (TMAX == 0) {
-      // many samples: two passes over global memory (second pass hits L1/L2)
+  if (TMAX == 0) {
+    // many samples: two passes over global memory (second pass hits L1/L2)
+    for (int e = tid; e < count; e += nthreads) {
       float acc = __ldg(base + e);
       for (int t = 1; t < T; ++t) acc = __fadd_rn(acc, __ldg(base + (size_t)t * t_stride + e));
-      mean = __fdiv_rn(acc, (float)T);
+      const float mean = __fdiv_rn(acc, (float)T);
       float s = 0.f;
       for (int t = 0; t < T; ++t) {
         float d = __fsub_rn(__ldg(base + (size_t)t * t_stride + e), mean);
         s = t == 0 ? __fmul_rn(d, d) : __fadd_rn(s, __fmul_rn(d, d));
       }
-      sd = __fsqrt_rn(__fdiv_rn(s, (float)T));
-    } else {
-      float v[TMAX == 0 ? 1 : TMAX];
-#pragma unroll
-      for (int t = 0; t < TMAX; ++t)
-        if (t < T) v[t] = __ldg(base + (size_t)t * t_stride + e);
-      moments_reg<(TMAX == 0 ? 1 : TMAX)>(v, T, mean, sd);
+      const float sd = __fsqrt_rn(__fdiv_rn(s, (float)T));
+      if (mean_out) mean_out[e] = mean;
+      if (std_out) std_out[e] = sd;
+      if (smem_mean) smem_mean[e] = mean;
     }
-    if (mean_out) mean_out[e] = mean;
-    if (std_out) std_out[e] = sd;
-    if (smem_mean) smem_mean[e] = mean;
+    return;
+  }
+  constexpr int TM = TMAX == 0 ? 1 : TMAX;
+  constexpr int U = TM <= 16 ? 2 : 1;  // elements in flight per thread (2 x T independent loads)
+  for (int e0 = tid; e0 < count; e0 += U * nthreads) {
+    float v[U][TM];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int e = e0 + u * nthreads;
+#pragma unroll
+      for (int t = 0; t < TM; ++t)
+        if (t < T && e < count) v[u][t] = __ldg(base + (size_t)t * t_stride + e);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int e = e0 + u * nthreads;
+      if (e < count) {
+        float mean, sd;
+        moments_reg<TM>(v[u], T, mean, sd);
+        if (mean_out) mean_out[e] = mean;
+        if (std_out) std_out[e] = sd;
+        if (smem_mean) smem_mean[e] = mean;
+      }
+    }
   }
 }
 
-template <int TMAX>
-__global__ void __launch_bounds__(kThreads, (TMAX == 0 || TMAX > 16) ? 1 : 3) decode_moments_kernel(const DecodeParams p) {
-  extern __shared__ float smem_mean[];  // [tile anchors * C]
+// FAST = the serving configuration (loss attenuation, l-norm decode, MC dropout on both heads,
+// T == TMAX): every mode switch folds away at compile time.
+template <int TMAX, bool FAST>
+__global__ void __launch_bounds__(kThreads, (TMAX == 0 || TMAX > 16) ? 1 : 4) decode_moments_kernel(const DecodeParams p) {
+  const int k_la = FAST ? 1 : p.la;
+  const int k_method = FAST ? (int)UDAL_DECODE_LNORM : p.method;
+  const int k_box_mc = FAST ? 1 : p.box_mc;
+  const int k_cls_mc = FAST ? 1 : p.cls_mc;
+  const int k_Tb = FAST ? TMAX : p.Tb;
+  const int k_Tc = FAST ? TMAX : p.Tc;
+  extern __shared__ float smem_mean[];  // [tile anchors * C] then the per-thread sample staging
+  float* smem_stage = smem_mean + p.stage_off;
+  __shared__ double smem_tbl[64];
+  if (threadIdx.x < 64) smem_tbl[threadIdx.x] = kExp2Table[threadIdx.x];
   const int b = blockIdx.y;
   const int tile = blockIdx.x;
   const int l = find_level(p.tile_off, p.geom.num_levels, tile);
@@ -271,8 +400,8 @@ __global__ void __launch_bounds__(kThreads, (TMAX == 0 || TMAX > 16) ? 1 : 3) de
     const float* base = p.cls.p[l] + ((size_t)b * hw + p0) * A * C;
     const size_t t_stride = (size_t)p.batch * plane;
     float* mo = p.out.mean_logits ? p.out.mean_logits + ((size_t)b * p.N + anchor0) * C : nullptr;
-    float* so = (p.out.std_logits && p.cls_mc) ? p.out.std_logits + ((size_t)b * p.N + anchor0) * C : nullptr;
-    logits_run<TMAX>(base, t_stride, p.Tc, count, mo, so, smem_mean, threadIdx.x, kThreads);
+    float* so = (p.out.std_logits && k_cls_mc) ? p.out.std_logits + ((size_t)b * p.N + anchor0) * C : nullptr;
+    logits_run<TMAX>(base, t_stride, k_Tc, count, mo, so, smem_mean, threadIdx.x, kThreads);
   }
   __syncthreads();
 
@@ -290,48 +419,83 @@ __global__ void __launch_bounds__(kThreads, (TMAX == 0 || TMAX > 16) ? 1 : 3) de
     const size_t plane = (size_t)hw * p.BC;
     const float* bb = p.box.p[l] + ((size_t)b * hw + px) * p.BC + a * 4;
     const size_t t_stride = (size_t)p.batch * plane;
-    const int T = p.Tb;
+    const int T = k_Tb;
     float m_lo, m_hi, sd_lo = 0.f, sd_hi = 0.f, al_lo = 0.f, al_hi = 0.f;
     if (TMAX != 0) {
       constexpr int TM = TMAX == 0 ? 1 : TMAX;
-      float lo[TM], hi[TM];
+      // (a) every load of this thread is issued first (2 x T independent 16-byte requests in
+      //     flight) and parked in shared memory; (b) a rolled loop decodes sample by sample.
+      float* st = smem_stage + threadIdx.x;  // slot (t, k) at st[(t * 4 + k) * kThreads]
+      {
+        float4 tt[TM], sg[TM];
 #pragma unroll
-      for (int t = 0; t < TM; ++t)
-        if (t < T) {
-          const float4 tt = __ldg(reinterpret_cast<const float4*>(bb + (size_t)t * t_stride));
-          const float t_c = axis ? tt.y : tt.x, t_s = axis ? tt.w : tt.z;
-          if (p.la) {
-            const float4 sg = __ldg(reinterpret_cast<const float4*>(bb + (size_t)t * t_stride + 4 * A));
-            float s_lo, s_hi;
-            decode_axis_la(p.method, a_lo, a_hi, t_c, t_s, axis ? sg.y : sg.x, axis ? sg.w : sg.z, lo[t], hi[t],
-                           s_lo, s_hi);
-            al_lo = t == 0 ? s_lo : __fadd_rn(al_lo, s_lo);
-            al_hi = t == 0 ? s_hi : __fadd_rn(al_hi, s_hi);
-          } else {
-            decode_axis_plain(a_lo, a_hi, t_c, t_s, lo[t], hi[t]);
+        for (int t = 0; t < TM; ++t)
+          if (t < T) {
+            tt[t] = __ldg(reinterpret_cast<const float4*>(bb + (size_t)t * t_stride));
+            if (k_la) sg[t] = __ldg(reinterpret_cast<const float4*>(bb + (size_t)t * t_stride + 4 * A));
           }
+#pragma unroll
+        for (int t = 0; t < TM; ++t)
+          if (t < T) {
+            st[(t * 4 + 0) * kThreads] = axis ? tt[t].y : tt[t].x;
+            st[(t * 4 + 1) * kThreads] = axis ? tt[t].w : tt[t].z;
+            if (k_la) {
+              st[(t * 4 + 2) * kThreads] = axis ? sg[t].y : sg[t].x;
+              st[(t * 4 + 3) * kThreads] = axis ? sg[t].w : sg[t].z;
+            }
+          }
+      }
+      float sum_lo = 0.f, sum_hi = 0.f;
+#pragma unroll 1
+      for (int t = 0; t < T; ++t) {
+        const float t_c = st[(t * 4 + 0) * kThreads], t_s = st[(t * 4 + 1) * kThreads];
+        float lo, hi;
+        if (k_la) {
+          float s_lo, s_hi;
+          decode_axis_la(k_method, smem_tbl, a_lo, a_hi, t_c, t_s, st[(t * 4 + 2) * kThreads],
+                         st[(t * 4 + 3) * kThreads], lo, hi, s_lo, s_hi);
+          al_lo = t == 0 ? s_lo : __fadd_rn(al_lo, s_lo);
+          al_hi = t == 0 ? s_hi : __fadd_rn(al_hi, s_hi);
+        } else {
+          decode_axis_plain(a_lo, a_hi, t_c, t_s, lo, hi);
         }
-      if (p.box_mc) {
-        moments_reg<TM>(lo, T, m_lo, sd_lo);
-        moments_reg<TM>(hi, T, m_hi, sd_hi);
-        al_lo = __fdiv_rn(al_lo, (float)T);
-        al_hi = __fdiv_rn(al_hi, (float)T);
+        st[(t * 4 + 0) * kThreads] = lo;
+        st[(t * 4 + 1) * kThreads] = hi;
+        sum_lo = t == 0 ? lo : __fadd_rn(sum_lo, lo);
+        sum_hi = t == 0 ? hi : __fadd_rn(sum_hi, hi);
+      }
+      if (k_box_mc) {
+        const float fT = (float)T;
+        m_lo = __fdiv_rn(sum_lo, fT);
+        m_hi = __fdiv_rn(sum_hi, fT);
+        float q_lo = 0.f, q_hi = 0.f;
+#pragma unroll 1
+        for (int t = 0; t < T; ++t) {
+          const float d0 = __fsub_rn(st[(t * 4 + 0) * kThreads], m_lo);
+          const float d1 = __fsub_rn(st[(t * 4 + 1) * kThreads], m_hi);
+          q_lo = t == 0 ? __fmul_rn(d0, d0) : __fadd_rn(q_lo, __fmul_rn(d0, d0));
+          q_hi = t == 0 ? __fmul_rn(d1, d1) : __fadd_rn(q_hi, __fmul_rn(d1, d1));
+        }
+        sd_lo = __fsqrt_rn(__fdiv_rn(q_lo, fT));
+        sd_hi = __fsqrt_rn(__fdiv_rn(q_hi, fT));
+        al_lo = __fdiv_rn(al_lo, fT);
+        al_hi = __fdiv_rn(al_hi, fT);
       } else {
-        m_lo = lo[0];
-        m_hi = hi[0];
+        m_lo = sum_lo;
+        m_hi = sum_hi;
       }
     } else {
       // many samples: decode twice (sum pass, deviation pass)
       float s_lo_sum = 0.f, s_hi_sum = 0.f, q_lo = 0.f, q_hi = 0.f;
       m_lo = m_hi = 0.f;
-      for (int pass = 0; pass < (p.box_mc ? 2 : 1); ++pass) {
+      for (int pass = 0; pass < (k_box_mc ? 2 : 1); ++pass) {
         for (int t = 0; t < T; ++t) {
           const float4 tt = __ldg(reinterpret_cast<const float4*>(bb + (size_t)t * t_stride));
           const float t_c = axis ? tt.y : tt.x, t_s = axis ? tt.w : tt.z;
           float lo, hi, s_lo = 0.f, s_hi = 0.f;
-          if (p.la) {
+          if (k_la) {
             const float4 sg = __ldg(reinterpret_cast<const float4*>(bb + (size_t)t * t_stride + 4 * A));
-            decode_axis_la(p.method, a_lo, a_hi, t_c, t_s, axis ? sg.y : sg.x, axis ? sg.w : sg.z, lo, hi, s_lo, s_hi);
+            decode_axis_la(k_method, smem_tbl, a_lo, a_hi, t_c, t_s, axis ? sg.y : sg.x, axis ? sg.w : sg.z, lo, hi, s_lo, s_hi);
           } else {
             decode_axis_plain(a_lo, a_hi, t_c, t_s, lo, hi);
           }
@@ -347,11 +511,11 @@ __global__ void __launch_bounds__(kThreads, (TMAX == 0 || TMAX > 16) ? 1 : 3) de
           }
         }
         if (pass == 0) {
-          m_lo = p.box_mc ? __fdiv_rn(s_lo_sum, (float)T) : s_lo_sum;
-          m_hi = p.box_mc ? __fdiv_rn(s_hi_sum, (float)T) : s_hi_sum;
+          m_lo = k_box_mc ? __fdiv_rn(s_lo_sum, (float)T) : s_lo_sum;
+          m_hi = k_box_mc ? __fdiv_rn(s_hi_sum, (float)T) : s_hi_sum;
         }
       }
-      if (p.box_mc) {
+      if (k_box_mc) {
         sd_lo = __fsqrt_rn(__fdiv_rn(q_lo, (float)T));
         sd_hi = __fsqrt_rn(__fdiv_rn(q_hi, (float)T));
         al_lo = __fdiv_rn(al_lo, (float)T);
@@ -366,10 +530,10 @@ __global__ void __launch_bounds__(kThreads, (TMAX == 0 || TMAX > 16) ? 1 : 3) de
     const size_t o = (size_t)b * p.N + n;
     if (axis == 0) {
       if (p.out.boxes) reinterpret_cast<float4*>(p.out.boxes)[o] = make_float4(m_lo, o_m_lo, m_hi, o_m_hi);
-      if (p.out.mcbox && p.box_mc)
+      if (p.out.mcbox && k_box_mc)
         reinterpret_cast<float4*>(p.out.mcbox)[o] = make_float4(sd_lo, o_sd_lo, sd_hi, o_sd_hi);
     } else {
-      if (p.out.albox && p.la)
+      if (p.out.albox && k_la)
         reinterpret_cast<float4*>(p.out.albox)[o] = make_float4(o_al_lo, al_lo, o_al_hi, al_hi);
       if (p.out.scores || p.out.classes) {
         const float* ml = smem_mean + (size_t)ii * C;
@@ -519,7 +683,8 @@ int fill_params(udal_ctx* ctx, const float* const* cls, const float* const* box,
     }
   }
   *total_tiles = off;
-  *smem = (size_t)tile_px * p.A * p.C * sizeof(float);
+  p.stage_off = (tile_px * p.A * p.C + 3) & ~3;
+  *smem = (size_t)p.stage_off * sizeof(float);
   for (int l = 0; l < UDAL_MAX_LEVELS; ++l) {
     p.cls.p[l] = (cls && l < c.num_levels) ? cls[l] : nullptr;
     p.box.p[l] = (box && l < c.num_levels) ? box[l] : nullptr;
@@ -554,8 +719,19 @@ int udal_launch_decode_moments(udal_ctx* ctx, const float* const* cls, const flo
   p.out = *out;
   const int T = p.Tc > p.Tb ? p.Tc : p.Tb;
   dim3 grid(tiles, batch);
-#define LAUNCH(TM)                                                                      \
-  decode_moments_kernel<TM><<<grid, kThreads, smem, ctx->stream>>>(p);                  \
+  const bool fast = p.la && p.method == UDAL_DECODE_LNORM && p.box_mc && p.cls_mc && p.Tb == p.Tc;
+  if (pick_tmax(T) != 0) smem += (size_t)4 * p.Tb * kThreads * sizeof(float);
+  UDAL_REQUIRE(smem <= 200 * 1024, "decode_moments: T=%d needs %zu bytes of shared memory", T, smem);
+#define LAUNCH_ONE(TM, F)                                                                                   \
+  {                                                                                                         \
+    if (smem > 48 * 1024)                                                                                   \
+      UDAL_CUDA(cudaFuncSetAttribute(decode_moments_kernel<TM, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                     (int)smem));                                                           \
+    decode_moments_kernel<TM, F><<<grid, kThreads, smem, ctx->stream>>>(p);                                 \
+  }
+#define LAUNCH(TM)                           \
+  if (fast && T == TM) LAUNCH_ONE(TM, true)  \
+  else LAUNCH_ONE(TM, false)                 \
   break;
   switch (pick_tmax(T)) {
     case 1: LAUNCH(1)
@@ -563,8 +739,9 @@ int udal_launch_decode_moments(udal_ctx* ctx, const float* const* cls, const flo
     case 10: LAUNCH(10)
     case 16: LAUNCH(16)
     case 32: LAUNCH(32)
-    default: LAUNCH(0)
+    default: LAUNCH_ONE(0, false) break;
   }
+#undef LAUNCH_ONE
 #undef LAUNCH
   UDAL_CHECK_LAUNCH(ctx);
   return UDAL_OK;
