@@ -360,7 +360,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="udal", choices=["udal", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH)
-    ap.add_argument("--heads-mode", default=os.environ.get("UDAL_HEADS_MODE", "fp32"))
+    ap.add_argument("--heads-mode", default=os.environ.get("UDAL_HEADS_MODE", "bf16"), help="bf16 (tcgen05 tensor cores, default) | fp32 (CUDA-core parity mode)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)

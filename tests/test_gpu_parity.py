@@ -348,3 +348,54 @@ def test_error_behaviour_matches_reference(u):
     one = dict(copy.deepcopy(params), mc_dropoutsamp=1)
     with pytest.raises(ValueError):  # T == 1 is only defined for batch 1 (postprocess.py:180-203)
         u.postprocess.postprocess_global(one, [c[:1] for c in cls], [b[:1] for b in box])
+
+
+# ---------------------------------------------------------------------------------------------
+# nms_np family (device kernels) against the fixtures produced by the reference's own nms_np.py
+# ---------------------------------------------------------------------------------------------
+NMS_NP_CFGS = {
+    "hard": dict(method="hard", iou_thresh=None, score_thresh=None, sigma=None),
+    "hard03": dict(method="hard", iou_thresh=0.3, score_thresh=None, sigma=None),
+    "gaussian": dict(method="gaussian", iou_thresh=None, score_thresh=None, sigma=None),
+    "gaussian_s03": dict(method="gaussian", iou_thresh=None, score_thresh=0.05, sigma=0.3),
+    "linear": dict(method="linear", iou_thresh=None, score_thresh=None, sigma=None),
+    "diou": dict(method="diou", iou_thresh=None, score_thresh=None, sigma=None),
+}
+
+
+@pytest.mark.parametrize("name", sorted(NMS_NP_CFGS))
+def test_nms_np_device_vs_reference_fixtures(u, name):
+    g = load_golden("nms_np")
+    cfg = NMS_NP_CFGS[name]
+    dets = np.column_stack((g["boxes"][:, [1, 0, 3, 2]], g["scores"]))
+    raw = u.nms_np.nms(dets.copy(), cfg)
+    ref = g["raw_" + name]
+    assert raw.shape == ref.shape
+    np.testing.assert_array_equal(raw[:, :4], ref[:, :4])           # same boxes in the same order
+    # gaussian decay goes through fp32 exp (NumPy SIMD vs CUDA expf): a few ulp on the scores
+    np.testing.assert_allclose(raw[:, 4], ref[:, 4], rtol=2e-6 if "gaussian" in name else 0, atol=0)
+    det = u.nms_np.per_class_nms(g["boxes"].copy(), g["scores"].copy(), g["classes"].copy(),
+                                 np.float32([3.0]), np.float32([1.25]), 5, 100, cfg)
+    np.testing.assert_allclose(det, g["det_" + name], rtol=2e-6 if "gaussian" in name else 0, atol=0)
+
+
+def test_nms_np_edge_cases(u):
+    from oracle import nms_np_ref
+    cfg = dict(method="hard", iou_thresh=0.5, score_thresh=None, sigma=None)
+    one = np.float32([[0, 0, 10, 10, 0.5]])
+    np.testing.assert_array_equal(u.nms_np.nms(one, cfg), nms_np_ref.nms(one.copy(), cfg))
+    assert u.nms_np.hard_nms(np.zeros((0, 5), np.float32)).shape == (0, 5)
+    with pytest.raises(ValueError, match="Unknown NMS method"):
+        u.nms_np.nms(one, dict(method="bogus"))
+    with pytest.raises(ValueError):
+        u.nms_np.hard_nms(np.zeros((9000, 5), np.float32))
+    rng = np.random.default_rng(2)
+    n = 5000
+    dets = np.column_stack((random_boxes(rng, n, 400)[:, [1, 0, 3, 2]], rng.permutation(n).astype(np.float32) / n))
+    for c in (cfg, dict(method="diou", iou_thresh=None, score_thresh=None, sigma=None),
+              dict(method="linear", iou_thresh=None, score_thresh=0.3, sigma=None)):
+        np.testing.assert_array_equal(u.nms_np.nms(dets.copy(), c), nms_np_ref.nms(dets.copy(), c))
+    dummy = u.nms_np.per_class_nms(np.zeros((0, 4), np.float32), np.zeros(0, np.float32), np.zeros(0, np.int32),
+                                   np.float32([9.0]), np.float32([1.0]), 3, 10, cfg)
+    np.testing.assert_array_equal(dummy, nms_np_ref.per_class_nms(np.zeros((0, 4), np.float32), np.zeros(0, np.float32),
+                                  np.zeros(0, np.int32), np.float32([9.0]), np.float32([1.0]), 3, 10, cfg))
