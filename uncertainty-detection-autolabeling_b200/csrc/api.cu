@@ -108,6 +108,7 @@ static void free_head(udal_head_weights_dev& h) {
   cudaFree(h.pw_bf16);
   cudaFree(h.pwp_bf16);
   cudaFree(h.fold_bias);
+  cudaFree(h.ig_w);
   h = udal_head_weights_dev();
 }
 

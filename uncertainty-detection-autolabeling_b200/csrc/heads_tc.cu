@@ -50,7 +50,8 @@ struct TcLayerParams {
   int tile_off[UDAL_MAX_LEVELS + 1];
   const void* in[UDAL_MAX_LEVELS];     // [NB_in,H,W,64] bf16 (or fp32 BiFPN features for layer 0)
   void* out[UDAL_MAX_LEVELS];          // [NB_out,H,W,64] bf16 or [NB_out,H,W,Cout] fp32
-  const float* scale[UDAL_MAX_LEVELS]; // [NB_out,64] keep-scale of the producer layer, or null
+  const float* scale[UDAL_MAX_LEVELS]; // [NB_out,64] keep-scale of the producer layer (folded into B), or null
+  const float* out_scale[UDAL_MAX_LEVELS]; // [NB_out,64] keep-scale of THIS layer's dropout (applied at store), or null
   const float* wf[UDAL_MAX_LEVELS];    // folded weights [Npad][64] fp32
   const float* fb[UDAL_MAX_LEVELS];    // folded bias [Npad]
   const float* dw;                     // [9][64]
@@ -301,6 +302,7 @@ __global__ void __launch_bounds__(kThreads, NPAD <= 64 ? 3 : 2) sepconv_tc_kerne
     if (pix_ok) {
       const size_t pix = ((size_t)nb * H + oy) * W + ox;
       const float* fb = sFb + col0;
+      const float* osc = p.out_scale[l] ? p.out_scale[l] + (size_t)nb * KF + col0 : nullptr;
       if (!p.out_fp32) {
         __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out[l]) + pix * KF + col0;
 #pragma unroll
@@ -310,6 +312,12 @@ __global__ void __launch_bounds__(kThreads, NPAD <= 64 ? 3 : 2) sepconv_tc_kerne
           for (int i = 0; i < 8; ++i) {
             v[i] = __uint_as_float(r[j][i]) + fb[j * 8 + i];
             if (p.act) v[i] = swish_fast(v[i]);
+          }
+          if (osc) {
+            const float4 s0 = __ldg(reinterpret_cast<const float4*>(osc + j * 8));
+            const float4 s1 = __ldg(reinterpret_cast<const float4*>(osc + j * 8) + 1);
+            v[0] *= s0.x; v[1] *= s0.y; v[2] *= s0.z; v[3] *= s0.w;
+            v[4] *= s1.x; v[5] *= s1.y; v[6] *= s1.z; v[7] *= s1.w;
           }
           uint4 o;
           o.x = pack_bf16(v[0], v[1]);
@@ -373,6 +381,11 @@ int npad_of(int cout) { return cout <= 64 ? 64 : 80; }
 
 }  // namespace
 
+int udal_heads_ig_build_weights(udal_ctx* ctx, const float* dw, const float* wf, int npad, void* wimg);
+int udal_heads_ig_layer(udal_ctx* ctx, const void* in, int NB, int H, int W, const void* wimg, const float* fb,
+                        int npad, int cout, int act, int out_fp32, const float* out_scale, void* out);
+int udal_heads_tc_use_ig = 1;  // 0: every layer through the per-tile kernel (debug / comparison)
+
 int udal_heads_tc_prepare(udal_ctx* ctx, int head) {
   const udal_config& c = ctx->cfg;
   udal_head_weights_dev& h = ctx->heads[head];
@@ -401,6 +414,21 @@ int udal_heads_tc_prepare(udal_ctx* ctx, int head) {
   fold_weights_kernel<<<(npad_p * KF + 255) / 256, 256, 0, ctx->stream>>>(
       h.pwp, h.bp, nullptr, nullptr, h.cout, npad_p, wf + (size_t)R * L * KF * KF, h.fold_bias + (size_t)R * L * KF);
   UDAL_CHECK_LAUNCH(ctx);
+  // implicit-GEMM weight images for tower layers >= 2 (per level) and the predict layer
+  if (R >= 2) {
+    const size_t tower_img = (size_t)9 * KF * KF, pred_img = (size_t)9 * npad_p * KF;
+    const size_t n_img = (size_t)(R - 2) * L * tower_img + pred_img;
+    if (h.ig_w) UDAL_CUDA(cudaFree(h.ig_w));
+    h.ig_w = nullptr;
+    UDAL_CUDA(cudaMalloc(&h.ig_w, n_img * 2));
+    __nv_bfloat16* img = reinterpret_cast<__nv_bfloat16*>(h.ig_w);
+    for (int r = 2; r < R; ++r)
+      for (int l = 0; l < L; ++l)
+        UDAL_TRY(udal_heads_ig_build_weights(ctx, h.dw + (size_t)r * 9 * KF, wf + ((size_t)r * L + l) * KF * KF, KF,
+                                             img + ((size_t)(r - 2) * L + l) * tower_img));
+    UDAL_TRY(udal_heads_ig_build_weights(ctx, h.dwp, wf + (size_t)R * L * KF * KF, npad_p,
+                                         img + (size_t)(R - 2) * L * tower_img));
+  }
   UDAL_CUDA(cudaStreamSynchronize(ctx->stream));
   return UDAL_OK;
 }
@@ -447,6 +475,7 @@ static int run_tower_tc(udal_ctx* ctx, int head, const float* const* feats, int 
     // layer 1 reads the sample-invariant layer-0 output: one CTA per (tile, image) loops the samples
     p.nt = (layer == 1 && mc) ? T : 1;
     const int grid_y = layer <= 1 ? B : NBt;
+    const bool use_ig = udal_heads_tc_use_ig && layer >= 2;
     for (int l = 0; l < L; ++l) {
       const size_t lvl = (size_t)ctx->level_pix_off[l] * KF;
       if (layer == 0) p.in[l] = feats[l];
@@ -455,8 +484,12 @@ static int run_tower_tc(udal_ctx* ctx, int head, const float* const* feats, int 
       if (predict) p.out[l] = outs[l];
       else if (layer == 0) p.out[l] = a0 + (size_t)B * lvl;
       else p.out[l] = pp + (size_t)(layer & 1) * NBt * P * KF + (size_t)NBt * lvl;
-      p.scale[l] = (mc && layer >= 1) ? scale_all + (((size_t)head * L + l) * R + (layer - 1)) * (size_t)NBt * KF
-                                      : nullptr;
+      // SpatialDropout2D bookkeeping: layer 0 stores its (sample invariant) output WITHOUT dropout and
+      // layer 1 folds that dropout (mask r = 0) into its B operand; every tower layer >= 1 applies its
+      // own dropout (mask r = layer) when it stores, so later consumers read ready-made inputs.
+      auto mask = [&](int r) { return scale_all + (((size_t)head * L + l) * R + r) * (size_t)NBt * KF; };
+      p.scale[l] = (mc && layer == 1) ? mask(0) : nullptr;
+      p.out_scale[l] = (mc && !predict && layer >= 1) ? mask(layer) : nullptr;
       if (predict) {
         p.wf[l] = wf_all + (size_t)R * L * KF * KF;
         p.fb[l] = h.fold_bias + (size_t)R * L * KF;
@@ -464,6 +497,18 @@ static int run_tower_tc(udal_ctx* ctx, int head, const float* const* feats, int 
         p.wf[l] = wf_all + ((size_t)layer * L + l) * KF * KF;
         p.fb[l] = h.fold_bias + ((size_t)layer * L + l) * KF;
       }
+      if (use_ig) {
+        const size_t tower_img = (size_t)9 * KF * KF;
+        const __nv_bfloat16* img = reinterpret_cast<const __nv_bfloat16*>(h.ig_w) +
+                                   (predict ? (size_t)(R - 2) * L * tower_img : ((size_t)(layer - 2) * L + l) * tower_img);
+        UDAL_TRY(udal_heads_ig_layer(ctx, p.in[l], NBt, p.h[l], p.w[l], img, p.fb[l], p.Npad, p.Cout, p.act, p.out_fp32,
+                                     p.out_scale[l], p.out[l]));
+      }
+    }
+    if (use_ig) continue;
+    if (!udal_heads_tc_use_ig && layer >= 2 && mc) {
+      // per-tile kernel for every layer: inputs already carry their dropout, nothing to fold
+      for (int l = 0; l < L; ++l) p.scale[l] = nullptr;
     }
     dim3 grid(total_tiles, grid_y);
     if (p.Npad == 64) sepconv_tc_kernel<64><<<grid, kThreads, SM_ALLOC, ctx->stream>>>(p);

@@ -27,6 +27,7 @@ struct udal_head_weights_dev {
   void* pw_bf16 = nullptr;
   void* pwp_bf16 = nullptr;
   float* fold_bias = nullptr;
+  void* ig_w = nullptr;  // implicit-GEMM weight images: [(R-2)*L tower layers >= 2][9][64][64] then predict [9][Npad][64], bf16
 };
 
 struct udal_scratch {
