@@ -29,18 +29,26 @@ namespace {
 
 constexpr int IG_TH = 16, IG_TW = 8;               // output tile: 16 rows x 8 px = 128 GEMM rows
 constexpr int IG_ROWS = IG_TH + 2, IG_PITCH = 16;  // staged halo tile: 18 rows, row pitch 16 px
-constexpr int IG_STAGE_BYTES = IG_ROWS * IG_PITCH * 128;  // 36 864
+constexpr int IG_STAGE_BYTES = IG_ROWS * IG_PITCH * 128;  // 36 864 (smem footprint of a stage)
+constexpr int IG_BOXW = IG_TW + 2;                        // pixels actually loaded per row
 constexpr int KF = 64;
 constexpr int kIgStages = 3;          // TMA ring depth
 constexpr int kIgThreads = 320;       // producer warp, MMA warp, 2 x 4 epilogue warps
 
 struct IgParams {
-  int H, W, tiles_x, tiles, items;   // items = tiles * NB
+  int num_levels, NB, items;             // items = sum_l tiles[l] * NB
+  int H[UDAL_MAX_LEVELS], W[UDAL_MAX_LEVELS], tiles_x[UDAL_MAX_LEVELS], tiles[UDAL_MAX_LEVELS];
+  int item_off[UDAL_MAX_LEVELS + 1];     // prefix of tiles[l] * NB (items are level major)
+  void* out[UDAL_MAX_LEVELS];            // [NB,H,W,64] bf16 or [NB,H,W,Cout] fp32
+  const float* out_scale[UDAL_MAX_LEVELS];  // [NB,64] keep-scale of THIS layer's dropout, or null
+  const float* ep_scale[UDAL_MAX_LEVELS];   // [NPAD] per-level BN scale (1 for the predict layer)
+  const float* ep_bias[UDAL_MAX_LEVELS];    // [NPAD] folded bias
+  const void* wimg;                      // bf16 [9][NPAD][64] pre-swizzled smem image (level independent)
   int Cout, act, out_fp32;
-  void* out;                         // [NB,H,W,64] bf16 or [NB,H,W,Cout] fp32
-  const float* out_scale;            // [NB,64] keep-scale of THIS layer's dropout, or null
-  const float* fb;                   // [NPAD] folded bias
-  const void* wimg;                  // bf16 [9][NPAD][64] pre-swizzled smem image
+};
+
+struct IgMaps {
+  CUtensorMap m[UDAL_MAX_LEVELS];
 };
 
 __device__ __forceinline__ uint32_t s32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -103,14 +111,32 @@ __device__ __forceinline__ float ig_swish(float x) {
   return fmaf(h, t, h);  // x * sigmoid(x) = h * tanh(h) + h
 }
 
+struct IgItem {
+  int l, nb, ty0, tx0;
+};
+__device__ __forceinline__ IgItem ig_item(const IgParams& p, int item) {
+  int l = 0;
+#pragma unroll
+  for (int i = 1; i < UDAL_MAX_LEVELS; ++i)
+    if (i < p.num_levels && item >= p.item_off[i]) l = i;
+  const int r = item - p.item_off[l];
+  const int nb = r / p.tiles[l], tile = r - nb * p.tiles[l];
+  IgItem it;
+  it.l = l;
+  it.nb = nb;
+  it.ty0 = (tile / p.tiles_x[l]) * IG_TH;
+  it.tx0 = (tile % p.tiles_x[l]) * IG_TW;
+  return it;
+}
+
 template <int NPAD>
-__global__ void __launch_bounds__(kIgThreads, 1) heads_ig_kernel(const __grid_constant__ CUtensorMap tmap,
+__global__ void __launch_bounds__(kIgThreads, 1) heads_ig_kernel(const __grid_constant__ IgMaps maps,
                                                                  const IgParams p) {
   constexpr int B_BYTES = 9 * NPAD * 128;
   constexpr int SM_B = 0;
   constexpr int SM_IN = SM_B + B_BYTES;                 // multiple of 1024 for NPAD = 64 | 80
   constexpr int SM_BAR = SM_IN + kIgStages * IG_STAGE_BYTES;  // barriers + tmem slot
-  constexpr int SM_FBS = SM_BAR + 128;                  // folded bias [NPAD] fp32
+  constexpr int SM_FBS = SM_BAR + 128;                  // per level: BN scale [NPAD] then folded bias [NPAD], fp32
   constexpr uint32_t kTmemCols = NPAD <= 64 ? 128 : 256;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = s32(smem_raw);
@@ -141,7 +167,11 @@ __global__ void __launch_bounds__(kIgThreads, 1) heads_ig_kernel(const __grid_co
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  if (threadIdx.x >= 64 && threadIdx.x < 64 + NPAD) sFb[threadIdx.x - 64] = __ldg(p.fb + threadIdx.x - 64);
+  for (int e = threadIdx.x; e < p.num_levels * NPAD; e += kIgThreads) {
+    const int l = e / NPAD, n = e - l * NPAD;
+    sFb[(2 * l) * NPAD + n] = __ldg(p.ep_scale[l] + n);
+    sFb[(2 * l + 1) * NPAD + n] = __ldg(p.ep_bias[l] + n);
+  }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -159,13 +189,19 @@ __global__ void __launch_bounds__(kIgThreads, 1) heads_ig_kernel(const __grid_co
       int it = 0, s = 0, ph = 0;
       for (int item = blockIdx.x; item < p.items; item += G, ++it) {
         bar_wait(bar_empty + 8 * s, ph ^ 1);  // stage free (first round passes immediately)
-        const int nb = item / p.tiles, tile = item - nb * p.tiles;
-        const int ty0 = (tile / p.tiles_x) * IG_TH, tx0 = (tile % p.tiles_x) * IG_TW;
-        bar_expect_tx(bar_full + 8 * s, IG_STAGE_BYTES);
-        asm volatile(
-            "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-            ::"r"(sb + SM_IN + s * IG_STAGE_BYTES), "l"(&tmap), "r"(bar_full + 8 * s), "r"(0), "r"(tx0 - 1), "r"(ty0 - 1), "r"(nb)
-            : "memory");
+        const IgItem w = ig_item(p, item);
+        // 18 row boxes of 10 pixels (the halo tile) into row slots of pitch 16 pixels: the 2 KB pitch
+        // keeps every 8-row UMMA group on the same swizzle phase, the 10-pixel boxes keep L2 traffic
+        // at 1.4x (instead of 2.25x) of the useful bytes
+        bar_expect_tx(bar_full + 8 * s, IG_ROWS * IG_BOXW * 128);
+        const uint32_t dst = sb + SM_IN + s * IG_STAGE_BYTES;
+#pragma unroll 1
+        for (int r = 0; r < IG_ROWS; ++r)
+          asm volatile(
+              "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+              ::"r"(dst + r * IG_PITCH * 128), "l"(&maps.m[w.l]), "r"(bar_full + 8 * s), "r"(0), "r"(w.tx0 - 1),
+              "r"(w.ty0 - 1 + r), "r"(w.nb)
+              : "memory");
         if (++s == kIgStages) {
           s = 0;
           ph ^= 1;
@@ -213,15 +249,20 @@ __global__ void __launch_bounds__(kIgThreads, 1) heads_ig_kernel(const __grid_co
     for (int item = blockIdx.x; item < p.items; item += G, ++it) {
       if ((it & 1) != g) continue;
       const int a = g;
-      const int nb = item / p.tiles, tile = item - nb * p.tiles;
-      const int oy = (tile / p.tiles_x) * IG_TH + (m >> 3), ox = (tile % p.tiles_x) * IG_TW + (m & 7);
-      const bool ok = oy < p.H && ox < p.W;
-      const size_t pix = ((size_t)nb * p.H + oy) * p.W + ox;
+      const IgItem w = ig_item(p, item);
+      const int nb = w.nb, H = p.H[w.l], W = p.W[w.l];
+      const int oy = w.ty0 + (m >> 3), ox = w.tx0 + (m & 7);
+      const bool ok = oy < H && ox < W;
+      const size_t pix = ((size_t)nb * H + oy) * W + ox;
+      const float* ep_s = sFb + (2 * w.l) * NPAD;
+      const float* ep_b = ep_s + NPAD;
+      const float* osc = p.out_scale[w.l];
+      void* outp = p.out[w.l];
       // this item's dropout keep-scales: fetched while the MMAs are still running
       float4 scv[KF / 4];
-      const bool has_sc = p.out_scale != nullptr && !p.out_fp32;
+      const bool has_sc = osc != nullptr && !p.out_fp32;
       if (has_sc) {
-        const float4* sc = reinterpret_cast<const float4*>(p.out_scale + (size_t)nb * KF);
+        const float4* sc = reinterpret_cast<const float4*>(osc + (size_t)nb * KF);
 #pragma unroll
         for (int i = 0; i < KF / 4; ++i) scv[i] = __ldg(sc + i);
       }
@@ -239,12 +280,15 @@ __global__ void __launch_bounds__(kIgThreads, 1) heads_ig_kernel(const __grid_co
         for (int j = 0; j < NPAD / 8; ++j) {
           const int n0 = j * 8;
           float v[8];
-          const float4 f0 = *reinterpret_cast<const float4*>(sFb + n0);
-          const float4 f1 = *reinterpret_cast<const float4*>(sFb + n0 + 4);
+          const float4 f0 = *reinterpret_cast<const float4*>(ep_b + n0);
+          const float4 f1 = *reinterpret_cast<const float4*>(ep_b + n0 + 4);
+          const float4 g0 = *reinterpret_cast<const float4*>(ep_s + n0);
+          const float4 g1 = *reinterpret_cast<const float4*>(ep_s + n0 + 4);
           const float fbv[8] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w};
+          const float gsv[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            v[i] = __uint_as_float(r[j][i]) + fbv[i];
+            v[i] = fmaf(__uint_as_float(r[j][i]), gsv[i], fbv[i]);  // BN scale + folded bias
             if (p.act) v[i] = ig_swish(v[i]);
           }
           if (!p.out_fp32) {
@@ -259,10 +303,10 @@ __global__ void __launch_bounds__(kIgThreads, 1) heads_ig_kernel(const __grid_co
               o.y = ig_pack(v[2], v[3]);
               o.z = ig_pack(v[4], v[5]);
               o.w = ig_pack(v[6], v[7]);
-              *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + pix * KF + n0) = o;
+              *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(outp) + pix * KF + n0) = o;
             }
           } else {
-            float* dst = reinterpret_cast<float*>(p.out) + pix * p.Cout + n0;
+            float* dst = reinterpret_cast<float*>(outp) + pix * p.Cout + n0;
             if ((p.Cout & 3) == 0 && n0 + 8 <= p.Cout) {
               *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
               *reinterpret_cast<float4*>(dst + 4) = make_float4(v[4], v[5], v[6], v[7]);
@@ -321,43 +365,56 @@ int udal_heads_ig_build_weights(udal_ctx* ctx, const float* dw, const float* wf,
   return UDAL_OK;
 }
 
-// one tower / predict layer of one level: in [NB,H,W,64] bf16 (dropout already applied by its producer)
-int udal_heads_ig_layer(udal_ctx* ctx, const void* in, int NB, int H, int W, const void* wimg, const float* fb,
-                        int npad, int cout, int act, int out_fp32, const float* out_scale, void* out) {
+// one tower (>= 2) or predict layer over ALL pyramid levels: in[l] [NB,H_l,W_l,64] bf16 (dropout already applied)
+int udal_heads_ig_layer(udal_ctx* ctx, const void* const* in, int NB, const void* wimg, const float* const* ep_scale,
+                        const float* const* ep_bias, int npad, int cout, int act, int out_fp32,
+                        const float* const* out_scale, void* const* out) {
   EncodeTiledFn encode = get_encode();
   UDAL_REQUIRE(encode != nullptr, "cuTensorMapEncodeTiled is not available from this driver");
-  CUtensorMap tmap;
-  const cuuint64_t gdim[4] = {(cuuint64_t)KF, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)NB};
-  const cuuint64_t gstr[3] = {(cuuint64_t)KF * 2, (cuuint64_t)W * KF * 2, (cuuint64_t)H * W * KF * 2};
-  const cuuint32_t box[4] = {(cuuint32_t)KF, (cuuint32_t)IG_PITCH, (cuuint32_t)IG_ROWS, 1u};
-  const cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
-  const CUresult r = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(in), gdim, gstr, box, estr,
-                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  UDAL_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d) for [%d,%d,%d,64]", (int)r, NB, H, W);
+  const udal_config& c = ctx->cfg;
+  IgMaps maps;
   IgParams p;
   memset(&p, 0, sizeof(p));
-  p.H = H;
-  p.W = W;
-  p.tiles_x = (W + IG_TW - 1) / IG_TW;
-  p.tiles = p.tiles_x * ((H + IG_TH - 1) / IG_TH);
-  p.items = p.tiles * NB;
+  memset(&maps, 0, sizeof(maps));
+  p.num_levels = c.num_levels;
+  p.NB = NB;
+  int off = 0;
+  for (int l = 0; l < c.num_levels; ++l) {
+    const int H = c.level_h[l], W = c.level_w[l];
+    const cuuint64_t gdim[4] = {(cuuint64_t)KF, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)NB};
+    const cuuint64_t gstr[3] = {(cuuint64_t)KF * 2, (cuuint64_t)W * KF * 2, (cuuint64_t)H * W * KF * 2};
+    const cuuint32_t box[4] = {(cuuint32_t)KF, (cuuint32_t)IG_BOXW, 1u, 1u};
+    const cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
+    const CUresult r = encode(&maps.m[l], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(in[l]), gdim, gstr, box,
+                              estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    UDAL_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d) for [%d,%d,%d,64]", (int)r, NB, H, W);
+    p.H[l] = H;
+    p.W[l] = W;
+    p.tiles_x[l] = (W + IG_TW - 1) / IG_TW;
+    p.tiles[l] = p.tiles_x[l] * ((H + IG_TH - 1) / IG_TH);
+    p.item_off[l] = off;
+    off += p.tiles[l] * NB;
+    p.out[l] = out[l];
+    p.out_scale[l] = out_scale ? out_scale[l] : nullptr;
+    p.ep_scale[l] = ep_scale[l];
+    p.ep_bias[l] = ep_bias[l];
+  }
+  for (int l = c.num_levels; l <= UDAL_MAX_LEVELS; ++l) p.item_off[l] = off;
+  p.items = off;
   p.Cout = cout;
   p.act = act;
   p.out_fp32 = out_fp32;
-  p.out = out;
-  p.out_scale = out_scale;
-  p.fb = fb;
   p.wimg = wimg;
   const int grid = p.items < UDAL_NUM_SMS ? p.items : UDAL_NUM_SMS;
   if (npad == 64) {
-    constexpr int smem = 9 * 64 * 128 + kIgStages * IG_STAGE_BYTES + 128 + 80 * 4 + 1024;
+    constexpr int smem = 9 * 64 * 128 + kIgStages * IG_STAGE_BYTES + 128 + UDAL_MAX_LEVELS * 2 * 64 * 4 + 1024;
     UDAL_CUDA(cudaFuncSetAttribute(heads_ig_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    heads_ig_kernel<64><<<grid, kIgThreads, smem, ctx->stream>>>(tmap, p);
+    heads_ig_kernel<64><<<grid, kIgThreads, smem, ctx->stream>>>(maps, p);
   } else {
-    constexpr int smem = 9 * 80 * 128 + kIgStages * IG_STAGE_BYTES + 128 + 80 * 4 + 1024;
+    constexpr int smem = 9 * 80 * 128 + kIgStages * IG_STAGE_BYTES + 128 + UDAL_MAX_LEVELS * 2 * 80 * 4 + 1024;
     UDAL_CUDA(cudaFuncSetAttribute(heads_ig_kernel<80>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    heads_ig_kernel<80><<<grid, kIgThreads, smem, ctx->stream>>>(tmap, p);
+    heads_ig_kernel<80><<<grid, kIgThreads, smem, ctx->stream>>>(maps, p);
   }
   UDAL_CHECK_LAUNCH(ctx);
   return UDAL_OK;

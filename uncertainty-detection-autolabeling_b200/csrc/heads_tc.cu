@@ -382,8 +382,9 @@ int npad_of(int cout) { return cout <= 64 ? 64 : 80; }
 }  // namespace
 
 int udal_heads_ig_build_weights(udal_ctx* ctx, const float* dw, const float* wf, int npad, void* wimg);
-int udal_heads_ig_layer(udal_ctx* ctx, const void* in, int NB, int H, int W, const void* wimg, const float* fb,
-                        int npad, int cout, int act, int out_fp32, const float* out_scale, void* out);
+int udal_heads_ig_layer(udal_ctx* ctx, const void* const* in, int NB, const void* wimg, const float* const* ep_scale,
+                        const float* const* ep_bias, int npad, int cout, int act, int out_fp32,
+                        const float* const* out_scale, void* const* out);
 int udal_heads_tc_use_ig = 1;  // 0: every layer through the per-tile kernel (debug / comparison)
 
 int udal_heads_tc_prepare(udal_ctx* ctx, int head) {
@@ -414,20 +415,29 @@ int udal_heads_tc_prepare(udal_ctx* ctx, int head) {
   fold_weights_kernel<<<(npad_p * KF + 255) / 256, 256, 0, ctx->stream>>>(
       h.pwp, h.bp, nullptr, nullptr, h.cout, npad_p, wf + (size_t)R * L * KF * KF, h.fold_bias + (size_t)R * L * KF);
   UDAL_CHECK_LAUNCH(ctx);
-  // implicit-GEMM weight images for tower layers >= 2 (per level) and the predict layer
+  // implicit-GEMM weight images (level independent: BN scale is applied in the epilogue) for tower
+  // layers >= 2 and the predict layer, plus a vector of ones as the predict layer's epilogue scale
   if (R >= 2) {
     const size_t tower_img = (size_t)9 * KF * KF, pred_img = (size_t)9 * npad_p * KF;
-    const size_t n_img = (size_t)(R - 2) * L * tower_img + pred_img;
+    const size_t n_img = (size_t)(R - 2) * tower_img + pred_img;
     if (h.ig_w) UDAL_CUDA(cudaFree(h.ig_w));
     h.ig_w = nullptr;
-    UDAL_CUDA(cudaMalloc(&h.ig_w, n_img * 2));
+    UDAL_CUDA(cudaMalloc(&h.ig_w, n_img * 2 + (size_t)kMaxN * sizeof(float)));
     __nv_bfloat16* img = reinterpret_cast<__nv_bfloat16*>(h.ig_w);
-    for (int r = 2; r < R; ++r)
-      for (int l = 0; l < L; ++l)
-        UDAL_TRY(udal_heads_ig_build_weights(ctx, h.dw + (size_t)r * 9 * KF, wf + ((size_t)r * L + l) * KF * KF, KF,
-                                             img + ((size_t)(r - 2) * L + l) * tower_img));
+    float* tmp;  // unscaled transposed pointwise weights [64][64] + dummy bias
+    UDAL_TRY(udal_scratch_get(ctx, SCR_MISC, ((size_t)KF * KF + KF) * sizeof(float), (void**)&tmp));
+    for (int r = 2; r < R; ++r) {
+      fold_weights_kernel<<<(KF * KF + 255) / 256, 256, 0, ctx->stream>>>(h.pw + (size_t)r * KF * KF, h.bias + (size_t)r * KF,
+                                                                        nullptr, nullptr, KF, KF, tmp, tmp + KF * KF);
+      UDAL_CHECK_LAUNCH(ctx);
+      UDAL_TRY(udal_heads_ig_build_weights(ctx, h.dw + (size_t)r * 9 * KF, tmp, KF, img + (size_t)(r - 2) * tower_img));
+    }
     UDAL_TRY(udal_heads_ig_build_weights(ctx, h.dwp, wf + (size_t)R * L * KF * KF, npad_p,
-                                         img + (size_t)(R - 2) * L * tower_img));
+                                         img + (size_t)(R - 2) * tower_img));
+    std::vector<float> ones(kMaxN, 1.0f);
+    UDAL_CUDA(cudaMemcpyAsync(reinterpret_cast<char*>(h.ig_w) + n_img * 2, ones.data(), kMaxN * sizeof(float),
+                              cudaMemcpyHostToDevice, ctx->stream));
+    UDAL_CUDA(cudaStreamSynchronize(ctx->stream));
   }
   UDAL_CUDA(cudaStreamSynchronize(ctx->stream));
   return UDAL_OK;
@@ -497,15 +507,18 @@ static int run_tower_tc(udal_ctx* ctx, int head, const float* const* feats, int 
         p.wf[l] = wf_all + ((size_t)layer * L + l) * KF * KF;
         p.fb[l] = h.fold_bias + ((size_t)layer * L + l) * KF;
       }
-      if (use_ig) {
-        const size_t tower_img = (size_t)9 * KF * KF;
-        const __nv_bfloat16* img = reinterpret_cast<const __nv_bfloat16*>(h.ig_w) +
-                                   (predict ? (size_t)(R - 2) * L * tower_img : ((size_t)(layer - 2) * L + l) * tower_img);
-        UDAL_TRY(udal_heads_ig_layer(ctx, p.in[l], NBt, p.h[l], p.w[l], img, p.fb[l], p.Npad, p.Cout, p.act, p.out_fp32,
-                                     p.out_scale[l], p.out[l]));
-      }
     }
-    if (use_ig) continue;
+    if (use_ig) {
+      const size_t tower_img = (size_t)9 * KF * KF, pred_img = (size_t)9 * npad_p * KF;
+      const __nv_bfloat16* img0 = reinterpret_cast<const __nv_bfloat16*>(h.ig_w);
+      const __nv_bfloat16* img = img0 + (predict ? (size_t)(R - 2) * tower_img : (size_t)(layer - 2) * tower_img);
+      const float* ones = reinterpret_cast<const float*>(img0 + (size_t)(R - 2) * tower_img + pred_img);
+      const float* ep_scale[UDAL_MAX_LEVELS];
+      for (int l = 0; l < L; ++l) ep_scale[l] = predict ? ones : h.bn_scale + ((size_t)layer * L + l) * KF;
+      UDAL_TRY(udal_heads_ig_layer(ctx, p.in, NBt, img, ep_scale, p.fb, p.Npad, p.Cout, p.act, p.out_fp32,
+                                   mc && !predict ? p.out_scale : nullptr, p.out));
+      continue;
+    }
     if (!udal_heads_tc_use_ig && layer >= 2 && mc) {
       // per-tile kernel for every layer: inputs already carry their dropout, nothing to fold
       for (int l = 0; l < L; ++l) p.scale[l] = nullptr;
