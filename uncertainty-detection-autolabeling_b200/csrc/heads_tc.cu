@@ -35,12 +35,14 @@ constexpr int kMaxN = 80;
 
 // shared memory map (offsets from a 1024-byte aligned base)
 constexpr int SM_A = 0;                         // [128][128 B]
-constexpr int SM_B = SM_A + TPX * 128;          // [kMaxN][128 B]
-constexpr int SM_IN = SM_B + kMaxN * 128;       // [180][64] bf16
+constexpr int SM_B = SM_A + TPX * 128;          // 2 x [kMaxN][128 B] (double buffered over the samples)
+constexpr int SM_IN = SM_B + 2 * kMaxN * 128;   // [180][64] bf16
 constexpr int SM_DW = SM_IN + HALO_PX * KF * 2; // [9][64] fp32
 constexpr int SM_FB = SM_DW + 9 * KF * 4;       // [kMaxN] fp32 folded bias
-constexpr int SM_MBAR = SM_FB + kMaxN * 4;      // mbarrier (8 B) + tmem base (4 B)
-constexpr int SM_TOTAL = SM_MBAR + 16;
+constexpr int kMaxT = 16;                       // samples whose keep-scales are staged in shared memory
+constexpr int SM_SC = SM_FB + kMaxN * 4;        // [2][kMaxT][64] fp32: producer-layer scales, this layer's scales
+constexpr int SM_MBAR = SM_SC + 2 * kMaxT * KF * 4;  // 2 mbarriers (16 B) + tmem base (4 B)
+constexpr int SM_TOTAL = SM_MBAR + 32;
 constexpr int SM_ALLOC = SM_TOTAL + 1024;       // slack for the manual 1024-byte alignment
 
 struct TcLayerParams {
@@ -132,9 +134,10 @@ __global__ void __launch_bounds__(kThreads, NPAD <= 64 ? 3 : 2) sepconv_tc_kerne
   uint8_t* sIn = smem + SM_IN;
   float* sDw = reinterpret_cast<float*>(smem + SM_DW);
   float* sFb = reinterpret_cast<float*>(smem + SM_FB);
+  float* sSc = reinterpret_cast<float*>(smem + SM_SC);
   const uint32_t mbar = sbase + SM_MBAR;
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + SM_MBAR + 8);
-  constexpr uint32_t kTmemCols = NPAD <= 64 ? 64 : 128;
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + SM_MBAR + 16);
+  constexpr uint32_t kTmemCols = NPAD <= 64 ? 128 : 256;  // two accumulators
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   int l = 0;
@@ -147,9 +150,12 @@ __global__ void __launch_bounds__(kThreads, NPAD <= 64 ? 3 : 2) sepconv_tc_kerne
   const int nb0 = blockIdx.y;
   const int in_img = p.in_per_sample ? nb0 : nb0 % p.batch;
 
-  if (tid == 0) mbar_init(mbar, 1);
+  if (tid == 0) {
+    mbar_init(mbar, 1);
+    mbar_init(mbar + 8, 1);
+  }
   if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sbase + SM_MBAR + 8),
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sbase + SM_MBAR + 16),
                  "r"(kTmemCols)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -158,6 +164,15 @@ __global__ void __launch_bounds__(kThreads, NPAD <= 64 ? 3 : 2) sepconv_tc_kerne
   // ---- stage depthwise weights, folded bias and the input tile (+halo) ----
   for (int e = tid; e < 9 * KF; e += kThreads) sDw[e] = __ldg(p.dw + e);
   if (tid < NPAD) sFb[tid] = __ldg(p.fb[l] + tid);
+  const bool sc_smem = p.nt <= kMaxT;  // keep-scales of all samples of this CTA staged once
+  if (sc_smem) {
+    for (int e = tid; e < p.nt * KF; e += kThreads) {
+      const int it = e / KF, k = e - it * KF;
+      const size_t row = (size_t)(it * p.batch + nb0) * KF + k;
+      sSc[e] = p.scale[l] ? __ldg(p.scale[l] + row) : 1.0f;
+      sSc[kMaxT * KF + e] = p.out_scale[l] ? __ldg(p.out_scale[l] + row) : 1.0f;
+    }
+  }
   if (p.in_fp32) {
     const float* src0 = reinterpret_cast<const float*>(p.in[l]) + (size_t)in_img * H * W * KF;
     for (int e = tid; e < HALO_PX * 8; e += kThreads) {
@@ -251,51 +266,95 @@ __global__ void __launch_bounds__(kThreads, NPAD <= 64 ? 3 : 2) sepconv_tc_kerne
   // instruction descriptor: D = f32, A = B = bf16, K-major both, N = NPAD, M = 128
   constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NPAD >> 3) << 17) | ((128u >> 4) << 24);
   const uint64_t adesc = umma_desc(sbase + SM_A);
-  const uint64_t bdesc = umma_desc(sbase + SM_B);
   constexpr int HALF = NPAD / 2;
   const int m = (warp & 3) * 32 + lane;       // accumulator row = pixel of the tile
   const int col0 = (warp >> 2) * HALF;        // this warp's slice of the N columns
   const int oy = ty0 + m / TW, ox = tx0 + m % TW;
   const bool pix_ok = oy < H && ox < W;
 
+  // ---- this thread's slice of the folded weights stays in registers for every sample ----
+  constexpr int NCH = (NPAD * 8 + kThreads - 1) / kThreads;  // 16-byte chunks of B per thread
+  float wreg[NCH][8];
+#pragma unroll
+  for (int u = 0; u < NCH; ++u) {
+    const int e = tid + u * kThreads;
+    if (e < NPAD * 8) {
+      const float4* wsrc = reinterpret_cast<const float4*>(p.wf[l] + (size_t)(e >> 3) * KF + (e & 7) * 8);
+      const float4 a = __ldg(wsrc), b = __ldg(wsrc + 1);
+      wreg[u][0] = a.x; wreg[u][1] = a.y; wreg[u][2] = a.z; wreg[u][3] = a.w;
+      wreg[u][4] = b.x; wreg[u][5] = b.y; wreg[u][6] = b.z; wreg[u][7] = b.w;
+    }
+  }
+  // B operand of sample `it` -> buffer it & 1: folded weights * keep-scale of the producer layer
+  auto prep_b = [&](int it) {
+    const float* sc = p.scale[l] ? p.scale[l] + (size_t)(it * p.batch + nb0) * KF : nullptr;
+    uint8_t* dstB = sB + (size_t)(it & 1) * (kMaxN * 128);
+#pragma unroll
+    for (int u = 0; u < NCH; ++u) {
+      const int e = tid + u * kThreads;
+      if (e < NPAD * 8) {
+        const int n = e >> 3, c = e & 7;
+        float w8[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) w8[i] = wreg[u][i];
+        if (sc) {
+          float4 s0, s1;
+          if (sc_smem) {
+            s0 = *reinterpret_cast<const float4*>(sSc + it * KF + c * 8);
+            s1 = *reinterpret_cast<const float4*>(sSc + it * KF + c * 8 + 4);
+          } else {
+            s0 = __ldg(reinterpret_cast<const float4*>(sc + c * 8));
+            s1 = __ldg(reinterpret_cast<const float4*>(sc + c * 8) + 1);
+          }
+          w8[0] *= s0.x; w8[1] *= s0.y; w8[2] *= s0.z; w8[3] *= s0.w;
+          w8[4] *= s1.x; w8[5] *= s1.y; w8[6] *= s1.z; w8[7] *= s1.w;
+        }
+        uint4 v;
+        v.x = pack_bf16(w8[0], w8[1]);
+        v.y = pack_bf16(w8[2], w8[3]);
+        v.z = pack_bf16(w8[4], w8[5]);
+        v.w = pack_bf16(w8[6], w8[7]);
+        *reinterpret_cast<uint4*>(dstB + (size_t)n * 128 + ((c ^ (n & 7)) << 4)) = v;
+      }
+    }
+  };
+  auto issue_mma = [&](int it) {  // one thread: 4 x tcgen05.mma into accumulator it & 1, then commit
+    tc_fence_after();
+    const uint64_t bd = umma_desc(sbase + SM_B + (uint32_t)(it & 1) * (kMaxN * 128));
+    const uint32_t d_tmem = tmem_base + (uint32_t)((it & 1) * NPAD);
+#pragma unroll
+    for (int k = 0; k < KF / 16; ++k)  // +32 bytes per K=16 step inside the 128-byte swizzle row
+      umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, k > 0 ? 1u : 0u);
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                     mbar + 8u * (uint32_t)(it & 1))
+                 : "memory");
+  };
+
+  // software pipeline over the samples: while the tensor core works on sample it+1 the CTA runs the
+  // epilogue of sample it; B operands and accumulators are double buffered
+  prep_b(0);
+  fence_async_smem();   // generic-proxy smem writes (A, B) -> visible to the tensor-core proxy
+  tc_fence_before();
+  __syncthreads();
+  if (tid == 0) issue_mma(0);
+
   for (int it = 0; it < p.nt; ++it) {
     const int nb = it * p.batch + nb0;
-    // ---- B operand: folded weights * keep-scale of the producer layer ----
-    const float* sc = p.scale[l] ? p.scale[l] + (size_t)nb * KF : nullptr;
-    for (int e = tid; e < NPAD * 8; e += kThreads) {
-      const int n = e >> 3, c = e & 7;
-      const float4* wsrc = reinterpret_cast<const float4*>(p.wf[l] + (size_t)n * KF + c * 8);
-      float4 a = __ldg(wsrc), b = __ldg(wsrc + 1);
-      if (sc) {
-        const float4 s0 = __ldg(reinterpret_cast<const float4*>(sc + c * 8));
-        const float4 s1 = __ldg(reinterpret_cast<const float4*>(sc + c * 8) + 1);
-        a.x *= s0.x; a.y *= s0.y; a.z *= s0.z; a.w *= s0.w;
-        b.x *= s1.x; b.y *= s1.y; b.z *= s1.z; b.w *= s1.w;
-      }
-      uint4 v;
-      v.x = pack_bf16(a.x, a.y);
-      v.y = pack_bf16(a.z, a.w);
-      v.z = pack_bf16(b.x, b.y);
-      v.w = pack_bf16(b.z, b.w);
-      *reinterpret_cast<uint4*>(sB + (size_t)n * 128 + ((c ^ (n & 7)) << 4)) = v;
+    if (it + 1 < p.nt) {
+      // buffer (it+1)&1 was last read by the MMA of sample it-1, whose completion every thread
+      // observed in the previous epilogue; accumulator (it+1)&1 was drained there as well
+      prep_b(it + 1);
+      fence_async_smem();
+      tc_fence_before();
+      __syncthreads();
+      if (tid == 0) issue_mma(it + 1);
     }
-    fence_async_smem();   // generic-proxy smem writes (A, B) -> visible to the tensor-core proxy
-    tc_fence_before();
-    __syncthreads();
-    if (tid == 0) {
-      tc_fence_after();
-#pragma unroll
-      for (int k = 0; k < KF / 16; ++k)  // +32 bytes per K=16 step inside the 128-byte swizzle row
-        umma_bf16(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, k > 0 ? 1u : 0u);
-      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mbar)
-                   : "memory");
-    }
-    mbar_wait(mbar, (uint32_t)(it & 1));
+    mbar_wait(mbar + 8u * (uint32_t)(it & 1), (uint32_t)((it >> 1) & 1));
     tc_fence_after();
 
     // ---- epilogue: TMEM -> registers -> bias / swish -> global ----
     uint32_t r[HALF / 8][8];
-    const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)col0;
+    const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((it & 1) * NPAD + col0);
 #pragma unroll
     for (int j = 0; j < HALF / 8; ++j) tmem_ld8(taddr + j * 8, r[j]);
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
@@ -314,8 +373,14 @@ __global__ void __launch_bounds__(kThreads, NPAD <= 64 ? 3 : 2) sepconv_tc_kerne
             if (p.act) v[i] = swish_fast(v[i]);
           }
           if (osc) {
-            const float4 s0 = __ldg(reinterpret_cast<const float4*>(osc + j * 8));
-            const float4 s1 = __ldg(reinterpret_cast<const float4*>(osc + j * 8) + 1);
+            float4 s0, s1;
+            if (sc_smem) {
+              s0 = *reinterpret_cast<const float4*>(sSc + (kMaxT + it) * KF + col0 + j * 8);
+              s1 = *reinterpret_cast<const float4*>(sSc + (kMaxT + it) * KF + col0 + j * 8 + 4);
+            } else {
+              s0 = __ldg(reinterpret_cast<const float4*>(osc + j * 8));
+              s1 = __ldg(reinterpret_cast<const float4*>(osc + j * 8) + 1);
+            }
             v[0] *= s0.x; v[1] *= s0.y; v[2] *= s0.z; v[3] *= s0.w;
             v[4] *= s1.x; v[5] *= s1.y; v[6] *= s1.z; v[7] *= s1.w;
           }
@@ -349,9 +414,9 @@ __global__ void __launch_bounds__(kThreads, NPAD <= 64 ? 3 : 2) sepconv_tc_kerne
         }
       }
     }
-    tc_fence_before();
-    __syncthreads();  // B tile and the accumulator may be overwritten by the next sample
   }
+  tc_fence_before();
+  __syncthreads();
 
   if (warp == 0) {
     tc_fence_after();
