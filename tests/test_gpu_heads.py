@@ -116,3 +116,20 @@ def test_heads_bf16_tensor_core_vs_oracle(u, size, C, T, batch, la, rc, rb):
         np.testing.assert_allclose(cls[l], rc_l, rtol=BF16_RTOL, atol=BF16_ATOL)
         np.testing.assert_allclose(box[l], rb_l, rtol=BF16_RTOL, atol=BF16_ATOL)
     print("bf16 heads max abs err", worst)
+
+
+def test_pipelined_sampler_matches_blocking_calls(u):
+    p = _cfg(u, (64, 96), 7, 4, heads_mode="bf16")
+    eng = u.engine.get_engine(p)
+    L, batch = len(eng.level_hw), 2
+    w = heads_ref.init_head_weights(eng.F, eng.R, L, eng.A, 7, True, randomize_bn=True)
+    batches = [heads_ref.make_features(eng.level_hw, batch, eng.F, seed=s) for s in range(5)]
+    scales = [np.float32([1.0, 1.5])] * 5
+    blocking = u.heads.HeadSampler(p, w)
+    ref = [blocking.detect(f, s, seed=100 + i) for i, (f, s) in enumerate(zip(batches, scales))]
+    pipe = u.heads.PipelinedSampler(p, w, depth=2)
+    got = list(pipe.map(batches, scales, seed=100))
+    assert len(got) == 5
+    for a, b in zip(got, ref):
+        for x, y in zip(a, b):
+            np.testing.assert_array_equal(x, y)

@@ -79,13 +79,15 @@ def _key(params, device_id, heads_mode):
 _engines = {}
 
 
-def get_engine(params, device_id=None, heads_mode=None, cls_mc=None, box_mc=None):
+def get_engine(params, device_id=None, heads_mode=None, cls_mc=None, box_mc=None, instance=0):
     """Cached Engine for this configuration.  ``cls_mc`` / ``box_mc`` override the flags derived
-    from the dropout rates (used when a caller passes already reduced class outputs)."""
+    from the dropout rates (used when a caller passes already reduced class outputs);
+    ``instance`` > 0 gives additional independent contexts (own stream + scratch) on the same GPU,
+    used to overlap the host<->device copies of one batch with the kernels of another."""
     if device_id is None:
         device_id = params.get("device", 0) or 0
     heads_mode = heads_mode or params.get("heads_mode", "fp32")
-    k = _key(params, device_id, heads_mode) + repr((cls_mc, box_mc))
+    k = _key(params, device_id, heads_mode) + repr((cls_mc, box_mc, instance))
     eng = _engines.get(k)
     if eng is None:
         eng = Engine(params, device_id, heads_mode, cls_mc=cls_mc, box_mc=box_mc)

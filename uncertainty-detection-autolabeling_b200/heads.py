@@ -13,12 +13,12 @@ from . import engine as _engine
 
 
 class HeadSampler:
-    def __init__(self, params, weights, device_id=None, heads_mode=None):
+    def __init__(self, params, weights, device_id=None, heads_mode=None, instance=0):
         if params.get("mc_dropout") and params.get("mc_dropoutrate"):
             raise ValueError("mc_dropoutrate > 0 (backbone MC dropout) changes the BiFPN features per "
                              "sample; the head sampler starts at the BiFPN outputs (head-only dropout)")
         self.params = params
-        self.engine = _engine.get_engine(params, device_id, heads_mode)
+        self.engine = _engine.get_engine(params, device_id, heads_mode, instance=instance)
         self.engine.set_head_weights(weights)
 
     def __call__(self, fpn_feats, masks=None, seed=0):
@@ -43,6 +43,30 @@ class HeadSampler:
             out = [o.copy_to_host(sync=False) for o in out]
             self.engine.ctx.sync()
         return tuple(out)
+
+
+class PipelinedSampler:
+    """Throughput front end for host-resident batches: ``depth`` independent contexts on one GPU
+    (own stream, scratch and staging each), one host thread per context.  While context k runs the
+    kernels of batch i, context k+1 is already copying batch i+1 host->device, so the PCIe copies
+    disappear behind the compute.  ``map(batches)`` yields the detection tuples in input order."""
+
+    def __init__(self, params, weights, device_id=None, heads_mode=None, depth=2):
+        self.samplers = [HeadSampler(params, weights, device_id, heads_mode, instance=i) for i in range(depth)]
+
+    def map(self, batches, image_scales=None, seed=0):
+        import concurrent.futures as cf
+
+        depth = len(self.samplers)
+        with cf.ThreadPoolExecutor(max_workers=depth) as pool:
+            pending = []
+            for i, feats in enumerate(batches):
+                sc = None if image_scales is None else image_scales[i]
+                pending.append(pool.submit(self.samplers[i % depth].detect, feats, sc, None, seed + i))
+                if len(pending) >= depth:
+                    yield pending.pop(0).result()
+            for f in pending:
+                yield f.result()
 
 
 def philox_keep_masks(shape, rate_class, rate_box, seed):
