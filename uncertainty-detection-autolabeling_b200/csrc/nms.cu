@@ -23,11 +23,13 @@
 // Arithmetic = oracle/nms_v5.c: fp32 IoU without "+1", weight = fp32(exp(fp64((scale*u)*u))).
 #include <math_constants.h>
 
+#include "fast_math64.cuh"
 #include "udal_common.cuh"
 
 namespace {
 
 constexpr int kWarpsPerBlock = 4;
+constexpr int kStageCap = 2048;  // candidates a staged (shared-memory resident) segment may hold
 
 struct NmsParams {
   const float* boxes;        // [images, img_stride, 4]
@@ -72,6 +74,12 @@ __device__ __forceinline__ float iou_v5(const float4 a, const float4 b) {
 __device__ __forceinline__ float soft_weight(float scale, float u) {
   return (float)exp((double)__fmul_rn(__fmul_rn(scale, u), u));
 }
+// same value through the table-based exp (rel. error ~1e-15: rounds to the same fp32 except ~1e-8 of the
+// arguments); exp(0) = 1 exactly, which is what makes non-overlapping boxes free
+__device__ __forceinline__ float soft_weight_fast(float scale, float u, const double* tbl) {
+  if (u == 0.f) return 1.f;
+  return (float)exp_fast((double)__fmul_rn(__fmul_rn(scale, u), u), tbl);
+}
 
 __device__ __forceinline__ float4 shfl_box(float4 v, int src) {
   float4 r;
@@ -87,12 +95,21 @@ __device__ __forceinline__ bool before(float s1, int r1, float s2, int r2) {
   return s1 > s2 || (s1 == s2 && r1 < r2);
 }
 
-__global__ void __launch_bounds__(kWarpsPerBlock * 32) nms_v5_sorted_kernel(const NmsParams p) {
-  extern __shared__ float4 smem_boxes[];  // [kWarpsPerBlock][max_out]
+// STAGED: one warp per CTA, the segment's candidates (score, box) and the re-insertion set live in
+// shared memory, so a pop costs shared-memory latency instead of chains of dependent global loads.
+template <bool STAGED>
+__global__ void __launch_bounds__((STAGED ? 1 : kWarpsPerBlock) * 32) nms_v5_sorted_kernel(const NmsParams p) {
+  constexpr int WPB = STAGED ? 1 : kWarpsPerBlock;
+  extern __shared__ float4 smem_boxes[];  // [WPB][max_out] (+ staged candidate arrays)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int s = blockIdx.x * kWarpsPerBlock + warp;
+  const int s = blockIdx.x * WPB + warp;
   if (s >= p.segments) return;
   float4* sel_box = smem_boxes + (size_t)warp * p.max_out;
+  float4* s_box = smem_boxes + (size_t)WPB * p.max_out;                    // [kStageCap]
+  float* s_score = reinterpret_cast<float*>(s_box + kStageCap);            // [kStageCap]
+  float* s_rscore = s_score + kStageCap;                                   // re-insertion set
+  int32_t* s_rrank = reinterpret_cast<int32_t*>(s_rscore + kStageCap);
+  int32_t* s_rbegin = s_rrank + kStageCap;
   const int image = s / p.segs_per_image;
   const float4* boxes = reinterpret_cast<const float4*>(p.boxes) + (size_t)image * p.img_stride;
   const float* scores = p.scores + (size_t)image * p.img_stride;
@@ -106,6 +123,20 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) nms_v5_sorted_kernel(cons
   int nsel = 0;
   float last_pop = CUDART_INF_F;
   bool emptied = false;
+  __shared__ double s_tbl[WPB][64];
+  s_tbl[warp][lane] = kExp2Table[lane];
+  s_tbl[warp][lane + 32] = kExp2Table[lane + 32];
+  __syncwarp();
+  if (STAGED) {
+    for (int j = lane; j < n; j += 32) {
+      const int row = cidx[j];
+      s_score[j] = scores[row];
+      s_box[j] = boxes[row];
+    }
+    __syncwarp();
+  }
+  auto score_at = [&](int j) -> float { return STAGED ? s_score[j] : scores[cidx[j]]; };
+  auto box_at = [&](int j) -> float4 { return STAGED ? s_box[j] : boxes[cidx[j]]; };
 
   if (!p.soft) {
     // ---------------- hard NMS: suppressed iff IoU with a selected box > (>=, old) threshold
@@ -117,10 +148,9 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) nms_v5_sorted_kernel(cons
       float sc = 0.f;
       int row = 0;
       if (j < n) {
-        row = cidx[j];
-        sc = scores[row];
+        sc = score_at(j);
         alive = sc > thr;
-        box = boxes[row];
+        box = box_at(j);
       }
       for (int q = 0; q < nsel && alive; ++q) {
         const float u = iou_v5(box, sel_box[q]);
@@ -131,6 +161,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) nms_v5_sorted_kernel(cons
         const int i = __ffs(mask) - 1;
         const float4 bi = shfl_box(box, i);
         if (lane == i) {
+          row = cidx[j];
           sel_box[nsel] = box;
           out_row[nsel] = row;
           if (out_rank) out_rank[nsel] = j;
@@ -153,9 +184,9 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) nms_v5_sorted_kernel(cons
     last_pop = CUDART_INF_F;
   } else {
     // ---------------- soft NMS: exact lazy-heap emulation
-    float* r_score = p.r_score + start;
-    int32_t* r_rank = p.r_rank + start;
-    int32_t* r_begin = p.r_begin + start;
+    float* r_score = STAGED ? s_rscore : p.r_score + start;
+    int32_t* r_rank = STAGED ? s_rrank : p.r_rank + start;
+    int32_t* r_begin = STAGED ? s_rbegin : p.r_begin + start;
     int next = 0, rn = 0;
     while (nsel < p.max_out) {
       // best re-inserted candidate
@@ -185,7 +216,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) nms_v5_sorted_kernel(cons
       float as = -CUDART_INF_F;
       bool have_a = false;
       if (next < n) {
-        as = scores[cidx[next]];
+        as = score_at(next);
         have_a = as > thr;
       }
       if (!have_a && bslot < 0) {
@@ -214,8 +245,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) nms_v5_sorted_kernel(cons
         __syncwarp();
       }
       last_pop = s0;
-      const int row = cidx[rank];
-      const float4 cbox = boxes[row];
+      const float4 cbox = box_at(rank);
       float sc = s0;
       bool hard = false, stop = false;
       for (int top = nsel - 1; top >= begin && !stop; top -= 32) {
@@ -224,7 +254,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) nms_v5_sorted_kernel(cons
         bool hq = false;
         if (q >= begin) {
           const float u = iou_v5(cbox, sel_box[q]);
-          w = soft_weight(p.scale, u);
+          w = soft_weight_fast(p.scale, u, s_tbl[warp]);
           if (p.variant_old) {
             if (!(u <= p.iou_thr)) w = 0.f;
             hq = u >= p.iou_thr;
@@ -252,7 +282,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) nms_v5_sorted_kernel(cons
         if (sc == s0) {
           if (lane == 0) {
             sel_box[nsel] = cbox;
-            out_row[nsel] = row;
+            out_row[nsel] = cidx[rank];
             if (out_rank) out_rank[nsel] = rank;
             out_score[nsel] = sc;
           }
@@ -463,12 +493,20 @@ int udal_nms_sorted(udal_ctx* ctx, const float* boxes, const float* scores, cons
     p.r_rank = (int32_t*)(scr + per * 4);
     p.r_begin = (int32_t*)(scr + per * 8);
   }
-  const size_t smem = (size_t)kWarpsPerBlock * p.max_out * sizeof(float4);
-  UDAL_REQUIRE(smem <= 200 * 1024, "max_output_size %d too large", p.max_out);
-  if (smem > 48 * 1024)
-    UDAL_CUDA(cudaFuncSetAttribute(nms_v5_sorted_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int blocks = (segments + kWarpsPerBlock - 1) / kWarpsPerBlock;
-  nms_v5_sorted_kernel<<<blocks, kWarpsPerBlock * 32, smem, ctx->stream>>>(p);
+  const bool staged = seg_n <= kStageCap;
+  if (staged) {
+    const size_t smem = (size_t)p.max_out * sizeof(float4) + (size_t)kStageCap * (16 + 4 + 12);
+    UDAL_REQUIRE(smem <= 200 * 1024, "max_output_size %d too large", p.max_out);
+    UDAL_CUDA(cudaFuncSetAttribute(nms_v5_sorted_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    nms_v5_sorted_kernel<true><<<segments, 32, smem, ctx->stream>>>(p);
+  } else {
+    const size_t smem = (size_t)kWarpsPerBlock * p.max_out * sizeof(float4);
+    UDAL_REQUIRE(smem <= 200 * 1024, "max_output_size %d too large", p.max_out);
+    if (smem > 48 * 1024)
+      UDAL_CUDA(cudaFuncSetAttribute(nms_v5_sorted_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int blocks = (segments + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    nms_v5_sorted_kernel<false><<<blocks, kWarpsPerBlock * 32, smem, ctx->stream>>>(p);
+  }
   UDAL_CHECK_LAUNCH(ctx);
   return UDAL_OK;
 }
