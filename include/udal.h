@@ -240,6 +240,11 @@ int udal_gather_rows(udal_ctx* ctx, const void* src, int batch, int64_t n_rows, 
 int udal_run(udal_ctx* ctx, const float* const* feats, int batch, const uint8_t* keep_masks,
              uint64_t seed, const float* image_scales, const udal_detections* out);
 
+/* per-layer CUDA-event timing of the head sampler (bench.py roofline): enable, run
+ * udal_heads_sample, then read ms[head * (R + 1) + layer]; *n = entries written (synchronises). */
+int udal_profile_layers(udal_ctx* ctx, int enable);
+int udal_get_layer_times(udal_ctx* ctx, float* ms, int cap, int* n);
+
 /* bytes of device scratch the context currently holds (grows on demand, never shrinks) */
 int udal_scratch_bytes(const udal_ctx* ctx, size_t* bytes);
 

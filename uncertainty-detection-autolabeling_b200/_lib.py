@@ -82,6 +82,9 @@ SIGNATURES = {
     "udal_device_count": (ctypes.c_int, [ctypes.POINTER(ctypes.c_int)]),
     "udal_num_anchors": (ctypes.c_int, [_VP, ctypes.POINTER(ctypes.c_int64)]),
     "udal_launch_count": (ctypes.c_int, [_VP, ctypes.POINTER(ctypes.c_int64)]),
+    "udal_profile_layers": (ctypes.c_int, [_VP, ctypes.c_int]),
+    "udal_get_layer_times": (ctypes.c_int, [_VP, ctypes.POINTER(ctypes.c_float), ctypes.c_int,
+                                            ctypes.POINTER(ctypes.c_int)]),
     "udal_scratch_bytes": (ctypes.c_int, [_VP, ctypes.POINTER(ctypes.c_size_t)]),
     "udal_set_anchors": (ctypes.c_int, [_VP, _VP, ctypes.c_int64]),
     "udal_set_head_weights": (ctypes.c_int, [_VP, ctypes.c_int] + [_VP] * 10),

@@ -222,6 +222,25 @@ int udal_launch_count(const udal_ctx* ctx, int64_t* n) {
   return UDAL_OK;
 }
 
+int udal_profile_layers(udal_ctx* ctx, int enable) {
+  UDAL_REQUIRE(ctx, "NULL ctx");
+  ctx->profile_layers = enable != 0;
+  for (cudaEvent_t e : ctx->layer_events) cudaEventDestroy(e);
+  ctx->layer_events.clear();
+  return UDAL_OK;
+}
+
+int udal_get_layer_times(udal_ctx* ctx, float* ms, int cap, int* n) {
+  UDAL_REQUIRE(ctx && ms && n, "NULL argument");
+  UDAL_CUDA(cudaStreamSynchronize(ctx->stream));
+  const int pairs = (int)ctx->layer_events.size() / 2;
+  *n = pairs < cap ? pairs : cap;
+  for (int i = 0; i < *n; ++i) UDAL_CUDA(cudaEventElapsedTime(&ms[i], ctx->layer_events[2 * i], ctx->layer_events[2 * i + 1]));
+  for (cudaEvent_t e : ctx->layer_events) cudaEventDestroy(e);
+  ctx->layer_events.clear();
+  return UDAL_OK;
+}
+
 int udal_scratch_bytes(const udal_ctx* ctx, size_t* bytes) {
   UDAL_REQUIRE(ctx && bytes, "NULL argument");
   size_t t = 0;

@@ -538,8 +538,17 @@ static int run_tower_tc(udal_ctx* ctx, int head, const float* const* feats, int 
   UDAL_CUDA(cudaFuncSetAttribute(sepconv_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_ALLOC));
   UDAL_CUDA(cudaFuncSetAttribute(sepconv_tc_kernel<80>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_ALLOC));
   const int npad_p = npad_of(h.cout);
+  auto mark = [&]() {
+    if (!ctx->profile_layers) return;
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) == cudaSuccess) {
+      cudaEventRecord(e, ctx->stream);
+      ctx->layer_events.push_back(e);
+    }
+  };
   for (int layer = 0; layer <= R; ++layer) {
     const bool predict = layer == R;
+    mark();
     p.dw = predict ? h.dwp : h.dw + (size_t)layer * 9 * KF;
     p.Cout = predict ? h.cout : KF;
     p.Npad = predict ? npad_p : KF;
@@ -582,6 +591,7 @@ static int run_tower_tc(udal_ctx* ctx, int head, const float* const* feats, int 
       for (int l = 0; l < L; ++l) ep_scale[l] = predict ? ones : h.bn_scale + ((size_t)layer * L + l) * KF;
       UDAL_TRY(udal_heads_ig_layer(ctx, p.in, NBt, img, ep_scale, p.fb, p.Npad, p.Cout, p.act, p.out_fp32,
                                    mc && !predict ? p.out_scale : nullptr, p.out));
+      mark();
       continue;
     }
     if (!udal_heads_tc_use_ig && layer >= 2 && mc) {
@@ -592,6 +602,7 @@ static int run_tower_tc(udal_ctx* ctx, int head, const float* const* feats, int 
     if (p.Npad == 64) sepconv_tc_kernel<64><<<grid, kThreads, SM_ALLOC, ctx->stream>>>(p);
     else sepconv_tc_kernel<80><<<grid, kThreads, SM_ALLOC, ctx->stream>>>(p);
     UDAL_CHECK_LAUNCH(ctx);
+    mark();
   }
   return UDAL_OK;
 }

@@ -50,6 +50,8 @@ struct udal_ctx {
   // named scratch slots, grown on demand
   udal_scratch scratch[20];
   std::vector<void*> user_allocs;
+  bool profile_layers = false;
+  std::vector<cudaEvent_t> layer_events;  // pairs (start, stop) in launch order
 };
 
 enum {
