@@ -93,9 +93,15 @@ BF16_RTOL = 3e-2
 
 
 @pytest.mark.parametrize("size,C,T,batch,la,rc,rb", [
-    ((64, 96), 7, 4, 2, True, 0.05, 0.05),
+    ((64, 96), 7, 4, 2, True, 0.05, 0.05),   # 63 class channels: predictions by per-thread row stores
     ((40, 200), 8, 2, 3, True, 0.0, 0.2),
     (128, 8, 1, 1, True, 0.0, 0.0),
+    # many work items per CTA of the persistent kernels (900 / 540 / 1840 items on 148 CTAs): ring
+    # wrap-around, accumulator and staging-tile reuse, every barrier phase
+    ((384, 1280), 8, 10, 1, True, 0.05, 0.05),
+    ((384, 1280), 8, 6, 1, True, 0.05, 0.05),
+    ((384, 640), 8, 10, 2, True, 0.05, 0.05),
+    ((192, 1280), 4, 5, 2, False, 0.05, 0.05),  # 36-channel predictions: one swizzled region + remainder
 ])
 def test_heads_bf16_tensor_core_vs_oracle(u, size, C, T, batch, la, rc, rb):
     p = _cfg(u, size, C, T, la, rc, rb, heads_mode="bf16")
@@ -106,6 +112,9 @@ def test_heads_bf16_tensor_core_vs_oracle(u, size, C, T, batch, la, rc, rb):
     masks = heads_ref.make_masks(T, L, eng.R, batch, eng.F, rc, rb, seed=5)
     sampler = u.heads.HeadSampler(p, w)
     cls, box = sampler(feats, masks=masks)
+    again = sampler(feats, masks=masks)  # the kernels are deterministic: a race would show up here
+    for x, y in zip(cls + box, again[0] + again[1]):
+        np.testing.assert_array_equal(x, y)
     rcls, rbox = heads_ref.heads_sample(feats, w, masks, rc, rb, T)
     worst = 0.0
     for l in range(L):

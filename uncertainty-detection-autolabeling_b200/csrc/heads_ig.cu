@@ -5,17 +5,21 @@
 //
 // so the CUDA cores do no convolution arithmetic at all.  Persistent, warp specialised, one CTA
 // per SM:
-//   warp 0  producer : TMA (cp.async.bulk.tensor.4d, 128B swizzle, zero OOB fill = SAME padding)
-//                      loads the 18x16-pixel halo tile of the next work item into a 2-stage ring;
-//                      loads the 9 x [N x 64] weight image once (cp.async.bulk), resident after that
+//   warp 0  producer : ONE TMA box per work item (cp.async.bulk.tensor.4d, 128B swizzle, zero OOB
+//                      fill = SAME padding): the 18x10-pixel halo tile, row pitch 10 px, into a
+//                      3-stage ring; loads the 9 x [N x 64] weight image once, resident after that
 //   warp 1  MMA      : one lane issues 36 x tcgen05.mma (M128, N = 64|80, K16) per tile; the A
 //                      operand of tap (dy,dx) is the SAME shared-memory tile addressed through a
-//                      UMMA descriptor whose start is shifted by (dy*16 + dx) pixel rows (row pitch
-//                      16 px = 2048 B, so every 8-row group keeps the same swizzle phase);
+//                      UMMA descriptor whose start is shifted by (dy*pitch + dx) pixel rows and whose
+//                      8-row group stride (SBO) is the row pitch; the 128B swizzle is a function of
+//                      the absolute shared-memory address, so neither needs 1 KB alignment;
 //                      accumulators double buffered in TMEM; tcgen05.commit releases the smem
 //                      stage and publishes the accumulator
-//   warps 2-5 epilogue: tcgen05.ld -> folded bias -> swish (tanh.approx) -> this layer's
-//                      SpatialDropout2D keep-scale -> bf16 store (or fp32 predictions)
+//   warps 2-9 epilogue: 2 groups x 4 warps; tcgen05.ld -> folded bias -> swish (tanh.approx) -> this
+//                      layer's SpatialDropout2D keep-scale -> bf16 (or fp32 predictions) into a
+//                      swizzled shared-memory staging tile -> TMA tensor store (coalesced, clips the
+//                      ragged right / bottom edge); per-thread row stores only when the channel
+//                      count breaks TMA's 16-byte stride rule (C = 7: 63 channels)
 // Work item = (16x8-pixel tile, (sample,image)); items are strided over the CTAs.
 //
 // Reference arithmetic replaced: efficientdet_keras.py:448-483 / 628-664 (_conv_bn_act and the
@@ -28,27 +32,57 @@
 namespace {
 
 constexpr int IG_TH = 16, IG_TW = 8;               // output tile: 16 rows x 8 px = 128 GEMM rows
-constexpr int IG_ROWS = IG_TH + 2, IG_PITCH = 16;  // staged halo tile: 18 rows, row pitch 16 px
-constexpr int IG_STAGE_BYTES = IG_ROWS * IG_PITCH * 128;  // 36 864 (smem footprint of a stage)
-constexpr int IG_BOXW = IG_TW + 2;                        // pixels actually loaded per row
+constexpr int IG_ROWS = IG_TH + 2;                 // staged halo tile: 18 rows
+constexpr int IG_BOXW = IG_TW + 2;                 // pixels loaded per row
 constexpr int KF = 64;
-constexpr int kIgStages = 3;          // TMA ring depth
 constexpr int kIgThreads = 320;       // producer warp, MMA warp, 2 x 4 epilogue warps
+constexpr int kIgMaxStages = 3;
+constexpr int kIgSmemLimit = 232448;  // 227 KB opt-in limit of sm_100
+
+// compile-time shape of one kernel variant
+//   NPAD   UMMA N (64 | 80)           NROWS  weight rows kept per tap (the MMA reads NPAD rows; rows
+//   STAGES TMA ring depth                    >= NROWS alias the next tap and feed unused columns)
+//   PREDICT epilogue flavour (compile time: no per-element branches)
+template <int NPAD_, int NROWS_, int STAGES_, bool PREDICT_>
+struct IgShape {
+  static constexpr int NPAD = NPAD_, NROWS = NROWS_, PITCH = IG_BOXW, STAGES = STAGES_;
+  static constexpr bool PREDICT = PREDICT_;  // false: tower layer (swish, dropout scale, bf16 out); true: fp32 predictions
+  static constexpr int B_BYTES = 9 * NROWS * 128;
+  static constexpr int STAGE_BYTES = IG_ROWS * PITCH * 128;
+  static constexpr int STAGE_STRIDE = (STAGE_BYTES + 1023) / 1024 * 1024;
+  // staging tile of one epilogue group: bf16 [128][64] (16 KB) or fp32 as 32-channel regions of
+  // [128][32] (16 KB each, 128B swizzle) plus a dense remainder region [128][NROWS - 64]
+  static constexpr int OUT_BYTES = !PREDICT ? 16384 : (NPAD == 64 ? 32768 : 32768 + 128 * (NROWS - 64) * 4);
+  static constexpr int SM_B = 0;
+  static constexpr int SM_IN = SM_B + B_BYTES;
+  static constexpr int SM_OUT = SM_IN + STAGES * STAGE_STRIDE;
+  static constexpr int SM_BAR = SM_OUT + 2 * OUT_BYTES;
+  static constexpr int SM_FBS = SM_BAR + 640;  // barriers (96 B) + 2 x 64 keep-scales
+  static constexpr int smem(int levels) { return SM_FBS + levels * 2 * NPAD * 4 + 1024; }
+  static_assert(B_BYTES % 1024 == 0 && OUT_BYTES % 1024 == 0, "swizzled regions must stay 1 KB aligned");
+  static_assert(STAGES <= kIgMaxStages, "barrier slots");
+};
 
 struct IgParams {
   int num_levels, NB, items;             // items = sum_l tiles[l] * NB
   int H[UDAL_MAX_LEVELS], W[UDAL_MAX_LEVELS], tiles_x[UDAL_MAX_LEVELS], tiles[UDAL_MAX_LEVELS];
   int item_off[UDAL_MAX_LEVELS + 1];     // prefix of tiles[l] * NB (items are level major)
   void* out[UDAL_MAX_LEVELS];            // [NB,H,W,64] bf16 or [NB,H,W,Cout] fp32
-  const float* out_scale[UDAL_MAX_LEVELS];  // [NB,64] keep-scale of THIS layer's dropout, or null
+  const float* out_scale[UDAL_MAX_LEVELS];  // [NB,64] keep-scale of THIS layer's dropout (sc_stride 64) or ones (0)
+  uint32_t tiles_magic[UDAL_MAX_LEVELS], tiles_x_magic[UDAL_MAX_LEVELS];  // ceil(2^32 / d) for the item decode
+  int sc_stride;
   const float* ep_scale[UDAL_MAX_LEVELS];   // [NPAD] per-level BN scale (1 for the predict layer)
   const float* ep_bias[UDAL_MAX_LEVELS];    // [NPAD] folded bias
-  const void* wimg;                      // bf16 [9][NPAD][64] pre-swizzled smem image (level independent)
-  int Cout, act, out_fp32;
+  const void* wimg;                      // bf16 [9][NROWS][64] pre-swizzled smem image (level independent)
+  int Cout;
+  int tma_store;                         // predictions through the staging tile + TMA store (Cout % 4 == 0)
+  int debug;                             // timing experiments only (wrong results): 1 = one tap, 2 = no epilogue math / stores, 4 = no TMA loads after the first ring fill
 };
 
 struct IgMaps {
-  CUtensorMap m[UDAL_MAX_LEVELS];
+  CUtensorMap m[UDAL_MAX_LEVELS];   // input halo boxes
+  CUtensorMap o[UDAL_MAX_LEVELS];   // output: bf16 [64 ch, 8, 16] box, or fp32 32-channel regions
+  CUtensorMap o2[UDAL_MAX_LEVELS];  // output: fp32 remainder region (Cout % 32 channels)
 };
 
 __device__ __forceinline__ uint32_t s32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -91,6 +125,15 @@ __device__ __forceinline__ void ig_mma(uint32_t tmem_d, uint64_t adesc, uint64_t
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
       : "memory");
 }
+__device__ __forceinline__ bool ig_elect_one() {  // true in exactly one lane of a converged warp
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void ig_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -104,8 +147,7 @@ __device__ __forceinline__ uint32_t ig_pack(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
 }
-__device__ __forceinline__ float ig_swish(float x) {
-  const float h = 0.5f * x;
+__device__ __forceinline__ float ig_swish_h(float h) {  // h = x / 2
   float t;
   asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
   return fmaf(h, t, h);  // x * sigmoid(x) = h * tanh(h) + h
@@ -114,43 +156,60 @@ __device__ __forceinline__ float ig_swish(float x) {
 struct IgItem {
   int l, nb, ty0, tx0;
 };
+// n / d and n % d through magic = ceil(2^32 / d) (0 stands for d = 1); exact for n * d < 2^32 after one
+// correction step
+__device__ __forceinline__ void ig_divmod(int n, int d, uint32_t magic, int& q, int& r) {
+  q = magic ? (int)__umulhi((uint32_t)n, magic) : n;
+  r = n - q * d;
+  if (r < 0) {
+    --q;
+    r += d;
+  }
+}
 __device__ __forceinline__ IgItem ig_item(const IgParams& p, int item) {
   int l = 0;
 #pragma unroll
   for (int i = 1; i < UDAL_MAX_LEVELS; ++i)
     if (i < p.num_levels && item >= p.item_off[i]) l = i;
   const int r = item - p.item_off[l];
-  const int nb = r / p.tiles[l], tile = r - nb * p.tiles[l];
+  int nb, tile, ty, tx;
+  ig_divmod(r, p.tiles[l], p.tiles_magic[l], nb, tile);
+  ig_divmod(tile, p.tiles_x[l], p.tiles_x_magic[l], ty, tx);
   IgItem it;
   it.l = l;
   it.nb = nb;
-  it.ty0 = (tile / p.tiles_x[l]) * IG_TH;
-  it.tx0 = (tile % p.tiles_x[l]) * IG_TW;
+  it.ty0 = ty * IG_TH;
+  it.tx0 = tx * IG_TW;
   return it;
 }
 
-template <int NPAD>
+__device__ __forceinline__ void ig_group_sync(int g) {  // the 128 threads of epilogue group g
+  asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
+}
+__device__ __forceinline__ void ig_tma_store(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(map),
+               "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+
+template <class S>
 __global__ void __launch_bounds__(kIgThreads, 1) heads_ig_kernel(const __grid_constant__ IgMaps maps,
                                                                  const IgParams p) {
-  constexpr int B_BYTES = 9 * NPAD * 128;
-  constexpr int SM_B = 0;
-  constexpr int SM_IN = SM_B + B_BYTES;                 // multiple of 1024 for NPAD = 64 | 80
-  constexpr int SM_BAR = SM_IN + kIgStages * IG_STAGE_BYTES;  // barriers + tmem slot
-  constexpr int SM_FBS = SM_BAR + 128;                  // per level: BN scale [NPAD] then folded bias [NPAD], fp32
+  constexpr int NPAD = S::NPAD, NROWS = S::NROWS, PITCH = S::PITCH, STAGES = S::STAGES;
   constexpr uint32_t kTmemCols = NPAD <= 64 ? 128 : 256;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = s32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
   const uint32_t sb = s32(smem);
   // barriers: full[3] @0  empty[3] @24  tfull[2] @48  tempty[2] @64  bfull @80  tmem slot @88
-  const uint32_t bar0 = sb + SM_BAR;
+  const uint32_t bar0 = sb + S::SM_BAR;
   const uint32_t bar_full = bar0, bar_empty = bar0 + 24, bar_tfull = bar0 + 48, bar_tempty = bar0 + 64, bar_b = bar0 + 80;
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + SM_BAR + 88);
-  float* sFb = reinterpret_cast<float*>(smem + SM_FBS);
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + S::SM_BAR + 88);
+  float* sFb = reinterpret_cast<float*>(smem + S::SM_FBS);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < kIgStages; ++i) {
+    for (int i = 0; i < STAGES; ++i) {
       bar_init(bar_full + 8 * i, 1);
       bar_init(bar_empty + 8 * i, 1);
     }
@@ -162,15 +221,17 @@ __global__ void __launch_bounds__(kIgThreads, 1) heads_ig_kernel(const __grid_co
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sb + SM_BAR + 88),
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sb + S::SM_BAR + 88),
                  "r"(kTmemCols)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  // epilogue constants; with swish the 0.5 of x*sigmoid(x) = h*tanh(h) + h, h = x/2, is folded in
+  const float half = S::PREDICT ? 1.0f : 0.5f;
   for (int e = threadIdx.x; e < p.num_levels * NPAD; e += kIgThreads) {
     const int l = e / NPAD, n = e - l * NPAD;
-    sFb[(2 * l) * NPAD + n] = __ldg(p.ep_scale[l] + n);
-    sFb[(2 * l + 1) * NPAD + n] = __ldg(p.ep_bias[l] + n);
+    sFb[(2 * l) * NPAD + n] = half * __ldg(p.ep_scale[l] + n);
+    sFb[(2 * l + 1) * NPAD + n] = half * __ldg(p.ep_bias[l] + n);
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -180,64 +241,78 @@ __global__ void __launch_bounds__(kIgThreads, 1) heads_ig_kernel(const __grid_co
 
   if (warp == 0) {
     // ===================== producer =====================
-    if (lane == 0) {
-      bar_expect_tx(bar_b, B_BYTES);
+    // (all three roles keep warp-uniform control flow: the TMA / MMA instructions take their operands from
+    // the warp's uniform registers, so a lane that has left a divergent region must never run ahead of
+    // the lane still inside it - every elected region ends in __syncwarp)
+    if (ig_elect_one()) {
+      bar_expect_tx(bar_b, S::B_BYTES);
       asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                       sb + SM_B),
-                   "l"(p.wimg), "r"(B_BYTES), "r"(bar_b)
+                       sb + S::SM_B),
+                   "l"(p.wimg), "r"(S::B_BYTES), "r"(bar_b)
                    : "memory");
-      int it = 0, s = 0, ph = 0;
-      for (int item = blockIdx.x; item < p.items; item += G, ++it) {
+    }
+    __syncwarp();
+    int s = 0, ph = 0, n_loaded = 0;
+    for (int item = blockIdx.x; item < p.items; item += G) {
+      const IgItem w = ig_item(p, item);
+      const uint32_t dst = sb + S::SM_IN + s * S::STAGE_STRIDE;
+      const bool skip = (p.debug & 4) && n_loaded++ >= STAGES;
+      if (ig_elect_one()) {
         bar_wait(bar_empty + 8 * s, ph ^ 1);  // stage free (first round passes immediately)
-        const IgItem w = ig_item(p, item);
-        // 18 row boxes of 10 pixels (the halo tile) into row slots of pitch 16 pixels: the 2 KB pitch
-        // keeps every 8-row UMMA group on the same swizzle phase, the 10-pixel boxes keep L2 traffic
-        // at 1.4x (instead of 2.25x) of the useful bytes
-        bar_expect_tx(bar_full + 8 * s, IG_ROWS * IG_BOXW * 128);
-        const uint32_t dst = sb + SM_IN + s * IG_STAGE_BYTES;
-#pragma unroll 1
-        for (int r = 0; r < IG_ROWS; ++r)
+        if (skip) {
+          bar_arrive(bar_full + 8 * s);
+        } else {
+          bar_expect_tx(bar_full + 8 * s, IG_ROWS * IG_BOXW * 128);
+          // the whole 18 x 10 pixel halo tile as one box; out-of-image pixels arrive as zeros
           asm volatile(
               "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-              ::"r"(dst + r * IG_PITCH * 128), "l"(&maps.m[w.l]), "r"(bar_full + 8 * s), "r"(0), "r"(w.tx0 - 1),
-              "r"(w.ty0 - 1 + r), "r"(w.nb)
+              ::"r"(dst), "l"(&maps.m[w.l]), "r"(bar_full + 8 * s), "r"(0), "r"(w.tx0 - 1), "r"(w.ty0 - 1), "r"(w.nb)
               : "memory");
-        if (++s == kIgStages) {
-          s = 0;
-          ph ^= 1;
         }
+      }
+      __syncwarp();
+      if (++s == STAGES) {
+        s = 0;
+        ph ^= 1;
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NPAD >> 3) << 17) | ((128u >> 4) << 24);
-      bar_wait(bar_b, 0);  // weights resident
-      int it = 0, s = 0, ph = 0;
-      for (int item = blockIdx.x; item < p.items; item += G, ++it) {
-        const int a = it & 1;
+    // The whole warp runs this loop: with warp-uniform control flow the descriptors stay in uniform
+    // registers and each tcgen05.mma is a single UTCHMMA (a lane-divergent `if (lane == 0)` makes the
+    // compiler wrap every instruction in a register-to-uniform waterfall loop, ~70 cycles per MMA
+    // instead of the 48 the operand fetch needs).  One elected lane issues.
+    constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NPAD >> 3) << 17) | ((128u >> 4) << 24);
+    if (lane == 0) bar_wait(bar_b, 0);  // weights resident
+    __syncwarp();
+    int it = 0, s = 0, ph = 0;
+    for (int item = blockIdx.x; item < p.items; item += G, ++it) {
+      const int a = it & 1;
+      const uint32_t in0 = sb + S::SM_IN + s * S::STAGE_STRIDE;
+      const uint32_t d_tmem = tmem_base + (uint32_t)(a * NPAD);
+      if (ig_elect_one()) {  // only this lane polls the barriers: 32 pollers would crowd the epilogue's smem traffic
         bar_wait(bar_tempty + 8 * a, ((it >> 1) & 1) ^ 1);  // accumulator drained by its epilogue group
         bar_wait(bar_full + 8 * s, ph);                      // halo tile landed
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t in0 = sb + SM_IN + s * IG_STAGE_BYTES;
-        const uint32_t d_tmem = tmem_base + (uint32_t)(a * NPAD);
 #pragma unroll
         for (int tap = 0; tap < 9; ++tap) {
+          if ((p.debug & 1) && tap != 0) continue;
           const int dy = tap / 3, dx = tap % 3;
           // the swizzle XOR is a function of the absolute shared-memory address bits, so a start
           // shifted by whole 128-byte rows needs no base offset (verified on hardware)
-          const uint64_t adesc = ig_desc(in0 + (uint32_t)((dy * IG_PITCH + dx) * 128), IG_PITCH * 128, 0);
-          const uint64_t bdesc = ig_desc(sb + SM_B + tap * NPAD * 128, 1024, 0);
+          const uint64_t adesc = ig_desc(in0 + (uint32_t)((dy * PITCH + dx) * 128), PITCH * 128, 0);
+          const uint64_t bdesc = ig_desc(sb + S::SM_B + tap * NROWS * 128, 1024, 0);
 #pragma unroll
           for (int k = 0; k < KF / 16; ++k)
             ig_mma(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (tap | k) ? 1u : 0u);
         }
         ig_commit(bar_empty + 8 * s);   // smem stage reusable once these MMAs retire
         ig_commit(bar_tfull + 8 * a);   // accumulator ready
-        if (++s == kIgStages) {
-          s = 0;
-          ph ^= 1;
-        }
+      }
+      __syncwarp();
+      if (++s == STAGES) {
+        s = 0;
+        ph ^= 1;
       }
     }
   } else {
@@ -245,28 +320,29 @@ __global__ void __launch_bounds__(kIgThreads, 1) heads_ig_kernel(const __grid_co
     const int g = (warp - 2) >> 2;
     const int q = warp & 3;                 // TMEM lane quarter this warp may access
     const int m = q * 32 + lane;            // GEMM row = pixel (m / 8, m % 8) of the tile
+    const bool elected = ((warp - 2) & 3) == 0 && lane == 0;
+    const bool staged = !S::PREDICT || p.tma_store;
+    uint8_t* const ob = smem + S::SM_OUT + g * S::OUT_BYTES;
+    const uint32_t swz = (uint32_t)(m & 7);
     int it = 0;
     for (int item = blockIdx.x; item < p.items; item += G, ++it) {
       if ((it & 1) != g) continue;
       const int a = g;
       const IgItem w = ig_item(p, item);
-      const int nb = w.nb, H = p.H[w.l], W = p.W[w.l];
-      const int oy = w.ty0 + (m >> 3), ox = w.tx0 + (m & 7);
-      const bool ok = oy < H && ox < W;
-      const size_t pix = ((size_t)nb * H + oy) * W + ox;
+      const int nb = w.nb;
       const float* ep_s = sFb + (2 * w.l) * NPAD;
       const float* ep_b = ep_s + NPAD;
-      const float* osc = p.out_scale[w.l];
-      void* outp = p.out[w.l];
-      // this item's dropout keep-scales: fetched while the MMAs are still running
-      float4 scv[KF / 4];
-      const bool has_sc = osc != nullptr && !p.out_fp32;
-      if (has_sc) {
-        const float4* sc = reinterpret_cast<const float4*>(osc + (size_t)nb * KF);
-#pragma unroll
-        for (int i = 0; i < KF / 4; ++i) scv[i] = __ldg(sc + i);
+      // this item's dropout keep-scales -> this group's slot in shared memory (the previous tile's math of
+      // the group ended before its second group barrier; the first barrier below publishes the slot)
+      float* const sSc = reinterpret_cast<float*>(smem + S::SM_BAR + 96) + g * KF;  // inside the barrier block: 2 x 256 B
+      if constexpr (!S::PREDICT) {
+        if (((warp - 2) & 3) == 1 && lane < KF / 4) {  // (predicated, no divergence)
+          const float4* sc = reinterpret_cast<const float4*>(p.out_scale[w.l] + (size_t)nb * p.sc_stride);
+          reinterpret_cast<float4*>(sSc)[lane] = __ldg(sc + lane);
+        }
       }
-      bar_wait(bar_tfull + 8 * a, (it >> 1) & 1);
+      if (lane == 0) bar_wait(bar_tfull + 8 * a, (it >> 1) & 1);  // one poller per warp
+      __syncwarp();
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * NPAD);
       uint32_t r[NPAD / 8][8];
@@ -275,50 +351,96 @@ __global__ void __launch_bounds__(kIgThreads, 1) heads_ig_kernel(const __grid_co
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       bar_arrive(bar_tempty + 8 * a);  // accumulator may be overwritten
-      if (ok) {
+      if (staged) {
+        // the TMA store of this group's previous tile must have finished reading the staging tile
+        if (elected) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        __syncwarp();
+        ig_group_sync(g);
+      }
+      if (p.debug & 2) {
+        // timing experiment: no epilogue arithmetic, no stores
+      } else if constexpr (!S::PREDICT) {
+        // ---- tower layer: BN scale + folded bias (both halved) -> swish -> dropout keep-scale -> bf16 ----
+#pragma unroll
+        for (int j = 0; j < KF / 8; ++j) {
+          const float4 f0 = *reinterpret_cast<const float4*>(ep_b + j * 8);
+          const float4 f1 = *reinterpret_cast<const float4*>(ep_b + j * 8 + 4);
+          const float4 g0 = *reinterpret_cast<const float4*>(ep_s + j * 8);
+          const float4 g1 = *reinterpret_cast<const float4*>(ep_s + j * 8 + 4);
+          const float fbv[8] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w};
+          const float gsv[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+          const float4 s0 = *reinterpret_cast<const float4*>(sSc + j * 8);
+          const float4 s1 = *reinterpret_cast<const float4*>(sSc + j * 8 + 4);
+          const float scl[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+          float v[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[i] = ig_swish_h(fmaf(__uint_as_float(r[j][i]), gsv[i], fbv[i])) * scl[i];
+          uint4 o;
+          o.x = ig_pack(v[0], v[1]);
+          o.y = ig_pack(v[2], v[3]);
+          o.z = ig_pack(v[4], v[5]);
+          o.w = ig_pack(v[6], v[7]);
+          *reinterpret_cast<uint4*>(ob + m * 128 + (((uint32_t)j ^ swz) << 4)) = o;
+        }
+      } else if (staged) {
+        // ---- predictions through the staging tile: 32-channel swizzled regions, then the dense remainder ----
+        const int nfull = p.Cout >> 5, rem = p.Cout - (nfull << 5);
 #pragma unroll
         for (int j = 0; j < NPAD / 8; ++j) {
           const int n0 = j * 8;
-          float v[8];
           const float4 f0 = *reinterpret_cast<const float4*>(ep_b + n0);
           const float4 f1 = *reinterpret_cast<const float4*>(ep_b + n0 + 4);
           const float4 g0 = *reinterpret_cast<const float4*>(ep_s + n0);
           const float4 g1 = *reinterpret_cast<const float4*>(ep_s + n0 + 4);
-          const float fbv[8] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w};
-          const float gsv[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            v[i] = fmaf(__uint_as_float(r[j][i]), gsv[i], fbv[i]);  // BN scale + folded bias
-            if (p.act) v[i] = ig_swish(v[i]);
-          }
-          if (!p.out_fp32) {
-            if (j < KF / 8) {
-              if (has_sc) {
-                const float4 s0 = scv[2 * (j < KF / 8 ? j : 0)], s1 = scv[2 * (j < KF / 8 ? j : 0) + 1];
-                v[0] *= s0.x; v[1] *= s0.y; v[2] *= s0.z; v[3] *= s0.w;
-                v[4] *= s1.x; v[5] *= s1.y; v[6] *= s1.z; v[7] *= s1.w;
-              }
-              uint4 o;
-              o.x = ig_pack(v[0], v[1]);
-              o.y = ig_pack(v[2], v[3]);
-              o.z = ig_pack(v[4], v[5]);
-              o.w = ig_pack(v[6], v[7]);
-              *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(outp) + pix * KF + n0) = o;
-            }
+          const float4 lo = make_float4(fmaf(__uint_as_float(r[j][0]), g0.x, f0.x), fmaf(__uint_as_float(r[j][1]), g0.y, f0.y),
+                                        fmaf(__uint_as_float(r[j][2]), g0.z, f0.z), fmaf(__uint_as_float(r[j][3]), g0.w, f0.w));
+          const float4 hi = make_float4(fmaf(__uint_as_float(r[j][4]), g1.x, f1.x), fmaf(__uint_as_float(r[j][5]), g1.y, f1.y),
+                                        fmaf(__uint_as_float(r[j][6]), g1.z, f1.z), fmaf(__uint_as_float(r[j][7]), g1.w, f1.w));
+          const int rg = n0 >> 5;
+          if (rg < nfull) {
+            const uint32_t c = (uint32_t)(n0 & 31) >> 2;  // 16-byte chunk inside the 128-byte region row
+            uint8_t* row = ob + rg * 16384 + m * 128;
+            *reinterpret_cast<float4*>(row + ((c ^ swz) << 4)) = lo;
+            *reinterpret_cast<float4*>(row + (((c + 1) ^ swz) << 4)) = hi;
           } else {
-            float* dst = reinterpret_cast<float*>(outp) + pix * p.Cout + n0;
-            if ((p.Cout & 3) == 0 && n0 + 8 <= p.Cout) {
-              *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
-              *reinterpret_cast<float4*>(dst + 4) = make_float4(v[4], v[5], v[6], v[7]);
-            } else {
-#pragma unroll
-              for (int i = 0; i < 8; ++i)
-                if (n0 + i < p.Cout) dst[i] = v[i];
-            }
+            const int c0 = n0 - (nfull << 5);
+            float* row = reinterpret_cast<float*>(ob + nfull * 16384) + m * rem;
+            if (c0 + 4 <= rem) *reinterpret_cast<float4*>(row + c0) = lo;
+            if (c0 + 8 <= rem) *reinterpret_cast<float4*>(row + c0 + 4) = hi;
           }
         }
+      } else {
+        // ---- predictions whose channel count breaks TMA's stride rule: per-thread row stores ----
+        const int H = p.H[w.l], W = p.W[w.l];
+        const int oy = w.ty0 + (m >> 3), ox = w.tx0 + (m & 7);
+        if (oy < H && ox < W) {
+          float* dst = reinterpret_cast<float*>(p.out[w.l]) + (((size_t)nb * H + oy) * W + ox) * p.Cout;
+#pragma unroll
+          for (int j = 0; j < NPAD / 8; ++j)
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              if (j * 8 + i < p.Cout) dst[j * 8 + i] = fmaf(__uint_as_float(r[j][i]), ep_s[j * 8 + i], ep_b[j * 8 + i]);
+        }
+      }
+      if (staged) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // staging writes -> visible to TMA
+        ig_group_sync(g);
+        if (elected && !(p.debug & 2)) {
+          const uint32_t src = s32(ob);
+          if constexpr (!S::PREDICT) {
+            ig_tma_store(&maps.o[w.l], src, 0, w.tx0, w.ty0, nb);
+          } else {
+            const int nfull = p.Cout >> 5, rem = p.Cout - (nfull << 5);
+            for (int rg = 0; rg < nfull; ++rg) ig_tma_store(&maps.o[w.l], src + rg * 16384, rg * 32, w.tx0, w.ty0, nb);
+            if (rem) ig_tma_store(&maps.o2[w.l], src + nfull * 16384, nfull * 32, w.tx0, w.ty0, nb);
+          }
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+        __syncwarp();  // lanes 1..31 must not start the next item while lane 0 still issues the store
       }
     }
+    if (staged && elected) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    __syncwarp();
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -328,14 +450,15 @@ __global__ void __launch_bounds__(kIgThreads, 1) heads_ig_kernel(const __grid_co
   }
 }
 
-// weight image: wimg[tap][n][k] = bf16( dw[tap][k] * wf[n][k] ) in the swizzled shared-memory layout
-__global__ void build_ig_weights_kernel(const float* __restrict__ dw, const float* __restrict__ wf, int npad,
+// weight image: wimg[tap][n][k] = bf16( dw[tap][k] * wf[n][k] ) in the swizzled shared-memory layout,
+// nrows rows per tap
+__global__ void build_ig_weights_kernel(const float* __restrict__ dw, const float* __restrict__ wf, int nrows,
                                         __nv_bfloat16* __restrict__ wimg) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= 9 * npad * KF) return;
-  const int k = i % KF, n = (i / KF) % npad, tap = i / (KF * npad);
+  if (i >= 9 * nrows * KF) return;
+  const int k = i % KF, n = (i / KF) % nrows, tap = i / (KF * nrows);
   const float v = dw[tap * KF + k] * wf[(size_t)n * KF + k];
-  const size_t byte = (size_t)tap * npad * 128 + (size_t)n * 128 + (size_t)((((k >> 3) ^ (n & 7)) << 4) + (k & 7) * 2);
+  const size_t byte = (size_t)tap * nrows * 128 + (size_t)n * 128 + (size_t)((((k >> 3) ^ (n & 7)) << 4) + (k & 7) * 2);
   wimg[byte / 2] = __float2bfloat16_rn(v);
 }
 
@@ -355,22 +478,71 @@ EncodeTiledFn get_encode() {
   return fn;
 }
 
-}  // namespace
+// [NB,H,W,ch] tensor map with a {c_box, x_box, y_box, 1} box
+int encode_nhwc(EncodeTiledFn encode, CUtensorMap* map, CUtensorMapDataType dt, int esize, const void* base, int NB, int H,
+                int W, int ch, int c_box, int x_box, int y_box, bool swizzle128) {
+  const cuuint64_t gdim[4] = {(cuuint64_t)ch, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)NB};
+  const cuuint64_t gstr[3] = {(cuuint64_t)ch * esize, (cuuint64_t)W * ch * esize, (cuuint64_t)H * W * ch * esize};
+  const cuuint32_t box[4] = {(cuuint32_t)c_box, (cuuint32_t)x_box, (cuuint32_t)y_box, 1u};
+  const cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
+  const CUresult r = encode(map, dt, 4, const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                            swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    udal_set_error("cuTensorMapEncodeTiled failed (%d) for [%d,%d,%d,%d] box {%d,%d,%d}", (int)r, NB, H, W, ch, c_box, x_box,
+                   y_box);
+    return UDAL_ERR_INVALID;
+  }
+  return UDAL_OK;
+}
 
-// builds the swizzled weight image of one (layer, level): out must hold 9*npad*64 bf16
-int udal_heads_ig_build_weights(udal_ctx* ctx, const float* dw, const float* wf, int npad, void* wimg) {
-  const int total = 9 * npad * KF;
-  build_ig_weights_kernel<<<(total + 255) / 256, 256, 0, ctx->stream>>>(dw, wf, npad, reinterpret_cast<__nv_bfloat16*>(wimg));
+template <class S>
+int launch_ig(udal_ctx* ctx, const IgMaps& maps, const IgParams& p, int grid) {
+  const int smem = S::smem(p.num_levels);
+  UDAL_REQUIRE(smem <= kIgSmemLimit, "implicit-GEMM head kernel needs %d bytes of shared memory", smem);
+  UDAL_CUDA(cudaFuncSetAttribute(heads_ig_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  heads_ig_kernel<S><<<grid, kIgThreads, smem, ctx->stream>>>(maps, p);
   UDAL_CHECK_LAUNCH(ctx);
   return UDAL_OK;
 }
 
-// one tower (>= 2) or predict layer over ALL pyramid levels: in[l] [NB,H_l,W_l,64] bf16 (dropout already applied)
-int udal_heads_ig_layer(udal_ctx* ctx, const void* const* in, int NB, const void* wimg, const float* const* ep_scale,
-                        const float* const* ep_bias, int npad, int cout, int act, int out_fp32,
-                        const float* const* out_scale, void* const* out) {
+// kernel variants: <NPAD, NROWS, STAGES, PREDICT>
+using IgTower = IgShape<64, 64, 3, false>;    // tower layers
+using IgPred64 = IgShape<64, 64, 3, true>;    // predict layers with <= 64 channels
+using IgPred72 = IgShape<80, 72, 3, true>;    // predict layers with 65..72 channels (A = 9, C = 8; box+sigma)
+using IgPred80 = IgShape<80, 80, 2, true>;    // predict layers with 73..80 channels
+static_assert(IgTower::smem(UDAL_MAX_LEVELS) <= kIgSmemLimit && IgPred64::smem(UDAL_MAX_LEVELS) <= kIgSmemLimit &&
+              IgPred80::smem(UDAL_MAX_LEVELS) <= kIgSmemLimit && IgPred72::smem(5) <= kIgSmemLimit, "shared-memory budget");
+
+}  // namespace
+
+// debug switches (ctypes-visible)
+int udal_ig_tma_store = 1;  // 0: predictions by per-thread row stores even when TMA's stride rule holds
+int udal_ig_debug = 0;      // timing experiments (IgParams::debug)
+
+// weight rows per tap the ig kernels expect for a layer with `cout` output channels
+int udal_heads_ig_rows(int cout, int num_levels) {
+  if (cout <= 64) return 64;
+  return (cout <= 72 && IgPred72::smem(num_levels) <= kIgSmemLimit) ? 72 : 80;
+}
+
+// builds the swizzled weight image of one layer: out must hold 9*nrows*64 bf16
+int udal_heads_ig_build_weights(udal_ctx* ctx, const float* dw, const float* wf, int nrows, void* wimg) {
+  const int total = 9 * nrows * KF;
+  build_ig_weights_kernel<<<(total + 255) / 256, 256, 0, ctx->stream>>>(dw, wf, nrows, reinterpret_cast<__nv_bfloat16*>(wimg));
+  UDAL_CHECK_LAUNCH(ctx);
+  return UDAL_OK;
+}
+
+// one tower (>= 2) or predict layer over ALL pyramid levels: in[l] [NB,H_l,W_l,64] bf16 (dropout already applied).
+// predict = 0: out[l] bf16 [NB,H,W,64] = swish(BN(conv)) * out_scale (out_scale null: no dropout; `ones` = 64 floats
+// of 1.0 on the device); predict = 1: out[l] fp32 [NB,H,W,cout] = conv + bias.
+int udal_heads_ig_layer(udal_ctx* ctx, const void* const* in, int NB, const void* wimg, int rows,
+                        const float* const* ep_scale, const float* const* ep_bias, int npad, int cout, int predict,
+                        const float* const* out_scale, const float* ones, void* const* out) {
   EncodeTiledFn encode = get_encode();
   UDAL_REQUIRE(encode != nullptr, "cuTensorMapEncodeTiled is not available from this driver");
+  UDAL_REQUIRE(rows == udal_heads_ig_rows(cout, ctx->cfg.num_levels), "weight image was built for another kernel variant");
   const udal_config& c = ctx->cfg;
   IgMaps maps;
   IgParams p;
@@ -378,44 +550,46 @@ int udal_heads_ig_layer(udal_ctx* ctx, const void* const* in, int NB, const void
   memset(&maps, 0, sizeof(maps));
   p.num_levels = c.num_levels;
   p.NB = NB;
+  // TMA needs 16-byte global strides: every bf16 layer qualifies, fp32 predictions when Cout % 4 == 0
+  p.tma_store = (!predict || (udal_ig_tma_store && (cout & 3) == 0)) ? 1 : 0;
+  p.sc_stride = out_scale ? KF : 0;
   int off = 0;
   for (int l = 0; l < c.num_levels; ++l) {
     const int H = c.level_h[l], W = c.level_w[l];
-    const cuuint64_t gdim[4] = {(cuuint64_t)KF, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)NB};
-    const cuuint64_t gstr[3] = {(cuuint64_t)KF * 2, (cuuint64_t)W * KF * 2, (cuuint64_t)H * W * KF * 2};
-    const cuuint32_t box[4] = {(cuuint32_t)KF, (cuuint32_t)IG_BOXW, 1u, 1u};
-    const cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
-    const CUresult r = encode(&maps.m[l], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(in[l]), gdim, gstr, box,
-                              estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    UDAL_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d) for [%d,%d,%d,64]", (int)r, NB, H, W);
+    UDAL_TRY(encode_nhwc(encode, &maps.m[l], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, in[l], NB, H, W, KF, KF, IG_BOXW, IG_ROWS,
+                         true));
+    if (!predict) {
+      UDAL_TRY(encode_nhwc(encode, &maps.o[l], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, out[l], NB, H, W, KF, KF, IG_TW, IG_TH, true));
+    } else if (p.tma_store) {
+      const int nfull = cout / 32, rem = cout % 32;
+      if (nfull)
+        UDAL_TRY(encode_nhwc(encode, &maps.o[l], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, out[l], NB, H, W, cout, 32, IG_TW, IG_TH,
+                             true));
+      if (rem)
+        UDAL_TRY(encode_nhwc(encode, &maps.o2[l], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, out[l], NB, H, W, cout, rem, IG_TW,
+                             IG_TH, false));
+    }
     p.H[l] = H;
     p.W[l] = W;
     p.tiles_x[l] = (W + IG_TW - 1) / IG_TW;
     p.tiles[l] = p.tiles_x[l] * ((H + IG_TH - 1) / IG_TH);
+    p.tiles_magic[l] = (uint32_t)((0x100000000ull + (uint64_t)p.tiles[l] - 1) / (uint64_t)p.tiles[l]);
+    p.tiles_x_magic[l] = (uint32_t)((0x100000000ull + (uint64_t)p.tiles_x[l] - 1) / (uint64_t)p.tiles_x[l]);
     p.item_off[l] = off;
+    UDAL_REQUIRE((int64_t)p.tiles[l] * NB * p.tiles[l] < (1ll << 32), "level %d: too many work items for the item decode", l);
     off += p.tiles[l] * NB;
     p.out[l] = out[l];
-    p.out_scale[l] = out_scale ? out_scale[l] : nullptr;
+    p.out_scale[l] = out_scale ? out_scale[l] : ones;
     p.ep_scale[l] = ep_scale[l];
     p.ep_bias[l] = ep_bias[l];
   }
   for (int l = c.num_levels; l <= UDAL_MAX_LEVELS; ++l) p.item_off[l] = off;
   p.items = off;
   p.Cout = cout;
-  p.act = act;
-  p.out_fp32 = out_fp32;
   p.wimg = wimg;
+  p.debug = udal_ig_debug;
   const int grid = p.items < UDAL_NUM_SMS ? p.items : UDAL_NUM_SMS;
-  if (npad == 64) {
-    constexpr int smem = 9 * 64 * 128 + kIgStages * IG_STAGE_BYTES + 128 + UDAL_MAX_LEVELS * 2 * 64 * 4 + 1024;
-    UDAL_CUDA(cudaFuncSetAttribute(heads_ig_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    heads_ig_kernel<64><<<grid, kIgThreads, smem, ctx->stream>>>(maps, p);
-  } else {
-    constexpr int smem = 9 * 80 * 128 + kIgStages * IG_STAGE_BYTES + 128 + UDAL_MAX_LEVELS * 2 * 80 * 4 + 1024;
-    UDAL_CUDA(cudaFuncSetAttribute(heads_ig_kernel<80>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    heads_ig_kernel<80><<<grid, kIgThreads, smem, ctx->stream>>>(maps, p);
-  }
-  UDAL_CHECK_LAUNCH(ctx);
-  return UDAL_OK;
+  if (!predict) return launch_ig<IgTower>(ctx, maps, p, grid);
+  if (npad == 64) return launch_ig<IgPred64>(ctx, maps, p, grid);
+  return rows == 72 ? launch_ig<IgPred72>(ctx, maps, p, grid) : launch_ig<IgPred80>(ctx, maps, p, grid);
 }

@@ -446,10 +446,11 @@ int npad_of(int cout) { return cout <= 64 ? 64 : 80; }
 
 }  // namespace
 
-int udal_heads_ig_build_weights(udal_ctx* ctx, const float* dw, const float* wf, int npad, void* wimg);
-int udal_heads_ig_layer(udal_ctx* ctx, const void* const* in, int NB, const void* wimg, const float* const* ep_scale,
-                        const float* const* ep_bias, int npad, int cout, int act, int out_fp32,
-                        const float* const* out_scale, void* const* out);
+int udal_heads_ig_rows(int cout, int num_levels);
+int udal_heads_ig_build_weights(udal_ctx* ctx, const float* dw, const float* wf, int nrows, void* wimg);
+int udal_heads_ig_layer(udal_ctx* ctx, const void* const* in, int NB, const void* wimg, int rows,
+                        const float* const* ep_scale, const float* const* ep_bias, int npad, int cout, int predict,
+                        const float* const* out_scale, const float* ones, void* const* out);
 int udal_heads_tc_use_ig = 1;  // 0: every layer through the per-tile kernel (debug / comparison)
 
 int udal_heads_tc_prepare(udal_ctx* ctx, int head) {
@@ -497,7 +498,8 @@ int udal_heads_tc_prepare(udal_ctx* ctx, int head) {
       UDAL_CHECK_LAUNCH(ctx);
       UDAL_TRY(udal_heads_ig_build_weights(ctx, h.dw + (size_t)r * 9 * KF, tmp, KF, img + (size_t)(r - 2) * tower_img));
     }
-    UDAL_TRY(udal_heads_ig_build_weights(ctx, h.dwp, wf + (size_t)R * L * KF * KF, npad_p,
+    h.ig_rows = udal_heads_ig_rows(h.cout, L);  // rows per tap of the predict image (<= npad_p)
+    UDAL_TRY(udal_heads_ig_build_weights(ctx, h.dwp, wf + (size_t)R * L * KF * KF, h.ig_rows,
                                          img + (size_t)(R - 2) * tower_img));
     std::vector<float> ones(kMaxN, 1.0f);
     UDAL_CUDA(cudaMemcpyAsync(reinterpret_cast<char*>(h.ig_w) + n_img * 2, ones.data(), kMaxN * sizeof(float),
@@ -589,8 +591,8 @@ static int run_tower_tc(udal_ctx* ctx, int head, const float* const* feats, int 
       const float* ones = reinterpret_cast<const float*>(img0 + (size_t)(R - 2) * tower_img + pred_img);
       const float* ep_scale[UDAL_MAX_LEVELS];
       for (int l = 0; l < L; ++l) ep_scale[l] = predict ? ones : h.bn_scale + ((size_t)layer * L + l) * KF;
-      UDAL_TRY(udal_heads_ig_layer(ctx, p.in, NBt, img, ep_scale, p.fb, p.Npad, p.Cout, p.act, p.out_fp32,
-                                   mc && !predict ? p.out_scale : nullptr, p.out));
+      UDAL_TRY(udal_heads_ig_layer(ctx, p.in, NBt, img, predict ? h.ig_rows : KF, ep_scale, p.fb, p.Npad, p.Cout,
+                                   predict ? 1 : 0, mc && !predict ? p.out_scale : nullptr, ones, p.out));
       mark();
       continue;
     }

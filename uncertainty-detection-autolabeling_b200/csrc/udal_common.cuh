@@ -27,6 +27,7 @@ struct udal_head_weights_dev {
   void* pw_bf16 = nullptr;
   void* pwp_bf16 = nullptr;
   float* fold_bias = nullptr;
+  int ig_rows = 0;       // weight rows per tap of the predict image in ig_w
   void* ig_w = nullptr;  // implicit-GEMM weight images: [(R-2)*L tower layers >= 2][9][64][64] then predict [9][Npad][64], bf16
 };
 
