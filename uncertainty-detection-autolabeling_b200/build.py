@@ -14,7 +14,7 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libudal.so")
 SOURCES = ["api.cu", "decode_moments.cu", "topk.cu", "nms.cu", "post.cu", "heads_fp32.cu",
-           "heads_tc.cu", "heads_ig.cu", "run.cu", "nms_np.cu"]
+           "heads_tc.cu", "heads_ig.cu", "heads_l1.cu", "run.cu", "nms_np.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-I", os.path.join(ROOT, "include"),
@@ -42,9 +42,10 @@ def build(force=False, verbose=False):
         obj = os.path.join(obj_dir, src.replace(".cu", ".o"))
         objs.append(obj)
         src_path = os.path.join(CSRC, src)
+        headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cuh")]
+        headers.append(os.path.join(ROOT, "include", "udal.h"))
         if (not force and os.path.exists(obj) and os.path.getmtime(obj) > os.path.getmtime(src_path)
-                and os.path.getmtime(obj) > os.path.getmtime(os.path.join(CSRC, "udal_common.cuh"))
-                and os.path.getmtime(obj) > os.path.getmtime(os.path.join(ROOT, "include", "udal.h"))):
+                and all(os.path.getmtime(obj) > os.path.getmtime(h) for h in headers)):
             continue
         cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src_path, "-o", obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))

@@ -451,6 +451,9 @@ int udal_heads_ig_build_weights(udal_ctx* ctx, const float* dw, const float* wf,
 int udal_heads_ig_layer(udal_ctx* ctx, const void* const* in, int NB, const void* wimg, int rows,
                         const float* const* ep_scale, const float* const* ep_bias, int npad, int cout, int predict,
                         const float* const* out_scale, const float* ones, void* const* out);
+int udal_heads_l1_layer(udal_ctx* ctx, const void* const* in, int NB, int T, const float* dw, const float* const* wf,
+                        const float* const* fb, const float* const* in_scale, const float* const* out_scale,
+                        const float* ones, float inv_keep, void* const* out);
 int udal_heads_tc_use_ig = 1;  // 0: every layer through the per-tile kernel (debug / comparison)
 
 int udal_heads_tc_prepare(udal_ctx* ctx, int head) {
@@ -583,6 +586,17 @@ static int run_tower_tc(udal_ctx* ctx, int head, const float* const* feats, int 
         p.wf[l] = wf_all + ((size_t)layer * L + l) * KF * KF;
         p.fb[l] = h.fold_bias + ((size_t)layer * L + l) * KF;
       }
+    }
+    if (udal_heads_tc_use_ig && layer == 1) {
+      // sample-invariant input: persistent kernel, one depthwise pass per image, T samples back to back
+      const size_t tower_img = (size_t)9 * KF * KF, pred_img = (size_t)9 * npad_p * KF;
+      const float* ones = reinterpret_cast<const float*>(reinterpret_cast<const __nv_bfloat16*>(h.ig_w) +
+                                                         (size_t)(R - 2) * tower_img + pred_img);
+      UDAL_TRY(udal_heads_l1_layer(ctx, p.in, B, mc ? T : 1, p.dw, p.wf, p.fb, mc ? p.scale : nullptr,
+                                   mc ? p.out_scale : nullptr, ones,
+                                   head == UDAL_HEAD_CLASS ? c.inv_keep_class : c.inv_keep_box, p.out));
+      mark();
+      continue;
     }
     if (use_ig) {
       const size_t tower_img = (size_t)9 * KF * KF, pred_img = (size_t)9 * npad_p * KF;

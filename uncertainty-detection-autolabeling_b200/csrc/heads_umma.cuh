@@ -1,0 +1,162 @@
+// Device / host helpers shared by the persistent tcgen05 head kernels (heads_ig.cu, heads_l1.cu): mbarrier,
+// TMA, UMMA descriptor and issue wrappers, the work-item decode and tensor-map encoding.  sm_100a only.
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include "udal_common.cuh"
+
+namespace {
+
+constexpr int IG_TH = 16, IG_TW = 8;               // output tile: 16 rows x 8 px = 128 GEMM rows
+constexpr int IG_ROWS = IG_TH + 2;                 // staged halo tile: 18 rows
+constexpr int IG_BOXW = IG_TW + 2;                 // pixels loaded per row
+constexpr int KF = 64;
+constexpr int kIgSmemLimit = 232448;  // 227 KB opt-in limit of sm_100
+
+__device__ __forceinline__ uint32_t s32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void bar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void bar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void bar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void bar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ uint64_t ig_desc(uint32_t saddr, uint32_t sbo_bytes, uint32_t base_off) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)(base_off & 7) << 49;
+  d |= (uint64_t)2 << 61;  // SWIZZLE_128B
+  return d;
+}
+__device__ __forceinline__ void ig_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ bool ig_elect_one() {  // true in exactly one lane of a converged warp
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ void ig_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void ig_ld8(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+}
+__device__ __forceinline__ uint32_t ig_pack(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ float ig_swish_h(float h) {  // h = x / 2
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+  return fmaf(h, t, h);  // x * sigmoid(x) = h * tanh(h) + h
+}
+
+struct IgItem {
+  int l, nb, ty0, tx0;
+};
+// n / d and n % d through magic = ceil(2^32 / d) (0 stands for d = 1); exact for n * d < 2^32 after one
+// correction step
+__device__ __forceinline__ void ig_divmod(int n, int d, uint32_t magic, int& q, int& r) {
+  q = magic ? (int)__umulhi((uint32_t)n, magic) : n;
+  r = n - q * d;
+  if (r < 0) {
+    --q;
+    r += d;
+  }
+}
+template <class P>
+__device__ __forceinline__ IgItem ig_item(const P& p, int item) {
+  int l = 0;
+#pragma unroll
+  for (int i = 1; i < UDAL_MAX_LEVELS; ++i)
+    if (i < p.num_levels && item >= p.item_off[i]) l = i;
+  const int r = item - p.item_off[l];
+  int nb, tile, ty, tx;
+  ig_divmod(r, p.tiles[l], p.tiles_magic[l], nb, tile);
+  ig_divmod(tile, p.tiles_x[l], p.tiles_x_magic[l], ty, tx);
+  IgItem it;
+  it.l = l;
+  it.nb = nb;
+  it.ty0 = ty * IG_TH;
+  it.tx0 = tx * IG_TW;
+  return it;
+}
+
+__device__ __forceinline__ void ig_group_sync(int g) {  // the 128 threads of epilogue group g
+  asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
+}
+__device__ __forceinline__ void ig_group_sync256(int g) {  // 256-thread epilogue groups
+  asm volatile("bar.sync %0, 256;" ::"r"(1 + g) : "memory");
+}
+__device__ __forceinline__ void ig_tma_store(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(map),
+               "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+// [NB,H,W,ch] tensor map with a {c_box, x_box, y_box, 1} box
+int encode_nhwc(EncodeTiledFn encode, CUtensorMap* map, CUtensorMapDataType dt, int esize, const void* base, int NB, int H,
+                int W, int ch, int c_box, int x_box, int y_box, bool swizzle128) {
+  const cuuint64_t gdim[4] = {(cuuint64_t)ch, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)NB};
+  const cuuint64_t gstr[3] = {(cuuint64_t)ch * esize, (cuuint64_t)W * ch * esize, (cuuint64_t)H * W * ch * esize};
+  const cuuint32_t box[4] = {(cuuint32_t)c_box, (cuuint32_t)x_box, (cuuint32_t)y_box, 1u};
+  const cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
+  const CUresult r = encode(map, dt, 4, const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                            swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    udal_set_error("cuTensorMapEncodeTiled failed (%d) for [%d,%d,%d,%d] box {%d,%d,%d}", (int)r, NB, H, W, ch, c_box, x_box,
+                   y_box);
+    return UDAL_ERR_INVALID;
+  }
+  return UDAL_OK;
+}
+
+}  // namespace
