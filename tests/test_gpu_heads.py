@@ -142,3 +142,35 @@ def test_pipelined_sampler_matches_blocking_calls(u):
     for a, b in zip(got, ref):
         for x, y in zip(a, b):
             np.testing.assert_array_equal(x, y)
+
+
+def test_run_tail_overlap_is_invisible(u):
+    """udal_run moves top-k / NMS / assemble to a second stream so that they overlap the next run's
+    heads; results must not depend on it, also when other entry points are called in between."""
+    import ctypes
+    p = _cfg(u, (128, 192), 8, 4, heads_mode="bf16")
+    eng = u.engine.get_engine(p)
+    L, batch = len(eng.level_hw), 3
+    w = heads_ref.init_head_weights(eng.F, eng.R, L, eng.A, 8, True, randomize_bn=True)
+    eng.set_head_weights(w)
+    feats = [[eng.ctx.to_device(f) for f in heads_ref.make_features(eng.level_hw, batch, eng.F, seed=s)] for s in range(4)]
+    scales = eng.ctx.to_device(np.float32([1.0, 1.5, 0.75]))
+    overlap = ctypes.c_int.in_dll(eng.lib, "udal_run_overlap")
+
+    def sweep():
+        outs = [eng.run(feats[i % 4], scales, None, seed=50 + i) for i in range(7)]   # back to back, no sync
+        mid = eng.topk(eng.ctx.to_device(np.arange(40, dtype=np.float32).reshape(2, 20)), 3)  # joins the tails
+        outs.append(eng.run(feats[1], scales, None, seed=99))
+        return [{k: v.numpy() for k, v in o.items()} for o in outs], mid[1].numpy()
+
+    try:
+        overlap.value = 0
+        ref, ref_mid = sweep()
+        overlap.value = 1
+        got, got_mid = sweep()
+    finally:
+        overlap.value = 1
+    np.testing.assert_array_equal(ref_mid, got_mid)
+    for a, b in zip(ref, got):
+        for k in a:
+            np.testing.assert_array_equal(a[k], b[k])

@@ -19,8 +19,25 @@ int udal_cuda_fail(cudaError_t e, const char* what, const char* file, int line) 
   return e == cudaErrorMemoryAllocation ? UDAL_ERR_NOMEM : UDAL_ERR_CUDA;
 }
 
+static bool scratch_banked(int slot) {
+  // the head sampler's slots are only ever touched on the context's own stream
+  return !(slot == SCR_HEADS_A || slot == SCR_HEADS_B || slot == SCR_HEADS_C || slot == SCR_PRE_A || slot == SCR_LEVEL_PTRS);
+}
+
+int udal_join(udal_ctx* ctx) {
+  if (ctx->in_run) return UDAL_OK;
+  for (int b = 0; b < 2; ++b)
+    if (ctx->post_pending[b]) {
+      UDAL_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_post[b], 0));
+      ctx->post_pending[b] = false;
+    }
+  ctx->scratch_bank = 0;
+  ctx->run_bank = 0;
+  return UDAL_OK;
+}
+
 int udal_scratch_get(udal_ctx* ctx, int slot, size_t bytes, void** out) {
-  udal_scratch& s = ctx->scratch[slot];
+  udal_scratch& s = ctx->scratch[slot + ((ctx->scratch_bank && scratch_banked(slot)) ? 20 : 0)];
   if (bytes == 0) bytes = 16;
   if (s.bytes < bytes) {
     if (s.ptr) {
@@ -85,8 +102,13 @@ int udal_create(const udal_config* cfg, udal_ctx** out) {
   ctx->num_pixels = off;
   ctx->num_anchors = off * cfg->anchors_per_loc;
   cudaError_t e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->post_stream, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev_start);
   if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev_stop);
+  for (int b = 0; b < 2 && e == cudaSuccess; ++b) {
+    e = cudaEventCreateWithFlags(&ctx->ev_pre[b], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_post[b], cudaEventDisableTiming);
+  }
   if (e != cudaSuccess) {
     delete ctx;
     return udal_cuda_fail(e, "stream/event creation", __FILE__, __LINE__);
@@ -116,6 +138,7 @@ int udal_destroy(udal_ctx* ctx) {
   if (!ctx) return UDAL_OK;
   cudaSetDevice(ctx->cfg.device);
   cudaStreamSynchronize(ctx->stream);
+  if (ctx->post_stream) cudaStreamSynchronize(ctx->post_stream);
   for (auto& s : ctx->scratch) cudaFree(s.ptr);
   for (void* p : ctx->user_allocs) cudaFree(p);
   cudaFree(ctx->anchors);
@@ -123,6 +146,11 @@ int udal_destroy(udal_ctx* ctx) {
   free_head(ctx->heads[1]);
   cudaEventDestroy(ctx->ev_start);
   cudaEventDestroy(ctx->ev_stop);
+  for (int b = 0; b < 2; ++b) {
+    if (ctx->ev_pre[b]) cudaEventDestroy(ctx->ev_pre[b]);
+    if (ctx->ev_post[b]) cudaEventDestroy(ctx->ev_post[b]);
+  }
+  if (ctx->post_stream) cudaStreamDestroy(ctx->post_stream);
   cudaStreamDestroy(ctx->own_stream);
   delete ctx;
   return UDAL_OK;
@@ -130,12 +158,14 @@ int udal_destroy(udal_ctx* ctx) {
 
 int udal_set_stream(udal_ctx* ctx, void* cuda_stream) {
   UDAL_REQUIRE(ctx, "NULL ctx");
+  UDAL_TRY(udal_join(ctx));
   ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
   return UDAL_OK;
 }
 
 int udal_sync(udal_ctx* ctx) {
   UDAL_REQUIRE(ctx, "NULL ctx");
+  UDAL_TRY(udal_join(ctx));
   UDAL_CUDA(cudaStreamSynchronize(ctx->stream));
   return UDAL_OK;
 }
@@ -152,6 +182,7 @@ int udal_malloc(udal_ctx* ctx, size_t bytes, void** dev_ptr) {
 
 int udal_free(udal_ctx* ctx, void* dev_ptr) {
   UDAL_REQUIRE(ctx, "NULL ctx");
+  UDAL_TRY(udal_join(ctx));
   if (!dev_ptr) return UDAL_OK;
   auto it = std::find(ctx->user_allocs.begin(), ctx->user_allocs.end(), dev_ptr);
   UDAL_REQUIRE(it != ctx->user_allocs.end(), "udal_free: pointer was not allocated by this context");
@@ -174,36 +205,42 @@ int udal_host_free(void* pinned_ptr) {
 
 int udal_memcpy_h2d(udal_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes) {
   UDAL_REQUIRE(ctx && (bytes == 0 || (dst_dev && src_host)), "NULL argument");
+  UDAL_TRY(udal_join(ctx));
   if (bytes) UDAL_CUDA(cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, ctx->stream));
   return UDAL_OK;
 }
 
 int udal_memcpy_d2h(udal_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes) {
   UDAL_REQUIRE(ctx && (bytes == 0 || (dst_host && src_dev)), "NULL argument");
+  UDAL_TRY(udal_join(ctx));
   if (bytes) UDAL_CUDA(cudaMemcpyAsync(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
   return UDAL_OK;
 }
 
 int udal_memcpy_d2d(udal_ctx* ctx, void* dst_dev, const void* src_dev, size_t bytes) {
   UDAL_REQUIRE(ctx && (bytes == 0 || (dst_dev && src_dev)), "NULL argument");
+  UDAL_TRY(udal_join(ctx));
   if (bytes) UDAL_CUDA(cudaMemcpyAsync(dst_dev, src_dev, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
   return UDAL_OK;
 }
 
 int udal_memset(udal_ctx* ctx, void* dst_dev, int value, size_t bytes) {
   UDAL_REQUIRE(ctx && (bytes == 0 || dst_dev), "NULL argument");
+  UDAL_TRY(udal_join(ctx));
   if (bytes) UDAL_CUDA(cudaMemsetAsync(dst_dev, value, bytes, ctx->stream));
   return UDAL_OK;
 }
 
 int udal_timer_start(udal_ctx* ctx) {
   UDAL_REQUIRE(ctx, "NULL ctx");
+  UDAL_TRY(udal_join(ctx));
   UDAL_CUDA(cudaEventRecord(ctx->ev_start, ctx->stream));
   return UDAL_OK;
 }
 
 int udal_timer_stop(udal_ctx* ctx, float* elapsed_ms) {
   UDAL_REQUIRE(ctx && elapsed_ms, "NULL argument");
+  UDAL_TRY(udal_join(ctx));
   UDAL_CUDA(cudaEventRecord(ctx->ev_stop, ctx->stream));
   UDAL_CUDA(cudaEventSynchronize(ctx->ev_stop));
   UDAL_CUDA(cudaEventElapsedTime(elapsed_ms, ctx->ev_start, ctx->ev_stop));
@@ -251,6 +288,7 @@ int udal_scratch_bytes(const udal_ctx* ctx, size_t* bytes) {
 
 int udal_set_anchors(udal_ctx* ctx, const float* anchors_host, int64_t num_anchors) {
   UDAL_REQUIRE(ctx && anchors_host, "NULL argument");
+  UDAL_TRY(udal_join(ctx));
   UDAL_REQUIRE(num_anchors == ctx->num_anchors, "anchor table has %lld rows, the level geometry gives %lld",
                (long long)num_anchors, (long long)ctx->num_anchors);
   if (!ctx->anchors) UDAL_CUDA(cudaMalloc(&ctx->anchors, (size_t)num_anchors * 16));
@@ -264,17 +302,20 @@ int udal_set_anchors(udal_ctx* ctx, const float* anchors_host, int64_t num_ancho
 int udal_decode_moments(udal_ctx* ctx, const float* const* cls, const float* const* box, int batch,
                         const udal_prenms_out* out) {
   UDAL_REQUIRE(ctx && cls && box && out, "NULL argument");
+  UDAL_TRY(udal_join(ctx));
   return udal_launch_decode_moments(ctx, cls, box, batch, out);
 }
 
 int udal_topk(udal_ctx* ctx, const float* values, int batch, int64_t m, int k, int32_t* idx_out, float* val_out) {
   UDAL_REQUIRE(ctx, "NULL ctx");
+  UDAL_TRY(udal_join(ctx));
   return udal_launch_topk(ctx, values, batch, m, k, idx_out, val_out);
 }
 
 int udal_nms_v5(udal_ctx* ctx, const float* boxes, const float* scores, int segments, int n, int32_t* sel_idx,
                 float* sel_scores, int32_t* valid) {
   UDAL_REQUIRE(ctx && boxes && scores && sel_idx && sel_scores && valid, "NULL argument");
+  UDAL_TRY(udal_join(ctx));
   return udal_launch_nms_v5(ctx, boxes, scores, segments, n, sel_idx, sel_scores, valid);
 }
 

@@ -204,6 +204,7 @@ extern "C" int udal_set_head_weights(udal_ctx* ctx, int head, const float* dw, c
                                      const float* bn_gamma, const float* bn_beta, const float* bn_mean,
                                      const float* bn_var, const float* dwp, const float* pwp, const float* bp) {
   UDAL_REQUIRE(ctx, "NULL ctx");
+  UDAL_TRY(udal_join(ctx));
   UDAL_REQUIRE(head == UDAL_HEAD_CLASS || head == UDAL_HEAD_BOX, "head must be 0 (class) or 1 (box)");
   UDAL_REQUIRE(dw && pw && bias && bn_gamma && bn_beta && bn_mean && bn_var && dwp && pwp && bp, "NULL weight pointer");
   const udal_config& c = ctx->cfg;
@@ -327,6 +328,7 @@ __global__ void scale_transpose_kernel(const float* __restrict__ src, float* __r
 extern "C" int udal_heads_sample(udal_ctx* ctx, const float* const* feats, int batch, const uint8_t* keep_masks,
                                  uint64_t seed, float* const* cls_out, float* const* box_out) {
   UDAL_REQUIRE(ctx && feats && cls_out && box_out, "NULL argument");
+  UDAL_TRY(udal_join(ctx));
   UDAL_REQUIRE(ctx->heads[0].set && ctx->heads[1].set, "head weights not set (udal_set_head_weights)");
   UDAL_REQUIRE(batch > 0, "batch must be positive");
   const udal_config& c = ctx->cfg;

@@ -221,6 +221,7 @@ __global__ void __launch_bounds__(kT) nms_np_soft_kernel(const float* __restrict
 extern "C" int udal_nms_np(udal_ctx* ctx, const float* dets_host, int n, int method, float iou_thresh, float sigma,
                            float score_thresh, float* kept_host, int32_t* num_kept) {
   UDAL_REQUIRE(ctx && num_kept, "NULL argument");
+  UDAL_TRY(udal_join(ctx));
   UDAL_REQUIRE(method >= NP_HARD && method <= NP_SOFT_HARD, "Unknown NMS method: %d", method);
   UDAL_REQUIRE(n >= 0 && n <= kMaxN, "nms_np: %d boxes, the device kernels take at most %d per call", n, kMaxN);
   *num_kept = 0;

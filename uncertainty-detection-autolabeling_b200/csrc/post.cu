@@ -256,11 +256,14 @@ __global__ void __launch_bounds__(256) merge_per_class_kernel(const MergeParams 
 
 }  // namespace
 
+int udal_run_overlap = 1;  // 0: udal_run keeps its whole tail on the context's stream
+
 extern "C" {
 
 int udal_postprocess_global(udal_ctx* ctx, const float* const* cls, const float* const* box, int batch,
                             const float* image_scales, const udal_detections* out) {
   UDAL_REQUIRE(ctx && cls && box && out, "NULL argument");
+  UDAL_TRY(udal_join(ctx));
   UDAL_REQUIRE(out->boxes && out->scores && out->classes && out->valid, "NULL output");
   const udal_config& c = ctx->cfg;
   UDAL_REQUIRE(c.max_nms_inputs == 0,
@@ -285,6 +288,21 @@ int udal_postprocess_global(udal_ctx* ctx, const float* const* cls, const float*
   pre.scores = (float*)(anc_buf + bn * 48);
   pre.classes = (int32_t*)(anc_buf + bn * 52);
   UDAL_TRY(udal_launch_decode_moments(ctx, cls, box, batch, &pre));
+  // inside a pipelined udal_run the rest (top-k pre-filter, NMS, assemble: a few warps per image) moves to
+  // the post stream, where it overlaps the head sampler of the next run
+  const bool tail_on_post = ctx->in_run && udal_run_overlap && ctx->post_stream != nullptr;
+  cudaStream_t main_stream = ctx->stream;
+  const int bank = ctx->scratch_bank;
+  if (tail_on_post) {
+    UDAL_CUDA(cudaEventRecord(ctx->ev_pre[bank], main_stream));
+    UDAL_CUDA(cudaStreamWaitEvent(ctx->post_stream, ctx->ev_pre[bank], 0));
+    ctx->stream = ctx->post_stream;
+  }
+  struct Restore {
+    udal_ctx* c;
+    cudaStream_t s;
+    ~Restore() { c->stream = s; }
+  } restore{ctx, main_stream};
   int32_t* sel_idx = (int32_t*)sel_buf;
   float* sel_scores = (float*)(sel_buf + (size_t)batch * mo * 4);
   int32_t* valid = (int32_t*)(sel_buf + (size_t)batch * mo * 8);
@@ -312,12 +330,17 @@ int udal_postprocess_global(udal_ctx* ctx, const float* const* cls, const float*
   a.out = *out;
   assemble_global_kernel<<<batch, 128, 0, ctx->stream>>>(a);
   UDAL_CHECK_LAUNCH(ctx);
+  if (tail_on_post) {
+    UDAL_CUDA(cudaEventRecord(ctx->ev_post[bank], ctx->post_stream));
+    ctx->post_pending[bank] = true;
+  }
   return UDAL_OK;
 }
 
 int udal_prenms_topk(udal_ctx* ctx, const float* const* cls, const float* const* box, int batch,
                      const udal_prenms_topk_out* out) {
   UDAL_REQUIRE(ctx && cls && box && out, "NULL argument");
+  UDAL_TRY(udal_join(ctx));
   const udal_config& c = ctx->cfg;
   const int k = c.max_nms_inputs;
   UDAL_REQUIRE(k > 0, "udal_prenms_topk needs max_nms_inputs > 0");
@@ -406,6 +429,7 @@ int udal_per_class_nms(udal_ctx* ctx, const float* boxes, const float* scores, c
                        int k, const float* image_scales, const float* logits, int64_t logit_rows,
                        int strict_reference, const udal_detections* out) {
   UDAL_REQUIRE(ctx && boxes && scores && classes && out, "NULL argument");
+  UDAL_TRY(udal_join(ctx));
   UDAL_REQUIRE(out->boxes && out->scores && out->classes && out->valid, "NULL output");
   UDAL_REQUIRE(batch > 0 && k > 0, "empty input");
   return per_class_from_candidates(ctx, boxes, scores, classes, nullptr, batch, k, image_scales, logits, logit_rows,
@@ -415,6 +439,7 @@ int udal_per_class_nms(udal_ctx* ctx, const float* boxes, const float* scores, c
 int udal_postprocess_per_class(udal_ctx* ctx, const float* const* cls, const float* const* box, int batch,
                                const float* image_scales, int strict_reference, const udal_detections* out) {
   UDAL_REQUIRE(ctx && cls && box && out, "NULL argument");
+  UDAL_TRY(udal_join(ctx));
   UDAL_REQUIRE(out->boxes && out->scores && out->classes && out->valid, "NULL output");
   const udal_config& c = ctx->cfg;
   const int k = c.max_nms_inputs;
@@ -457,6 +482,7 @@ __global__ void concat_channels_kernel(const float* __restrict__ a, int ca, cons
 
 int udal_concat_channels(udal_ctx* ctx, const float* a, int ca, const float* b, int cb, int64_t rows, float* out) {
   UDAL_REQUIRE(ctx && a && b && out && ca > 0 && cb > 0, "bad argument");
+  UDAL_TRY(udal_join(ctx));
   const int64_t total = rows * (ca + cb);
   if (total == 0) return UDAL_OK;
   concat_channels_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(a, ca, b, cb, rows, out);
@@ -483,6 +509,7 @@ __global__ void gather_rows_kernel(const uint32_t* __restrict__ src, int64_t n_r
 int udal_gather_rows(udal_ctx* ctx, const void* src, int batch, int64_t n_rows, int width, const int32_t* idx, int m,
                      int mode, void* out) {
   UDAL_REQUIRE(ctx && src && idx && out && width > 0, "bad argument");
+  UDAL_TRY(udal_join(ctx));
   const int64_t total = (int64_t)batch * m * width;
   if (total == 0) return UDAL_OK;
   gather_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>((const uint32_t*)src, n_rows, width, idx,
@@ -521,6 +548,7 @@ int udal_format_detections(udal_ctx* ctx, const float* boxes, int box_stride, co
                            const float* classes, int class_stride, const float* image_ids, const float* widths,
                            int flip, const float* logits, int nlogits, int batch, int max_out, float* out) {
   UDAL_REQUIRE(ctx && boxes && scores && classes && image_ids && out, "NULL argument");
+  UDAL_TRY(udal_join(ctx));
   UDAL_REQUIRE(!flip || widths, "flip needs the original image widths");
   if (!logits) nlogits = 0;
   const int64_t rows = (int64_t)batch * max_out;
@@ -546,6 +574,7 @@ __global__ void transform_detections_kernel(const float* in, int64_t rows, int i
 
 int udal_transform_detections(udal_ctx* ctx, const float* in, int64_t rows, int in_cols, float* out) {
   UDAL_REQUIRE(ctx && in && out && in_cols >= 7, "bad argument");
+  UDAL_TRY(udal_join(ctx));
   if (rows == 0) return UDAL_OK;
   transform_detections_kernel<<<(unsigned)((rows + 127) / 128), 128, 0, ctx->stream>>>(in, rows, in_cols, out);
   UDAL_CHECK_LAUNCH(ctx);

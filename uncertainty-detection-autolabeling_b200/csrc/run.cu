@@ -4,6 +4,17 @@
 extern "C" int udal_run(udal_ctx* ctx, const float* const* feats, int batch, const uint8_t* keep_masks,
                         uint64_t seed, const float* image_scales, const udal_detections* out) {
   UDAL_REQUIRE(ctx && feats && out, "NULL argument");
+  // Pipelining across calls: the tail of the previous run (top-k / NMS / assemble) may still be in flight
+  // on the post stream.  This run's heads start right away; its decode kernel writes scratch bank
+  // `run_bank`, whose previous user (two runs ago) is waited for first.
+  struct RunScope {
+    udal_ctx* c;
+    explicit RunScope(udal_ctx* x) : c(x) { c->in_run = true; }
+    ~RunScope() {
+      c->in_run = false;
+      c->scratch_bank = 0;
+    }
+  } scope(ctx);
   const udal_config& c = ctx->cfg;
   const int L = c.num_levels, T = c.mc_samples;
   const int ccls = c.anchors_per_loc * c.num_classes, cbox = udal_box_channels(ctx);
@@ -19,6 +30,20 @@ extern "C" int udal_run(udal_ctx* ctx, const float* const* feats, int batch, con
     box[l] = buf + ncls + (size_t)(c.box_mc ? T : 1) * batch * ctx->level_pix_off[l] * cbox;
   }
   UDAL_TRY(udal_heads_sample(ctx, feats, batch, keep_masks, seed, cls, box));
-  if (c.max_nms_inputs > 0) return udal_postprocess_per_class(ctx, cls, box, batch, image_scales, 0, out);
+  const int bank = ctx->run_bank;
+  if (ctx->post_pending[bank]) {
+    UDAL_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_post[bank], 0));
+    ctx->post_pending[bank] = false;
+  }
+  ctx->scratch_bank = bank;
+  ctx->run_bank = bank ^ 1;
+  if (c.max_nms_inputs > 0) {
+    // the per-class variant stays on one stream: join the other bank's tail as well
+    if (ctx->post_pending[bank ^ 1]) {
+      UDAL_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_post[bank ^ 1], 0));
+      ctx->post_pending[bank ^ 1] = false;
+    }
+    return udal_postprocess_per_class(ctx, cls, box, batch, image_scales, 0, out);
+  }
   return udal_postprocess_global(ctx, cls, box, batch, image_scales, out);
 }

@@ -48,8 +48,16 @@ struct udal_ctx {
   bool anchors_set = false;
   udal_head_weights_dev heads[2];
   int64_t launches = 0;
-  // named scratch slots, grown on demand
-  udal_scratch scratch[20];
+  // named scratch slots, grown on demand; the post-processing slots exist twice (banks) so that the
+  // NMS tail of one udal_run may still read them while the next run's decode kernel writes the other set
+  udal_scratch scratch[2 * 20];
+  int scratch_bank = 0;         // bank udal_scratch_get resolves banked slots to
+  // udal_run pipelining: top-k / NMS / assemble of run i on post_stream overlap the heads of run i+1
+  cudaStream_t post_stream = nullptr;
+  cudaEvent_t ev_pre[2] = {nullptr, nullptr}, ev_post[2] = {nullptr, nullptr};
+  bool post_pending[2] = {false, false};
+  int run_bank = 0;
+  bool in_run = false;
   std::vector<void*> user_allocs;
   bool profile_layers = false;
   std::vector<cudaEvent_t> layer_events;  // pairs (start, stop) in launch order
@@ -78,6 +86,9 @@ enum {
 void udal_set_error(const char* fmt, ...);
 int udal_cuda_fail(cudaError_t e, const char* what, const char* file, int line);
 int udal_scratch_get(udal_ctx* ctx, int slot, size_t bytes, void** out);
+// makes the context's stream wait for every udal_run tail still in flight on post_stream (no-op inside
+// udal_run).  Every entry point that enqueues work or copies on the context's stream calls it first.
+int udal_join(udal_ctx* ctx);
 
 #define UDAL_CUDA(call)                                                      \
   do {                                                                       \
