@@ -48,8 +48,21 @@ def algorithmic_work(eng, batch):
     dense = Tn * P * (2 * R * 2 * F * F + 2 * F * cc + 2 * F * cb)           # pointwise + predict 1x1
     depthwise = Tn * P * (2 * (R + 1) * 18 * F)                               # both heads
     k2_bytes = Tn * eng.N * (8 * 4 + C * 4) + eng.N * (3 * 16 + 4 + 4 + 2 * C * 4)
+    # per tower layer, as launched (one kernel per layer and head): activations in + out, sepconv FLOPs
+    act = P * F * 2  # one bf16 activation map of one (sample, image)
+    layers = []
+    for head, cout in (("class", cc), ("box", cb)):
+        for layer in range(R + 1):
+            predict = layer == R
+            n_in = 1 if layer <= 1 else Tn           # layer 0 / 1 read sample-invariant inputs
+            n_out = 1 if layer == 0 else Tn
+            b_in = n_in * (P * F * 4 if layer == 0 else act)
+            b_out = n_out * (P * cout * 4 if predict else act)
+            fl = n_out * P * (2 * F * (cout if predict else F) + 18 * F)
+            layers.append(dict(name="%s/%s" % (head, "predict" if predict else "layer%d" % layer),
+                               bytes=float(batch) * (b_in + b_out), flops=float(batch) * fl))
     return dict(heads_flops=float(batch) * (dense + depthwise), heads_dense_flops=float(batch) * dense,
-                decode_bytes=float(batch) * k2_bytes)
+                decode_bytes=float(batch) * k2_bytes, layers=layers)
 
 
 class ClockSampler(threading.Thread):
@@ -90,6 +103,16 @@ class ClockSampler(threading.Thread):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx,
                 "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture
+    (profiles/ncu_traffic.json: {kernel function name: bytes}); {} if absent."""
+    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        return json.load(open(path))
+    except (OSError, ValueError):
+        return {}
 
 
 def measured_peaks():
@@ -249,6 +272,9 @@ def run_gpu(args):
         eng.heads_sample(feats_dev, None, i, out=(cls_bufs, box_bufs))
     heads_ms = ctx.timer_stop() / reps
     heads_launches = (ctx.launch_count() - l0) // reps
+    layer_ms = [ctx.layer_times(lambda: eng.heads_sample(feats_dev, None, 40 + i, out=(cls_bufs, box_bufs)))
+                for i in range(3)]
+    layer_ms = [float(np.median(x)) for x in zip(*layer_ms)] if layer_ms and layer_ms[0] else []
     pre = eng.decode_moments(cls_bufs, box_bufs, batch)
     ctx.timer_start()
     for i in range(reps):
@@ -311,6 +337,24 @@ def run_gpu(args):
     value = world * batch * args.steps / (total_ms / 1e3)
     heads_tflops = work["heads_flops"] / (heads_ms / 1e3) / 1e12
     n_dom = max(1, heads_launches - 2)  # the tower layers (two small mask kernels excluded)
+    # per-kernel rooflines: every kernel of the step against the bound that applies to it
+    traffic = ncu_traffic()
+    kernels = []
+    kernel_names = {0: "sepconv_tc_kernel<64>", 1: "heads_l1_kernel", 2: "heads_ig_kernel<tower>"}
+    for i, ms in enumerate(layer_ms if args.heads_mode != "fp32" else []):
+        lay = work["layers"][i]
+        r_idx = i % (eng.R + 1)
+        kn = "heads_ig_kernel<predict>" if r_idx == eng.R else kernel_names.get(r_idx, "heads_ig_kernel<tower>")
+        gbs = lay["bytes"] / (ms / 1e3) / 1e9
+        tfl = lay["flops"] / (ms / 1e3) / 1e12
+        kernels.append({"kernel": kn, "what": lay["name"], "ms": ms, "bound": "hbm", "achieved_GBs": gbs,
+                        "frac_of_hbm": gbs / hbm_peak, "algorithmic_TFLOPs": tfl, "frac_of_bf16": tfl / tf_sustained})
+    dec_gbs = work["decode_bytes"] / (decode_ms / 1e3) / 1e9
+    kernels.append({"kernel": "decode_moments_kernel<%d,1>" % eng.T, "what": "decode + MC moments", "ms": decode_ms,
+                    "bound": "hbm", "achieved_GBs": dec_gbs, "frac_of_hbm": dec_gbs / hbm_peak})
+    kernels.append({"kernel": "topk_* + nms_v5_sorted_kernel", "what": "score pre-filter + global soft-NMS (one warp per image)",
+                    "ms": nms_ms, "bound": "latency", "us_per_image": 1e3 * nms_ms / batch})
+    dominant = max((k for k in kernels if k["bound"] == "hbm"), key=lambda k: k["ms"])
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
@@ -333,17 +377,18 @@ def run_gpu(args):
                 "blocking_ms_per_step": e2e_blocking_ms},
         "gpu_launches": int(launches),
         "roofline": {
-            "kernel": "sepconv_layer_kernel (head towers, %d launches/step)" % n_dom,
-            "bound": "tensor", "achieved": heads_tflops, "peak": tf_sustained, "unit": "TFLOP/s",
-            "frac": heads_tflops / tf_sustained, "traffic": None, "peak_source": how + " (sustained bf16)",
-            "note": "algorithmic heads FLOPs (SURVEY 8d, incl. depthwise) / CUDA-event time of the heads phase",
+            "kernel": dominant["kernel"], "what": dominant["what"], "bound": "hbm",
+            "achieved": dominant["achieved_GBs"], "peak": hbm_peak, "unit": "GB/s",
+            "frac": dominant["achieved_GBs"] / hbm_peak,
+            "traffic": traffic.get(dominant["kernel"].split("<")[0]),
+            "launch_ms": dominant["ms"], "peak_source": how + " (HBM copy)",
+            "note": "algorithmic bytes of one launch (SURVEY 8d: T*N*(32+4C) read + N*(56+8C) written per image, x batch) / "
+                    "CUDA-event time of that launch on the launching stream; traffic = ncu dram bytes per launch "
+                    "(profiles/, null if no capture for this kernel)",
         },
-        "kernels": {
-            "heads_ms": heads_ms, "decode_moments_ms": decode_ms, "nms_topk_ms": nms_ms, "post_total_ms": post_ms,
-            "decode_moments_GBs": work["decode_bytes"] / (decode_ms / 1e3) / 1e9,
-            "decode_moments_frac_of_hbm": work["decode_bytes"] / (decode_ms / 1e3) / 1e9 / hbm_peak,
-            "hbm_peak_GBs": hbm_peak,
-        },
+        "kernels": kernels,
+        "phases_ms": {"heads": heads_ms, "decode_moments": decode_ms, "nms_topk": nms_ms, "post_total": post_ms,
+                      "heads_TFLOPs_algorithmic": heads_tflops, "heads_frac_of_bf16_sustained": heads_tflops / tf_sustained},
     }
     if not args.no_cpu_baseline:
         import torch

@@ -136,6 +136,19 @@ class Context:
         _lib.check(self.lib.udal_launch_count(self.handle, ctypes.byref(n)))
         return n.value
 
+    def layer_times(self, fn):
+        """CUDA-event time of every head-tower layer launched by ``fn()`` (udal_profile_layers):
+        list of ms, class tower layers 0..R then box tower layers 0..R."""
+        _lib.check(self.lib.udal_profile_layers(self.handle, 1))
+        try:
+            fn()
+            ms = (ctypes.c_float * 64)()
+            n = ctypes.c_int(0)
+            _lib.check(self.lib.udal_get_layer_times(self.handle, ms, 64, ctypes.byref(n)))
+        finally:
+            _lib.check(self.lib.udal_profile_layers(self.handle, 0))
+        return [float(ms[i]) for i in range(n.value)]
+
     def scratch_bytes(self):
         n = ctypes.c_size_t(0)
         _lib.check(self.lib.udal_scratch_bytes(self.handle, ctypes.byref(n)))
