@@ -1,0 +1,32 @@
+"""Development helper: per-layer CUDA-event times of udal_run at the bench shape (fused and unfused)."""
+import ctypes
+import sys
+
+import numpy as np
+
+sys.path.insert(0, ".")
+import udal_b200 as u
+from oracle import heads_ref
+
+batch = 64
+p = u.hparams_config.get_detection_config(
+    "efficientdet-d0", image_size=(384, 1280), num_classes=8, enable_softmax=True, loss_attenuation=True,
+    mc_dropout=True, mc_classheadrate=0.05, mc_boxheadrate=0.05, mc_dropoutsamp=10, heads_mode="bf16")
+eng = u.engine.get_engine(p)
+L = len(eng.level_hw)
+eng.set_head_weights(heads_ref.init_head_weights(eng.F, eng.R, L, eng.A, 8, True, seed=2024))
+rng = np.random.default_rng(1)
+feats = [eng.ctx.to_device(rng.standard_normal((batch, h, w, eng.F), dtype=np.float32)) for h, w in eng.level_hw]
+scales = eng.ctx.to_device(np.ones(batch, np.float32))
+fused = ctypes.c_int.in_dll(eng.lib, "udal_run_fused")
+for f in (0, 1):
+    fused.value = f
+    for i in range(3):
+        eng.run(feats, scales, None, seed=i)
+    eng.ctx.sync()
+    t = eng.ctx.layer_times(lambda: eng.run(feats, scales, None, seed=9))
+    eng.ctx.timer_start()
+    for i in range(5):
+        eng.run(feats, scales, None, seed=20 + i)
+    ms = eng.ctx.timer_stop() / 5
+    print("fused=%d  layer ms %s  sum %.3f  step %.3f ms" % (f, [round(x, 3) for x in t], sum(t), ms), flush=True)

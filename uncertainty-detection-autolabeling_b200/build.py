@@ -14,7 +14,7 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libudal.so")
 SOURCES = ["api.cu", "decode_moments.cu", "topk.cu", "nms.cu", "post.cu", "heads_fp32.cu",
-           "heads_tc.cu", "heads_ig.cu", "heads_l1.cu", "run.cu", "nms_np.cu"]
+           "heads_tc.cu", "heads_ig.cu", "heads_l1.cu", "heads_fused.cu", "run.cu", "nms_np.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-I", os.path.join(ROOT, "include"),
@@ -57,7 +57,9 @@ def build(force=False, verbose=False):
         failed |= p.returncode != 0
     if failed:
         raise RuntimeError("nvcc failed")
-    subprocess.check_call([nvcc, "-shared", "-o", LIB] + objs + ["-lcudart_static", "-ldl", "-lrt", "-lpthread"])
+    # --no-undefined: a symbol declared with the wrong linkage must fail here, not when ctypes loads the library
+    subprocess.check_call([nvcc, "-shared", "-o", LIB] + objs +
+                          ["-lcudart_static", "-ldl", "-lrt", "-lpthread", "-Xlinker", "--no-undefined"])
     return LIB
 
 

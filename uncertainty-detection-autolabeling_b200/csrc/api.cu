@@ -26,6 +26,9 @@ static bool scratch_banked(int slot) {
 
 int udal_join(udal_ctx* ctx) {
   if (ctx->in_run) return UDAL_OK;
+  // the current device is per host thread: a caller that drives several contexts from a thread pool
+  // (scheduler.py, PipelinedSampler) must not have to remember cudaSetDevice
+  UDAL_CUDA(cudaSetDevice(ctx->cfg.device));
   for (int b = 0; b < 2; ++b)
     if (ctx->post_pending[b]) {
       UDAL_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_post[b], 0));

@@ -198,7 +198,7 @@ int upload(udal_ctx* ctx, float** dst, const float* src, size_t n) {
 
 int udal_heads_tc_prepare(udal_ctx* ctx, int head);  // heads_tc.cu
 int udal_heads_tc_sample(udal_ctx* ctx, const float* const* feats, int batch, const float* scale, float* const* cls_out,
-                         float* const* box_out);
+                         float* const* box_out, const udal_prenms_out* fused_pre);
 
 extern "C" int udal_set_head_weights(udal_ctx* ctx, int head, const float* dw, const float* pw, const float* bias,
                                      const float* bn_gamma, const float* bn_beta, const float* bn_mean,
@@ -325,15 +325,15 @@ __global__ void scale_transpose_kernel(const float* __restrict__ src, float* __r
   dst[((((size_t)head * L + l) * R + rr) * (size_t)(T * B) + (size_t)t * B + b) * F + f] = src[i];
 }
 
-extern "C" int udal_heads_sample(udal_ctx* ctx, const float* const* feats, int batch, const uint8_t* keep_masks,
-                                 uint64_t seed, float* const* cls_out, float* const* box_out) {
-  UDAL_REQUIRE(ctx && feats && cls_out && box_out, "NULL argument");
-  UDAL_TRY(udal_join(ctx));
+// fused_pre != null: the predict layers are fused with K2 and write the per-anchor tensors of *fused_pre
+// instead of the [T,...] head outputs (udal_run, serving configuration; heads_fused.cu)
+static int heads_sample_impl(udal_ctx* ctx, const float* const* feats, int batch, const uint8_t* keep_masks, uint64_t seed,
+                             float* const* cls_out, float* const* box_out, const udal_prenms_out* fused_pre) {
   UDAL_REQUIRE(ctx->heads[0].set && ctx->heads[1].set, "head weights not set (udal_set_head_weights)");
   UDAL_REQUIRE(batch > 0, "batch must be positive");
   const udal_config& c = ctx->cfg;
   for (int l = 0; l < c.num_levels; ++l)
-    UDAL_REQUIRE(feats[l] && cls_out[l] && box_out[l], "level %d pointer is NULL", l);
+    UDAL_REQUIRE(feats[l] && (fused_pre || (cls_out[l] && box_out[l])), "level %d pointer is NULL", l);
   const int T = c.mc_samples, L = c.num_levels, R = c.repeats, F = c.num_filters;
   const int64_t total = (int64_t)T * 2 * L * R * batch * F;
   float* scale_raw;
@@ -347,8 +347,21 @@ extern "C" int udal_heads_sample(udal_ctx* ctx, const float* const* feats, int b
     scale_transpose_kernel<<<(int)((total + 255) / 256), 256, 0, ctx->stream>>>(scale_raw, scale, T, L, R, batch, F);
     UDAL_CHECK_LAUNCH(ctx);
   }
-  if (c.heads_mode == UDAL_HEADS_BF16_TC) return udal_heads_tc_sample(ctx, feats, batch, scale, cls_out, box_out);
+  if (c.heads_mode == UDAL_HEADS_BF16_TC) return udal_heads_tc_sample(ctx, feats, batch, scale, cls_out, box_out, fused_pre);
+  UDAL_REQUIRE(!fused_pre, "the fused predict + decode kernels need heads_mode bf16");
   UDAL_TRY(run_tower_fp32(ctx, UDAL_HEAD_CLASS, feats, batch, scale, cls_out));
   UDAL_TRY(run_tower_fp32(ctx, UDAL_HEAD_BOX, feats, batch, scale, box_out));
   return UDAL_OK;
+}
+
+extern "C" int udal_heads_sample(udal_ctx* ctx, const float* const* feats, int batch, const uint8_t* keep_masks,
+                                 uint64_t seed, float* const* cls_out, float* const* box_out) {
+  UDAL_REQUIRE(ctx && feats && cls_out && box_out, "NULL argument");
+  UDAL_TRY(udal_join(ctx));
+  return heads_sample_impl(ctx, feats, batch, keep_masks, seed, cls_out, box_out, nullptr);
+}
+
+int udal_heads_sample_fused(udal_ctx* ctx, const float* const* feats, int batch, const uint8_t* keep_masks, uint64_t seed,
+                            const udal_prenms_out* pre) {
+  return heads_sample_impl(ctx, feats, batch, keep_masks, seed, nullptr, nullptr, pre);
 }

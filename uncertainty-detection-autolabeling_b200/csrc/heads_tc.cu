@@ -454,6 +454,8 @@ int udal_heads_ig_layer(udal_ctx* ctx, const void* const* in, int NB, const void
 int udal_heads_l1_layer(udal_ctx* ctx, const void* const* in, int NB, int T, const float* dw, const float* const* wf,
                         const float* const* fb, const float* const* in_scale, const float* const* out_scale,
                         const float* ones, float inv_keep, void* const* out);
+int udal_heads_fused_predict(udal_ctx* ctx, int head, const void* const* in, int NB, int T, const void* wimg, int rows,
+                             const float* bias, const udal_prenms_out* pre);
 int udal_heads_tc_use_ig = 1;  // 0: every layer through the per-tile kernel (debug / comparison)
 
 int udal_heads_tc_prepare(udal_ctx* ctx, int head) {
@@ -514,7 +516,7 @@ int udal_heads_tc_prepare(udal_ctx* ctx, int head) {
 }
 
 static int run_tower_tc(udal_ctx* ctx, int head, const float* const* feats, int batch, const float* scale_all,
-                        float* const* outs) {
+                        float* const* outs, const udal_prenms_out* fused_pre) {
   const udal_config& c = ctx->cfg;
   const udal_head_weights_dev& h = ctx->heads[head];
   const int R = c.repeats, L = c.num_levels, T = c.mc_samples, B = batch;
@@ -570,7 +572,7 @@ static int run_tower_tc(udal_ctx* ctx, int head, const float* const* feats, int 
       if (layer == 0) p.in[l] = feats[l];
       else if (layer == 1) p.in[l] = a0 + (size_t)B * lvl;
       else p.in[l] = pp + (size_t)((layer - 1) & 1) * NBt * P * KF + (size_t)NBt * lvl;
-      if (predict) p.out[l] = outs[l];
+      if (predict) p.out[l] = outs ? outs[l] : nullptr;
       else if (layer == 0) p.out[l] = a0 + (size_t)B * lvl;
       else p.out[l] = pp + (size_t)(layer & 1) * NBt * P * KF + (size_t)NBt * lvl;
       // SpatialDropout2D bookkeeping: layer 0 stores its (sample invariant) output WITHOUT dropout and
@@ -595,6 +597,14 @@ static int run_tower_tc(udal_ctx* ctx, int head, const float* const* feats, int 
       UDAL_TRY(udal_heads_l1_layer(ctx, p.in, B, mc ? T : 1, p.dw, p.wf, p.fb, mc ? p.scale : nullptr,
                                    mc ? p.out_scale : nullptr, ones,
                                    head == UDAL_HEAD_CLASS ? c.inv_keep_class : c.inv_keep_box, p.out));
+      mark();
+      continue;
+    }
+    if (predict && fused_pre) {
+      // predict layer + MC moments / decode in one kernel: the [T,...] head outputs never reach HBM
+      UDAL_REQUIRE(udal_heads_tc_use_ig && mc && R >= 2, "fused predict kernels: configuration not covered");
+      const __nv_bfloat16* img = reinterpret_cast<const __nv_bfloat16*>(h.ig_w) + (size_t)(R - 2) * 9 * KF * KF;
+      UDAL_TRY(udal_heads_fused_predict(ctx, head, p.in, B, T, img, h.ig_rows, p.fb[0], fused_pre));
       mark();
       continue;
     }
@@ -624,11 +634,12 @@ static int run_tower_tc(udal_ctx* ctx, int head, const float* const* feats, int 
 }
 
 int udal_heads_tc_sample(udal_ctx* ctx, const float* const* feats, int batch, const float* scale, float* const* cls_out,
-                         float* const* box_out) {
+                         float* const* box_out, const udal_prenms_out* fused_pre) {
   for (int l = 0; l < ctx->cfg.num_levels; ++l)
-    UDAL_REQUIRE(((uintptr_t)feats[l] & 15) == 0 && ((uintptr_t)cls_out[l] & 15) == 0 && ((uintptr_t)box_out[l] & 15) == 0,
+    UDAL_REQUIRE(((uintptr_t)feats[l] & 15) == 0 &&
+                     (fused_pre || (((uintptr_t)cls_out[l] & 15) == 0 && ((uintptr_t)box_out[l] & 15) == 0)),
                  "level %d: feature / output pointers must be 16-byte aligned", l);
-  UDAL_TRY(run_tower_tc(ctx, UDAL_HEAD_CLASS, feats, batch, scale, cls_out));
-  UDAL_TRY(run_tower_tc(ctx, UDAL_HEAD_BOX, feats, batch, scale, box_out));
+  UDAL_TRY(run_tower_tc(ctx, UDAL_HEAD_CLASS, feats, batch, scale, fused_pre ? nullptr : cls_out, fused_pre));
+  UDAL_TRY(run_tower_tc(ctx, UDAL_HEAD_BOX, feats, batch, scale, fused_pre ? nullptr : box_out, fused_pre));
   return UDAL_OK;
 }

@@ -141,6 +141,23 @@ EncodeTiledFn get_encode() {
   return fn;
 }
 
+// 4-D tensor map with explicit byte strides of dimensions 1..3 and a {b0, b1, b2, 1} box
+int encode_strided(EncodeTiledFn encode, CUtensorMap* map, CUtensorMapDataType dt, const void* base, const cuuint64_t (&gdim)[4],
+                   const cuuint64_t (&gstr)[3], int b0, int b1, int b2, bool swizzle128) {
+  const cuuint32_t box[4] = {(cuuint32_t)b0, (cuuint32_t)b1, (cuuint32_t)b2, 1u};
+  const cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
+  const CUresult r = encode(map, dt, 4, const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                            swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    udal_set_error("cuTensorMapEncodeTiled failed (%d) for dims {%llu,%llu,%llu,%llu} box {%d,%d,%d}", (int)r,
+                   (unsigned long long)gdim[0], (unsigned long long)gdim[1], (unsigned long long)gdim[2],
+                   (unsigned long long)gdim[3], b0, b1, b2);
+    return UDAL_ERR_INVALID;
+  }
+  return UDAL_OK;
+}
+
 // [NB,H,W,ch] tensor map with a {c_box, x_box, y_box, 1} box
 int encode_nhwc(EncodeTiledFn encode, CUtensorMap* map, CUtensorMapDataType dt, int esize, const void* base, int NB, int H,
                 int W, int ch, int c_box, int x_box, int y_box, bool swizzle128) {

@@ -260,18 +260,21 @@ int udal_run_overlap = 1;  // 0: udal_run keeps its whole tail on the context's 
 
 extern "C" {
 
-int udal_postprocess_global(udal_ctx* ctx, const float* const* cls, const float* const* box, int batch,
-                            const float* image_scales, const udal_detections* out) {
-  UDAL_REQUIRE(ctx && cls && box && out, "NULL argument");
-  UDAL_TRY(udal_join(ctx));
-  UDAL_REQUIRE(out->boxes && out->scores && out->classes && out->valid, "NULL output");
+}  // extern "C"
+
+// scratch of the global variant: per-anchor tensors written by K2 (or the fused predict kernels) and the
+// NMS selection; resolved in the context's current scratch bank
+struct GlobalScratch {
+  udal_prenms_out pre;
+  int32_t* sel_idx;
+  float* sel_scores;
+  int32_t* valid;
+};
+
+static int global_scratch(udal_ctx* ctx, int batch, GlobalScratch* g) {
   const udal_config& c = ctx->cfg;
-  UDAL_REQUIRE(c.max_nms_inputs == 0,
-               "postprocess_global with max_nms_inputs > 0 is not a functional combination in the reference "
-               "(rank mismatch at postprocess.py:615-616); use postprocess_per_class");
   const int64_t N = ctx->num_anchors;
-  const int C = c.num_classes;
-  const int mo = c.max_output_size;
+  const int C = c.num_classes, mo = c.max_output_size;
   const size_t bn = (size_t)batch * N;
   float* logit_buf;
   UDAL_TRY(udal_scratch_get(ctx, SCR_POST_A, bn * C * 4 * 2, (void**)&logit_buf));
@@ -279,17 +282,27 @@ int udal_postprocess_global(udal_ctx* ctx, const float* const* cls, const float*
   UDAL_TRY(udal_scratch_get(ctx, SCR_POST_B, bn * (16 * 3 + 4 + 4), (void**)&anc_buf));
   char* sel_buf;
   UDAL_TRY(udal_scratch_get(ctx, SCR_POST_D, (size_t)batch * (mo * 8 + 4), (void**)&sel_buf));
-  udal_prenms_out pre;
-  pre.mean_logits = logit_buf;
-  pre.std_logits = logit_buf + bn * C;
-  pre.boxes = (float*)anc_buf;
-  pre.albox = (float*)(anc_buf + bn * 16);
-  pre.mcbox = (float*)(anc_buf + bn * 32);
-  pre.scores = (float*)(anc_buf + bn * 48);
-  pre.classes = (int32_t*)(anc_buf + bn * 52);
-  UDAL_TRY(udal_launch_decode_moments(ctx, cls, box, batch, &pre));
-  // inside a pipelined udal_run the rest (top-k pre-filter, NMS, assemble: a few warps per image) moves to
-  // the post stream, where it overlaps the head sampler of the next run
+  g->pre.mean_logits = logit_buf;
+  g->pre.std_logits = logit_buf + bn * C;
+  g->pre.boxes = (float*)anc_buf;
+  g->pre.albox = (float*)(anc_buf + bn * 16);
+  g->pre.mcbox = (float*)(anc_buf + bn * 32);
+  g->pre.scores = (float*)(anc_buf + bn * 48);
+  g->pre.classes = (int32_t*)(anc_buf + bn * 52);
+  g->sel_idx = (int32_t*)sel_buf;
+  g->sel_scores = (float*)(sel_buf + (size_t)batch * mo * 4);
+  g->valid = (int32_t*)(sel_buf + (size_t)batch * mo * 8);
+  return UDAL_OK;
+}
+
+// top-k pre-filter + NMS + assemble from the per-anchor tensors.  Inside a pipelined udal_run this tail (a
+// few warps per image) moves to the post stream, where it overlaps the head sampler of the next run.
+static int global_tail(udal_ctx* ctx, const GlobalScratch& g, int batch, const float* image_scales,
+                       const udal_detections* out) {
+  const udal_config& c = ctx->cfg;
+  const int64_t N = ctx->num_anchors;
+  const int C = c.num_classes, mo = c.max_output_size;
+  const udal_prenms_out& pre = g.pre;
   const bool tail_on_post = ctx->in_run && udal_run_overlap && ctx->post_stream != nullptr;
   cudaStream_t main_stream = ctx->stream;
   const int bank = ctx->scratch_bank;
@@ -303,10 +316,7 @@ int udal_postprocess_global(udal_ctx* ctx, const float* const* cls, const float*
     cudaStream_t s;
     ~Restore() { c->stream = s; }
   } restore{ctx, main_stream};
-  int32_t* sel_idx = (int32_t*)sel_buf;
-  float* sel_scores = (float*)(sel_buf + (size_t)batch * mo * 4);
-  int32_t* valid = (int32_t*)(sel_buf + (size_t)batch * mo * 8);
-  UDAL_TRY(udal_launch_nms_v5(ctx, pre.boxes, pre.scores, batch, (int)N, sel_idx, sel_scores, valid));
+  UDAL_TRY(udal_launch_nms_v5(ctx, pre.boxes, pre.scores, batch, (int)N, g.sel_idx, g.sel_scores, g.valid));
   AssembleParams a;
   a.batch = batch;
   a.max_out = mo;
@@ -317,9 +327,9 @@ int udal_postprocess_global(udal_ctx* ctx, const float* const* cls, const float*
   a.has_mcclass = c.cls_mc ? 1 : 0;
   a.img_h = (float)c.image_h;
   a.img_w = (float)c.image_w;
-  a.sel_idx = sel_idx;
-  a.sel_scores = sel_scores;
-  a.valid = valid;
+  a.sel_idx = g.sel_idx;
+  a.sel_scores = g.sel_scores;
+  a.valid = g.valid;
   a.boxes = pre.boxes;
   a.albox = pre.albox;
   a.mcbox = pre.mcbox;
@@ -335,6 +345,36 @@ int udal_postprocess_global(udal_ctx* ctx, const float* const* cls, const float*
     ctx->post_pending[bank] = true;
   }
   return UDAL_OK;
+}
+
+int udal_heads_sample_fused(udal_ctx* ctx, const float* const* feats, int batch, const uint8_t* keep_masks, uint64_t seed,
+                            const udal_prenms_out* pre);
+
+// udal_run, serving configuration: BiFPN features -> detections with the predict layers fused with K2
+int udal_run_global_fused(udal_ctx* ctx, const float* const* feats, int batch, const uint8_t* keep_masks, uint64_t seed,
+                          const float* image_scales, const udal_detections* out) {
+  UDAL_REQUIRE(out->boxes && out->scores && out->classes && out->valid, "NULL output");
+  GlobalScratch g;
+  UDAL_TRY(global_scratch(ctx, batch, &g));
+  UDAL_TRY(udal_heads_sample_fused(ctx, feats, batch, keep_masks, seed, &g.pre));
+  return global_tail(ctx, g, batch, image_scales, out);
+}
+
+extern "C" {
+
+int udal_postprocess_global(udal_ctx* ctx, const float* const* cls, const float* const* box, int batch,
+                            const float* image_scales, const udal_detections* out) {
+  UDAL_REQUIRE(ctx && cls && box && out, "NULL argument");
+  UDAL_TRY(udal_join(ctx));
+  UDAL_REQUIRE(out->boxes && out->scores && out->classes && out->valid, "NULL output");
+  const udal_config& c = ctx->cfg;
+  UDAL_REQUIRE(c.max_nms_inputs == 0,
+               "postprocess_global with max_nms_inputs > 0 is not a functional combination in the reference "
+               "(rank mismatch at postprocess.py:615-616); use postprocess_per_class");
+  GlobalScratch g;
+  UDAL_TRY(global_scratch(ctx, batch, &g));
+  UDAL_TRY(udal_launch_decode_moments(ctx, cls, box, batch, &g.pre));
+  return global_tail(ctx, g, batch, image_scales, out);
 }
 
 int udal_prenms_topk(udal_ctx* ctx, const float* const* cls, const float* const* box, int batch,

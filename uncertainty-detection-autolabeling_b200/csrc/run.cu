@@ -1,9 +1,14 @@
 // udal_run: BiFPN features -> detections in one call (heads + post-processing).
 #include "udal_common.cuh"
 
+int udal_heads_fused_ok(const udal_ctx* ctx);
+int udal_run_global_fused(udal_ctx* ctx, const float* const* feats, int batch, const uint8_t* keep_masks, uint64_t seed,
+                          const float* image_scales, const udal_detections* out);
+
 extern "C" int udal_run(udal_ctx* ctx, const float* const* feats, int batch, const uint8_t* keep_masks,
                         uint64_t seed, const float* image_scales, const udal_detections* out) {
   UDAL_REQUIRE(ctx && feats && out, "NULL argument");
+  UDAL_CUDA(cudaSetDevice(ctx->cfg.device));
   // Pipelining across calls: the tail of the previous run (top-k / NMS / assemble) may still be in flight
   // on the post stream.  This run's heads start right away; its decode kernel writes scratch bank
   // `run_bank`, whose previous user (two runs ago) is waited for first.
@@ -16,6 +21,18 @@ extern "C" int udal_run(udal_ctx* ctx, const float* const* feats, int batch, con
     }
   } scope(ctx);
   const udal_config& c = ctx->cfg;
+  if (udal_heads_fused_ok(ctx)) {
+    // serving configuration: the predict layers write the per-anchor statistics straight into this run's
+    // scratch bank, so its previous user (the tail of two runs ago) is waited for before the heads start
+    const int bank = ctx->run_bank;
+    if (ctx->post_pending[bank]) {
+      UDAL_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_post[bank], 0));
+      ctx->post_pending[bank] = false;
+    }
+    ctx->scratch_bank = bank;
+    ctx->run_bank = bank ^ 1;
+    return udal_run_global_fused(ctx, feats, batch, keep_masks, seed, image_scales, out);
+  }
   const int L = c.num_levels, T = c.mc_samples;
   const int ccls = c.anchors_per_loc * c.num_classes, cbox = udal_box_channels(ctx);
   const size_t P = (size_t)ctx->num_pixels;
