@@ -115,6 +115,14 @@ def ncu_traffic():
         return {}
 
 
+def lib_int(eng, name):
+    import ctypes
+    try:
+        return ctypes.c_int.in_dll(eng.lib, name).value
+    except ValueError:
+        return 0
+
+
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -272,9 +280,17 @@ def run_gpu(args):
         eng.heads_sample(feats_dev, None, i, out=(cls_bufs, box_bufs))
     heads_ms = ctx.timer_stop() / reps
     heads_launches = (ctx.launch_count() - l0) // reps
-    layer_ms = [ctx.layer_times(lambda: eng.heads_sample(feats_dev, None, 40 + i, out=(cls_bufs, box_bufs)))
-                for i in range(3)]
+    # per-layer times of the kernels udal_run actually launches (serving configuration: predict layers fused
+    # with K2), and of the stand-alone head sampler (predict layers writing the [T,...] outputs)
+    def run_layers(i):
+        ctx.sync()  # the previous run's NMS tail (post stream) would otherwise overlap the first layers
+        return ctx.layer_times(lambda: eng.run(feats_dev, scales_dev, None, seed=40 + i))
+
+    layer_ms = [run_layers(i) for i in range(3)]
     layer_ms = [float(np.median(x)) for x in zip(*layer_ms)] if layer_ms and layer_ms[0] else []
+    layer_ms_unfused = [ctx.layer_times(lambda: eng.heads_sample(feats_dev, None, 40 + i, out=(cls_bufs, box_bufs)))
+                        for i in range(3)]
+    layer_ms_unfused = [float(np.median(x)) for x in zip(*layer_ms_unfused)] if layer_ms_unfused and layer_ms_unfused[0] else []
     pre = eng.decode_moments(cls_bufs, box_bufs, batch)
     ctx.timer_start()
     for i in range(reps):
@@ -341,27 +357,54 @@ def run_gpu(args):
     traffic = ncu_traffic()
     kernels = []
     kernel_names = {0: "sepconv_tc_kernel<64>", 1: "heads_l1_kernel", 2: "heads_ig_kernel<tower>"}
+    fused_run = args.heads_mode != "fp32" and lib_int(eng, "udal_run_fused") and eng.C == 8 and eng.A == 9
+    n_anchor = float(batch) * eng.N
     for i, ms in enumerate(layer_ms if args.heads_mode != "fp32" else []):
-        lay = work["layers"][i]
+        lay = dict(work["layers"][i])
         r_idx = i % (eng.R + 1)
         kn = "heads_ig_kernel<predict>" if r_idx == eng.R else kernel_names.get(r_idx, "heads_ig_kernel<tower>")
+        if r_idx == eng.R and fused_run:
+            # predict layer fused with K2: reads the T activation maps, writes the per-anchor tensors only
+            is_cls = i < eng.R + 1
+            kn = "heads_fused_kernel<%s>" % ("class" if is_cls else "box")
+            out_b = n_anchor * ((2 * eng.C * 4 + 8) if is_cls else 48)
+            lay["bytes"] = float(batch) * eng.T * eng.P * eng.F * 2 + out_b
+            lay["name"] += " + %s" % ("logit moments, argmax, sigmoid" if is_cls else "decode, box moments")
         gbs = lay["bytes"] / (ms / 1e3) / 1e9
         tfl = lay["flops"] / (ms / 1e3) / 1e12
         kernels.append({"kernel": kn, "what": lay["name"], "ms": ms, "bound": "hbm", "achieved_GBs": gbs,
                         "frac_of_hbm": gbs / hbm_peak, "algorithmic_TFLOPs": tfl, "frac_of_bf16": tfl / tf_sustained})
-    dec_gbs = work["decode_bytes"] / (decode_ms / 1e3) / 1e9
-    kernels.append({"kernel": "decode_moments_kernel<%d,1>" % eng.T, "what": "decode + MC moments", "ms": decode_ms,
-                    "bound": "hbm", "achieved_GBs": dec_gbs, "frac_of_hbm": dec_gbs / hbm_peak})
     kernels.append({"kernel": "topk_* + nms_v5_sorted_kernel", "what": "score pre-filter + global soft-NMS (one warp per image)",
                     "ms": nms_ms, "bound": "latency", "us_per_image": 1e3 * nms_ms / batch})
-    dominant = max((k for k in kernels if k["bound"] == "hbm"), key=lambda k: k["ms"])
+    # kernels of the stand-alone entry points (not launched by udal_run in the serving configuration)
+    standalone = []
+    for i, ms in enumerate(layer_ms_unfused if fused_run else []):
+        if i % (eng.R + 1) == eng.R:
+            lay = work["layers"][i]
+            gbs = lay["bytes"] / (ms / 1e3) / 1e9
+            standalone.append({"kernel": "heads_ig_kernel<predict>", "what": lay["name"] + " (HeadSampler.__call__)", "ms": ms,
+                               "bound": "hbm", "achieved_GBs": gbs, "frac_of_hbm": gbs / hbm_peak})
+    dec_gbs = work["decode_bytes"] / (decode_ms / 1e3) / 1e9
+    dec = {"kernel": "decode_moments_kernel<%d,1>" % eng.T, "what": "decode + MC moments (postprocess.* entry points)",
+           "ms": decode_ms, "bound": "hbm", "achieved_GBs": dec_gbs, "frac_of_hbm": dec_gbs / hbm_peak}
+    (standalone if fused_run else kernels).append(dec)
+    # dominant kernel = the kernel function with the largest total time inside one step
+    totals = {}
+    for k in kernels:
+        if k["bound"] == "hbm":
+            totals.setdefault(k["kernel"], []).append(k)
+    dom_name = max(totals, key=lambda n: sum(k["ms"] for k in totals[n]))
+    dom_launches = totals[dom_name]
+    dominant = {"kernel": dom_name, "what": " | ".join(k["what"] for k in dom_launches),
+                "ms": float(np.mean([k["ms"] for k in dom_launches])), "launches_per_step": len(dom_launches),
+                "achieved_GBs": float(np.mean([k["achieved_GBs"] for k in dom_launches]))}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32" if args.heads_mode == "fp32" else "bf16", "data": "synthetic",
         "config": {
             "workload": "EfficientDet-D0 1280x384 (BASELINE configs[1]): BiFPN feats -> T=10 MC-dropout heads -> "
-                        "decode+moments -> global gaussian soft-NMS",
+                        "decode+moments (fused into the predict layers) -> global gaussian soft-NMS",
             "batch_per_gpu": batch, "num_classes": NUM_CLASSES, "T": T, "anchors": eng.N,
             "heads_mode": args.heads_mode, "parallelism": "image-sharded x%d, no collective" % world,
             "l2": "inputs larger than L2 (features %.0f MB + GBs of head activations per step)" % (h2d / 1e6),
@@ -380,13 +423,16 @@ def run_gpu(args):
             "kernel": dominant["kernel"], "what": dominant["what"], "bound": "hbm",
             "achieved": dominant["achieved_GBs"], "peak": hbm_peak, "unit": "GB/s",
             "frac": dominant["achieved_GBs"] / hbm_peak,
-            "traffic": traffic.get(dominant["kernel"].split("<")[0]),
-            "launch_ms": dominant["ms"], "peak_source": how + " (HBM copy)",
-            "note": "algorithmic bytes of one launch (SURVEY 8d: T*N*(32+4C) read + N*(56+8C) written per image, x batch) / "
-                    "CUDA-event time of that launch on the launching stream; traffic = ncu dram bytes per launch "
-                    "(profiles/, null if no capture for this kernel)",
+            "traffic": traffic.get(dominant["kernel"], traffic.get(dominant["kernel"].split("<")[0])),
+            "launch_ms": dominant["ms"], "launches_per_step": dominant["launches_per_step"],
+            "peak_source": how + " (HBM copy)",
+            "note": "dominant kernel = largest total time per step; achieved = algorithmic bytes of one launch (the "
+                    "layer's activations in + out, SURVEY 8d accounting) / CUDA-event time of that launch on the launching "
+                    "stream, mean over its launches of the step; traffic = ncu dram bytes per launch (profiles/, null if "
+                    "no capture for this kernel)",
         },
         "kernels": kernels,
+        "standalone_kernels": standalone,
         "phases_ms": {"heads": heads_ms, "decode_moments": decode_ms, "nms_topk": nms_ms, "post_total": post_ms,
                       "heads_TFLOPs_algorithmic": heads_tflops, "heads_frac_of_bf16_sustained": heads_tflops / tf_sustained},
     }
