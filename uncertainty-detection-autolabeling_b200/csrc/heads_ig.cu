@@ -300,16 +300,26 @@ __global__ void __launch_bounds__(kIgThreads, 1) heads_ig_kernel(const __grid_co
           }
         }
       } else {
-        // ---- predictions whose channel count breaks TMA's stride rule: per-thread row stores ----
-        const int H = p.H[w.l], W = p.W[w.l];
-        const int oy = w.ty0 + (m >> 3), ox = w.tx0 + (m & 7);
-        if (oy < H && ox < W) {
-          float* dst = reinterpret_cast<float*>(p.out[w.l]) + (((size_t)nb * H + oy) * W + ox) * p.Cout;
+        // ---- predictions whose channel count breaks TMA's 16-byte stride rule (C = 7: 63 channels): dense
+        //      staging tile [128 px][Cout], then every tile row - one contiguous run of 8 px x Cout floats
+        //      in global memory - is copied out with coalesced 4-byte stores ----
+        const int H = p.H[w.l], W = p.W[w.l], Cout = p.Cout;
+        float* stg = reinterpret_cast<float*>(ob);
+        ig_group_sync(g);  // the previous tile's copy loop of this group is done with the staging tile
 #pragma unroll
-          for (int j = 0; j < NPAD / 8; ++j)
+        for (int j = 0; j < NPAD / 8; ++j)
 #pragma unroll
-            for (int i = 0; i < 8; ++i)
-              if (j * 8 + i < p.Cout) dst[j * 8 + i] = fmaf(__uint_as_float(r[j][i]), ep_s[j * 8 + i], ep_b[j * 8 + i]);
+          for (int i = 0; i < 8; ++i)
+            if (j * 8 + i < Cout) stg[m * Cout + j * 8 + i] = fmaf(__uint_as_float(r[j][i]), ep_s[j * 8 + i], ep_b[j * 8 + i]);
+        ig_group_sync(g);
+        const int gt = threadIdx.x - 64 - g * 128;           // thread of the group
+        const int run = min(IG_TW, W - w.tx0) * Cout;        // floats per tile row inside the image
+        const int rows = min(IG_TH, H - w.ty0);
+        float* dst0 = reinterpret_cast<float*>(p.out[w.l]) + (((size_t)nb * H + w.ty0) * W + w.tx0) * Cout;
+        for (int row = 0; row < rows; ++row) {
+          const float* src = stg + row * IG_TW * Cout;
+          float* dst = dst0 + (size_t)row * W * Cout;
+          for (int e = gt; e < run; e += 128) dst[e] = src[e];
         }
       }
       if (staged) {
