@@ -226,6 +226,41 @@ int udal_format_detections(udal_ctx* ctx, const float* boxes, int box_stride, co
  * [id,x,y,w,h,score,class]; in [rows,in_cols], out [rows,7]. */
 int udal_transform_detections(udal_ctx* ctx, const float* in, int64_t rows, int in_cols, float* out);
 
+/* ---- calibrated uncertainties + auto-label threshold pass ------------------- */
+enum {
+  UDAL_CALIB_NONE = 0,
+  UDAL_CALIB_TS_ALL = 1,           /* utils_box.py:424-426  uncert / temps[0] */
+  UDAL_CALIB_TS_PERCOO = 2,        /* :441-452              uncert[:, j] / temps[j] */
+  UDAL_CALIB_ISO_ALL = 3,          /* :420-422              table 0 */
+  UDAL_CALIB_ISO_PERCOO = 4,       /* :428-439              table j */
+  UDAL_CALIB_ISO_PERCLSCOO = 5,    /* :454-466              table (class - 1) * 4 + j */
+  UDAL_CALIB_REL_ISO_PERCLSCOO = 6 /* :468-494              same on float16(uncert / [h,w,h,w]), times the norm */
+};
+typedef struct {
+  int32_t calib_method_box;
+  int32_t num_tables;      /* isotonic tables (sklearn X_thresholds_ / y_thresholds_), concatenated: */
+  const float* table_x;    /*   knots of table t at [table_off[t], table_off[t+1]) - device pointers */
+  const float* table_y;
+  const int32_t* table_off;
+  float temps[4];
+  float class_temp;        /* logits / class_temp before the softmax (1 = uncalibrated; CalibrateClass ts_all) */
+  float w_entropy;         /* opt_params of the selected uncertainties ("ENT", "ALBOX"); 0 = not selected */
+  float w_albox;
+  float threshold;         /* mean(opt_thrs) */
+  float min_score;
+  int32_t strict_reference; /* 1: after calibration every row uses the FIRST detection's std (infer_model.py:688-691) */
+} udal_autolabel_params;
+/* Per image: entropy of softmax(logits) (infer_model.py:585-595), calibrated aleatoric std
+ * (utils_box.py:404-524), relative std (utils_box.py:279-292), opt_uncert = w_entropy * entropy +
+ * w_albox * mean(relative std), decision[b] = all(opt_uncert[score > min_score] < threshold)
+ * (infer_model.py:742-764; 1 = label automatically, 0 = examine).  boxes [B,M,box_stride] with the box at
+ * columns 0..3 and the aleatoric std at albox_col..+3 (-1: none); classes [B,M,class_stride], id in column 0.
+ * All pointers device memory. */
+int udal_autolabel(udal_ctx* ctx, const float* boxes, int box_stride, int albox_col, const float* scores,
+                   const float* classes, int class_stride, const float* logits, int num_classes, int batch,
+                   int max_out, const udal_autolabel_params* prm, float* entropy, float* calib_albox,
+                   float* rel_albox, float* opt_uncert, int32_t* decision);
+
 /* layout helpers used by the Python mirror (device pointers):
  * out[r] = a[r] ++ b[r] for r < rows (tf.concat on the last axis) */
 int udal_concat_channels(udal_ctx* ctx, const float* a, int ca, const float* b, int cb,

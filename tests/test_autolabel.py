@@ -1,0 +1,122 @@
+"""calibrated-uncertainty application + auto-label threshold pass.
+CPU: the oracle against golden vectors produced by the reference's own calibrate_boxuncert /
+relativize_uncert (tests/golden/make_golden_autolabel.py).  GPU: udal_autolabel against the oracle."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import autolabel_ref as ar
+
+G = np.load(os.path.join(os.path.dirname(__file__), "golden", "autolabel.npz"))
+C = 7
+
+
+def _tables(prefix):
+    off = G[prefix + "_off"]
+    return [(G[prefix + "_tx"][off[i]:off[i + 1]], G[prefix + "_ty"][off[i]:off[i + 1]]) for i in range(len(off) - 1)]
+
+
+METHODS = {
+    "ts_all": dict(temps=[float(G["temp_all"])]),
+    "ts_percoo": dict(temps=G["temps_percoo"]),
+    "iso_all": dict(tables=_tables("abs")[:1]),
+    "iso_percoo": dict(tables=_tables("abs")[:4]),
+    "iso_perclscoo": dict(tables=_tables("abs")),
+    "rel_iso_perclscoo": dict(tables=_tables("rel")),
+}
+
+
+@pytest.mark.parametrize("method", sorted(METHODS))
+def test_oracle_calibration_matches_reference(method):
+    got = ar.calibrate_boxuncert(method, G["albox"], G["classes"], G["boxes"], C, **METHODS[method])
+    ref = G[method]
+    assert got.shape == ref.shape
+    assert got.dtype == ref.dtype
+    np.testing.assert_array_equal(got, ref)
+
+
+def test_oracle_entropy_relativize_decision_match_reference():
+    np.testing.assert_array_equal(ar.entropy_of_logits(G["logits"]), G["entropy"])
+    np.testing.assert_array_equal(ar.relativize_uncert(G["boxes"], G["albox"]), G["rel_plain"])
+    w = G["opt_params"]
+    thr = float(np.mean(G["opt_thrs"]))
+    plain = ar.autolabel_image(G["boxes"], G["albox"], G["scores"], G["classes"], G["logits"], C, w[0], w[1], thr,
+                               float(G["min_score"]), method=None)
+    np.testing.assert_allclose(plain["opt_uncert"], G["opt_plain"], rtol=1e-6, equal_nan=True)
+    assert plain["auto_label"] == bool(G["decision_plain"])
+    strict = ar.autolabel_image(G["boxes"], G["albox"], G["scores"], G["classes"], G["logits"], C, w[0], w[1], thr,
+                                float(G["min_score"]), method="iso_perclscoo", tables=_tables("abs"), strict_reference=True)
+    np.testing.assert_allclose(strict["rel_albox"], G["rel_first_row"], rtol=1e-6)
+    np.testing.assert_allclose(strict["opt_uncert"], G["opt_strict"], rtol=1e-6)
+    assert strict["auto_label"] == bool(G["decision_strict"])
+
+
+def _detections(batch, seed):
+    """The golden image plus perturbed copies, in the postprocess_global output layout."""
+    rng = np.random.default_rng(seed)
+    M = G["boxes"].shape[0]
+    boxes = np.zeros((batch, M, 12), np.float32)
+    scores = np.zeros((batch, M), np.float32)
+    classes = np.zeros((batch, M, 1 + C), np.float32)
+    logits = np.zeros((batch, M, C), np.float32)
+    for b in range(batch):
+        jitter = 1.0 if b == 0 else rng.uniform(0.7, 1.3)
+        boxes[b, :, 0:4] = G["boxes"]
+        boxes[b, :, 4:8] = np.nan_to_num(G["albox"]) * jitter if b else G["albox"]
+        boxes[b, :, 8:12] = rng.uniform(0, 2, (M, 4))
+        scores[b] = G["scores"] if b == 0 else rng.permutation(G["scores"])
+        classes[b, :, 0] = G["classes"] if b == 0 else rng.integers(1, C + 1, M)
+        logits[b] = G["logits"] * jitter
+    return boxes, scores, classes, np.full(batch, M, np.int32), logits
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("method,strict", [(None, True), ("ts_all", True), ("ts_percoo", False), ("iso_all", True),
+                                           ("iso_percoo", False), ("iso_perclscoo", True), ("iso_perclscoo", False),
+                                           ("rel_iso_perclscoo", False)])
+def test_device_autolabel_matches_oracle(method, strict):
+    import udal_b200 as u
+    batch = 5
+    det = _detections(batch, 3)
+    kw = METHODS.get(method, {})
+    tables = [u.autolabel.IsotonicTable(x, y) for x, y in kw.get("tables", [])]
+    params = dict(num_classes=C, thr_sel_uncert=["ENT", "ALBOX"], calib_method_box=method, min_score=float(G["min_score"]))
+    labeler = u.autolabel.AutoLabeler(params, G["opt_params"], G["opt_thrs"], tables=tables, temps=kw.get("temps"),
+                                      strict_reference=strict)
+    got = labeler.decide(det)
+    thr = float(np.mean(G["opt_thrs"]))
+    for b in range(batch):
+        ref = ar.autolabel_image(det[0][b, :, 0:4], det[0][b, :, 4:8], det[1][b], det[2][b, :, 0], det[4][b], C,
+                                 G["opt_params"][0], G["opt_params"][1], thr, float(G["min_score"]), method=method,
+                                 tables=kw.get("tables"), temps=kw.get("temps"), strict_reference=strict)
+        np.testing.assert_allclose(got["entropy"][b], ref["entropy"], rtol=2e-5, atol=1e-6)
+        np.testing.assert_allclose(got["calib_albox"][b], ref["calib_albox"], rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(got["rel_albox"][b], ref["rel_albox"], rtol=1e-5, atol=1e-7)
+        np.testing.assert_allclose(got["opt_uncert"][b], ref["opt_uncert"], rtol=2e-5, atol=1e-6)
+        margin = np.abs(ref["opt_uncert"][det[1][b] > float(G["min_score"])] - thr).min()
+        if margin > 1e-4:  # not a knife-edge case
+            assert bool(got["auto_label"][b]) == ref["auto_label"]
+    # the golden image itself reproduces the reference's decisions
+    if method is None:
+        assert bool(got["auto_label"][0]) == bool(G["decision_plain"])
+    if method == "iso_perclscoo" and strict:
+        assert bool(got["auto_label"][0]) == bool(G["decision_strict"])
+
+
+@pytest.mark.gpu
+def test_autolabel_on_device_detections_and_errors():
+    import udal_b200 as u
+    det = _detections(3, 9)
+    eng = u.postprocess._any_engine()
+    dev = tuple(eng.ctx.to_device(x) for x in det)
+    labeler = u.autolabel.AutoLabeler(dict(num_classes=C, thr_sel_uncert=["ENT"], calib_method_box=None, min_score=0.4),
+                                      [1.0], [1.5])
+    host = labeler.decide(det)
+    on_dev = labeler.decide(dev)
+    np.testing.assert_array_equal(on_dev["opt_uncert"].numpy(), host["opt_uncert"])
+    np.testing.assert_array_equal(on_dev["opt_uncert"].numpy(), host["entropy"])      # weight 1 on ENT only
+    with pytest.raises(ValueError):
+        u.autolabel.AutoLabeler(dict(num_classes=C, calib_method_box="bogus"), [0.5, 0.5], [0.5])
+    with pytest.raises(ValueError):
+        u.autolabel.AutoLabeler(dict(num_classes=C, calib_method_box="iso_percoo"), [0.5, 0.5], [0.5], tables=[])

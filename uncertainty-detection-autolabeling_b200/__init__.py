@@ -7,14 +7,15 @@ reference's own Python entry points.
 
 Modules mirror the reference: ``postprocess``, ``anchors``, ``nms_np``, ``utils_box``,
 ``utils_extra``, ``hparams_config``, ``utils``; ``heads`` and ``scheduler`` are the new entry
-points for the head sampler and the multi-GPU image scheduler.  Everything computes on the GPU
+points for the head sampler and the multi-GPU image scheduler, ``autolabel`` the calibrated-uncertainty /
+auto-label threshold pass of the InferImages loop.  Everything computes on the GPU
 through ``libudal.so``; importing fails loudly when the library is missing (no CPU fallback).
 """
 from . import _lib
 
 _lib.load()  # fail loudly at import time if the CUDA library is missing
 
-from . import anchors, device, engine, heads, hparams_config, nms_np, postprocess, scheduler, utils, utils_box, utils_extra  # noqa: E402,F401
+from . import anchors, autolabel, device, engine, heads, hparams_config, nms_np, postprocess, scheduler, utils, utils_box, utils_extra  # noqa: E402,F401
 
-__all__ = ["anchors", "device", "engine", "heads", "hparams_config", "nms_np", "postprocess",
+__all__ = ["anchors", "autolabel", "device", "engine", "heads", "hparams_config", "nms_np", "postprocess",
            "scheduler", "utils", "utils_box", "utils_extra"]

@@ -114,6 +114,23 @@ SIGNATURES = {
                                    ctypes.POINTER(ctypes.c_int32)]),
 }
 
+
+
+class AutolabelParams(ctypes.Structure):
+    """include/udal.h: udal_autolabel_params"""
+    _fields_ = [("calib_method_box", ctypes.c_int32), ("num_tables", ctypes.c_int32),
+                ("table_x", ctypes.c_void_p), ("table_y", ctypes.c_void_p), ("table_off", ctypes.c_void_p),
+                ("temps", ctypes.c_float * 4), ("class_temp", ctypes.c_float), ("w_entropy", ctypes.c_float),
+                ("w_albox", ctypes.c_float), ("threshold", ctypes.c_float), ("min_score", ctypes.c_float),
+                ("strict_reference", ctypes.c_int32)]
+
+
+CALIB_METHODS = {None: 0, "none": 0, "ts_all": 1, "ts_percoo": 2, "iso_all": 3, "iso_percoo": 4,
+                 "iso_perclscoo": 5, "rel_iso_perclscoo": 6}
+SIGNATURES["udal_autolabel"] = (ctypes.c_int, [_VP, _VP, ctypes.c_int, ctypes.c_int, _VP, _VP, ctypes.c_int, _VP,
+                                               ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                               ctypes.POINTER(AutolabelParams), _VP, _VP, _VP, _VP, _VP])
+
 _lib = None
 
 
