@@ -19,8 +19,12 @@ rng = np.random.default_rng(1)
 feats = [eng.ctx.to_device(rng.standard_normal((batch, h, w, eng.F), dtype=np.float32)) for h, w in eng.level_hw]
 scales = eng.ctx.to_device(np.ones(batch, np.float32))
 fused = ctypes.c_int.in_dll(eng.lib, "udal_run_fused")
-for f in (0, 1):
+unst = ctypes.c_int.in_dll(eng.lib, "udal_nms_post_unstaged")
+rsv = ctypes.c_int.in_dll(eng.lib, "udal_run_reserved_sms")
+for f, un, rs in ((1, 0, 0), (1, 0, 4), (1, 1, 4), (1, 0, 8), (1, 1, 8), (1, 1, 12), (1, 0, 16)):
     fused.value = f
+    unst.value = un
+    rsv.value = rs
     for i in range(3):
         eng.run(feats, scales, None, seed=i)
     eng.ctx.sync()
@@ -29,4 +33,5 @@ for f in (0, 1):
     for i in range(5):
         eng.run(feats, scales, None, seed=20 + i)
     ms = eng.ctx.timer_stop() / 5
+    print("nms_post_unstaged=%d reserved=%d" % (un, rs), end="  ")
     print("fused=%d  layer ms %s  sum %.3f  step %.3f ms" % (f, [round(x, 3) for x in t], sum(t), ms), flush=True)

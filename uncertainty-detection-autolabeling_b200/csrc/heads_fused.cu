@@ -489,7 +489,7 @@ int udal_heads_fused_predict(udal_ctx* ctx, int head, const void* const* in, int
     return encode_strided(encode, map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, base + (size_t)ctx->level_pix_off[l] * ch, gdim, gstr, ch,
                           IG_TW, IG_TH, false);
   };
-  const int grid = p.items < UDAL_NUM_SMS ? p.items : UDAL_NUM_SMS;
+  const int grid = udal_persistent_grid(ctx, p.items);
   if (head == UDAL_HEAD_CLASS) {
     UDAL_REQUIRE(pre->mean_logits && pre->std_logits && pre->scores && pre->classes, "fused class head: NULL output");
     p.mean_logits = pre->mean_logits;

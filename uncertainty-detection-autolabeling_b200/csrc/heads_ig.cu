@@ -454,7 +454,7 @@ int udal_heads_ig_layer(udal_ctx* ctx, const void* const* in, int NB, const void
   p.Cout = cout;
   p.wimg = wimg;
   p.debug = udal_ig_debug;
-  const int grid = p.items < UDAL_NUM_SMS ? p.items : UDAL_NUM_SMS;
+  const int grid = udal_persistent_grid(ctx, p.items);
   if (!predict) return launch_ig<IgTower>(ctx, maps, p, grid);
   if (npad == 64) return launch_ig<IgPred64>(ctx, maps, p, grid);
   return rows == 72 ? launch_ig<IgPred72>(ctx, maps, p, grid) : launch_ig<IgPred80>(ctx, maps, p, grid);

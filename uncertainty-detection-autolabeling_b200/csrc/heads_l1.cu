@@ -376,7 +376,7 @@ int udal_heads_l1_layer(udal_ctx* ctx, const void* const* in, int NB, int T, con
   }
   for (int l = c.num_levels; l <= UDAL_MAX_LEVELS; ++l) p.item_off[l] = off;
   p.items = off;
-  const int grid = p.items < UDAL_NUM_SMS ? p.items : UDAL_NUM_SMS;
+  const int grid = udal_persistent_grid(ctx, p.items);
   UDAL_REQUIRE(c.num_levels <= kL1MaxLevels, "the tensor-core head sampler keeps the weights of at most %d pyramid levels "
                "resident (got %d) - use heads_mode fp32", kL1MaxLevels, c.num_levels);
   const int smem = l1_smem(c.num_levels);

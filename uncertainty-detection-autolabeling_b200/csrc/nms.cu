@@ -454,6 +454,8 @@ __global__ void fill_segments_kernel(int32_t* starts, int32_t* counts, int segme
 
 }  // namespace
 
+int udal_nms_post_unstaged = 1;  // debug switch: 0 keeps the staged kernel on the post stream as well
+
 // sorted-candidate NMS over generic segments (internal)
 int udal_nms_sorted(udal_ctx* ctx, const float* boxes, const float* scores, const int32_t* cand_idx,
                     const int32_t* seg_start, const int32_t* seg_count, const float* next_score,
@@ -493,7 +495,12 @@ int udal_nms_sorted(udal_ctx* ctx, const float* boxes, const float* scores, cons
     p.r_rank = (int32_t*)(scr + per * 4);
     p.r_begin = (int32_t*)(scr + per * 8);
   }
-  const bool staged = seg_n <= kStageCap;
+  // The staged variant (64 KB of shared memory per segment) is the fastest stand-alone; on the post stream of
+  // back-to-back udal_run calls the kernel has to co-reside with the persistent head kernels of the next run,
+  // which leave < 20 KB per SM: there the candidates stay in global memory (L1 / L2 hits) and the latency
+  // hides behind the heads.
+  const bool staged = seg_n <= kStageCap &&
+                      !(ctx->in_run && ctx->run_pipelined && ctx->stream == ctx->post_stream && udal_nms_post_unstaged);
   if (staged) {
     const size_t smem = (size_t)p.max_out * sizeof(float4) + (size_t)kStageCap * (16 + 4 + 12);
     UDAL_REQUIRE(smem <= 200 * 1024, "max_output_size %d too large", p.max_out);

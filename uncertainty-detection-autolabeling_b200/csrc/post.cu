@@ -257,6 +257,7 @@ __global__ void __launch_bounds__(256) merge_per_class_kernel(const MergeParams 
 }  // namespace
 
 int udal_run_overlap = 1;  // 0: udal_run keeps its whole tail on the context's stream
+int udal_run_reserved_sms = 4;  // SMs the persistent head kernels of a pipelined udal_run leave to the post stream
 
 extern "C" {
 

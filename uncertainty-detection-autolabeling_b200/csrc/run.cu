@@ -21,6 +21,10 @@ extern "C" int udal_run(udal_ctx* ctx, const float* const* feats, int batch, con
     }
   } scope(ctx);
   const udal_config& c = ctx->cfg;
+  ctx->run_pipelined = false;
+  for (int b = 0; b < 2; ++b)
+    if (ctx->post_pending[b] && cudaEventQuery(ctx->ev_post[b]) == cudaErrorNotReady) ctx->run_pipelined = true;
+  (void)cudaGetLastError();  // cudaErrorNotReady is not an error
   if (udal_heads_fused_ok(ctx)) {
     // serving configuration: the predict layers write the per-anchor statistics straight into this run's
     // scratch bank, so its previous user (the tail of two runs ago) is waited for before the heads start

@@ -58,6 +58,7 @@ struct udal_ctx {
   bool post_pending[2] = {false, false};
   int run_bank = 0;
   bool in_run = false;
+  bool run_pipelined = false;   // this udal_run was issued while the previous run's tail was still executing
   std::vector<void*> user_allocs;
   bool profile_layers = false;
   std::vector<cudaEvent_t> layer_events;  // pairs (start, stop) in launch order
@@ -115,6 +116,20 @@ int udal_join(udal_ctx* ctx);
     int s__ = (call);             \
     if (s__ != UDAL_OK) return s__; \
   } while (0)
+
+// CTAs of a persistent (one CTA per SM) head kernel.  When udal_run calls arrive back to back (the previous
+// run's tail is still executing: throughput mode) a few SMs stay free for that top-k / NMS tail on the post
+// stream (udal_run_reserved_sms), which otherwise only gets the gaps between the head kernels.  A caller
+// that waits for every result (latency mode) gets all SMs and the faster shared-memory-staged NMS.
+extern int udal_run_reserved_sms;
+extern int udal_run_overlap;
+static inline int udal_persistent_grid(const udal_ctx* ctx, int items) {
+  int sms = UDAL_NUM_SMS;
+  if (ctx->in_run && ctx->run_pipelined && udal_run_overlap && udal_run_reserved_sms > 0 &&
+      udal_run_reserved_sms < UDAL_NUM_SMS / 2)
+    sms -= udal_run_reserved_sms;
+  return items < sms ? items : sms;
+}
 
 // level pointer tables passed to kernels by value
 struct udal_level_ptrs {
