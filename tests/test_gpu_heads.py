@@ -102,6 +102,9 @@ BF16_RTOL = 3e-2
     ((384, 1280), 8, 6, 1, True, 0.05, 0.05),
     ((384, 640), 8, 10, 2, True, 0.05, 0.05),
     ((192, 1280), 4, 5, 2, False, 0.05, 0.05),  # 36-channel predictions: one swizzled region + remainder
+    ((64, 96), 10, 3, 2, True, 0.05, 0.05),     # BDD100K label map: 90 class channels = 2 chunks of 45
+    ((360, 640), 10, 4, 1, True, 0.05, 0.05),   # the same on the 1280x720 aspect (odd level sizes 45x80 ... 3x5)
+    (128, 20, 2, 1, True, 0.05, 0.0),           # 180 class channels = 3 chunks of 60
 ])
 def test_heads_bf16_tensor_core_vs_oracle(u, size, C, T, batch, la, rc, rb):
     p = _cfg(u, size, C, T, la, rc, rb, heads_mode="bf16")

@@ -71,6 +71,7 @@ struct IgParams {
   const float* ep_bias[UDAL_MAX_LEVELS];    // [NPAD] folded bias
   const void* wimg;                      // bf16 [9][NROWS][64] pre-swizzled smem image (level independent)
   int Cout;
+  int ch_off, ch_total;                  // predictions: this launch writes channels [ch_off, ch_off + Cout) of ch_total
   int tma_store;                         // predictions through the staging tile + TMA store (Cout % 4 == 0)
   int debug;                             // timing experiments only (wrong results): 1 = one tap, 2 = no epilogue math / stores, 4 = no TMA loads after the first ring fill
 };
@@ -313,13 +314,25 @@ __global__ void __launch_bounds__(kIgThreads, 1) heads_ig_kernel(const __grid_co
             if (j * 8 + i < Cout) stg[m * Cout + j * 8 + i] = fmaf(__uint_as_float(r[j][i]), ep_s[j * 8 + i], ep_b[j * 8 + i]);
         ig_group_sync(g);
         const int gt = threadIdx.x - 64 - g * 128;           // thread of the group
-        const int run = min(IG_TW, W - w.tx0) * Cout;        // floats per tile row inside the image
-        const int rows = min(IG_TH, H - w.ty0);
-        float* dst0 = reinterpret_cast<float*>(p.out[w.l]) + (((size_t)nb * H + w.ty0) * W + w.tx0) * Cout;
-        for (int row = 0; row < rows; ++row) {
-          const float* src = stg + row * IG_TW * Cout;
-          float* dst = dst0 + (size_t)row * W * Cout;
-          for (int e = gt; e < run; e += 128) dst[e] = src[e];
+        const int npx = min(IG_TW, W - w.tx0), rows = min(IG_TH, H - w.ty0);
+        float* dst0 = reinterpret_cast<float*>(p.out[w.l]) + (((size_t)nb * H + w.ty0) * W + w.tx0) * p.ch_total + p.ch_off;
+        if (p.ch_total == Cout) {
+          const int run = npx * Cout;                        // floats per tile row inside the image
+          for (int row = 0; row < rows; ++row) {
+            const float* src = stg + row * IG_TW * Cout;
+            float* dst = dst0 + (size_t)row * W * Cout;
+            for (int e = gt; e < run; e += 128) dst[e] = src[e];
+          }
+        } else {
+          // channel chunk of a wider prediction: one run of Cout floats per pixel; warp = pixel, lane = channel
+          for (int pp = gt >> 5; pp < rows * IG_TW; pp += 4) {
+            const int row = pp >> 3, px = pp & 7;
+            if (px < npx) {
+              const float* src = stg + pp * Cout;
+              float* dst = dst0 + ((size_t)row * W + px) * p.ch_total;
+              for (int cc = gt & 31; cc < Cout; cc += 32) dst[cc] = src[cc];
+            }
+          }
         }
       }
       if (staged) {
@@ -405,10 +418,12 @@ int udal_heads_ig_build_weights(udal_ctx* ctx, const float* dw, const float* wf,
 // of 1.0 on the device); predict = 1: out[l] fp32 [NB,H,W,cout] = conv + bias.
 int udal_heads_ig_layer(udal_ctx* ctx, const void* const* in, int NB, const void* wimg, int rows,
                         const float* const* ep_scale, const float* const* ep_bias, int npad, int cout, int predict,
-                        const float* const* out_scale, const float* ones, void* const* out) {
+                        const float* const* out_scale, const float* ones, void* const* out, int ch_off, int ch_total) {
   EncodeTiledFn encode = get_encode();
   UDAL_REQUIRE(encode != nullptr, "cuTensorMapEncodeTiled is not available from this driver");
   UDAL_REQUIRE(rows == udal_heads_ig_rows(cout, ctx->cfg.num_levels), "weight image was built for another kernel variant");
+  if (ch_total == 0) ch_total = cout;
+  UDAL_REQUIRE(ch_off >= 0 && ch_off + cout <= ch_total && (predict || ch_total == cout), "bad channel chunk");
   const udal_config& c = ctx->cfg;
   IgMaps maps;
   IgParams p;
@@ -417,7 +432,9 @@ int udal_heads_ig_layer(udal_ctx* ctx, const void* const* in, int NB, const void
   p.num_levels = c.num_levels;
   p.NB = NB;
   // TMA needs 16-byte global strides: every bf16 layer qualifies, fp32 predictions when Cout % 4 == 0
-  p.tma_store = (!predict || (udal_ig_tma_store && (cout & 3) == 0)) ? 1 : 0;
+  p.tma_store = (!predict || (udal_ig_tma_store && (cout & 3) == 0 && ch_total == cout)) ? 1 : 0;
+  p.ch_off = ch_off;
+  p.ch_total = ch_total;
   p.sc_stride = out_scale ? KF : 0;
   int off = 0;
   for (int l = 0; l < c.num_levels; ++l) {

@@ -425,19 +425,21 @@ __global__ void __launch_bounds__(kThreads, NPAD <= 64 ? 3 : 2) sepconv_tc_kerne
 }
 
 // folded weights: wf[n][k] = W[k][n] * bn_scale[n];  fb[n] = bias[n] * bn_scale[n] + bn_shift[n]
+// columns [n0, n0 + cout) of the [64][ldw] weight matrix (ldw = 0: ldw = cout, n0 = 0)
 __global__ void fold_weights_kernel(const float* __restrict__ w, const float* __restrict__ bias,
                                     const float* __restrict__ bn_scale, const float* __restrict__ bn_shift, int cout,
-                                    int npad, float* __restrict__ wf, float* __restrict__ fb) {
+                                    int npad, float* __restrict__ wf, float* __restrict__ fb, int n0 = 0, int ldw = 0) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ldw == 0) ldw = cout;
   if (i < npad * KF) {
     const int n = i / KF, k = i % KF;
     float v = 0.f;
-    if (n < cout) v = w[(size_t)k * cout + n] * (bn_scale ? bn_scale[n] : 1.f);
+    if (n < cout) v = w[(size_t)k * ldw + n0 + n] * (bn_scale ? bn_scale[n0 + n] : 1.f);
     wf[i] = v;
   }
   if (i < npad) {
     float v = 0.f;
-    if (i < cout) v = bn_scale ? fmaf(bias[i], bn_scale[i], bn_shift[i]) : bias[i];
+    if (i < cout) v = bn_scale ? fmaf(bias[n0 + i], bn_scale[n0 + i], bn_shift[n0 + i]) : bias[n0 + i];
     fb[i] = v;
   }
 }
@@ -450,7 +452,7 @@ int udal_heads_ig_rows(int cout, int num_levels);
 int udal_heads_ig_build_weights(udal_ctx* ctx, const float* dw, const float* wf, int nrows, void* wimg);
 int udal_heads_ig_layer(udal_ctx* ctx, const void* const* in, int NB, const void* wimg, int rows,
                         const float* const* ep_scale, const float* const* ep_bias, int npad, int cout, int predict,
-                        const float* const* out_scale, const float* ones, void* const* out);
+                        const float* const* out_scale, const float* ones, void* const* out, int ch_off = 0, int ch_total = 0);
 int udal_heads_l1_layer(udal_ctx* ctx, const void* const* in, int NB, int T, const float* dw, const float* const* wf,
                         const float* const* fb, const float* const* in_scale, const float* const* out_scale,
                         const float* ones, float inv_keep, void* const* out);
@@ -463,9 +465,12 @@ int udal_heads_tc_prepare(udal_ctx* ctx, int head) {
   udal_head_weights_dev& h = ctx->heads[head];
   UDAL_REQUIRE(c.num_filters == KF, "the tensor-core head sampler is built for fpn_num_filters = 64 (D0); got %d - "
                "use heads_mode fp32", c.num_filters);
-  UDAL_REQUIRE(h.cout <= kMaxN, "predict layer with %d channels exceeds the tensor-core tile (%d)", h.cout, kMaxN);
   const int R = c.repeats, L = c.num_levels;
-  const int npad_p = npad_of(h.cout);
+  // predict layers with more than 80 channels (C > 8 classes) run as equal chunks of at most 64 channels
+  h.pred_chunks = h.cout <= kMaxN ? 1 : (h.cout + KF - 1) / KF;
+  h.pred_chunk = h.pred_chunks == 1 ? h.cout : (h.cout + h.pred_chunks - 1) / h.pred_chunks;
+  UDAL_REQUIRE(h.pred_chunks == 1 || R >= 2, "predict layers with more than %d channels need box_class_repeats >= 2", kMaxN);
+  const int npad_p = h.pred_chunks == 1 ? npad_of(h.cout) : h.pred_chunks * KF;  // rows of the folded predict matrix
   const size_t n_w = (size_t)R * L * KF * KF + (size_t)npad_p * KF;
   const size_t n_b = (size_t)R * L * KF + (size_t)npad_p;
   if (h.pw_bf16) UDAL_CUDA(cudaFree(h.pw_bf16));
@@ -483,9 +488,19 @@ int udal_heads_tc_prepare(udal_ctx* ctx, int head) {
           wf + o * KF * KF, h.fold_bias + o * KF);
       UDAL_CHECK_LAUNCH(ctx);
     }
-  fold_weights_kernel<<<(npad_p * KF + 255) / 256, 256, 0, ctx->stream>>>(
-      h.pwp, h.bp, nullptr, nullptr, h.cout, npad_p, wf + (size_t)R * L * KF * KF, h.fold_bias + (size_t)R * L * KF);
-  UDAL_CHECK_LAUNCH(ctx);
+  if (h.pred_chunks == 1) {
+    fold_weights_kernel<<<(npad_p * KF + 255) / 256, 256, 0, ctx->stream>>>(
+        h.pwp, h.bp, nullptr, nullptr, h.cout, npad_p, wf + (size_t)R * L * KF * KF, h.fold_bias + (size_t)R * L * KF);
+    UDAL_CHECK_LAUNCH(ctx);
+  } else {
+    for (int q = 0; q < h.pred_chunks; ++q) {
+      const int n0 = q * h.pred_chunk, nc = h.cout - n0 < h.pred_chunk ? h.cout - n0 : h.pred_chunk;
+      fold_weights_kernel<<<(KF * KF + 255) / 256, 256, 0, ctx->stream>>>(
+          h.pwp, h.bp, nullptr, nullptr, nc, KF, wf + (size_t)R * L * KF * KF + (size_t)q * KF * KF,
+          h.fold_bias + (size_t)R * L * KF + (size_t)q * KF, n0, h.cout);
+      UDAL_CHECK_LAUNCH(ctx);
+    }
+  }
   // implicit-GEMM weight images (level independent: BN scale is applied in the epilogue) for tower
   // layers >= 2 and the predict layer, plus a vector of ones as the predict layer's epilogue scale
   if (R >= 2) {
@@ -503,9 +518,16 @@ int udal_heads_tc_prepare(udal_ctx* ctx, int head) {
       UDAL_CHECK_LAUNCH(ctx);
       UDAL_TRY(udal_heads_ig_build_weights(ctx, h.dw + (size_t)r * 9 * KF, tmp, KF, img + (size_t)(r - 2) * tower_img));
     }
-    h.ig_rows = udal_heads_ig_rows(h.cout, L);  // rows per tap of the predict image (<= npad_p)
-    UDAL_TRY(udal_heads_ig_build_weights(ctx, h.dwp, wf + (size_t)R * L * KF * KF, h.ig_rows,
-                                         img + (size_t)(R - 2) * tower_img));
+    if (h.pred_chunks == 1) {
+      h.ig_rows = udal_heads_ig_rows(h.cout, L);  // rows per tap of the predict image (<= npad_p)
+      UDAL_TRY(udal_heads_ig_build_weights(ctx, h.dwp, wf + (size_t)R * L * KF * KF, h.ig_rows,
+                                           img + (size_t)(R - 2) * tower_img));
+    } else {
+      h.ig_rows = KF;
+      for (int q = 0; q < h.pred_chunks; ++q)
+        UDAL_TRY(udal_heads_ig_build_weights(ctx, h.dwp, wf + (size_t)R * L * KF * KF + (size_t)q * KF * KF, KF,
+                                             img + (size_t)(R - 2) * tower_img + (size_t)q * tower_img));
+    }
     std::vector<float> ones(kMaxN, 1.0f);
     UDAL_CUDA(cudaMemcpyAsync(reinterpret_cast<char*>(h.ig_w) + n_img * 2, ones.data(), kMaxN * sizeof(float),
                               cudaMemcpyHostToDevice, ctx->stream));
@@ -544,7 +566,7 @@ static int run_tower_tc(udal_ctx* ctx, int head, const float* const* feats, int 
   p.batch = B;
   UDAL_CUDA(cudaFuncSetAttribute(sepconv_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_ALLOC));
   UDAL_CUDA(cudaFuncSetAttribute(sepconv_tc_kernel<80>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_ALLOC));
-  const int npad_p = npad_of(h.cout);
+  const int npad_p = h.pred_chunks == 1 ? npad_of(h.cout) : h.pred_chunks * KF;
   auto mark = [&]() {
     if (!ctx->profile_layers) return;
     cudaEvent_t e;
@@ -615,6 +637,17 @@ static int run_tower_tc(udal_ctx* ctx, int head, const float* const* feats, int 
       const float* ones = reinterpret_cast<const float*>(img0 + (size_t)(R - 2) * tower_img + pred_img);
       const float* ep_scale[UDAL_MAX_LEVELS];
       for (int l = 0; l < L; ++l) ep_scale[l] = predict ? ones : h.bn_scale + ((size_t)layer * L + l) * KF;
+      if (predict && h.pred_chunks > 1) {
+        for (int q = 0; q < h.pred_chunks; ++q) {
+          const int n0 = q * h.pred_chunk, nc = h.cout - n0 < h.pred_chunk ? h.cout - n0 : h.pred_chunk;
+          const float* fbq[UDAL_MAX_LEVELS];
+          for (int l = 0; l < L; ++l) fbq[l] = p.fb[l] + (size_t)q * KF;
+          UDAL_TRY(udal_heads_ig_layer(ctx, p.in, NBt, img + (size_t)q * tower_img, KF, ep_scale, fbq, KF, nc, 1, nullptr, ones,
+                                       p.out, n0, h.cout));
+        }
+        mark();
+        continue;
+      }
       UDAL_TRY(udal_heads_ig_layer(ctx, p.in, NBt, img, predict ? h.ig_rows : KF, ep_scale, p.fb, p.Npad, p.Cout,
                                    predict ? 1 : 0, mc && !predict ? p.out_scale : nullptr, ones, p.out));
       mark();
@@ -624,6 +657,7 @@ static int run_tower_tc(udal_ctx* ctx, int head, const float* const* feats, int 
       // per-tile kernel for every layer: inputs already carry their dropout, nothing to fold
       for (int l = 0; l < L; ++l) p.scale[l] = nullptr;
     }
+    UDAL_REQUIRE(p.Npad <= kMaxN, "predict layer with %d channels: the per-tile kernel handles at most %d", h.cout, kMaxN);
     dim3 grid(total_tiles, grid_y);
     if (p.Npad == 64) sepconv_tc_kernel<64><<<grid, kThreads, SM_ALLOC, ctx->stream>>>(p);
     else sepconv_tc_kernel<80><<<grid, kThreads, SM_ALLOC, ctx->stream>>>(p);
