@@ -40,15 +40,28 @@ extern "C" int udal_run(udal_ctx* ctx, const float* const* feats, int batch, con
   const int L = c.num_levels, T = c.mc_samples;
   const int ccls = c.anchors_per_loc * c.num_classes, cbox = udal_box_channels(ctx);
   const size_t P = (size_t)ctx->num_pixels;
-  const size_t ncls = (size_t)(c.cls_mc ? T : 1) * batch * P * ccls;
-  const size_t nbox = (size_t)(c.box_mc ? T : 1) * batch * P * cbox;
+  // per-level head outputs in one scratch block, every level starting on a 16-byte boundary (odd channel
+  // counts such as 63 = 9 anchors x 7 classes would otherwise misalign the following levels)
+  const size_t tc = (size_t)(c.cls_mc ? T : 1) * batch, tb = (size_t)(c.box_mc ? T : 1) * batch;
+  size_t off_cls[UDAL_MAX_LEVELS], off_box[UDAL_MAX_LEVELS], total = 0;
+  for (int l = 0; l < L; ++l) {
+    const size_t px = (size_t)c.level_h[l] * c.level_w[l];
+    off_cls[l] = total;
+    total += (tc * px * ccls + 3) & ~(size_t)3;
+  }
+  for (int l = 0; l < L; ++l) {
+    const size_t px = (size_t)c.level_h[l] * c.level_w[l];
+    off_box[l] = total;
+    total += (tb * px * cbox + 3) & ~(size_t)3;
+  }
+  (void)P;
   float* buf;
-  UDAL_TRY(udal_scratch_get(ctx, SCR_PRE_A, (ncls + nbox) * sizeof(float), (void**)&buf));
+  UDAL_TRY(udal_scratch_get(ctx, SCR_PRE_A, total * sizeof(float), (void**)&buf));
   float* cls[UDAL_MAX_LEVELS];
   float* box[UDAL_MAX_LEVELS];
   for (int l = 0; l < L; ++l) {
-    cls[l] = buf + (size_t)(c.cls_mc ? T : 1) * batch * ctx->level_pix_off[l] * ccls;
-    box[l] = buf + ncls + (size_t)(c.box_mc ? T : 1) * batch * ctx->level_pix_off[l] * cbox;
+    cls[l] = buf + off_cls[l];
+    box[l] = buf + off_box[l];
   }
   UDAL_TRY(udal_heads_sample(ctx, feats, batch, keep_masks, seed, cls, box));
   const int bank = ctx->run_bank;
