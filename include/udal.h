@@ -275,7 +275,7 @@ int udal_gather_rows(udal_ctx* ctx, const void* src, int batch, int64_t n_rows, 
  * Replaces EfficientDetNet.call MC branch + postprocess_global / postprocess_per_class
  * (efficientdet_keras.py:999-1050, 1102-1116).  Asynchronous: outputs are valid after udal_sync (or any
  * later call on this context, all of which are ordered after it).  In the serving configuration (bf16
- * heads, A = 9, C = 8, loss attenuation, l-norm, MC dropout on both heads, global NMS) the predict layers
+ * heads, A = 9, C = 7 or 8, loss attenuation, l-norm, MC dropout on both heads, global NMS) the predict layers
  * are fused with the decode / MC moments (no [T,...] head outputs in HBM; box quantities within ~1e-6
  * relative of the stand-alone fp64 decode), and the top-k / NMS / assemble tail runs on a second stream
  * underneath the next udal_run.  Debug switches exported as ints: udal_run_fused, udal_run_overlap. */

@@ -134,6 +134,7 @@ static void free_head(udal_head_weights_dev& h) {
   cudaFree(h.pwp_bf16);
   cudaFree(h.fold_bias);
   cudaFree(h.ig_w);
+  cudaFree(h.fused_w);
   h = udal_head_weights_dev();
 }
 

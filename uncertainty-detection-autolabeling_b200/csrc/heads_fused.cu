@@ -3,7 +3,7 @@
 // head outputs to HBM.  The T samples of a (16x8-pixel tile, image) run back to back on one CTA and the
 // epilogue threads keep the Monte-Carlo statistics of their anchors in registers:
 //
-//   class head : per (anchor, class) logit the sequential fp32 sum (-> mean, bit-identical to the
+//   class head : (7 or 8 classes) per (anchor, class) logit the sequential fp32 sum (-> mean, bit-identical to the
 //                stand-alone decode kernel), the first sample and the sum of squared deviations from it
 //                (-> population std); at the last sample also argmax / sigmoid score per anchor
 //                (utils_extra.py:220-244, postprocess.py:123-135, 284)
@@ -52,7 +52,7 @@ struct FuParams {
   const float* bias;                     // [80]
   const float* anchors;                  // [N,4]
   long long N;                           // anchors per image
-  float* mean_logits;                    // class head outputs [NB,N,8]
+  float* mean_logits;                    // class head outputs [NB,N,NC]
   float* std_logits;
   float* scores;                         // [NB,N]
   int32_t* classes;
@@ -111,7 +111,8 @@ __device__ __forceinline__ void fu_ld4(uint32_t taddr, uint32_t (&r)[4]) {
                : "memory");
 }
 
-template <bool BOX>
+// NC = classes per anchor of the class head (7: KITTI map of the reference YAMLs, 8); the box head ignores it
+template <bool BOX, int NC>
 __global__ void __launch_bounds__(kFuThreads, 1) heads_fused_kernel(const __grid_constant__ FuMaps maps, const FuParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = s32(smem_raw);
@@ -230,15 +231,17 @@ __global__ void __launch_bounds__(kFuThreads, 1) heads_fused_kernel(const __grid
       const int oy = w.ty0 + (m >> 3), ox = w.tx0 + (m & 7);
       const bool ok = oy < H && ox < W;
       if (!BOX) {
-        // ---- class head: 3 anchors x 8 classes = 24 logits per thread ----
-        float sum[24], x0[24], s2[24];
+        // ---- class head: 3 anchors x NC classes = CH logits per thread, at accumulator columns cg * CH .. ----
+        constexpr int CH = 3 * NC, ROW = 9 * NC;  // logits per thread / per pixel
+        constexpr bool TMA_OUT = (ROW * 4) % 16 == 0;  // TMA needs 16-byte strides: NC = 8 (288 B), not 7 (252 B)
+        float sum[CH], x0[CH], s2[CH];
         for (int t = 0; t < T; ++t, ++j) {
           const int a = j & 1;
           if (lane == 0) bar_wait(bar_tfull + 8 * a, (j >> 1) & 1);
           __syncwarp();
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * FU_NPAD + cg * 24);
-          uint32_t r[3][8];
+          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * FU_NPAD + cg * CH);
+          uint32_t r[3][8];  // 24 columns from the thread's first one (the tail past CH is not used)
 #pragma unroll
           for (int u = 0; u < 3; ++u) ig_ld8(taddr + u * 8, r[u]);
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
@@ -246,23 +249,23 @@ __global__ void __launch_bounds__(kFuThreads, 1) heads_fused_kernel(const __grid
           __syncwarp();
           if (lane == 0) bar_arrive(bar_tempty + 8 * a);
 #pragma unroll
-          for (int u = 0; u < 3; ++u) {
-            const float4 b0 = *reinterpret_cast<const float4*>(sBias + cg * 24 + u * 8);
-            const float4 b1 = *reinterpret_cast<const float4*>(sBias + cg * 24 + u * 8 + 4);
-            const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              const int c = u * 8 + e;
-              const float x = __fadd_rn(__uint_as_float(r[u][e]), bb[e]);  // = fma(acc, 1, bias) of the predict layer
-              if (t == 0) {
-                sum[c] = x;
-                x0[c] = x;
-                s2[c] = 0.f;
-              } else {
-                sum[c] = __fadd_rn(sum[c], x);
-                const float d = x - x0[c];
-                s2[c] = fmaf(d, d, s2[c]);
-              }
+          for (int c = 0; c < CH; ++c) {
+            float bia;
+            if constexpr (CH % 4 == 0) {
+              const float4 b4 = *reinterpret_cast<const float4*>(sBias + cg * CH + (c & ~3));  // one LDS.128 per 4 logits after CSE
+              bia = (c & 3) == 0 ? b4.x : (c & 3) == 1 ? b4.y : (c & 3) == 2 ? b4.z : b4.w;
+            } else {
+              bia = sBias[cg * CH + c];
+            }
+            const float x = __fadd_rn(__uint_as_float(r[c >> 3][c & 7]), bia);  // = fma(acc, 1, bias) of the predict layer
+            if (t == 0) {
+              sum[c] = x;
+              x0[c] = x;
+              s2[c] = 0.f;
+            } else {
+              sum[c] = __fadd_rn(sum[c], x);
+              const float d = x - x0[c];
+              s2[c] = fmaf(d, d, s2[c]);
             }
           }
         }
@@ -270,35 +273,51 @@ __global__ void __launch_bounds__(kFuThreads, 1) heads_fused_kernel(const __grid
         if (elected) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // previous item's stores
         __syncwarp();
         fu_epi_sync();
-        float* st = sOut + m * 72 + cg * 24;
-        float mean[24];
+        float* st = sOut + m * ROW + cg * CH;
+        float mean[CH];
 #pragma unroll
-        for (int c = 0; c < 24; ++c) mean[c] = __fdiv_rn(sum[c], fT);
+        for (int c = 0; c < CH; ++c) mean[c] = __fdiv_rn(sum[c], fT);
+        if (CH % 4 == 0 && ROW % 4 == 0) {
 #pragma unroll
-        for (int v = 0; v < 6; ++v)
-          reinterpret_cast<float4*>(st)[v] = make_float4(mean[4 * v], mean[4 * v + 1], mean[4 * v + 2], mean[4 * v + 3]);
+          for (int v = 0; v < CH / 4; ++v)
+            reinterpret_cast<float4*>(st)[v] = make_float4(mean[4 * v], mean[4 * v + 1], mean[4 * v + 2], mean[4 * v + 3]);
+        } else {
+#pragma unroll
+          for (int c = 0; c < CH; ++c) st[c] = mean[c];
+        }
 #pragma unroll
         for (int ai = 0; ai < 3; ++ai) {
-          float best = mean[ai * 8];
+          float best = mean[ai * NC];
           int arg = 0;
 #pragma unroll
-          for (int c = 1; c < 8; ++c)
-            if (mean[ai * 8 + c] > best) {
-              best = mean[ai * 8 + c];
+          for (int c = 1; c < NC; ++c)
+            if (mean[ai * NC + c] > best) {
+              best = mean[ai * NC + c];
               arg = c;
             }
           sOut2[m * 9 + cg * 3 + ai] = sigmoid_ref(best);
           reinterpret_cast<int32_t*>(sOut2 + 128 * 9)[m * 9 + cg * 3 + ai] = arg;
         }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        // a tile row (8 px) of a per-anchor tensor with `w` values per pixel is one contiguous run in global memory
+        auto copy_rows = [&](const float* src, float* dst_base, int width) {
+          for (int idx = etid; idx < IG_TH * IG_TW * width; idx += 384) {
+            const int row = idx / (IG_TW * width), col = idx - row * (IG_TW * width);
+            if (w.ty0 + row < H && w.tx0 + col / width < W)
+              dst_base[((size_t)w.nb * (size_t)(p.N / 9) + (size_t)(p.pix_off[w.l] + (w.ty0 + row) * W + w.tx0)) * width + col] = src[idx];
+          }
+        };
+        if constexpr (TMA_OUT) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         fu_epi_sync();
-        if (elected) {
-          ig_tma_store(&maps.o[0][w.l], s32(sOut), 0, w.tx0, w.ty0, w.nb);
-          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        if constexpr (TMA_OUT) {
+          if (elected) {
+            ig_tma_store(&maps.o[0][w.l], s32(sOut), 0, w.tx0, w.ty0, w.nb);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          }
+        } else {
+          copy_rows(sOut, p.mean_logits, ROW);
         }
-        // scores / classes: every tile row is one contiguous run of 8 px x 9 anchors in [NB,N]
-        for (int idx = etid; idx < IG_TH * 72; idx += 384) {
+        for (int idx = etid; idx < IG_TH * 72; idx += 384) {  // scores and classes: 8 px x 9 anchors per tile row
           const int row = idx / 72, col = idx - row * 72;
           if (w.ty0 + row < H && w.tx0 + col / 9 < W) {
             const size_t o = (size_t)w.nb * (size_t)p.N + 9ull * (size_t)(p.pix_off[w.l] + (w.ty0 + row) * W + w.tx0) + col;
@@ -307,23 +326,30 @@ __global__ void __launch_bounds__(kFuThreads, 1) heads_fused_kernel(const __grid
           }
         }
         __syncwarp();
-        fu_epi_sync();  // the mean tile has been read by the TMA store
+        fu_epi_sync();  // the mean tile has been read
+        float sd[CH];
 #pragma unroll
-        for (int v = 0; v < 6; ++v) {
-          float sd[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int c = 4 * v + e;
-            const float s1 = sum[c] - fT * x0[c];                         // sum of the deviations from the first sample
-            sd[e] = fu_sqrt(fmaxf(fmaf(-s1 * rT, s1, s2[c]), 0.f) * rT);  // population std, shifted one-pass form
-          }
-          reinterpret_cast<float4*>(st)[v] = make_float4(sd[0], sd[1], sd[2], sd[3]);
+        for (int c = 0; c < CH; ++c) {
+          const float s1 = sum[c] - fT * x0[c];                          // sum of the deviations from the first sample
+          sd[c] = fu_sqrt(fmaxf(fmaf(-s1 * rT, s1, s2[c]), 0.f) * rT);   // population std, shifted one-pass form
         }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        if (CH % 4 == 0 && ROW % 4 == 0) {
+#pragma unroll
+          for (int v = 0; v < CH / 4; ++v)
+            reinterpret_cast<float4*>(st)[v] = make_float4(sd[4 * v], sd[4 * v + 1], sd[4 * v + 2], sd[4 * v + 3]);
+        } else {
+#pragma unroll
+          for (int c = 0; c < CH; ++c) st[c] = sd[c];
+        }
+        if constexpr (TMA_OUT) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         fu_epi_sync();
-        if (elected) {
-          ig_tma_store(&maps.o[1][w.l], s32(sOut), 0, w.tx0, w.ty0, w.nb);
-          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        if constexpr (TMA_OUT) {
+          if (elected) {
+            ig_tma_store(&maps.o[1][w.l], s32(sOut), 0, w.tx0, w.ty0, w.nb);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+        } else {
+          copy_rows(sOut, p.std_logits, ROW);
         }
         __syncwarp();
       } else {
@@ -438,7 +464,7 @@ int udal_run_fused = 1;  // 0: udal_run always goes through predict layers + dec
 int udal_heads_fused_ok(const udal_ctx* ctx) {
   const udal_config& c = ctx->cfg;
   return udal_run_fused && c.heads_mode == UDAL_HEADS_BF16_TC && c.repeats >= 2 && c.num_filters == KF && c.anchors_per_loc == 9 &&
-         c.num_classes == 8 && c.loss_attenuation && c.decode_method == UDAL_DECODE_LNORM && c.cls_mc && c.box_mc &&
+         (c.num_classes == 8 || c.num_classes == 7) && c.loss_attenuation && c.decode_method == UDAL_DECODE_LNORM && c.cls_mc && c.box_mc &&
          c.max_nms_inputs == 0 && c.mc_samples >= 2;
 }
 
@@ -496,12 +522,18 @@ int udal_heads_fused_predict(udal_ctx* ctx, int head, const void* const* in, int
     p.std_logits = pre->std_logits;
     p.scores = pre->scores;
     p.classes = pre->classes;
-    for (int l = 0; l < c.num_levels; ++l) {
-      UDAL_TRY(out_map(&maps.o[0][l], pre->mean_logits, l, 72));
-      UDAL_TRY(out_map(&maps.o[1][l], pre->std_logits, l, 72));
+    if (c.num_classes == 8) {
+      for (int l = 0; l < c.num_levels; ++l) {
+        UDAL_TRY(out_map(&maps.o[0][l], pre->mean_logits, l, 72));
+        UDAL_TRY(out_map(&maps.o[1][l], pre->std_logits, l, 72));
+      }
+      UDAL_CUDA(cudaFuncSetAttribute(heads_fused_kernel<false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, FU_SMEM));
+      heads_fused_kernel<false, 8><<<grid, kFuThreads, FU_SMEM, ctx->stream>>>(maps, p);
+    } else {
+      UDAL_REQUIRE(c.num_classes == 7, "fused class head: %d classes not covered", c.num_classes);
+      UDAL_CUDA(cudaFuncSetAttribute(heads_fused_kernel<false, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize, FU_SMEM));
+      heads_fused_kernel<false, 7><<<grid, kFuThreads, FU_SMEM, ctx->stream>>>(maps, p);
     }
-    UDAL_CUDA(cudaFuncSetAttribute(heads_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FU_SMEM));
-    heads_fused_kernel<false><<<grid, kFuThreads, FU_SMEM, ctx->stream>>>(maps, p);
   } else {
     UDAL_REQUIRE(pre->boxes && pre->albox && pre->mcbox, "fused box head: NULL output");
     p.boxes = pre->boxes;
@@ -512,8 +544,8 @@ int udal_heads_fused_predict(udal_ctx* ctx, int head, const void* const* in, int
       UDAL_TRY(out_map(&maps.o[1][l], pre->albox, l, 36));
       UDAL_TRY(out_map(&maps.o[2][l], pre->mcbox, l, 36));
     }
-    UDAL_CUDA(cudaFuncSetAttribute(heads_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FU_SMEM));
-    heads_fused_kernel<true><<<grid, kFuThreads, FU_SMEM, ctx->stream>>>(maps, p);
+    UDAL_CUDA(cudaFuncSetAttribute(heads_fused_kernel<true, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, FU_SMEM));
+    heads_fused_kernel<true, 8><<<grid, kFuThreads, FU_SMEM, ctx->stream>>>(maps, p);
   }
   UDAL_CHECK_LAUNCH(ctx);
   return UDAL_OK;

@@ -528,6 +528,20 @@ int udal_heads_tc_prepare(udal_ctx* ctx, int head) {
         UDAL_TRY(udal_heads_ig_build_weights(ctx, h.dwp, wf + (size_t)R * L * KF * KF + (size_t)q * KF * KF, KF,
                                              img + (size_t)(R - 2) * tower_img + (size_t)q * tower_img));
     }
+    // predict layer image of the fused predict + K2 kernels: always 72 rows per tap (zero rows past cout)
+    if (h.fused_w) UDAL_CUDA(cudaFree(h.fused_w));
+    h.fused_w = nullptr;
+    if (h.cout <= 72) {
+      constexpr size_t kImg = (size_t)9 * 72 * KF * 2;
+      UDAL_CUDA(cudaMalloc(&h.fused_w, kImg + kMaxN * sizeof(float)));
+      float* tmpw;
+      UDAL_TRY(udal_scratch_get(ctx, SCR_MISC, ((size_t)kMaxN * KF + kMaxN) * sizeof(float), (void**)&tmpw));
+      fold_weights_kernel<<<(kMaxN * KF + 255) / 256, 256, 0, ctx->stream>>>(
+          h.pwp, h.bp, nullptr, nullptr, h.cout, kMaxN, tmpw, reinterpret_cast<float*>(reinterpret_cast<char*>(h.fused_w) + kImg));
+      UDAL_CHECK_LAUNCH(ctx);
+      UDAL_TRY(udal_heads_ig_build_weights(ctx, h.dwp, tmpw, 72, h.fused_w));
+      UDAL_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
     std::vector<float> ones(kMaxN, 1.0f);
     UDAL_CUDA(cudaMemcpyAsync(reinterpret_cast<char*>(h.ig_w) + n_img * 2, ones.data(), kMaxN * sizeof(float),
                               cudaMemcpyHostToDevice, ctx->stream));
@@ -624,9 +638,9 @@ static int run_tower_tc(udal_ctx* ctx, int head, const float* const* feats, int 
     }
     if (predict && fused_pre) {
       // predict layer + MC moments / decode in one kernel: the [T,...] head outputs never reach HBM
-      UDAL_REQUIRE(udal_heads_tc_use_ig && mc && R >= 2, "fused predict kernels: configuration not covered");
-      const __nv_bfloat16* img = reinterpret_cast<const __nv_bfloat16*>(h.ig_w) + (size_t)(R - 2) * 9 * KF * KF;
-      UDAL_TRY(udal_heads_fused_predict(ctx, head, p.in, B, T, img, h.ig_rows, p.fb[0], fused_pre));
+      UDAL_REQUIRE(udal_heads_tc_use_ig && mc && R >= 2 && h.fused_w, "fused predict kernels: configuration not covered");
+      const float* fbias = reinterpret_cast<const float*>(reinterpret_cast<const char*>(h.fused_w) + (size_t)9 * 72 * KF * 2);
+      UDAL_TRY(udal_heads_fused_predict(ctx, head, p.in, B, T, h.fused_w, 72, fbias, fused_pre));
       mark();
       continue;
     }
