@@ -123,3 +123,17 @@ def test_philox_reference_vector():
     # statistical sanity of the uniform stream
     k = u.heads.philox_keep_masks((8, 2, 5, 3, 4, 64), 0.05, 0.3, 1234)
     assert abs(k[:, 0].mean() - 0.95) < 0.01 and abs(k[:, 1].mean() - 0.7) < 0.01
+
+
+def test_autolabel_params_struct_matches_c_layout(tmp_path):
+    import udal_b200 as u
+    src = tmp_path / "sz2.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "udal.h"\nint main(){printf("%zu %zu %zu %zu\\n", '
+                   'sizeof(udal_autolabel_params), offsetof(udal_autolabel_params, table_off), '
+                   'offsetof(udal_autolabel_params, class_temp), offsetof(udal_autolabel_params, strict_reference));return 0;}\n')
+    exe = tmp_path / "sz2"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    size, o1, o2, o3 = map(int, subprocess.check_output([str(exe)]).split())
+    P = u._lib.AutolabelParams
+    assert ctypes.sizeof(P) == size
+    assert P.table_off.offset == o1 and P.class_temp.offset == o2 and P.strict_reference.offset == o3
