@@ -248,24 +248,40 @@ __global__ void __launch_bounds__(kFuThreads, 1) heads_fused_kernel(const __grid
           asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
           __syncwarp();
           if (lane == 0) bar_arrive(bar_tempty + 8 * a);
+          if constexpr (NC == 8) {
 #pragma unroll
-          for (int c = 0; c < CH; ++c) {
-            float bia;
-            if constexpr (CH % 4 == 0) {
-              const float4 b4 = *reinterpret_cast<const float4*>(sBias + cg * CH + (c & ~3));  // one LDS.128 per 4 logits after CSE
-              bia = (c & 3) == 0 ? b4.x : (c & 3) == 1 ? b4.y : (c & 3) == 2 ? b4.z : b4.w;
-            } else {
-              bia = sBias[cg * CH + c];
+            for (int u = 0; u < 3; ++u) {
+              const float4 b0 = *reinterpret_cast<const float4*>(sBias + cg * 24 + u * 8);
+              const float4 b1 = *reinterpret_cast<const float4*>(sBias + cg * 24 + u * 8 + 4);
+              const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                const int c = u * 8 + e;
+                const float x = __fadd_rn(__uint_as_float(r[u][e]), bb[e]);  // = fma(acc, 1, bias) of the predict layer
+                if (t == 0) {
+                  sum[c] = x;
+                  x0[c] = x;
+                  s2[c] = 0.f;
+                } else {
+                  sum[c] = __fadd_rn(sum[c], x);
+                  const float d = x - x0[c];
+                  s2[c] = fmaf(d, d, s2[c]);
+                }
+              }
             }
-            const float x = __fadd_rn(__uint_as_float(r[c >> 3][c & 7]), bia);  // = fma(acc, 1, bias) of the predict layer
-            if (t == 0) {
-              sum[c] = x;
-              x0[c] = x;
-              s2[c] = 0.f;
-            } else {
-              sum[c] = __fadd_rn(sum[c], x);
-              const float d = x - x0[c];
-              s2[c] = fmaf(d, d, s2[c]);
+          } else {
+#pragma unroll
+            for (int c = 0; c < CH; ++c) {
+              const float x = __fadd_rn(__uint_as_float(r[c >> 3][c & 7]), sBias[cg * CH + c]);
+              if (t == 0) {
+                sum[c] = x;
+                x0[c] = x;
+                s2[c] = 0.f;
+              } else {
+                sum[c] = __fadd_rn(sum[c], x);
+                const float d = x - x0[c];
+                s2[c] = fmaf(d, d, s2[c]);
+              }
             }
           }
         }
@@ -277,7 +293,7 @@ __global__ void __launch_bounds__(kFuThreads, 1) heads_fused_kernel(const __grid
         float mean[CH];
 #pragma unroll
         for (int c = 0; c < CH; ++c) mean[c] = __fdiv_rn(sum[c], fT);
-        if (CH % 4 == 0 && ROW % 4 == 0) {
+        if constexpr (CH % 4 == 0 && ROW % 4 == 0) {
 #pragma unroll
           for (int v = 0; v < CH / 4; ++v)
             reinterpret_cast<float4*>(st)[v] = make_float4(mean[4 * v], mean[4 * v + 1], mean[4 * v + 2], mean[4 * v + 3]);
@@ -327,19 +343,25 @@ __global__ void __launch_bounds__(kFuThreads, 1) heads_fused_kernel(const __grid
         }
         __syncwarp();
         fu_epi_sync();  // the mean tile has been read
-        float sd[CH];
+        // population std, shifted one-pass form: s1 = sum of the deviations from the first sample
+        if constexpr (CH % 4 == 0 && ROW % 4 == 0) {
 #pragma unroll
-        for (int c = 0; c < CH; ++c) {
-          const float s1 = sum[c] - fT * x0[c];                          // sum of the deviations from the first sample
-          sd[c] = fu_sqrt(fmaxf(fmaf(-s1 * rT, s1, s2[c]), 0.f) * rT);   // population std, shifted one-pass form
-        }
-        if (CH % 4 == 0 && ROW % 4 == 0) {
+          for (int v = 0; v < CH / 4; ++v) {
+            float sd[4];
 #pragma unroll
-          for (int v = 0; v < CH / 4; ++v)
-            reinterpret_cast<float4*>(st)[v] = make_float4(sd[4 * v], sd[4 * v + 1], sd[4 * v + 2], sd[4 * v + 3]);
+            for (int e = 0; e < 4; ++e) {
+              const int c = 4 * v + e;
+              const float s1 = sum[c] - fT * x0[c];
+              sd[e] = fu_sqrt(fmaxf(fmaf(-s1 * rT, s1, s2[c]), 0.f) * rT);
+            }
+            reinterpret_cast<float4*>(st)[v] = make_float4(sd[0], sd[1], sd[2], sd[3]);
+          }
         } else {
 #pragma unroll
-          for (int c = 0; c < CH; ++c) st[c] = sd[c];
+          for (int c = 0; c < CH; ++c) {
+            const float s1 = sum[c] - fT * x0[c];
+            st[c] = fu_sqrt(fmaxf(fmaf(-s1 * rT, s1, s2[c]), 0.f) * rT);
+          }
         }
         if constexpr (TMA_OUT) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         fu_epi_sync();
