@@ -21,7 +21,9 @@ scales = eng.ctx.to_device(np.ones(batch, np.float32))
 fused = ctypes.c_int.in_dll(eng.lib, "udal_run_fused")
 unst = ctypes.c_int.in_dll(eng.lib, "udal_nms_post_unstaged")
 rsv = ctypes.c_int.in_dll(eng.lib, "udal_run_reserved_sms")
-for f, un, rs in ((1, 0, 0), (1, 0, 4), (1, 1, 4), (1, 0, 8), (1, 1, 8), (1, 1, 12), (1, 0, 16)):
+tl = ctypes.c_int.in_dll(eng.lib, "udal_run_debug_timeline")
+tl.value = 1 if "--timeline" in sys.argv else 0
+for f, un, rs in ((1, 0, 0), (1, 1, 4)):
     fused.value = f
     unst.value = un
     rsv.value = rs
@@ -30,8 +32,17 @@ for f, un, rs in ((1, 0, 0), (1, 0, 4), (1, 1, 4), (1, 0, 8), (1, 1, 8), (1, 1, 
     eng.ctx.sync()
     t = eng.ctx.layer_times(lambda: eng.run(feats, scales, None, seed=9))
     eng.ctx.timer_start()
-    for i in range(5):
+    for i in range(8):
         eng.run(feats, scales, None, seed=20 + i)
-    ms = eng.ctx.timer_stop() / 5
+    # per-layer times of a run issued right behind another one (its tail overlaps these layers)
+    lib = eng.lib
+    lib.udal_profile_layers(eng.ctx.handle, 1)
+    eng.run(feats, scales, None, seed=77)
+    ms8 = (ctypes.c_float * 64)()
+    n8 = ctypes.c_int(0)
+    ms = eng.ctx.timer_stop() / 9
+    lib.udal_get_layer_times(eng.ctx.handle, ms8, 64, ctypes.byref(n8))
+    lib.udal_profile_layers(eng.ctx.handle, 0)
+    print("   pipelined layer ms %s sum %.3f" % ([round(ms8[i], 3) for i in range(n8.value)], sum(ms8[i] for i in range(n8.value))))
     print("nms_post_unstaged=%d reserved=%d" % (un, rs), end="  ")
     print("fused=%d  layer ms %s  sum %.3f  step %.3f ms" % (f, [round(x, 3) for x in t], sum(t), ms), flush=True)

@@ -688,6 +688,7 @@ int udal_heads_tc_sample(udal_ctx* ctx, const float* const* feats, int batch, co
                      (fused_pre || (((uintptr_t)cls_out[l] & 15) == 0 && ((uintptr_t)box_out[l] & 15) == 0)),
                  "level %d: feature / output pointers must be 16-byte aligned", l);
   UDAL_TRY(run_tower_tc(ctx, UDAL_HEAD_CLASS, feats, batch, scale, fused_pre ? nullptr : cls_out, fused_pre));
+  if (fused_pre && ctx->between_heads) UDAL_TRY(ctx->between_heads(ctx, ctx->between_heads_arg));
   UDAL_TRY(run_tower_tc(ctx, UDAL_HEAD_BOX, feats, batch, scale, fused_pre ? nullptr : box_out, fused_pre));
   return UDAL_OK;
 }

@@ -558,8 +558,43 @@ int udal_nms_prefilter_k(const udal_ctx* ctx, int n) {
   return k;
 }
 
-// Global NMS over [S,n] boxes/scores (unsorted): top-K pre-filter + sorted kernel + exact redo of
-// flagged segments.  Everything is enqueued; no host synchronisation.
+// Global NMS over [S,n] boxes/scores (unsorted) in two steps so that a pipelined udal_run can take the
+// bandwidth-bound pre-filter on its main stream as soon as the scores exist and leave only the latency-bound
+// selection to the post stream:
+//   udal_nms_prefilter : exact top-K of the scores (+ the best excluded one) and the segment table
+//   udal_nms_select    : sorted-candidate kernel + exact redo of flagged segments
+// Everything is enqueued; no host synchronisation.
+int udal_nms_prefilter(udal_ctx* ctx, const float* scores, int segments, int n, udal_nms_plan* plan) {
+  UDAL_REQUIRE(segments > 0 && n > 0, "udal_nms_prefilter: bad sizes");
+  const int kk = udal_nms_prefilter_k(ctx, n);   // candidates handed to the sorted kernel
+  const int kq = kk < n ? kk + 1 : kk;          // top-k query size (one extra = best excluded)
+  char* scr;
+  const size_t per = (size_t)segments * kq;
+  UDAL_TRY(udal_scratch_get(ctx, SCR_PRE_B, per * 8 + (size_t)segments * 4, (void**)&scr));
+  plan->kk = kk;
+  plan->kq = kq;
+  plan->tk_idx = (int32_t*)scr;
+  plan->tk_val = (float*)(scr + per * 4);
+  plan->flag = (int32_t*)(scr + per * 8);
+  UDAL_TRY(udal_launch_topk(ctx, scores, segments, n, kq, plan->tk_idx, plan->tk_val));
+  // segment s: candidates tk_idx[s*kq .. s*kq+kk), rows index image s
+  UDAL_TRY(udal_scratch_get(ctx, SCR_MISC, (size_t)segments * 8, (void**)&plan->starts));
+  fill_segments_kernel<<<(segments + 255) / 256, 256, 0, ctx->stream>>>(plan->starts, plan->starts + segments, segments, kq, kk);
+  UDAL_CHECK_LAUNCH(ctx);
+  return UDAL_OK;
+}
+
+int udal_nms_select(udal_ctx* ctx, const float* boxes, const float* scores, int segments, int n, const udal_nms_plan& plan,
+                    int32_t* sel_idx, float* sel_scores, int32_t* valid) {
+  UDAL_REQUIRE(((uintptr_t)boxes & 15) == 0, "boxes must be 16-byte aligned");
+  const int kk = plan.kk, kq = plan.kq;
+  const float* next = kk < n ? plan.tk_val + kk : nullptr;
+  UDAL_TRY(udal_nms_sorted(ctx, boxes, scores, plan.tk_idx, plan.starts, plan.starts + segments, next, kq, segments, kq,
+                           1, n, (int64_t)segments * kq, sel_idx, nullptr, sel_scores, valid, plan.flag));
+  if (kk < n) UDAL_TRY(udal_nms_full(ctx, boxes, scores, segments, n, plan.flag, sel_idx, sel_scores, valid));
+  return UDAL_OK;
+}
+
 int udal_launch_nms_v5(udal_ctx* ctx, const float* boxes, const float* scores, int segments, int n,
                        int32_t* sel_idx, float* sel_scores, int32_t* valid) {
   const int max_out = ctx->cfg.max_output_size;
@@ -571,23 +606,7 @@ int udal_launch_nms_v5(udal_ctx* ctx, const float* boxes, const float* scores, i
     UDAL_CUDA(cudaMemsetAsync(valid, 0, (size_t)segments * 4, ctx->stream));
     return UDAL_OK;
   }
-  const int kk = udal_nms_prefilter_k(ctx, n);   // candidates handed to the sorted kernel
-  const int kq = kk < n ? kk + 1 : kk;          // top-k query size (one extra = best excluded)
-  char* scr;
-  const size_t per = (size_t)segments * kq;
-  UDAL_TRY(udal_scratch_get(ctx, SCR_PRE_B, per * 8 + (size_t)segments * 4, (void**)&scr));
-  int32_t* tk_idx = (int32_t*)scr;
-  float* tk_val = (float*)(scr + per * 4);
-  int32_t* flag = (int32_t*)(scr + per * 8);
-  UDAL_TRY(udal_launch_topk(ctx, scores, segments, n, kq, tk_idx, tk_val));
-  // segment s: candidates tk_idx[s*kq .. s*kq+kk), rows index image s
-  int32_t* starts;
-  UDAL_TRY(udal_scratch_get(ctx, SCR_MISC, (size_t)segments * 8, (void**)&starts));
-  fill_segments_kernel<<<(segments + 255) / 256, 256, 0, ctx->stream>>>(starts, starts + segments, segments, kq, kk);
-  UDAL_CHECK_LAUNCH(ctx);
-  const float* next = kk < n ? tk_val + kk : nullptr;
-  UDAL_TRY(udal_nms_sorted(ctx, boxes, scores, tk_idx, starts, starts + segments, next, kq, segments, kq,
-                           1, n, (int64_t)segments * kq, sel_idx, nullptr, sel_scores, valid, flag));
-  if (kk < n) UDAL_TRY(udal_nms_full(ctx, boxes, scores, segments, n, flag, sel_idx, sel_scores, valid));
-  return UDAL_OK;
+  udal_nms_plan plan;
+  UDAL_TRY(udal_nms_prefilter(ctx, scores, segments, n, &plan));
+  return udal_nms_select(ctx, boxes, scores, segments, n, plan, sel_idx, sel_scores, valid);
 }

@@ -62,6 +62,9 @@ struct udal_ctx {
   int run_bank = 0;
   bool in_run = false;
   bool run_pipelined = false;   // this udal_run was issued while the previous run's tail was still executing
+  // fused udal_run: called between the class head and the box head (the scores exist, the boxes do not yet)
+  int (*between_heads)(udal_ctx*, void*) = nullptr;
+  void* between_heads_arg = nullptr;
   std::vector<void*> user_allocs;
   bool profile_layers = false;
   std::vector<cudaEvent_t> layer_events;  // pairs (start, stop) in launch order
@@ -201,3 +204,14 @@ int udal_nms_sorted(udal_ctx* ctx, const float* boxes, const float* scores, cons
 int udal_nms_full(udal_ctx* ctx, const float* boxes, const float* scores, int segments, int n,
                   const int32_t* flag, int32_t* sel_row, float* sel_scores, int32_t* valid);
 int udal_nms_prefilter_k(const udal_ctx* ctx, int n);
+// top-K pre-filter of a global NMS (scratch of the context's current bank) and the selection that consumes it
+struct udal_nms_plan {
+  int kk = 0, kq = 0;
+  int32_t* tk_idx = nullptr;
+  float* tk_val = nullptr;
+  int32_t* flag = nullptr;
+  int32_t* starts = nullptr;
+};
+int udal_nms_prefilter(udal_ctx* ctx, const float* scores, int segments, int n, udal_nms_plan* plan);
+int udal_nms_select(udal_ctx* ctx, const float* boxes, const float* scores, int segments, int n, const udal_nms_plan& plan,
+                    int32_t* sel_idx, float* sel_scores, int32_t* valid);
