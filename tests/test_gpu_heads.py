@@ -187,6 +187,9 @@ def test_run_tail_overlap_is_invisible(u):
     ((128, 192), 4, 3, 7),       # KITTI label map of the reference YAMLs: 63 logits per pixel, no TMA store
     ((40, 200), 3, 2, 7),
     ((384, 1280), 10, 1, 7),
+    ((128, 192), 4, 3, 10),      # BDD100K label map: 90 logits per pixel, the N = 96 variant of the class kernel
+    ((40, 200), 3, 2, 10),
+    ((720, 1280), 3, 1, 10),     # BASELINE configs[2] geometry (non-integer strides: 720 -> 23 rows at level 5)
 ])
 def test_fused_predict_decode_matches_unfused(u, size, T, batch, C):
     """Serving configuration (A=9, C=8, loss attenuation, l-norm, MC dropout on both heads): udal_run fuses

@@ -83,8 +83,10 @@ __global__ void __launch_bounds__(320, 1) umma_bench_kernel(Args a, long long* o
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(a.n >> 3) << 17) | ((128u >> 4) << 24);
     const uint32_t a0 = sb + a.a_shift, b0 = sb + 72 * 1024;
     uint32_t parity = 0;
-    long long best = 1ll << 60;
+    long long best = 1ll << 60, best_ns = 0;
     for (int rep = 0; rep < 3; ++rep) {
+      unsigned long long g0, g1;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g0));
       const long long t0 = clock64();
       if (a.commit_every == 0) {
         for (int i = 0; i < a.iters; ++i) {
@@ -132,10 +134,15 @@ __global__ void __launch_bounds__(320, 1) umma_bench_kernel(Args a, long long* o
       }
       parity ^= 1;
       const long long t1 = clock64();
-      if (t1 - t0 < best) best = t1 - t0;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g1));
+      if (t1 - t0 < best) {
+        best = t1 - t0;
+        best_ns = (long long)(g1 - g0);
+      }
     }
     if (threadIdx.x == 0) {
       out[blockIdx.x] = best;
+      out[gridDim.x + blockIdx.x] = best_ns;
       stop_flag = 1;
       asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s32(&bar2)) : "memory");
     }
@@ -174,16 +181,21 @@ __global__ void __launch_bounds__(320, 1) umma_bench_kernel(Args a, long long* o
 
 static void run(const char* name, Args a, int grid) {
   long long* d;
-  cudaMalloc(&d, sizeof(long long) * grid);
+  cudaMalloc(&d, sizeof(long long) * grid * 2);
   const int smem = 200 * 1024;
   cudaFuncSetAttribute(umma_bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   umma_bench_kernel<<<grid, 320, smem>>>(a, d);
   cudaError_t e = cudaDeviceSynchronize();
-  long long h[148] = {0};
-  cudaMemcpy(h, d, sizeof(long long) * grid, cudaMemcpyDeviceToHost);
-  long long mx = 0;
-  for (int i = 0; i < grid; ++i) mx = h[i] > mx ? h[i] : mx;
-  printf("%-48s N=%3d grid=%3d pollers=%d commit_every=%d x%d  %7.1f cycles/MMA  (%s)\n", name, a.n, grid, a.pollers, a.commit_every * 4, a.commits_per, (double)mx / (4.0 * a.iters), cudaGetErrorString(e));
+  long long h[296] = {0};
+  cudaMemcpy(h, d, sizeof(long long) * grid * 2, cudaMemcpyDeviceToHost);
+  long long mx = 0, ns = 1;
+  for (int i = 0; i < grid; ++i)
+    if (h[i] > mx) {
+      mx = h[i];
+      ns = h[grid + i];
+    }
+  // SM clock during the measurement = cycles / globaltimer ns (the tensor pipe under load may run below the idle clock)
+  printf("%-48s N=%3d grid=%3d pollers=%d commit_every=%d x%d iters=%d  %7.1f cycles/MMA  %6.0f MHz  (%s)\n", name, a.n, grid, a.pollers, a.commit_every * 4, a.commits_per, a.iters, (double)mx / (4.0 * a.iters), 1e3 * (double)mx / (double)ns, cudaGetErrorString(e));
   cudaFree(d);
 }
 
@@ -194,6 +206,8 @@ int main() {
     run("head-kernel tile pattern, 1 commit/tile", Args{n, 2, 1280, 1024, 16, 16, 32, 32, 0, iters, 9, 1, 0}, 148);
     run("head-kernel tile pattern, 2 commits/tile", Args{n, 2, 1280, 1024, 16, 16, 32, 32, 0, iters, 9, 2, 0}, 148);
     run("head-kernel tile pattern, 0 commits/tile", Args{n, 2, 1280, 1024, 16, 16, 32, 32, 0, iters, 9, 0, 0}, 148);
+    // sustained: ~25 ms of back-to-back MMAs per repetition, long enough for the power management to settle
+    run("head-kernel tile pattern, sustained", Args{n, 2, 1280, 1024, 16, 16, 32, 32, 0, iters * 70, 9, 1, 0}, 148);
   }
   return 0;
 }

@@ -22,6 +22,8 @@
 // box quantities from the fp32 decode (~1e-6 relative).
 // Per-anchor results leave through shared-memory staging tiles and TMA tensor stores ([B, H_l, W_l, 72] /
 // [.., 36] views of the [B, N, C] / [B, N, 4] outputs), which also clip the ragged tile edges.
+#include <type_traits>
+
 #include "udal_common.cuh"
 #include "heads_umma.cuh"
 #include "decode_math.cuh"
@@ -29,18 +31,32 @@
 namespace {
 
 constexpr int kFuThreads = 64 + 12 * 32;
-constexpr int FU_NPAD = 80, FU_NROWS = 72, FU_STAGES = 3;
 constexpr int FU_STAGE = (IG_ROWS * IG_BOXW * 128 + 1023) / 1024 * 1024;
-constexpr int FU_B = 0;
-constexpr int FU_B_BYTES = 9 * FU_NROWS * 128;
-constexpr int FU_IN = FU_B + FU_B_BYTES;
-constexpr int FU_OUT = FU_IN + FU_STAGES * FU_STAGE;   // staging tile [128 px][72] fp32 (class) / 3 x [128 px][36] (box)
-constexpr int FU_OUT2 = FU_OUT + 128 * 72 * 4;          // class: scores [128][9] fp32, classes [128][9] i32; box: mcbox [128][36]
-constexpr int FU_BAR = FU_OUT2 + 128 * 36 * 4;         // barriers + tmem slot (128 B)
-constexpr int FU_TBL = FU_BAR + 128;                   // 64 doubles: 2^(j/64) table of exp_fast
-constexpr int FU_BIAS = FU_TBL + 512;                  // [80] fp32 predict bias
-constexpr int FU_SMEM = FU_BIAS + FU_NPAD * 4 + 1024;
-static_assert(FU_SMEM <= kIgSmemLimit, "shared-memory budget");
+constexpr int FU_MAX_STAGES = 4;
+// compile-time shape of one kernel variant (offsets from a 1024-byte aligned base)
+//   NPAD   UMMA N                       NROWS  weight rows kept per tap (multiple of 8)
+//   STAGES TMA ring depth               OUT_BYTES / OUT2_BYTES  the two staging areas
+template <int NPAD_, int NROWS_, int STAGES_, int OUT_BYTES_, int OUT2_BYTES_>
+struct FuShape {
+  static constexpr int NPAD = NPAD_, NROWS = NROWS_, STAGES = STAGES_;
+  static constexpr int B = 0;
+  static constexpr int B_BYTES = 9 * NROWS * 128;
+  static constexpr int IN = B + B_BYTES;
+  static constexpr int OUT = IN + STAGES * FU_STAGE;   // class: [128 px][9 NC] fp32; box: boxes | albox, 2 x [128 px][36]
+  static constexpr int OUT2 = OUT + OUT_BYTES_;        // class: scores [128][9] fp32, classes [128][9] i32; box: mcbox [128][36]
+  static constexpr int BAR = OUT2 + OUT2_BYTES_;       // barriers + tmem slot (128 B)
+  static constexpr int TBL = BAR + 128;                // 64 doubles: 2^(j/64) table of exp_fast
+  static constexpr int BIAS = TBL + 512;               // [NPAD] fp32 predict bias
+  static constexpr int SMEM = BIAS + NPAD * 4 + 1024;
+  static_assert(B_BYTES % 1024 == 0 && STAGES <= FU_MAX_STAGES && 2 * NPAD <= 256, "layout");
+  static_assert(SMEM <= kIgSmemLimit, "shared-memory budget");
+};
+// A = 9 anchors: 63 / 72 logits (7 / 8 classes) and the 72 box + sigma channels share one shape; 10 classes (90 logits,
+// e.g. the BDD100K map) need N = 96, whose 108 KB weight image leaves room for a 2-stage ring
+using FuShape72 = FuShape<80, 72, 3, 128 * 72 * 4, 128 * 36 * 4>;
+using FuShape96 = FuShape<96, 96, 2, 128 * 90 * 4, 128 * 9 * 8>;
+template <bool BOX, int NC>
+using FuShapeOf = typename std::conditional<(BOX || NC <= 8), FuShape72, FuShape96>::type;
 
 struct FuParams {
   int num_levels, NB, T, items;          // NB = images; items = sum_l tiles[l] * NB (level major)
@@ -48,8 +64,8 @@ struct FuParams {
   int item_off[UDAL_MAX_LEVELS + 1];
   uint32_t tiles_magic[UDAL_MAX_LEVELS], tiles_x_magic[UDAL_MAX_LEVELS];
   int pix_off[UDAL_MAX_LEVELS + 1];      // prefix of H_l * W_l
-  const void* wimg;                      // bf16 [9][72][64] swizzled weight image of the predict layer
-  const float* bias;                     // [80]
+  const void* wimg;                      // bf16 [9][NROWS][64] swizzled weight image of the predict layer
+  const float* bias;                     // [NPAD]
   const float* anchors;                  // [N,4]
   long long N;                           // anchors per image
   float* mean_logits;                    // class head outputs [NB,N,NC]
@@ -111,9 +127,13 @@ __device__ __forceinline__ void fu_ld4(uint32_t taddr, uint32_t (&r)[4]) {
                : "memory");
 }
 
-// NC = classes per anchor of the class head (7: KITTI map of the reference YAMLs, 8); the box head ignores it
+// NC = classes per anchor of the class head (7: KITTI map of the reference YAMLs, 8, 10: BDD100K); the box head
+// ignores it
 template <bool BOX, int NC>
 __global__ void __launch_bounds__(kFuThreads, 1) heads_fused_kernel(const __grid_constant__ FuMaps maps, const FuParams p) {
+  using S = FuShapeOf<BOX, NC>;
+  constexpr int FU_NPAD = S::NPAD, FU_NROWS = S::NROWS, FU_STAGES = S::STAGES, FU_B = S::B, FU_B_BYTES = S::B_BYTES,
+                FU_IN = S::IN, FU_OUT = S::OUT, FU_OUT2 = S::OUT2, FU_BAR = S::BAR, FU_TBL = S::TBL, FU_BIAS = S::BIAS;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = s32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
@@ -241,9 +261,41 @@ __global__ void __launch_bounds__(kFuThreads, 1) heads_fused_kernel(const __grid
           __syncwarp();
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * FU_NPAD + cg * CH);
-          uint32_t r[3][8];  // 24 columns from the thread's first one (the tail past CH is not used)
+          constexpr int NLD = (CH + 7) / 8;
+          static_assert(2 * CH + NLD * 8 <= FU_NPAD, "accumulator columns read past the thread's logits stay inside N");
+          if constexpr (NC > 8) {
+            // 30 logits x (sum, first sample, squared deviations) already fill the register file: the accumulator is
+            // read 8 columns at a time (the MMA of the next sample takes ~2000 cycles, the extra load latency hides)
 #pragma unroll
-          for (int u = 0; u < 3; ++u) ig_ld8(taddr + u * 8, r[u]);
+            for (int u = 0; u < NLD; ++u) {
+              uint32_t r8[8];
+              ig_ld8(taddr + u * 8, r8);
+              asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                const int c = u * 8 + e;
+                if (c < CH) {
+                  const float x = __fadd_rn(__uint_as_float(r8[e]), sBias[cg * CH + c]);
+                  if (t == 0) {
+                    sum[c] = x;
+                    x0[c] = x;
+                    s2[c] = 0.f;
+                  } else {
+                    sum[c] = __fadd_rn(sum[c], x);
+                    const float d = x - x0[c];
+                    s2[c] = fmaf(d, d, s2[c]);
+                  }
+                }
+              }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) bar_arrive(bar_tempty + 8 * a);
+            continue;
+          }
+          uint32_t r[NLD][8];  // NLD x 8 columns from the thread's first one (the tail past CH is not used)
+#pragma unroll
+          for (int u = 0; u < NLD; ++u) ig_ld8(taddr + u * 8, r[u]);
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
           asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
           __syncwarp();
@@ -486,7 +538,7 @@ int udal_run_fused = 1;  // 0: udal_run always goes through predict layers + dec
 int udal_heads_fused_ok(const udal_ctx* ctx) {
   const udal_config& c = ctx->cfg;
   return udal_run_fused && c.heads_mode == UDAL_HEADS_BF16_TC && c.repeats >= 2 && c.num_filters == KF && c.anchors_per_loc == 9 &&
-         (c.num_classes == 8 || c.num_classes == 7) && c.loss_attenuation && c.decode_method == UDAL_DECODE_LNORM && c.cls_mc && c.box_mc &&
+         (c.num_classes == 8 || c.num_classes == 7 || c.num_classes == 10) && c.loss_attenuation && c.decode_method == UDAL_DECODE_LNORM && c.cls_mc && c.box_mc &&
          c.max_nms_inputs == 0 && c.mc_samples >= 2;
 }
 
@@ -497,7 +549,8 @@ int udal_heads_fused_predict(udal_ctx* ctx, int head, const void* const* in, int
                              const float* bias, const udal_prenms_out* pre) {
   EncodeTiledFn encode = get_encode();
   UDAL_REQUIRE(encode != nullptr, "cuTensorMapEncodeTiled is not available from this driver");
-  UDAL_REQUIRE(rows == FU_NROWS, "fused predict kernels expect the 72-row weight image");
+  const bool wide = head == UDAL_HEAD_CLASS && ctx->cfg.num_classes > 8;  // 90 logits per pixel: the N = 96 shape
+  UDAL_REQUIRE(rows == (wide ? FuShape96::NROWS : FuShape72::NROWS), "fused predict kernel: weight image with %d rows per tap", rows);
   UDAL_REQUIRE(ctx->anchors_set, "anchor table not set");
   const udal_config& c = ctx->cfg;
   FuMaps maps;
@@ -549,12 +602,15 @@ int udal_heads_fused_predict(udal_ctx* ctx, int head, const void* const* in, int
         UDAL_TRY(out_map(&maps.o[0][l], pre->mean_logits, l, 72));
         UDAL_TRY(out_map(&maps.o[1][l], pre->std_logits, l, 72));
       }
-      UDAL_CUDA(cudaFuncSetAttribute(heads_fused_kernel<false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, FU_SMEM));
-      heads_fused_kernel<false, 8><<<grid, kFuThreads, FU_SMEM, ctx->stream>>>(maps, p);
+      UDAL_CUDA(cudaFuncSetAttribute(heads_fused_kernel<false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, FuShape72::SMEM));
+      heads_fused_kernel<false, 8><<<grid, kFuThreads, FuShape72::SMEM, ctx->stream>>>(maps, p);
+    } else if (c.num_classes == 7) {
+      UDAL_CUDA(cudaFuncSetAttribute(heads_fused_kernel<false, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize, FuShape72::SMEM));
+      heads_fused_kernel<false, 7><<<grid, kFuThreads, FuShape72::SMEM, ctx->stream>>>(maps, p);
     } else {
-      UDAL_REQUIRE(c.num_classes == 7, "fused class head: %d classes not covered", c.num_classes);
-      UDAL_CUDA(cudaFuncSetAttribute(heads_fused_kernel<false, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize, FU_SMEM));
-      heads_fused_kernel<false, 7><<<grid, kFuThreads, FU_SMEM, ctx->stream>>>(maps, p);
+      UDAL_REQUIRE(c.num_classes == 10, "fused class head: %d classes not covered", c.num_classes);
+      UDAL_CUDA(cudaFuncSetAttribute(heads_fused_kernel<false, 10>, cudaFuncAttributeMaxDynamicSharedMemorySize, FuShape96::SMEM));
+      heads_fused_kernel<false, 10><<<grid, kFuThreads, FuShape96::SMEM, ctx->stream>>>(maps, p);
     }
   } else {
     UDAL_REQUIRE(pre->boxes && pre->albox && pre->mcbox, "fused box head: NULL output");
@@ -566,8 +622,8 @@ int udal_heads_fused_predict(udal_ctx* ctx, int head, const void* const* in, int
       UDAL_TRY(out_map(&maps.o[1][l], pre->albox, l, 36));
       UDAL_TRY(out_map(&maps.o[2][l], pre->mcbox, l, 36));
     }
-    UDAL_CUDA(cudaFuncSetAttribute(heads_fused_kernel<true, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, FU_SMEM));
-    heads_fused_kernel<true, 8><<<grid, kFuThreads, FU_SMEM, ctx->stream>>>(maps, p);
+    UDAL_CUDA(cudaFuncSetAttribute(heads_fused_kernel<true, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, FuShape72::SMEM));
+    heads_fused_kernel<true, 8><<<grid, kFuThreads, FuShape72::SMEM, ctx->stream>>>(maps, p);
   }
   UDAL_CHECK_LAUNCH(ctx);
   return UDAL_OK;

@@ -528,19 +528,23 @@ int udal_heads_tc_prepare(udal_ctx* ctx, int head) {
         UDAL_TRY(udal_heads_ig_build_weights(ctx, h.dwp, wf + (size_t)R * L * KF * KF + (size_t)q * KF * KF, KF,
                                              img + (size_t)(R - 2) * tower_img + (size_t)q * tower_img));
     }
-    // predict layer image of the fused predict + K2 kernels: always 72 rows per tap (zero rows past cout)
+    // predict layer image of the fused predict + K2 kernels: 72 rows per tap (zero rows past cout) and an 80-entry bias,
+    // or 96 / 96 for the 90 logits of a 10-class head
     if (h.fused_w) UDAL_CUDA(cudaFree(h.fused_w));
     h.fused_w = nullptr;
-    if (h.cout <= 72) {
-      constexpr size_t kImg = (size_t)9 * 72 * KF * 2;
-      UDAL_CUDA(cudaMalloc(&h.fused_w, kImg + kMaxN * sizeof(float)));
+    h.fused_rows = 0;
+    if (h.cout <= 96) {
+      const int frows = h.cout <= 72 ? 72 : 96, fpad = h.cout <= 72 ? kMaxN : 96;
+      const size_t img_bytes = (size_t)9 * frows * KF * 2;
+      UDAL_CUDA(cudaMalloc(&h.fused_w, img_bytes + fpad * sizeof(float)));
       float* tmpw;
-      UDAL_TRY(udal_scratch_get(ctx, SCR_MISC, ((size_t)kMaxN * KF + kMaxN) * sizeof(float), (void**)&tmpw));
-      fold_weights_kernel<<<(kMaxN * KF + 255) / 256, 256, 0, ctx->stream>>>(
-          h.pwp, h.bp, nullptr, nullptr, h.cout, kMaxN, tmpw, reinterpret_cast<float*>(reinterpret_cast<char*>(h.fused_w) + kImg));
+      UDAL_TRY(udal_scratch_get(ctx, SCR_MISC, ((size_t)fpad * KF + fpad) * sizeof(float), (void**)&tmpw));
+      fold_weights_kernel<<<(fpad * KF + 255) / 256, 256, 0, ctx->stream>>>(
+          h.pwp, h.bp, nullptr, nullptr, h.cout, fpad, tmpw, reinterpret_cast<float*>(reinterpret_cast<char*>(h.fused_w) + img_bytes));
       UDAL_CHECK_LAUNCH(ctx);
-      UDAL_TRY(udal_heads_ig_build_weights(ctx, h.dwp, tmpw, 72, h.fused_w));
+      UDAL_TRY(udal_heads_ig_build_weights(ctx, h.dwp, tmpw, frows, h.fused_w));
       UDAL_CUDA(cudaStreamSynchronize(ctx->stream));
+      h.fused_rows = frows;
     }
     std::vector<float> ones(kMaxN, 1.0f);
     UDAL_CUDA(cudaMemcpyAsync(reinterpret_cast<char*>(h.ig_w) + n_img * 2, ones.data(), kMaxN * sizeof(float),
@@ -639,8 +643,8 @@ static int run_tower_tc(udal_ctx* ctx, int head, const float* const* feats, int 
     if (predict && fused_pre) {
       // predict layer + MC moments / decode in one kernel: the [T,...] head outputs never reach HBM
       UDAL_REQUIRE(udal_heads_tc_use_ig && mc && R >= 2 && h.fused_w, "fused predict kernels: configuration not covered");
-      const float* fbias = reinterpret_cast<const float*>(reinterpret_cast<const char*>(h.fused_w) + (size_t)9 * 72 * KF * 2);
-      UDAL_TRY(udal_heads_fused_predict(ctx, head, p.in, B, T, h.fused_w, 72, fbias, fused_pre));
+      const float* fbias = reinterpret_cast<const float*>(reinterpret_cast<const char*>(h.fused_w) + (size_t)9 * h.fused_rows * KF * 2);
+      UDAL_TRY(udal_heads_fused_predict(ctx, head, p.in, B, T, h.fused_w, h.fused_rows, fbias, fused_pre));
       mark();
       continue;
     }

@@ -28,7 +28,8 @@ struct udal_head_weights_dev {
   void* pwp_bf16 = nullptr;
   float* fold_bias = nullptr;
   int ig_rows = 0;       // weight rows per tap of the predict image in ig_w
-  void* fused_w = nullptr;  // predict layer for the fused kernels: bf16 [9][72][64] image, then bias [80] fp32
+  void* fused_w = nullptr;  // predict layer for the fused kernels: bf16 [9][fused_rows][64] image, then bias [80 | 96] fp32
+  int fused_rows = 0;       // 72 (cout <= 72) or 96
   int pred_chunks = 1;   // > 1: predict layer with more than 80 channels, run as chunks of pred_chunk channels
   int pred_chunk = 0;
   void* ig_w = nullptr;  // implicit-GEMM weight images: [(R-2)*L tower layers >= 2][9][64][64] then predict [9][Npad][64], bf16
