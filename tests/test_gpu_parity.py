@@ -278,7 +278,10 @@ def test_per_class_nms_mirror_vs_oracle(u):
 # ---------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("C,T,batch,size,method", [(7, 10, 2, (64, 96), "gaussian"), (8, 1, 1, 64, "hard"),
                                                    (10, 30, 1, 64, "gaussian"), (90, 4, 2, 64, "hard"),
-                                                   (3, 40, 1, 64, "gaussian")])
+                                                   (3, 40, 1, 64, "gaussian"),
+                                                   # 17..32 samples: chunked loads of the decode kernel (chunk edges)
+                                                   (8, 20, 2, (64, 96), "gaussian"), (7, 17, 1, 64, "hard"),
+                                                   (8, 32, 1, 64, "gaussian"), (10, 24, 3, (64, 96), "gaussian")])
 def test_postprocess_global_vs_oracle_random(u, C, T, batch, size, method):
     p = u.hparams_config.get_detection_config(
         "efficientdet-d0", image_size=size, num_classes=C, enable_softmax=True, loss_attenuation=True,

@@ -217,8 +217,9 @@ __device__ __forceinline__ void logits_run(const float* __restrict__ base, size_
 
 // FAST = the serving configuration (loss attenuation, l-norm decode, MC dropout on both heads,
 // T == TMAX): every mode switch folds away at compile time.
-template <int TMAX, bool FAST>
-__global__ void __launch_bounds__(kThreads, (TMAX == 0 || TMAX > 16) ? 1 : 4) decode_moments_kernel(const DecodeParams p) {
+// TCH: samples per load chunk of the 17..32-sample path.
+template <int TMAX, bool FAST, int TCH_ = 4>
+__global__ void __launch_bounds__(kThreads, TMAX == 0 ? 1 : (TMAX > 16 ? 2 : 4)) decode_moments_kernel(const DecodeParams p) {
   const int k_la = FAST ? 1 : p.la;
   const int k_method = FAST ? (int)UDAL_DECODE_LNORM : p.method;
   const int k_box_mc = FAST ? 1 : p.box_mc;
@@ -266,7 +267,79 @@ __global__ void __launch_bounds__(kThreads, (TMAX == 0 || TMAX > 16) ? 1 : 4) de
     const size_t t_stride = (size_t)p.batch * plane;
     const int T = k_Tb;
     float m_lo, m_hi, sd_lo = 0.f, sd_hi = 0.f, al_lo = 0.f, al_hi = 0.f;
-    if (TMAX != 0) {
+    if (TMAX > 16) {
+      // 17..32 samples: the loads go out in chunks of TCH samples (2 x TCH independent 16-byte requests per thread;
+      // all 2 x T at once would need 256 registers), each chunk is parked in shared memory and decoded by a rolled
+      // loop; the decoded corners of all samples stay in shared memory for the two-pass standard deviation.
+      // (2 T + 4 TCH) floats per thread instead of 4 T, so that several CTAs fit an SM (the fp64 decode chains
+      // need the warps: the kernel is issue / latency bound, not HBM bound).
+      constexpr int TCH = TCH_;
+      float* sd = smem_stage + threadIdx.x;                      // (lo, hi) of sample t at sd[(t * 2 + k) * kThreads]
+      float* sr = smem_stage + 2 * T * kThreads + threadIdx.x;   // raw chunk: slot (u, k) at sr[(u * 4 + k) * kThreads]
+      float sum_lo = 0.f, sum_hi = 0.f;
+#pragma unroll 1
+      for (int t0 = 0; t0 < T; t0 += TCH) {
+        {
+          float4 tt[TCH], sg[TCH];
+#pragma unroll
+          for (int u = 0; u < TCH; ++u)
+            if (t0 + u < T) {
+              tt[u] = __ldg(reinterpret_cast<const float4*>(bb + (size_t)(t0 + u) * t_stride));
+              if (k_la) sg[u] = __ldg(reinterpret_cast<const float4*>(bb + (size_t)(t0 + u) * t_stride + 4 * A));
+            }
+#pragma unroll
+          for (int u = 0; u < TCH; ++u)
+            if (t0 + u < T) {
+              sr[(u * 4 + 0) * kThreads] = axis ? tt[u].y : tt[u].x;
+              sr[(u * 4 + 1) * kThreads] = axis ? tt[u].w : tt[u].z;
+              if (k_la) {
+                sr[(u * 4 + 2) * kThreads] = axis ? sg[u].y : sg[u].x;
+                sr[(u * 4 + 3) * kThreads] = axis ? sg[u].w : sg[u].z;
+              }
+            }
+        }
+        const int tn = min(TCH, T - t0);
+#pragma unroll 1
+        for (int u = 0; u < tn; ++u) {
+          const int t = t0 + u;
+          const float t_c = sr[(u * 4 + 0) * kThreads], t_s = sr[(u * 4 + 1) * kThreads];
+          float lo, hi;
+          if (k_la) {
+            float s_lo, s_hi;
+            decode_axis_la(k_method, smem_tbl, a_lo, a_hi, t_c, t_s, sr[(u * 4 + 2) * kThreads], sr[(u * 4 + 3) * kThreads], lo,
+                           hi, s_lo, s_hi);
+            al_lo = t == 0 ? s_lo : __fadd_rn(al_lo, s_lo);
+            al_hi = t == 0 ? s_hi : __fadd_rn(al_hi, s_hi);
+          } else {
+            decode_axis_plain(a_lo, a_hi, t_c, t_s, lo, hi);
+          }
+          sd[(t * 2 + 0) * kThreads] = lo;
+          sd[(t * 2 + 1) * kThreads] = hi;
+          sum_lo = t == 0 ? lo : __fadd_rn(sum_lo, lo);
+          sum_hi = t == 0 ? hi : __fadd_rn(sum_hi, hi);
+        }
+      }
+      if (k_box_mc) {
+        const float fT = (float)T;
+        m_lo = __fdiv_rn(sum_lo, fT);
+        m_hi = __fdiv_rn(sum_hi, fT);
+        float q_lo = 0.f, q_hi = 0.f;
+#pragma unroll 1
+        for (int t = 0; t < T; ++t) {
+          const float d0 = __fsub_rn(sd[(t * 2 + 0) * kThreads], m_lo);
+          const float d1 = __fsub_rn(sd[(t * 2 + 1) * kThreads], m_hi);
+          q_lo = t == 0 ? __fmul_rn(d0, d0) : __fadd_rn(q_lo, __fmul_rn(d0, d0));
+          q_hi = t == 0 ? __fmul_rn(d1, d1) : __fadd_rn(q_hi, __fmul_rn(d1, d1));
+        }
+        sd_lo = __fsqrt_rn(__fdiv_rn(q_lo, fT));
+        sd_hi = __fsqrt_rn(__fdiv_rn(q_hi, fT));
+        al_lo = __fdiv_rn(al_lo, fT);
+        al_hi = __fdiv_rn(al_hi, fT);
+      } else {
+        m_lo = sum_lo;
+        m_hi = sum_hi;
+      }
+    } else if (TMAX != 0) {
       constexpr int TM = TMAX == 0 ? 1 : TMAX;
       // (a) every load of this thread is issued first (2 x T independent 16-byte requests in
       //     flight) and parked in shared memory; (b) a rolled loop decodes sample by sample.
@@ -555,6 +628,8 @@ int pick_tmax(int T) {
 
 }  // namespace
 
+int udal_decode_chunk = 4;  // samples per load chunk of the 17..32-sample decode path (2 | 4 | 8; tuning switch)
+
 int udal_launch_decode_moments(udal_ctx* ctx, const float* const* cls, const float* const* box,
                                int batch, const udal_prenms_out* out) {
   DecodeParams p;
@@ -565,26 +640,32 @@ int udal_launch_decode_moments(udal_ctx* ctx, const float* const* cls, const flo
   const int T = p.Tc > p.Tb ? p.Tc : p.Tb;
   dim3 grid(tiles, batch);
   const bool fast = p.la && p.method == UDAL_DECODE_LNORM && p.box_mc && p.cls_mc && p.Tb == p.Tc;
-  if (pick_tmax(T) != 0) smem += (size_t)4 * p.Tb * kThreads * sizeof(float);
+  const int chunk = udal_decode_chunk == 2 || udal_decode_chunk == 8 ? udal_decode_chunk : 4;
+  if (pick_tmax(T) > 16) smem += (size_t)(2 * p.Tb + 4 * chunk) * kThreads * sizeof(float);
+  else if (pick_tmax(T) != 0) smem += (size_t)4 * p.Tb * kThreads * sizeof(float);
   UDAL_REQUIRE(smem <= 200 * 1024, "decode_moments: T=%d needs %zu bytes of shared memory", T, smem);
-#define LAUNCH_ONE(TM, F)                                                                                   \
-  {                                                                                                         \
-    if (smem > 48 * 1024)                                                                                   \
-      UDAL_CUDA(cudaFuncSetAttribute(decode_moments_kernel<TM, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                     (int)smem));                                                           \
-    decode_moments_kernel<TM, F><<<grid, kThreads, smem, ctx->stream>>>(p);                                 \
+#define LAUNCH_ONE(TM, F, CH)                                                                                   \
+  {                                                                                                             \
+    if (smem > 48 * 1024)                                                                                       \
+      UDAL_CUDA(cudaFuncSetAttribute(decode_moments_kernel<TM, F, CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                     (int)smem));                                                               \
+    decode_moments_kernel<TM, F, CH><<<grid, kThreads, smem, ctx->stream>>>(p);                                 \
   }
-#define LAUNCH(TM)                           \
-  if (fast && T == TM) LAUNCH_ONE(TM, true)  \
-  else LAUNCH_ONE(TM, false)                 \
+#define LAUNCH(TM)                              \
+  if (fast && T == TM) LAUNCH_ONE(TM, true, 4)  \
+  else LAUNCH_ONE(TM, false, 4)                 \
   break;
   switch (pick_tmax(T)) {
     case 1: LAUNCH(1)
     case 4: LAUNCH(4)
     case 10: LAUNCH(10)
     case 16: LAUNCH(16)
-    case 32: LAUNCH(32)
-    default: LAUNCH_ONE(0, false) break;
+    case 32:
+      if (chunk == 2) LAUNCH_ONE(32, false, 2)
+      else if (chunk == 8) LAUNCH_ONE(32, false, 8)
+      else LAUNCH_ONE(32, false, 4)
+      break;
+    default: LAUNCH_ONE(0, false, 4) break;
   }
 #undef LAUNCH_ONE
 #undef LAUNCH
