@@ -130,6 +130,48 @@ def test_heads_bf16_tensor_core_vs_oracle(u, size, C, T, batch, la, rc, rb):
     print("bf16 heads max abs err", worst)
 
 
+@pytest.mark.parametrize("model,size,C,T,batch,la,rc,rb", [
+    ("efficientdet-d2", (64, 96), 10, 3, 2, True, 0.05, 0.05),    # F = 112 (BASELINE configs[4] width), 90 class channels
+    ("efficientdet-d1", (40, 200), 7, 2, 3, True, 0.0, 0.2),      # F = 88, ragged levels, deterministic class head
+    ("efficientdet-d2", 128, 8, 1, 1, False, 0.0, 0.0),           # no MC dropout, no loss attenuation (36 box channels)
+    ("efficientdet-d2", (384, 640), 10, 5, 1, True, 0.05, 0.05),  # many work items per CTA: ring wrap-around, every phase
+    ("efficientdet-d2", 64, 20, 2, 1, True, 0.05, 0.0),           # 180 class channels = 2 predict chunks of <= 128
+])
+def test_heads_wide_tensor_core_vs_oracle(u, model, size, C, T, batch, la, rc, rb):
+    """fpn_num_filters 88 / 112 (D1 / D2) on the tensor cores: channels zero-padded to 128, depthwise on the CUDA cores,
+    pointwise on tcgen05 (heads_wide.cu).  Same bf16 tolerance as the 64-channel path."""
+    p = u.hparams_config.get_detection_config(
+        model, image_size=size, num_classes=C, enable_softmax=True, loss_attenuation=la,
+        mc_dropout=bool(rc or rb), mc_classheadrate=rc, mc_boxheadrate=rb, mc_dropoutsamp=T, heads_mode="bf16")
+    eng = u.engine.get_engine(p)
+    assert eng.F in (88, 112)
+    L = len(eng.level_hw)
+    w = heads_ref.init_head_weights(eng.F, eng.R, L, eng.A, C, la, seed=9, randomize_bn=True)
+    feats = heads_ref.make_features(eng.level_hw, batch, eng.F, seed=11)
+    masks = heads_ref.make_masks(T, L, eng.R, batch, eng.F, rc, rb, seed=5)
+    sampler = u.heads.HeadSampler(p, w)
+    cls, box = sampler(feats, masks=masks)
+    again = sampler(feats, masks=masks)
+    for x, y in zip(cls + box, again[0] + again[1]):
+        np.testing.assert_array_equal(x, y)
+    rcls, rbox = heads_ref.heads_sample(feats, w, masks, rc, rb, T)
+    worst = 0.0
+    for l in range(L):
+        rc_l = rcls[l] if rc else rcls[l][0]
+        rb_l = rbox[l] if rb else rbox[l][0]
+        assert cls[l].shape == rc_l.shape and box[l].shape == rb_l.shape
+        worst = max(worst, float(np.abs(cls[l] - rc_l).max()), float(np.abs(box[l] - rb_l).max()))
+        np.testing.assert_allclose(cls[l], rc_l, rtol=BF16_RTOL, atol=BF16_ATOL)
+        np.testing.assert_allclose(box[l], rb_l, rtol=BF16_RTOL, atol=BF16_ATOL)
+    print("wide bf16 heads max abs err", worst)
+    # features -> detections through udal_run (predict layers + decode_moments + NMS) equals the two-stage path
+    scales = np.linspace(1.0, 1.5, batch).astype(np.float32)
+    det = sampler.detect(feats, scales, masks=masks)
+    two = u.postprocess.postprocess_global(p, cls, box, scales)
+    for a, b in zip(det, two):
+        np.testing.assert_array_equal(a, b)
+
+
 def test_pipelined_sampler_matches_blocking_calls(u):
     p = _cfg(u, (64, 96), 7, 4, heads_mode="bf16")
     eng = u.engine.get_engine(p)

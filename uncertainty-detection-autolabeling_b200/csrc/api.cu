@@ -135,6 +135,8 @@ static void free_head(udal_head_weights_dev& h) {
   cudaFree(h.fold_bias);
   cudaFree(h.ig_w);
   cudaFree(h.fused_w);
+  cudaFree(h.wide_w);
+  cudaFree(h.wide_f);
   h = udal_head_weights_dev();
 }
 

@@ -460,11 +460,17 @@ int udal_heads_fused_predict(udal_ctx* ctx, int head, const void* const* in, int
                              const float* bias, const udal_prenms_out* pre);
 int udal_heads_tc_use_ig = 1;  // 0: every layer through the per-tile kernel (debug / comparison)
 
+int udal_heads_wide_ok(const udal_ctx* ctx);  // heads_wide.cu: 64 < fpn_num_filters <= 128
+int udal_heads_wide_prepare(udal_ctx* ctx, int head);
+int udal_heads_wide_sample(udal_ctx* ctx, const float* const* feats, int batch, const float* scale, float* const* cls_out,
+                           float* const* box_out);
+
 int udal_heads_tc_prepare(udal_ctx* ctx, int head) {
   const udal_config& c = ctx->cfg;
   udal_head_weights_dev& h = ctx->heads[head];
-  UDAL_REQUIRE(c.num_filters == KF, "the tensor-core head sampler is built for fpn_num_filters = 64 (D0); got %d - "
-               "use heads_mode fp32", c.num_filters);
+  if (udal_heads_wide_ok(ctx)) return udal_heads_wide_prepare(ctx, head);
+  UDAL_REQUIRE(c.num_filters == KF, "the tensor-core head sampler is built for fpn_num_filters = 64 (D0) and 68..128 "
+               "(D1, D2); got %d - use heads_mode fp32", c.num_filters);
   const int R = c.repeats, L = c.num_levels;
   // predict layers with more than 80 channels (C > 8 classes) run as equal chunks of at most 64 channels
   h.pred_chunks = h.cout <= kMaxN ? 1 : (h.cout + KF - 1) / KF;
@@ -687,6 +693,10 @@ static int run_tower_tc(udal_ctx* ctx, int head, const float* const* feats, int 
 
 int udal_heads_tc_sample(udal_ctx* ctx, const float* const* feats, int batch, const float* scale, float* const* cls_out,
                          float* const* box_out, const udal_prenms_out* fused_pre) {
+  if (udal_heads_wide_ok(ctx)) {
+    UDAL_REQUIRE(!fused_pre, "the fused predict + decode kernels are built for fpn_num_filters = 64");
+    return udal_heads_wide_sample(ctx, feats, batch, scale, cls_out, box_out);
+  }
   for (int l = 0; l < ctx->cfg.num_levels; ++l)
     UDAL_REQUIRE(((uintptr_t)feats[l] & 15) == 0 &&
                      (fused_pre || (((uintptr_t)cls_out[l] & 15) == 0 && ((uintptr_t)box_out[l] & 15) == 0)),

@@ -82,6 +82,29 @@ __device__ __forceinline__ float ig_swish_h(float h) {  // h = x / 2
   return fmaf(h, t, h);  // x * sigmoid(x) = h * tanh(h) + h
 }
 
+// two independent fp32 FMAs in one issue slot (FFMA2): acc = a * b + acc per half; bit-identical to fmaf per element
+__device__ __forceinline__ void ig_ffma2(float2& acc, const float2 a, const float2 b) {
+  unsigned long long c = *reinterpret_cast<unsigned long long*>(&acc);
+  asm("fma.rn.f32x2 %0, %1, %2, %0;"
+      : "+l"(c)
+      : "l"(*reinterpret_cast<const unsigned long long*>(&a)), "l"(*reinterpret_cast<const unsigned long long*>(&b)));
+  acc = *reinterpret_cast<float2*>(&c);
+}
+
+__device__ __forceinline__ float2 ig_fma2(const float2 a, const float2 b, const float2 c) {  // a * b + c per half
+  unsigned long long d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;"
+      : "=l"(d)
+      : "l"(*reinterpret_cast<const unsigned long long*>(&a)), "l"(*reinterpret_cast<const unsigned long long*>(&b)),
+        "l"(*reinterpret_cast<const unsigned long long*>(&c)));
+  return *reinterpret_cast<float2*>(&d);
+}
+__device__ __forceinline__ float ig_tanh(float x) {
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(x));
+  return t;
+}
+
 struct IgItem {
   int l, nb, ty0, tx0;
 };

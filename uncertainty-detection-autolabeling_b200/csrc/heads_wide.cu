@@ -1,0 +1,581 @@
+// K1 for head widths other than 64 (bf16 tensor-core mode): fpn_num_filters in (64, 128] - EfficientDet-D1 (88) and
+// D2 (112, BASELINE configs[4]) - with the channels zero-padded to 128.
+//
+// The implicit-GEMM kernels of heads_ig.cu keep a 9-tap weight image resident (9 x N x K bf16); at K = N = 128
+// that image is 288 KB and no longer fits an SM, so this kernel splits the separable conv the classic way:
+//
+//   warp 0      producer : TMA box (18 x 10 px halo tile x 128 ch bf16, zero OOB fill = SAME padding), 2-stage ring;
+//                          loads the [128 n][128 k] pointwise weight image once (32 KB, resident)
+//   warps 2-9   builders : depthwise 3x3 on the CUDA cores (fp32 accumulate; thread = 4 channels x 1 tile column,
+//                          sliding down the rows), times the SpatialDropout2D keep-scale of the producer layer (it
+//                          commutes with the depthwise conv) -> A operand [128 px][128 ch] bf16 in the K-major
+//                          128B-swizzled UMMA layout (two 64-channel atoms), double buffered
+//   warp 1      MMA      : 8 x tcgen05.mma (M128 N128 K16) per tile, accumulators double buffered in TMEM
+//   warps 10-17 epilogue : lane quarter x column half: tcgen05.ld -> BN scale / folded bias -> swish -> bf16 staging
+//                          tile -> 2 TMA tensor stores (tower layers), or + bias -> fp32 staging -> coalesced rows of
+//                          32 channels (predict layers, any channel count; > 128 channels run as chunks)
+// Work item = (16x8-pixel tile, (sample, image)), strided over one CTA per SM.
+//
+// Reference arithmetic replaced: efficientdet_keras.py:448-483 / 628-664 (_conv_bn_act, the predict SeparableConv2D)
+// and the MC loop 979-1050; numerics as the 64-channel path: bf16 operands (depthwise output rounded once), fp32
+// accumulation, BN applied to the fp32 accumulator.
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include "udal_common.cuh"
+#include "heads_umma.cuh"
+
+namespace {
+
+constexpr int WF = 128;                                   // padded channel count
+constexpr int kWdBuilderWarps = 8, kWdEpiWarps = 8;
+constexpr int kWdThreads = 64 + 32 * (kWdBuilderWarps + kWdEpiWarps);
+constexpr int WD_STAGE = IG_ROWS * IG_BOXW * WF * 2;      // 46 080: halo tile, linear [18][10][128] bf16
+// shared memory map (offsets from a 1024-byte aligned base)
+constexpr int WD_A = 0;                                   // 2 x (2 atoms x [128 px][128 B]) depthwise output (UMMA A)
+constexpr int WD_B = WD_A + 2 * 32768;                    // 2 atoms x [128 n][128 B] pointwise weights (UMMA B)
+constexpr int WD_OUT = WD_B + 32768;                      // staging: bf16 2 atoms x [128][128 B], or fp32 2 x [128][33]
+constexpr int WD_IN = WD_OUT + 34816;                     // 2 x halo tile
+constexpr int WD_BAR = WD_IN + 2 * WD_STAGE;              // mbarriers + tmem slot
+constexpr int WD_EP = WD_BAR + 256;                      // [2][128] fp32 epilogue scale | bias of the current item's level
+constexpr int WD_SMEM = WD_EP + 1024 + 1024;
+static_assert(WD_STAGE % 1024 == 0 && WD_IN % 1024 == 0, "alignment");
+static_assert(2 * 128 * 33 * 4 <= 34816, "fp32 staging of the predict epilogue");
+static_assert(WD_SMEM <= kIgSmemLimit, "shared-memory budget");
+
+struct WdParams {
+  int num_levels, NB, items;             // NB = (sample, image) pairs written; items = sum_l tiles[l] * NB (level major)
+  int H[UDAL_MAX_LEVELS], W[UDAL_MAX_LEVELS], tiles_x[UDAL_MAX_LEVELS], tiles[UDAL_MAX_LEVELS];
+  int item_off[UDAL_MAX_LEVELS + 1];
+  uint32_t tiles_magic[UDAL_MAX_LEVELS], tiles_x_magic[UDAL_MAX_LEVELS];
+  int in_nb;                             // images of the input tensor: input image of pair nb = nb % in_nb
+  int F;                                 // real channel count (row stride of in_scale)
+  const float* in_scale[UDAL_MAX_LEVELS];   // [NB][F] keep-scale of the producer layer's dropout, or null
+  const float* ep[UDAL_MAX_LEVELS];      // [2][128]: epilogue scale (BN scale | 1), folded bias
+  const float* dw;                       // [9][128] depthwise weights (zero past F)
+  const void* wimg;                      // bf16 2 atoms x [128 n][64 k], 128B swizzle
+  void* out[UDAL_MAX_LEVELS];            // tower: [NB,H,W,128] bf16 (through the tensor maps); predict: [NB,H,W,ch_total] fp32
+  int predict, Cout, ch_off, ch_total;   // predict: this launch writes channels [ch_off, ch_off + Cout)
+  int debug;                             // timing experiments only (wrong results): 1 = no depthwise math, 2 = no epilogue math / stores
+};
+
+struct WdMaps {
+  CUtensorMap in[UDAL_MAX_LEVELS];    // [in_nb,H,W,128] bf16, box {128,10,18,1}, no swizzle
+  CUtensorMap out[UDAL_MAX_LEVELS];   // [NB,H,W,128] bf16, box {64,8,16,1}, 128B swizzle
+};
+
+__device__ __forceinline__ void wd_epi_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ void wd_half_sync(int hc) { asm volatile("bar.sync %0, 128;" ::"r"(2 + hc) : "memory"); }
+
+__global__ void __launch_bounds__(kWdThreads, 1) heads_wide_kernel(const __grid_constant__ WdMaps maps, const WdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = s32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
+  const uint32_t sb = s32(smem);
+  // barriers: in_full[2] @0  in_empty[2] @16  a_full[2] @32  a_empty[2] @48  tfull[2] @64  tempty[2] @80  bfull @96  slot @104
+  const uint32_t bar0 = sb + WD_BAR;
+  const uint32_t in_full = bar0, in_empty = bar0 + 16, a_full = bar0 + 32, a_empty = bar0 + 48, tfull = bar0 + 64,
+                 tempty = bar0 + 80, bar_b = bar0 + 96;
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + WD_BAR + 104);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int G = gridDim.x;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 2; ++i) {
+      bar_init(in_full + 8 * i, 1);
+      bar_init(in_empty + 8 * i, kWdBuilderWarps);  // one arrival per builder warp
+      bar_init(a_full + 8 * i, kWdBuilderWarps);
+      bar_init(a_empty + 8 * i, 1);
+      bar_init(tfull + 8 * i, 1);
+      bar_init(tempty + 8 * i, kWdEpiWarps);        // one arrival per epilogue warp
+    }
+    bar_init(bar_b, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(sb + WD_BAR + 104) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== producer (warp-uniform loop, one elected lane issues) =====================
+    if (ig_elect_one()) {
+      bar_expect_tx(bar_b, 32768);
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sb + WD_B),
+                   "l"(p.wimg), "r"(32768), "r"(bar_b)
+                   : "memory");
+    }
+    __syncwarp();
+    int i = 0;
+    for (int item = blockIdx.x; item < p.items; item += G, ++i) {
+      const IgItem w = ig_item(p, item);
+      const int s = i & 1;
+      const int nb_in = w.nb % p.in_nb;
+      if (ig_elect_one()) {
+        bar_wait(in_empty + 8 * s, ((i >> 1) & 1) ^ 1);
+        bar_expect_tx(in_full + 8 * s, WD_STAGE);
+        asm volatile(
+            "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+            ::"r"(sb + WD_IN + s * WD_STAGE), "l"(&maps.in[w.l]), "r"(in_full + 8 * s), "r"(0), "r"(w.tx0 - 1), "r"(w.ty0 - 1),
+            "r"(nb_in)
+            : "memory");
+      }
+      __syncwarp();
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(WF >> 3) << 17) | ((128u >> 4) << 24);
+    if (lane == 0) bar_wait(bar_b, 0);  // weights resident
+    __syncwarp();
+    int i = 0;
+    for (int item = blockIdx.x; item < p.items; item += G, ++i) {
+      const int ab = i & 1;
+      const uint32_t d_tmem = tmem_base + (uint32_t)(ab * WF);
+      if (ig_elect_one()) {
+        bar_wait(a_full + 8 * ab, (i >> 1) & 1);          // depthwise output of this item in place
+        bar_wait(tempty + 8 * ab, ((i >> 1) & 1) ^ 1);    // accumulator drained
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+        for (int k = 0; k < WF / 16; ++k) {
+          const uint32_t koff = (uint32_t)((k >> 2) * 16384 + (k & 3) * 32);
+          const uint64_t adesc = ig_desc(sb + WD_A + ab * 32768 + koff, 1024, 0);
+          const uint64_t bdesc = ig_desc(sb + WD_B + koff, 1024, 0);
+          ig_mma(d_tmem, adesc, bdesc, idesc, k ? 1u : 0u);
+        }
+        ig_commit(a_empty + 8 * ab);   // A buffer reusable once these MMAs retire
+        ig_commit(tfull + 8 * ab);     // accumulator ready
+      }
+      __syncwarp();
+    }
+  } else if (warp < 2 + kWdBuilderWarps) {
+    // ===================== builders: depthwise 3x3 -> A operand =====================
+    const int tid = threadIdx.x - 64;
+    const int q4 = tid & 31, x = tid >> 5;  // channel quad (4 q4 .. 4 q4 + 3), tile column
+    float2 wgt[9][2];
+#pragma unroll
+    for (int tp = 0; tp < 9; ++tp) {
+      const float4 w4 = __ldg(reinterpret_cast<const float4*>(p.dw + tp * WF) + q4);
+      wgt[tp][0] = make_float2(w4.x, w4.y);
+      wgt[tp][1] = make_float2(w4.z, w4.w);
+    }
+    const bool real = 4 * q4 < p.F;  // F % 4 == 0: a quad is entirely real or entirely padding
+    int i = 0;
+    for (int item = blockIdx.x; item < p.items; item += G, ++i) {
+      const IgItem w = ig_item(p, item);
+      const int s = i & 1, ab = i & 1;
+      float4 sc = make_float4(1.f, 1.f, 1.f, 1.f);
+      if (p.in_scale[w.l] && real) sc = __ldg(reinterpret_cast<const float4*>(p.in_scale[w.l] + (size_t)w.nb * p.F) + q4);
+      if (lane == 0) {
+        bar_wait(in_full + 8 * s, (i >> 1) & 1);          // halo tile landed
+        bar_wait(a_empty + 8 * ab, ((i >> 1) & 1) ^ 1);   // the MMAs of item i-2 are done with this A buffer
+      }
+      __syncwarp();
+      const uint8_t* sIn = smem + WD_IN + s * WD_STAGE;
+      uint8_t* sA = smem + WD_A + ab * 32768 + (q4 >> 4) * 16384;
+      const uint32_t chunk = (uint32_t)((q4 & 15) >> 1), sub = (uint32_t)(q4 & 1) * 8;
+#pragma unroll 1
+      for (int half = (p.debug & 1) ? 2 : 0; half < 2; ++half) {  // tile rows 8 half .. 8 half + 7 (halo rows 8 half .. 8 half + 9)
+        float2 acc[8][2];  // packed pairs: the 9 x 4 FMAs per pixel issue as 18 FFMA2
+#pragma unroll
+        for (int y = 0; y < 8; ++y) acc[y][0] = acc[y][1] = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int r = 0; r < 10; ++r) {
+#pragma unroll
+          for (int dx = 0; dx < 3; ++dx) {
+            const uint2 raw2 = *reinterpret_cast<const uint2*>(sIn + (size_t)((8 * half + r) * IG_BOXW + x + dx) * (WF * 2) + q4 * 8);
+            const float2 v01 = make_float2(__uint_as_float(raw2.x << 16), __uint_as_float(raw2.x & 0xffff0000u));
+            const float2 v23 = make_float2(__uint_as_float(raw2.y << 16), __uint_as_float(raw2.y & 0xffff0000u));
+#pragma unroll
+            for (int dy = 0; dy < 3; ++dy) {
+              const int y = r - dy;
+              if (y >= 0 && y < 8) {
+                ig_ffma2(acc[y][0], v01, wgt[dy * 3 + dx][0]);
+                ig_ffma2(acc[y][1], v23, wgt[dy * 3 + dx][1]);
+              }
+            }
+          }
+          if (r >= 2) {
+            const int y = r - 2;
+            const int m = (8 * half + y) * IG_TW + x;
+            uint2 o;
+            o.x = ig_pack(acc[y][0].x * sc.x, acc[y][0].y * sc.y);
+            o.y = ig_pack(acc[y][1].x * sc.z, acc[y][1].y * sc.w);
+            *reinterpret_cast<uint2*>(sA + (size_t)m * 128 + ((chunk ^ (uint32_t)(m & 7)) << 4) + sub) = o;
+          }
+        }
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // A tile -> visible to the tensor core
+      __syncwarp();
+      if (lane == 0) {
+        bar_arrive(a_full + 8 * ab);
+        bar_arrive(in_empty + 8 * s);
+      }
+    }
+  } else {
+    // ===================== epilogue: 4 lane quarters x 2 column halves =====================
+    const int ew = warp - 2 - kWdBuilderWarps;
+    const int q = warp & 3;                 // TMEM lane quarter this warp may access
+    const int hc = ew >> 2;                 // column half: accumulator columns 64 hc .. 64 hc + 63
+    const int m = q * 32 + lane;            // GEMM row = pixel (m / 8, m % 8) of the tile
+    const bool elected = ew == 0 && lane == 0;
+    const uint32_t swz = (uint32_t)(m & 7);
+    uint8_t* const ob = smem + WD_OUT;
+    int i = 0;
+    for (int item = blockIdx.x; item < p.items; item += G, ++i) {
+      const IgItem w = ig_item(p, item);
+      const int ab = i & 1;
+      // this item's epilogue table -> shared memory (tower: halved, x*sigmoid(x) = h*tanh(h) + h with h = x/2); the
+      // previous item's readers passed its last group barrier, the first barrier below publishes the table
+      float* const sEp = reinterpret_cast<float*>(smem + WD_EP);
+      {
+        const int et = threadIdx.x - 64 - 32 * kWdBuilderWarps;
+        if (!p.predict) {
+          sEp[et] = 0.5f * __ldg(p.ep[w.l] + et);
+        } else if ((et & 127) < 64) {  // predict: each column-half group (own barrier) loads the 64 biases it reads
+          const int n = WF + hc * 64 + (et & 127);
+          sEp[n] = __ldg(p.ep[w.l] + n);
+        }
+      }
+      const float4* eps = reinterpret_cast<const float4*>(sEp + hc * 64);
+      const float4* epb = reinterpret_cast<const float4*>(sEp + WF + hc * 64);
+      if (lane == 0) bar_wait(tfull + 8 * ab, (i >> 1) & 1);
+      __syncwarp();
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * WF + hc * 64);
+      if (p.debug & 2) {
+        uint32_t r8[8];
+        ig_ld8(taddr, r8);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) bar_arrive(tempty + 8 * ab);
+      } else if (!p.predict) {
+        // ---- tower layer: BN scale + folded bias -> swish -> bf16 staging tile (atom hc) -> TMA store ----
+        if (elected) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // staging tile free again
+        __syncwarp();
+        wd_epi_sync();
+#pragma unroll
+        for (int pass = 0; pass < 2; ++pass) {
+          uint32_t r[4][8];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) ig_ld8(taddr + pass * 32 + u * 8, r[u]);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          if (pass == 1) {
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) bar_arrive(tempty + 8 * ab);  // accumulator may be overwritten
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int j = pass * 4 + u;  // 16-byte chunk (8 channels) inside the atom row
+            const float4 g0 = eps[2 * j], g1 = eps[2 * j + 1];
+            const float4 f0 = epb[2 * j], f1 = epb[2 * j + 1];
+            const float2 gs[4] = {make_float2(g0.x, g0.y), make_float2(g0.z, g0.w), make_float2(g1.x, g1.y), make_float2(g1.z, g1.w)};
+            const float2 fb[4] = {make_float2(f0.x, f0.y), make_float2(f0.z, f0.w), make_float2(f1.x, f1.y), make_float2(f1.z, f1.w)};
+            float v[8];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {  // packed pairs: 2 FFMA2 + 2 MUFU per 2 outputs
+              const float2 h = ig_fma2(make_float2(__uint_as_float(r[u][2 * e]), __uint_as_float(r[u][2 * e + 1])), gs[e], fb[e]);
+              const float2 sw = ig_fma2(h, make_float2(ig_tanh(h.x), ig_tanh(h.y)), h);
+              v[2 * e] = sw.x;
+              v[2 * e + 1] = sw.y;
+            }
+            uint4 o;
+            o.x = ig_pack(v[0], v[1]);
+            o.y = ig_pack(v[2], v[3]);
+            o.z = ig_pack(v[4], v[5]);
+            o.w = ig_pack(v[6], v[7]);
+            *reinterpret_cast<uint4*>(ob + hc * 16384 + m * 128 + (((uint32_t)j ^ swz) << 4)) = o;
+          }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // staging writes -> visible to TMA
+        wd_epi_sync();
+        if (elected) {
+          ig_tma_store(&maps.out[w.l], s32(ob), 0, w.tx0, w.ty0, w.nb);
+          ig_tma_store(&maps.out[w.l], s32(ob) + 16384, 64, w.tx0, w.ty0, w.nb);
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+        __syncwarp();
+      } else {
+        // ---- predict layer: + bias -> fp32 staging [128 px][33] of this column half -> rows of 32 channels ----
+        const int H = p.H[w.l], W = p.W[w.l];
+        float* const stg = reinterpret_cast<float*>(ob) + hc * (128 * 33);
+        const int ht = threadIdx.x - 64 - 32 * kWdBuilderWarps - hc * 128;  // thread of the column-half group
+#pragma unroll 1
+        for (int pass = 0; pass < 2; ++pass) {
+          const int c0 = hc * 64 + pass * 32;  // first accumulator column of the pass
+          uint32_t r[4][8];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) ig_ld8(taddr + pass * 32 + u * 8, r[u]);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          if (pass == 1) {
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) bar_arrive(tempty + 8 * ab);
+          }
+          wd_half_sync(hc);  // the previous pass's copy loop is done with the staging tile
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const float4 f0 = epb[pass * 8 + 2 * u], f1 = epb[pass * 8 + 2 * u + 1];
+            const float fb[8] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w};
+#pragma unroll
+            for (int e = 0; e < 8; ++e) stg[m * 33 + u * 8 + e] = __fadd_rn(__uint_as_float(r[u][e]), fb[e]);
+          }
+          wd_half_sync(hc);
+          const int nch = min(32, p.Cout - c0);  // channels of this pass that exist
+          if (nch > 0) {
+            for (int pp = ht >> 5; pp < 128; pp += 4) {  // warp = pixel, lane = channel
+              const int oy = w.ty0 + (pp >> 3), ox = w.tx0 + (pp & 7);
+              if (oy < H && ox < W && lane < nch)
+                reinterpret_cast<float*>(p.out[w.l])[(((size_t)w.nb * H + oy) * W + ox) * p.ch_total + p.ch_off + c0 + lane] =
+                    stg[pp * 33 + lane];
+            }
+          }
+        }
+      }
+    }
+    if (!p.predict && elected) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    __syncwarp();
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem_base) : "memory");
+  }
+}
+
+// fp32 [n_px][F] features -> bf16 [n_px][128], zero past F
+__global__ void wide_convert_kernel(const float* __restrict__ in, size_t n_px, int F, __nv_bfloat16* __restrict__ out) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // one thread per 4 output channels
+  if (i >= n_px * (WF / 4)) return;
+  const size_t px = i / (WF / 4);
+  const int c = (int)(i % (WF / 4)) * 4;
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (c < F) v = __ldg(reinterpret_cast<const float4*>(in + px * F + c));
+  uint2 o;
+  o.x = ig_pack(v.x, v.y);
+  o.y = ig_pack(v.z, v.w);
+  *reinterpret_cast<uint2*>(out + px * WF + c) = o;
+}
+
+// weight image of one pointwise matrix: wimg[atom = k / 64][n][k % 64] = bf16(w[k][n0 + n]) (n < cout, k < F), 128B swizzle
+__global__ void wide_weights_kernel(const float* __restrict__ w, int F, int ldw, int n0, int cout, __nv_bfloat16* __restrict__ wimg) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= WF * WF) return;
+  const int k = i % WF, n = i / WF;
+  float v = 0.f;
+  if (k < F && n < cout) v = w[(size_t)k * ldw + n0 + n];
+  const int kk = k & 63;
+  const size_t byte = (size_t)(k >> 6) * 16384 + (size_t)n * 128 + (size_t)((((kk >> 3) ^ (n & 7)) << 4) + (kk & 7) * 2);
+  wimg[byte / 2] = __float2bfloat16_rn(v);
+}
+
+// dst[9][128] = src[9][F] zero padded
+__global__ void wide_dw_kernel(const float* __restrict__ src, int F, float* __restrict__ dst) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 9 * WF) return;
+  const int c = i % WF, tp = i / WF;
+  dst[i] = c < F ? src[tp * F + c] : 0.f;
+}
+
+// ep[0][n] = scale, ep[1][n] = bias*scale + shift (tower) or ep = (1, bias) (predict), zero padded
+__global__ void wide_ep_kernel(const float* __restrict__ bias, const float* __restrict__ bn_scale, const float* __restrict__ bn_shift,
+                               int n0, int cout, float* __restrict__ ep) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= WF) return;
+  float s = 0.f, b = 0.f;
+  if (n < cout) {
+    s = bn_scale ? bn_scale[n0 + n] : 1.f;
+    b = bn_scale ? fmaf(bias[n0 + n], bn_scale[n0 + n], bn_shift[n0 + n]) : bias[n0 + n];
+  }
+  ep[n] = s;
+  ep[WF + n] = b;
+}
+
+}  // namespace
+
+int udal_wide_debug = 0;  // timing experiments (WdParams::debug)
+
+int udal_heads_wide_ok(const udal_ctx* ctx) { return ctx->cfg.num_filters > KF && ctx->cfg.num_filters <= WF; }
+
+// builds the padded weight tables of one head: images [R + chunks][2][128][64] bf16, dw [R + 1][9][128],
+// ep [R][L][2][128] + [chunks][2][128]
+int udal_heads_wide_prepare(udal_ctx* ctx, int head) {
+  const udal_config& c = ctx->cfg;
+  udal_head_weights_dev& h = ctx->heads[head];
+  const int F = c.num_filters, R = c.repeats, L = c.num_levels;
+  UDAL_REQUIRE(udal_heads_wide_ok(ctx) && F % 4 == 0, "wide tensor-core heads: fpn_num_filters %d not in (64, 128]", F);
+  const int chunks = (h.cout + WF - 1) / WF;
+  h.wide_chunks = chunks;
+  if (h.wide_w) UDAL_CUDA(cudaFree(h.wide_w));
+  if (h.wide_f) UDAL_CUDA(cudaFree(h.wide_f));
+  h.wide_w = nullptr;
+  h.wide_f = nullptr;
+  const size_t n_img = (size_t)(R + chunks) * WF * WF;
+  const size_t n_f = (size_t)(R + 1) * 9 * WF + ((size_t)R * L + chunks) * 2 * WF;
+  UDAL_CUDA(cudaMalloc(&h.wide_w, n_img * 2));
+  UDAL_CUDA(cudaMalloc(&h.wide_f, n_f * sizeof(float)));
+  __nv_bfloat16* img = reinterpret_cast<__nv_bfloat16*>(h.wide_w);
+  float* dwp = h.wide_f;
+  float* ep = h.wide_f + (size_t)(R + 1) * 9 * WF;
+  const int tb = 256;
+  for (int r = 0; r < R; ++r) {
+    wide_weights_kernel<<<(WF * WF + tb - 1) / tb, tb, 0, ctx->stream>>>(h.pw + (size_t)r * F * F, F, F, 0, F, img + (size_t)r * WF * WF);
+    UDAL_CHECK_LAUNCH(ctx);
+    wide_dw_kernel<<<(9 * WF + tb - 1) / tb, tb, 0, ctx->stream>>>(h.dw + (size_t)r * 9 * F, F, dwp + (size_t)r * 9 * WF);
+    UDAL_CHECK_LAUNCH(ctx);
+    for (int l = 0; l < L; ++l) {
+      const size_t o = (size_t)r * L + l;
+      wide_ep_kernel<<<1, WF, 0, ctx->stream>>>(h.bias + (size_t)r * F, h.bn_scale + o * F, h.bn_shift + o * F, 0, F, ep + o * 2 * WF);
+      UDAL_CHECK_LAUNCH(ctx);
+    }
+  }
+  wide_dw_kernel<<<(9 * WF + tb - 1) / tb, tb, 0, ctx->stream>>>(h.dwp, F, dwp + (size_t)R * 9 * WF);
+  UDAL_CHECK_LAUNCH(ctx);
+  for (int q = 0; q < chunks; ++q) {
+    const int n0 = q * WF, nc = h.cout - n0 < WF ? h.cout - n0 : WF;
+    wide_weights_kernel<<<(WF * WF + tb - 1) / tb, tb, 0, ctx->stream>>>(h.pwp, F, h.cout, n0, nc, img + (size_t)(R + q) * WF * WF);
+    UDAL_CHECK_LAUNCH(ctx);
+    wide_ep_kernel<<<1, WF, 0, ctx->stream>>>(h.bp, nullptr, nullptr, n0, nc, ep + ((size_t)R * L + q) * 2 * WF);
+    UDAL_CHECK_LAUNCH(ctx);
+  }
+  UDAL_CUDA(cudaStreamSynchronize(ctx->stream));
+  return UDAL_OK;
+}
+
+static int launch_wide(udal_ctx* ctx, const void* const* in, int in_nb, int NB, const float* const* in_scale, const float* dw,
+                       const void* wimg, const float* const* ep, int predict, int cout, int ch_off, int ch_total,
+                       void* const* out) {
+  EncodeTiledFn encode = get_encode();
+  UDAL_REQUIRE(encode != nullptr, "cuTensorMapEncodeTiled is not available from this driver");
+  const udal_config& c = ctx->cfg;
+  WdMaps maps;
+  WdParams p;
+  memset(&p, 0, sizeof(p));
+  memset(&maps, 0, sizeof(maps));
+  p.num_levels = c.num_levels;
+  p.NB = NB;
+  p.in_nb = in_nb;
+  p.F = c.num_filters;
+  p.dw = dw;
+  p.wimg = wimg;
+  p.predict = predict;
+  p.Cout = cout;
+  p.ch_off = ch_off;
+  p.ch_total = ch_total;
+  p.debug = udal_wide_debug;
+  int off = 0;
+  for (int l = 0; l < c.num_levels; ++l) {
+    const int H = c.level_h[l], W = c.level_w[l];
+    UDAL_TRY(encode_nhwc(encode, &maps.in[l], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, in[l], in_nb, H, W, WF, WF, IG_BOXW, IG_ROWS, false));
+    if (!predict)
+      UDAL_TRY(encode_nhwc(encode, &maps.out[l], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, out[l], NB, H, W, WF, 64, IG_TW, IG_TH, true));
+    p.H[l] = H;
+    p.W[l] = W;
+    p.tiles_x[l] = (W + IG_TW - 1) / IG_TW;
+    p.tiles[l] = p.tiles_x[l] * ((H + IG_TH - 1) / IG_TH);
+    p.tiles_magic[l] = (uint32_t)((0x100000000ull + (uint64_t)p.tiles[l] - 1) / (uint64_t)p.tiles[l]);
+    p.tiles_x_magic[l] = (uint32_t)((0x100000000ull + (uint64_t)p.tiles_x[l] - 1) / (uint64_t)p.tiles_x[l]);
+    UDAL_REQUIRE((int64_t)p.tiles[l] * NB * p.tiles[l] < (1ll << 32), "level %d: too many work items for the item decode", l);
+    p.item_off[l] = off;
+    off += p.tiles[l] * NB;
+    p.in_scale[l] = in_scale ? in_scale[l] : nullptr;
+    p.ep[l] = ep[l];
+    p.out[l] = out[l];
+  }
+  for (int l = c.num_levels; l <= UDAL_MAX_LEVELS; ++l) p.item_off[l] = off;
+  p.items = off;
+  const int grid = udal_persistent_grid(ctx, p.items);
+  UDAL_CUDA(cudaFuncSetAttribute(heads_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WD_SMEM));
+  heads_wide_kernel<<<grid, kWdThreads, WD_SMEM, ctx->stream>>>(maps, p);
+  UDAL_CHECK_LAUNCH(ctx);
+  return UDAL_OK;
+}
+
+// one head: R tower layers + the predict layer(s); feats16[l] = bf16 [B,H_l,W_l,128] features (wide_convert_kernel),
+// scale_all = the keep-scale table [2][L][R][T*B][F] of heads_fp32.cu, outs[l] fp32 [NBt,H_l,W_l,cout]
+static int run_tower_wide(udal_ctx* ctx, int head, const __nv_bfloat16* const* feats16, int batch, const float* scale_all,
+                          float* const* outs) {
+  const udal_config& c = ctx->cfg;
+  const udal_head_weights_dev& h = ctx->heads[head];
+  const int F = c.num_filters, R = c.repeats, L = c.num_levels, T = c.mc_samples, B = batch;
+  const bool mc = head == UDAL_HEAD_CLASS ? c.cls_mc != 0 : c.box_mc != 0;
+  const int NBt = mc ? T * B : B;
+  const size_t P = (size_t)ctx->num_pixels;
+  __nv_bfloat16 *a0, *pp;
+  UDAL_TRY(udal_scratch_get(ctx, SCR_HEADS_A, (size_t)B * P * WF * 2, (void**)&a0));
+  UDAL_TRY(udal_scratch_get(ctx, SCR_HEADS_B, 2 * (size_t)NBt * P * WF * 2, (void**)&pp));
+  const __nv_bfloat16* img = reinterpret_cast<const __nv_bfloat16*>(h.wide_w);
+  const float* dwp = h.wide_f;
+  const float* ep_all = h.wide_f + (size_t)(R + 1) * 9 * WF;
+  auto mark = [&]() {
+    if (!ctx->profile_layers) return;
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) == cudaSuccess) {
+      cudaEventRecord(e, ctx->stream);
+      ctx->layer_events.push_back(e);
+    }
+  };
+  for (int layer = 0; layer <= R; ++layer) {
+    const bool predict = layer == R;
+    const void* in[UDAL_MAX_LEVELS];
+    void* out[UDAL_MAX_LEVELS];
+    const float* in_scale[UDAL_MAX_LEVELS];
+    const float* ep[UDAL_MAX_LEVELS];
+    const int nb_out = layer == 0 ? B : NBt;
+    const int in_nb = layer <= 1 ? B : NBt;
+    for (int l = 0; l < L; ++l) {
+      const size_t lvl = (size_t)ctx->level_pix_off[l] * WF;
+      if (layer == 0) in[l] = feats16[l];
+      else if (layer == 1) in[l] = a0 + (size_t)B * lvl;
+      else in[l] = pp + (size_t)((layer - 1) & 1) * NBt * P * WF + (size_t)NBt * lvl;
+      if (predict) out[l] = outs[l];
+      else if (layer == 0) out[l] = a0 + (size_t)B * lvl;
+      else out[l] = pp + (size_t)(layer & 1) * NBt * P * WF + (size_t)NBt * lvl;
+      // SpatialDropout2D of the producer layer (layer - 1), applied to the depthwise output (it commutes)
+      in_scale[l] = (mc && layer >= 1) ? scale_all + (((size_t)head * L + l) * R + (layer - 1)) * (size_t)NBt * F : nullptr;
+      ep[l] = predict ? nullptr : ep_all + ((size_t)layer * L + l) * 2 * WF;
+    }
+    mark();
+    if (!predict) {
+      UDAL_TRY(launch_wide(ctx, in, in_nb, nb_out, (mc && layer >= 1) ? in_scale : nullptr, dwp + (size_t)layer * 9 * WF,
+                           img + (size_t)layer * WF * WF, ep, 0, WF, 0, WF, out));
+    } else {
+      for (int q = 0; q < h.wide_chunks; ++q) {
+        const int n0 = q * WF, nc = h.cout - n0 < WF ? h.cout - n0 : WF;
+        for (int l = 0; l < L; ++l) ep[l] = ep_all + ((size_t)R * L + q) * 2 * WF;
+        UDAL_TRY(launch_wide(ctx, in, in_nb, nb_out, (mc && layer >= 1) ? in_scale : nullptr, dwp + (size_t)R * 9 * WF,
+                             img + (size_t)(R + q) * WF * WF, ep, 1, nc, n0, h.cout, out));
+      }
+    }
+    mark();
+  }
+  return UDAL_OK;
+}
+
+int udal_heads_wide_sample(udal_ctx* ctx, const float* const* feats, int batch, const float* scale, float* const* cls_out,
+                           float* const* box_out) {
+  const udal_config& c = ctx->cfg;
+  const int L = c.num_levels, F = c.num_filters;
+  const size_t P = (size_t)ctx->num_pixels;
+  __nv_bfloat16* f16;
+  UDAL_TRY(udal_scratch_get(ctx, SCR_HEADS_D, (size_t)batch * P * WF * 2, (void**)&f16));
+  const __nv_bfloat16* feats16[UDAL_MAX_LEVELS];
+  for (int l = 0; l < L; ++l) {
+    UDAL_REQUIRE(((uintptr_t)feats[l] & 15) == 0, "level %d: feature pointers must be 16-byte aligned", l);
+    __nv_bfloat16* dst = f16 + (size_t)batch * ctx->level_pix_off[l] * WF;
+    const size_t n_px = (size_t)batch * c.level_h[l] * c.level_w[l];
+    const size_t nthr = n_px * (WF / 4);
+    wide_convert_kernel<<<(unsigned)((nthr + 255) / 256), 256, 0, ctx->stream>>>(feats[l], n_px, F, dst);
+    UDAL_CHECK_LAUNCH(ctx);
+    feats16[l] = dst;
+  }
+  UDAL_TRY(run_tower_wide(ctx, UDAL_HEAD_CLASS, feats16, batch, scale, cls_out));
+  UDAL_TRY(run_tower_wide(ctx, UDAL_HEAD_BOX, feats16, batch, scale, box_out));
+  return UDAL_OK;
+}

@@ -32,6 +32,10 @@ struct udal_head_weights_dev {
   int fused_rows = 0;       // 72 (cout <= 72) or 96
   int pred_chunks = 1;   // > 1: predict layer with more than 80 channels, run as chunks of pred_chunk channels
   int pred_chunk = 0;
+  // heads wider than 64 channels (heads_wide.cu): channels zero-padded to 128
+  void* wide_w = nullptr;   // bf16 pointwise images [R + wide_chunks][2 atoms][128 n][64 k]
+  float* wide_f = nullptr;  // depthwise [R + 1][9][128], then epilogue (scale | bias) [R][L][2][128] + [wide_chunks][2][128]
+  int wide_chunks = 0;      // predict layer as chunks of <= 128 channels
   void* ig_w = nullptr;  // implicit-GEMM weight images: [(R-2)*L tower layers >= 2][9][64][64] then predict [9][Npad][64], bf16
 };
 
@@ -89,6 +93,7 @@ enum {
   SCR_POST_C,
   SCR_POST_D,
   SCR_POST_C2,
+  SCR_HEADS_D,
 };
 
 void udal_set_error(const char* fmt, ...);
