@@ -34,13 +34,14 @@ constexpr int WD_STAGE = IG_ROWS * IG_BOXW * WF * 2;      // 46 080: halo tile, 
 // shared memory map (offsets from a 1024-byte aligned base)
 constexpr int WD_A = 0;                                   // 2 x (2 atoms x [128 px][128 B]) depthwise output (UMMA A)
 constexpr int WD_B = WD_A + 2 * 32768;                    // 2 atoms x [128 n][128 B] pointwise weights (UMMA B)
-constexpr int WD_OUT = WD_B + 32768;                      // staging: bf16 2 atoms x [128][128 B], or fp32 2 x [128][33]
+constexpr int WD_OUT = WD_B + 32768;                      // staging: bf16 2 atoms x [128][128 B], or fp32 2 x [128][34]
 constexpr int WD_IN = WD_OUT + 34816;                     // 2 x halo tile
 constexpr int WD_BAR = WD_IN + 2 * WD_STAGE;              // mbarriers + tmem slot
 constexpr int WD_EP = WD_BAR + 256;                      // [2][128] fp32 epilogue scale | bias of the current item's level
 constexpr int WD_SMEM = WD_EP + 1024 + 1024;
 static_assert(WD_STAGE % 1024 == 0 && WD_IN % 1024 == 0, "alignment");
-static_assert(2 * 128 * 33 * 4 <= 34816, "fp32 staging of the predict epilogue");
+constexpr int WD_STG_STRIDE = 34;                         // floats per pixel row of the fp32 staging tile (32 + pad, even)
+static_assert(2 * 128 * WD_STG_STRIDE * 4 <= 34816, "fp32 staging of the predict epilogue");
 static_assert(WD_SMEM <= kIgSmemLimit, "shared-memory budget");
 
 struct WdParams {
@@ -301,9 +302,9 @@ __global__ void __launch_bounds__(kWdThreads, 1) heads_wide_kernel(const __grid_
         }
         __syncwarp();
       } else {
-        // ---- predict layer: + bias -> fp32 staging [128 px][33] of this column half -> rows of 32 channels ----
+        // ---- predict layer: + bias -> fp32 staging [128 px][34] of this column half -> rows of 32 channels ----
         const int H = p.H[w.l], W = p.W[w.l];
-        float* const stg = reinterpret_cast<float*>(ob) + hc * (128 * 33);
+        float* const stg = reinterpret_cast<float*>(ob) + hc * (128 * WD_STG_STRIDE);
         const int ht = threadIdx.x - 64 - 32 * kWdBuilderWarps - hc * 128;  // thread of the column-half group
 #pragma unroll 1
         for (int pass = 0; pass < 2; ++pass) {
@@ -323,16 +324,35 @@ __global__ void __launch_bounds__(kWdThreads, 1) heads_wide_kernel(const __grid_
             const float4 f0 = epb[pass * 8 + 2 * u], f1 = epb[pass * 8 + 2 * u + 1];
             const float fb[8] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w};
 #pragma unroll
-            for (int e = 0; e < 8; ++e) stg[m * 33 + u * 8 + e] = __fadd_rn(__uint_as_float(r[u][e]), fb[e]);
+            for (int e = 0; e < 8; e += 2)
+              *reinterpret_cast<float2*>(stg + m * WD_STG_STRIDE + u * 8 + e) =
+                  make_float2(__fadd_rn(__uint_as_float(r[u][e]), fb[e]), __fadd_rn(__uint_as_float(r[u][e + 1]), fb[e + 1]));
           }
           wd_half_sync(hc);
           const int nch = min(32, p.Cout - c0);  // channels of this pass that exist
           if (nch > 0) {
-            for (int pp = ht >> 5; pp < 128; pp += 4) {  // warp = pixel, lane = channel
-              const int oy = w.ty0 + (pp >> 3), ox = w.tx0 + (pp & 7);
-              if (oy < H && ox < W && lane < nch)
-                reinterpret_cast<float*>(p.out[w.l])[(((size_t)w.nb * H + oy) * W + ox) * p.ch_total + p.ch_off + c0 + lane] =
-                    stg[pp * 33 + lane];
+            float* const dst0 = reinterpret_cast<float*>(p.out[w.l]) + (((size_t)w.nb * H + w.ty0) * W + w.tx0) * p.ch_total + p.ch_off + c0;
+            const size_t row_stride = (size_t)W * p.ch_total;
+            const int wg = ht >> 5;
+            if (((p.ch_total | p.ch_off) & 1) == 0) {
+              // 8-byte stores: half-warp = one pixel (16 channel pairs), thread keeps its tile column, loop over the rows
+              const int col = wg * 2 + (lane >> 4), cp = 2 * (lane & 15);
+              if (w.tx0 + col < W && cp < nch) {
+                const float* src = stg + col * WD_STG_STRIDE + cp;
+                float* dst = dst0 + (size_t)col * p.ch_total + cp;
+                const int rows = min(IG_TH, H - w.ty0);
+                if (cp + 1 < nch) {
+                  for (int row = 0; row < rows; ++row)
+                    *reinterpret_cast<float2*>(dst + row * row_stride) = *reinterpret_cast<const float2*>(src + row * (IG_TW * WD_STG_STRIDE));
+                } else {
+                  for (int row = 0; row < rows; ++row) dst[row * row_stride] = src[row * (IG_TW * WD_STG_STRIDE)];
+                }
+              }
+            } else {
+              for (int pp = wg; pp < 128; pp += 4) {  // warp = pixel, lane = channel
+                const int oy = w.ty0 + (pp >> 3), ox = w.tx0 + (pp & 7);
+                if (oy < H && ox < W && lane < nch) dst0[(size_t)(pp >> 3) * row_stride + (size_t)(pp & 7) * p.ch_total + lane] = stg[pp * WD_STG_STRIDE + lane];
+              }
             }
           }
         }
