@@ -267,23 +267,27 @@ __global__ void __launch_bounds__(kFuThreads, 1) heads_fused_kernel(const __grid
             // 30 logits x (sum, first sample, squared deviations) already fill the register file: the accumulator is
             // read 8 columns at a time (the MMA of the next sample takes ~2000 cycles, the extra load latency hides)
 #pragma unroll
+            static_assert(CH % 2 == 0, "packed pairs");
             for (int u = 0; u < NLD; ++u) {
               uint32_t r8[8];
               ig_ld8(taddr + u * 8, r8);
               asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-              for (int e = 0; e < 8; ++e) {
+              for (int e = 0; e < 8; e += 2) {
                 const int c = u * 8 + e;
                 if (c < CH) {
-                  const float x = __fadd_rn(__uint_as_float(r8[e]), sBias[cg * CH + c]);
+                  const float2 x = ig_add2(make_float2(__uint_as_float(r8[e]), __uint_as_float(r8[e + 1])),
+                                           *reinterpret_cast<const float2*>(sBias + cg * CH + c));
                   if (t == 0) {
-                    sum[c] = x;
-                    x0[c] = x;
-                    s2[c] = 0.f;
+                    sum[c] = x.x; sum[c + 1] = x.y;
+                    x0[c] = x.x; x0[c + 1] = x.y;
+                    s2[c] = s2[c + 1] = 0.f;
                   } else {
-                    sum[c] = __fadd_rn(sum[c], x);
-                    const float d = x - x0[c];
-                    s2[c] = fmaf(d, d, s2[c]);
+                    const float2 sm = ig_add2(make_float2(sum[c], sum[c + 1]), x);
+                    const float2 d = ig_sub2(x, make_float2(x0[c], x0[c + 1]));
+                    const float2 q = ig_fma2(d, d, make_float2(s2[c], s2[c + 1]));
+                    sum[c] = sm.x; sum[c + 1] = sm.y;
+                    s2[c] = q.x; s2[c + 1] = q.y;
                   }
                 }
               }
@@ -307,17 +311,20 @@ __global__ void __launch_bounds__(kFuThreads, 1) heads_fused_kernel(const __grid
               const float4 b1 = *reinterpret_cast<const float4*>(sBias + cg * 24 + u * 8 + 4);
               const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-              for (int e = 0; e < 8; ++e) {
+              for (int e = 0; e < 8; e += 2) {  // packed pairs (FADD2 / FFMA2): the same IEEE operations, half the issue slots
                 const int c = u * 8 + e;
-                const float x = __fadd_rn(__uint_as_float(r[u][e]), bb[e]);  // = fma(acc, 1, bias) of the predict layer
+                // = fma(acc, 1, bias) of the predict layer
+                const float2 x = ig_add2(make_float2(__uint_as_float(r[u][e]), __uint_as_float(r[u][e + 1])), make_float2(bb[e], bb[e + 1]));
                 if (t == 0) {
-                  sum[c] = x;
-                  x0[c] = x;
-                  s2[c] = 0.f;
+                  sum[c] = x.x; sum[c + 1] = x.y;
+                  x0[c] = x.x; x0[c + 1] = x.y;
+                  s2[c] = s2[c + 1] = 0.f;
                 } else {
-                  sum[c] = __fadd_rn(sum[c], x);
-                  const float d = x - x0[c];
-                  s2[c] = fmaf(d, d, s2[c]);
+                  const float2 sm = ig_add2(make_float2(sum[c], sum[c + 1]), x);
+                  const float2 d = ig_sub2(x, make_float2(x0[c], x0[c + 1]));
+                  const float2 q = ig_fma2(d, d, make_float2(s2[c], s2[c + 1]));
+                  sum[c] = sm.x; sum[c + 1] = sm.y;
+                  s2[c] = q.x; s2[c + 1] = q.y;
                 }
               }
             }

@@ -99,6 +99,27 @@ __device__ __forceinline__ float2 ig_fma2(const float2 a, const float2 b, const 
         "l"(*reinterpret_cast<const unsigned long long*>(&c)));
   return *reinterpret_cast<float2*>(&d);
 }
+__device__ __forceinline__ float2 ig_add2(const float2 a, const float2 b) {  // FADD2
+  unsigned long long d;
+  asm("add.rn.f32x2 %0, %1, %2;"
+      : "=l"(d)
+      : "l"(*reinterpret_cast<const unsigned long long*>(&a)), "l"(*reinterpret_cast<const unsigned long long*>(&b)));
+  return *reinterpret_cast<float2*>(&d);
+}
+__device__ __forceinline__ float2 ig_sub2(const float2 a, const float2 b) {
+  unsigned long long d;
+  asm("sub.rn.f32x2 %0, %1, %2;"
+      : "=l"(d)
+      : "l"(*reinterpret_cast<const unsigned long long*>(&a)), "l"(*reinterpret_cast<const unsigned long long*>(&b)));
+  return *reinterpret_cast<float2*>(&d);
+}
+__device__ __forceinline__ float2 ig_mul2(const float2 a, const float2 b) {  // FMUL2
+  unsigned long long d;
+  asm("mul.rn.f32x2 %0, %1, %2;"
+      : "=l"(d)
+      : "l"(*reinterpret_cast<const unsigned long long*>(&a)), "l"(*reinterpret_cast<const unsigned long long*>(&b)));
+  return *reinterpret_cast<float2*>(&d);
+}
 __device__ __forceinline__ float ig_tanh(float x) {
   float t;
   asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(x));
