@@ -1,0 +1,64 @@
+"""BASELINE configs[4]: EfficientDet-D2 768x768, 10 classes, MC-dropout T = 30, auto-label threshold pass.
+
+    python tools/autolabel_pass.py [--images 512] [--batch 16] [--out profiles/xx.json]
+
+One GPU's share of the 4096-image job (4096 / 8 GPUs = 512 images; the path is image-parallel, no collective):
+per batch  BiFPN features (resident in HBM) -> wide tensor-core heads x T -> decode + MC moments -> global soft-NMS
+-> calibrated / relative aleatoric std, entropy, weighted threshold decision (udal_autolabel) -> decisions to the host.
+Synthetic constants of SURVEY 8d config 5: opt_params [0.5, 0.5], thr 0.5, min_score 0.4.
+"""
+import argparse
+import json
+import sys
+import time
+
+import numpy as np
+
+sys.path.insert(0, ".")
+import udal_b200 as u
+from oracle import heads_ref
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--images", type=int, default=512)
+ap.add_argument("--batch", type=int, default=16)
+ap.add_argument("--heads-mode", default="bf16")
+ap.add_argument("--out", default=None)
+args = ap.parse_args()
+
+C, T = 10, 30
+p = u.hparams_config.get_detection_config(
+    "efficientdet-d2", image_size=(768, 768), num_classes=C, enable_softmax=True, loss_attenuation=True,
+    mc_dropout=True, mc_classheadrate=0.05, mc_boxheadrate=0.05, mc_dropoutsamp=T, heads_mode=args.heads_mode)
+eng = u.engine.get_engine(p)
+eng.set_head_weights(heads_ref.init_head_weights(eng.F, eng.R, len(eng.level_hw), eng.A, C, True, seed=2024))
+rng = np.random.default_rng(1234)
+feats = [eng.ctx.to_device(rng.standard_normal((args.batch, h, w, eng.F), dtype=np.float32)) for h, w in eng.level_hw]
+scales = eng.ctx.to_device(np.ones(args.batch, np.float32))
+labeler = u.autolabel.AutoLabeler(dict(num_classes=C, thr_sel_uncert=["ENT", "ALBOX"], calib_method_box=None, min_score=0.4),
+                                  opt_params=[0.5, 0.5], opt_thrs=[0.5])
+
+
+def step(seed):
+    det = eng.run(feats, scales, None, seed=seed)
+    out = labeler.decide((det["boxes"], det["scores"], det["classes"], det["valid"], det["logits"]))
+    return out["auto_label"].numpy()   # D2H of the decisions (synchronises)
+
+
+for i in range(2):
+    step(i)
+n_steps = (args.images + args.batch - 1) // args.batch
+labels = []
+eng.ctx.sync()
+t0 = time.perf_counter()
+for i in range(n_steps):
+    labels.append(step(100 + i))
+eng.ctx.sync()
+sec = time.perf_counter() - t0
+n = n_steps * args.batch
+res = {"config": "BASELINE configs[4]: EfficientDet-D2 768x768, C=10, T=30, auto-label threshold pass", "heads_mode": args.heads_mode,
+       "images": n, "batch": args.batch, "seconds": sec, "images_per_s_per_gpu": n / sec,
+       "projected_s_for_4096_images_on_8_gpus": 4096 / 8 / (n / sec), "anchors": eng.N,
+       "auto_labelled_fraction": float(np.mean(np.concatenate(labels))), "scratch_GB": eng.ctx.scratch_bytes() / 1e9}
+print(json.dumps(res))
+if args.out:
+    json.dump(res, open(args.out, "w"), indent=1)
