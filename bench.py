@@ -158,6 +158,10 @@ def cpu_port_step(images, seed=0):
 cpu_port_step.w = None
 
 
+WORKLOAD = ("EfficientDet-D0 1280x384 (BASELINE configs[1]): BiFPN feats -> T=10 MC-dropout heads -> "
+            "decode+moments (fused into the predict layers) -> global gaussian soft-NMS")
+
+
 def run_reference(args):
     import torch
     rank = int(os.environ.get("RANK", "0"))
@@ -180,8 +184,10 @@ def run_reference(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
-        "config": {"workload": "EfficientDet-D0 1280x384 C=%d T=%d heads+decode+global soft-NMS" % (NUM_CLASSES, T),
-                   "sample_images_per_step": sample_images},
+        # the GPU arm's config (same workload, classes, T, anchors); each CPU step is a bounded sample of it
+        "config": {"workload": WORKLOAD, "batch_per_gpu": args.batch, "num_classes": NUM_CLASSES, "T": T,
+                   "sample_images_per_step": sample_images, "heads_mode": "fp32 (torch-CPU conv oracle)",
+                   "parallelism": "host cores of rank 0"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": "%d images per step x %d steps of the same workload (torch-CPU conv heads x T "
                                    "+ NumPy/C post-processing oracle); TensorFlow 2.10 reference not installable"
@@ -205,8 +211,19 @@ def run_gpu(args):
         import torch
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep stdout to the one JSON line
+        # NCCL announces its version on stdout when the communicator comes up: create it now, with fd 1 pointing at
+        # stderr, so that stdout carries the one JSON line and nothing else
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     import udal_b200 as u
     from oracle import heads_ref  # synthetic weight / feature generators only (SURVEY 8d seeds)
 
@@ -403,8 +420,7 @@ def run_gpu(args):
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32" if args.heads_mode == "fp32" else "bf16", "data": "synthetic",
         "config": {
-            "workload": "EfficientDet-D0 1280x384 (BASELINE configs[1]): BiFPN feats -> T=10 MC-dropout heads -> "
-                        "decode+moments (fused into the predict layers) -> global gaussian soft-NMS",
+            "workload": WORKLOAD,
             "batch_per_gpu": batch, "num_classes": NUM_CLASSES, "T": T, "anchors": eng.N,
             "heads_mode": args.heads_mode, "parallelism": "image-sharded x%d, no collective" % world,
             "l2": "inputs larger than L2 (features %.0f MB + GBs of head activations per step)" % (h2d / 1e6),

@@ -264,6 +264,21 @@ __global__ void __launch_bounds__(kL1Threads, 1) heads_l1_kernel(const __grid_co
     const bool elected = (ew & 7) == 0 && lane == 0;
     float* const sSc = reinterpret_cast<float*>(smem + L1_SC) + g * KF;
     const uint32_t swz = (uint32_t)(m & 7);
+    // keep-scales of the group's samples are fetched one sample ahead by 16 lanes of one warp: the global-load latency
+    // (the whole group would otherwise wait for it at its first barrier, every sample) hides under the previous sample
+    const bool sc_loader = (ew & 7) == 1 && lane < KF / 4;
+    auto load_scales = [&](int ii, int tt) -> float4 {  // sample tt of this CTA's ii-th item
+      while (tt >= T) {
+        tt -= T;
+        ++ii;
+      }
+      const int it2 = blockIdx.x + ii * G;
+      if (it2 >= p.items) return make_float4(0.f, 0.f, 0.f, 0.f);
+      const IgItem w2 = ig_item(p, it2);
+      return __ldg(reinterpret_cast<const float4*>(p.out_scale[w2.l] + (size_t)(tt * p.NB + w2.nb) * p.sc_stride) + lane);
+    };
+    float4 sc_next = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (sc_loader) sc_next = load_scales(0, g);  // the group's first sample: j = g
     int i = 0, j = 0;
     for (int item = blockIdx.x; item < p.items; item += G, ++i) {
       const IgItem w = ig_item(p, item);
@@ -274,10 +289,11 @@ __global__ void __launch_bounds__(kL1Threads, 1) heads_l1_kernel(const __grid_co
         const int nb = t * p.NB + w.nb;
         uint8_t* const ob = smem + L1_OUT + g * 16384;
         // this sample's keep-scales -> the group's slot (published by the first group barrier below; the
-        // previous tile's readers passed its second barrier)
-        if ((ew & 7) == 1 && lane < KF / 4)
-          reinterpret_cast<float4*>(sSc)[lane] =
-              __ldg(reinterpret_cast<const float4*>(p.out_scale[w.l] + (size_t)nb * p.sc_stride) + lane);
+        // previous tile's readers passed its second barrier); then the fetch for the group's next sample (j + 2)
+        if (sc_loader) {
+          reinterpret_cast<float4*>(sSc)[lane] = sc_next;
+          sc_next = load_scales(i, t + 2);
+        }
         if (lane == 0) bar_wait(tfull + 8 * q, (j >> 2) & 1);
         __syncwarp();
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");

@@ -257,9 +257,9 @@ __global__ void __launch_bounds__(256) merge_per_class_kernel(const MergeParams 
 }  // namespace
 
 int udal_run_overlap = 1;  // 0: udal_run keeps its whole tail on the context's stream
-int udal_run_reserved_sms = 4;
+int udal_run_reserved_sms = 4;     // SMs the persistent head kernels of a pipelined udal_run leave to the post stream
 int udal_run_prefilter_on_main = 0;
-int udal_run_debug_timeline = 0;  // development: print when the tail of every udal_run started / ended relative to its heads  // SMs the persistent head kernels of a pipelined udal_run leave to the post stream
+int udal_run_debug_timeline = 0;   // development: print when the tail of every udal_run started / ended relative to its heads
 
 extern "C" {
 
