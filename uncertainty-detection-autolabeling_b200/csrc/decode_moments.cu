@@ -167,13 +167,14 @@ __device__ __forceinline__ int find_level(const int* off, int nl, int v) {
 // logits: elementwise MC mean / std over a contiguous run of `count` floats.
 // src(t) = base + t * t_stride; dst offsets are shared by mean/std.
 // -------------------------------------------------------------------------------------------
-template <int TMAX>
+template <int TMAX, bool TWO_PASS = false>
 __device__ __forceinline__ void logits_run(const float* __restrict__ base, size_t t_stride, int T,
                                            int count, float* __restrict__ mean_out,
                                            float* __restrict__ std_out, float* smem_mean, int tid,
                                            int nthreads) {
-  if (TMAX == 0) {
-    // many samples: two passes over global memory (second pass hits L1/L2)
+  if (TMAX == 0 || TWO_PASS) {
+    // many samples: two passes over global memory (second pass hits L1/L2).  For 17..24 samples this keeps the
+    // kernel under 85 registers, i.e. 3 resident CTAs per SM instead of 2
     for (int e = tid; e < count; e += nthreads) {
       float acc = __ldg(base + e);
       for (int t = 1; t < T; ++t) acc = __fadd_rn(acc, __ldg(base + (size_t)t * t_stride + e));
@@ -217,9 +218,9 @@ __device__ __forceinline__ void logits_run(const float* __restrict__ base, size_
 
 // FAST = the serving configuration (loss attenuation, l-norm decode, MC dropout on both heads,
 // T == TMAX): every mode switch folds away at compile time.
-// TCH: samples per load chunk of the 17..32-sample path.
-template <int TMAX, bool FAST, int TCH_ = 4>
-__global__ void __launch_bounds__(kThreads, TMAX == 0 ? 1 : (TMAX > 16 ? 2 : 4)) decode_moments_kernel(const DecodeParams p) {
+// TCH: samples per load chunk of the 17..32-sample path.  LEAN (17..24 samples): logits in two passes, 3 CTAs per SM.
+template <int TMAX, bool FAST, int TCH_ = 4, bool LEAN = false>
+__global__ void __launch_bounds__(kThreads, TMAX == 0 ? 1 : (TMAX > 16 ? (LEAN ? 3 : 2) : 4)) decode_moments_kernel(const DecodeParams p) {
   const int k_la = FAST ? 1 : p.la;
   const int k_method = FAST ? (int)UDAL_DECODE_LNORM : p.method;
   const int k_box_mc = FAST ? 1 : p.box_mc;
@@ -247,7 +248,7 @@ __global__ void __launch_bounds__(kThreads, TMAX == 0 ? 1 : (TMAX > 16 ? 2 : 4))
     const size_t t_stride = (size_t)p.batch * plane;
     float* mo = p.out.mean_logits ? p.out.mean_logits + ((size_t)b * p.N + anchor0) * C : nullptr;
     float* so = (p.out.std_logits && k_cls_mc) ? p.out.std_logits + ((size_t)b * p.N + anchor0) * C : nullptr;
-    logits_run<TMAX>(base, t_stride, k_Tc, count, mo, so, smem_mean, threadIdx.x, kThreads);
+    logits_run<TMAX, LEAN>(base, t_stride, k_Tc, count, mo, so, smem_mean, threadIdx.x, kThreads);
   }
   __syncthreads();
 
@@ -644,12 +645,12 @@ int udal_launch_decode_moments(udal_ctx* ctx, const float* const* cls, const flo
   if (pick_tmax(T) > 16) smem += (size_t)(2 * p.Tb + 4 * chunk) * kThreads * sizeof(float);
   else if (pick_tmax(T) != 0) smem += (size_t)4 * p.Tb * kThreads * sizeof(float);
   UDAL_REQUIRE(smem <= 200 * 1024, "decode_moments: T=%d needs %zu bytes of shared memory", T, smem);
-#define LAUNCH_ONE(TM, F, CH)                                                                                   \
-  {                                                                                                             \
-    if (smem > 48 * 1024)                                                                                       \
-      UDAL_CUDA(cudaFuncSetAttribute(decode_moments_kernel<TM, F, CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                     (int)smem));                                                               \
-    decode_moments_kernel<TM, F, CH><<<grid, kThreads, smem, ctx->stream>>>(p);                                 \
+#define LAUNCH_ONE(TM, F, ...)                                                                                           \
+  {                                                                                                                      \
+    if (smem > 48 * 1024)                                                                                                \
+      UDAL_CUDA(cudaFuncSetAttribute(decode_moments_kernel<TM, F, __VA_ARGS__>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                     (int)smem));                                                                        \
+    decode_moments_kernel<TM, F, __VA_ARGS__><<<grid, kThreads, smem, ctx->stream>>>(p);                                 \
   }
 #define LAUNCH(TM)                              \
   if (fast && T == TM) LAUNCH_ONE(TM, true, 4)  \
@@ -663,6 +664,7 @@ int udal_launch_decode_moments(udal_ctx* ctx, const float* const* cls, const flo
     case 32:
       if (chunk == 2) LAUNCH_ONE(32, false, 2)
       else if (chunk == 8) LAUNCH_ONE(32, false, 8)
+      else if (T <= 24) LAUNCH_ONE(32, false, 4, true)  // (2 T + 16) KB + the logit tile: three CTAs fit an SM
       else LAUNCH_ONE(32, false, 4)
       break;
     default: LAUNCH_ONE(0, false, 4) break;
