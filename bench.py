@@ -225,13 +225,12 @@ def run_gpu(args):
             os.dup2(saved, 1)
             os.close(saved)
     import udal_b200 as u
-    from oracle import heads_ref  # synthetic weight / feature generators only (SURVEY 8d seeds)
 
     p = workload_params(args.heads_mode)
     eng = u.engine.get_engine(p, device_id=local_rank)
     ctx = eng.ctx
     L = len(eng.level_hw)
-    weights = heads_ref.init_head_weights(eng.F, eng.R, L, eng.A, eng.C, True, seed=2024)
+    weights = u.synthetic.init_head_weights(eng.F, eng.R, L, eng.A, eng.C, True, seed=2024)  # SURVEY 8d seeds
     sampler = u.heads.HeadSampler(p, weights, device_id=local_rank)
     batch = args.batch
     rng = np.random.default_rng(1234 + rank)

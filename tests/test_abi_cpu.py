@@ -137,3 +137,33 @@ def test_autolabel_params_struct_matches_c_layout(tmp_path):
     P = u._lib.AutolabelParams
     assert ctypes.sizeof(P) == size
     assert P.table_off.offset == o1 and P.class_temp.offset == o2 and P.strict_reference.offset == o3
+
+
+def test_synthetic_generators_match_the_oracle_copy():
+    """bench.py / tools take their synthetic weights, features and masks from the package (the product never imports
+    oracle/); the oracle keeps its own copy of the generators - both must give the same arrays for the same seeds."""
+    import importlib.util
+    import os
+    import numpy as np
+    from oracle import heads_ref
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "uncertainty-detection-autolabeling_b200",
+                        "synthetic.py")
+    spec = importlib.util.spec_from_file_location("udal_synthetic_standalone", path)  # no libudal needed
+    syn = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(syn)
+    for kw in (dict(seed=2024), dict(seed=9, randomize_bn=True)):
+        a = syn.init_head_weights(64, 3, 5, 9, 8, True, **kw)
+        b = heads_ref.init_head_weights(64, 3, 5, 9, 8, True, **kw)
+        for head in ("class", "box"):
+            for key in ("dw", "pw", "b"):
+                for x, y in zip(a[head][key], b[head][key]):
+                    np.testing.assert_array_equal(x, y)
+            for key in ("dwp", "pwp", "bp"):
+                np.testing.assert_array_equal(a[head][key], b[head][key])
+            for ra, rb in zip(a[head]["bn"], b[head]["bn"]):
+                for la, lb in zip(ra, rb):
+                    for key in la:
+                        np.testing.assert_array_equal(la[key], lb[key])
+    np.testing.assert_array_equal(syn.make_masks(4, 5, 3, 2, 64, 0.05, 0.1, seed=5), heads_ref.make_masks(4, 5, 3, 2, 64, 0.05, 0.1, seed=5))
+    for x, y in zip(syn.make_features([(4, 6), (2, 3)], 2, 64, seed=11), heads_ref.make_features([(4, 6), (2, 3)], 2, 64, seed=11)):
+        np.testing.assert_array_equal(x, y)

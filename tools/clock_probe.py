@@ -8,7 +8,6 @@ import pynvml
 
 sys.path.insert(0, ".")
 import udal_b200 as u
-from oracle import heads_ref
 
 batch = 64
 p = u.hparams_config.get_detection_config(
@@ -16,7 +15,7 @@ p = u.hparams_config.get_detection_config(
     mc_dropout=True, mc_classheadrate=0.05, mc_boxheadrate=0.05, mc_dropoutsamp=10, heads_mode="bf16")
 eng = u.engine.get_engine(p)
 L = len(eng.level_hw)
-eng.set_head_weights(heads_ref.init_head_weights(eng.F, eng.R, L, eng.A, 8, True, seed=2024))
+eng.set_head_weights(u.synthetic.init_head_weights(eng.F, eng.R, L, eng.A, 8, True, seed=2024))
 rng = np.random.default_rng(1)
 feats = [eng.ctx.to_device(rng.standard_normal((batch, h, w, eng.F), dtype=np.float32)) for h, w in eng.level_hw]
 scales = eng.ctx.to_device(np.ones(batch, np.float32))

@@ -8,7 +8,6 @@ import numpy as np
 
 sys.path.insert(0, ".")
 import udal_b200 as u
-from oracle import heads_ref
 
 H, W, C, T, batch = [int(x) for x in sys.argv[1:6]]
 model = sys.argv[6] if len(sys.argv) > 6 else "efficientdet-d0"
@@ -17,7 +16,7 @@ p = u.hparams_config.get_detection_config(
     model, image_size=(H, W), num_classes=C, enable_softmax=True, loss_attenuation=True,
     mc_dropout=True, mc_classheadrate=0.05, mc_boxheadrate=0.05, mc_dropoutsamp=T, heads_mode=mode)
 eng = u.engine.get_engine(p)
-eng.set_head_weights(heads_ref.init_head_weights(eng.F, eng.R, len(eng.level_hw), eng.A, C, True, seed=2024))
+eng.set_head_weights(u.synthetic.init_head_weights(eng.F, eng.R, len(eng.level_hw), eng.A, C, True, seed=2024))
 rng = np.random.default_rng(1)
 feats = [eng.ctx.to_device(rng.standard_normal((batch, h, w, eng.F), dtype=np.float32)) for h, w in eng.level_hw]
 scales = eng.ctx.to_device(np.ones(batch, np.float32))

@@ -6,14 +6,13 @@ import numpy as np
 
 sys.path.insert(0, ".")
 import udal_b200 as u
-from oracle import heads_ref
 
 batch = 64
 p = u.hparams_config.get_detection_config(
     "efficientdet-d0", image_size=(384, 1280), num_classes=8, enable_softmax=True, loss_attenuation=True,
     mc_dropout=True, mc_classheadrate=0.05, mc_boxheadrate=0.05, mc_dropoutsamp=10, heads_mode="bf16")
 eng = u.engine.get_engine(p)
-w = heads_ref.init_head_weights(eng.F, eng.R, len(eng.level_hw), eng.A, 8, True, seed=2024)
+w = u.synthetic.init_head_weights(eng.F, eng.R, len(eng.level_hw), eng.A, 8, True, seed=2024)
 rng = np.random.default_rng(1)
 pinned = [u.device.PinnedArray((batch, h, ww, eng.F)) for h, ww in eng.level_hw]
 for pa in pinned:

@@ -15,7 +15,7 @@ from . import _lib
 
 _lib.load()  # fail loudly at import time if the CUDA library is missing
 
-from . import anchors, autolabel, device, engine, heads, hparams_config, nms_np, postprocess, scheduler, serving, utils, utils_box, utils_extra, wire  # noqa: E402,F401
+from . import anchors, autolabel, device, engine, heads, hparams_config, nms_np, postprocess, scheduler, serving, synthetic, utils, utils_box, utils_extra, wire  # noqa: E402,F401
 
-__all__ = ["anchors", "autolabel", "device", "engine", "heads", "hparams_config", "nms_np", "postprocess",
+__all__ = ["anchors", "autolabel", "device", "engine", "heads", "hparams_config", "nms_np", "postprocess", "synthetic",
            "scheduler", "serving", "utils", "utils_box", "utils_extra", "wire"]

@@ -1,0 +1,82 @@
+"""Synthetic inputs of the named shapes: random-init head weights with the reference's initialisers,
+BiFPN feature maps and SpatialDropout2D keep masks.  Used by ``bench.py``, ``tools/`` and the examples - there is no
+network for checkpoints or datasets.  Pure NumPy; ``oracle/heads_ref.py`` (test infrastructure) carries its own copy of
+these generators, ``tests/test_abi_cpu.py`` checks that the two stay identical.
+
+Weight dict layout = the argument of ``Engine.set_head_weights`` / ``HeadSampler``:
+{"class": tower, "box": tower}, tower = dict(dw[R][3,3,F], pw[R][F,F], b[R][F], bn[R][L]{gamma,beta,mean,var},
+dwp[3,3,F], pwp[F,Cout], bp[Cout]); keep masks [T, 2 (0 = class, 1 = box), L, R, B, F] uint8.
+"""
+import math
+
+import numpy as np
+
+HEAD_CLASS, HEAD_BOX = 0, 1
+
+
+def _trunc_normal(rng, shape, std):
+    # tf.initializers.variance_scaling(): truncated normal, stddev = sqrt(scale/fan_in)/.8796
+    out = rng.standard_normal(shape)
+    bad = np.abs(out) > 2
+    while bad.any():
+        out[bad] = rng.standard_normal(int(bad.sum()))
+        bad = np.abs(out) > 2
+    return (out * (std / 0.87962566103423978)).astype(np.float32)
+
+
+def init_head_weights(num_filters, repeats, num_levels, num_anchors, num_classes, loss_attenuation,
+                      seed=2024, randomize_bn=False):
+    """Random weights with the reference's initialisers (efficientdet_keras.py:493-494, 510,
+    587-588).  ``randomize_bn`` draws non-trivial BN statistics so per-level BN is exercised."""
+    rng = np.random.default_rng(seed)
+    f = num_filters
+
+    def tower(cout, bias_value):
+        w = {
+            "dw": [_trunc_normal(rng, (3, 3, f), math.sqrt(1.0 / 9.0)) for _ in range(repeats)],
+            "pw": [_trunc_normal(rng, (f, f), math.sqrt(1.0 / f)) for _ in range(repeats)],
+            "b": [np.zeros(f, np.float32) for _ in range(repeats)],
+            "bn": [],
+            "dwp": _trunc_normal(rng, (3, 3, f), math.sqrt(1.0 / 9.0)),
+            "pwp": _trunc_normal(rng, (f, cout), math.sqrt(1.0 / f)),
+            "bp": np.full(cout, bias_value, np.float32),
+        }
+        for _ in range(repeats):
+            per_level = []
+            for _ in range(num_levels):
+                if randomize_bn:
+                    per_level.append({
+                        "gamma": rng.uniform(0.5, 1.5, f).astype(np.float32),
+                        "beta": rng.normal(0, 0.2, f).astype(np.float32),
+                        "mean": rng.normal(0, 0.2, f).astype(np.float32),
+                        "var": rng.uniform(0.5, 1.5, f).astype(np.float32),
+                    })
+                else:
+                    per_level.append({
+                        "gamma": np.ones(f, np.float32), "beta": np.zeros(f, np.float32),
+                        "mean": np.zeros(f, np.float32), "var": np.ones(f, np.float32),
+                    })
+            w["bn"].append(per_level)
+        if randomize_bn:
+            w["b"] = [rng.normal(0, 0.1, f).astype(np.float32) for _ in range(repeats)]
+        return w
+
+    box_out = 4 * num_anchors * (2 if loss_attenuation else 1)
+    return {
+        "class": tower(num_anchors * num_classes, -math.log((1 - 0.01) / 0.01)),
+        "box": tower(box_out, 0.0),
+    }
+
+
+def make_masks(num_samples, num_levels, repeats, batch, num_filters, rate_class, rate_box, seed=7):
+    rng = np.random.default_rng(seed)
+    u = rng.random((num_samples, 2, num_levels, repeats, batch, num_filters))
+    keep = np.empty(u.shape, np.uint8)
+    keep[:, HEAD_CLASS] = u[:, HEAD_CLASS] >= rate_class
+    keep[:, HEAD_BOX] = u[:, HEAD_BOX] >= rate_box
+    return keep
+
+
+def make_features(level_shapes, batch, num_filters, seed=1234):
+    rng = np.random.default_rng(seed)
+    return [rng.standard_normal((batch, h, w, num_filters)).astype(np.float32) for h, w in level_shapes]
