@@ -372,7 +372,7 @@ def run_gpu(args):
     # per-kernel rooflines: every kernel of the step against the bound that applies to it
     traffic = ncu_traffic()
     kernels = []
-    kernel_names = {0: "sepconv_tc_kernel<64>", 1: "heads_l1_kernel", 2: "heads_ig_kernel<tower>"}
+    kernel_names = {0: "heads_wide_kernel<64>", 1: "heads_l1_kernel", 2: "heads_ig_kernel<tower>"}
     fused_run = args.heads_mode != "fp32" and lib_int(eng, "udal_run_fused") and eng.C == 8 and eng.A == 9
     n_anchor = float(batch) * eng.N
     for i, ms in enumerate(layer_ms if args.heads_mode != "fp32" else []):

@@ -28,6 +28,8 @@ def family(name):
         return "heads_fused_kernel<box>"
     if "heads_ig_kernel" in name:
         return "heads_ig_kernel<predict>" if re.search(r"IgShape<[^>]*(\(bool\)1|true)>", name) else "heads_ig_kernel<tower>"
+    if "heads_wide_kernel" in name:
+        return "heads_wide_kernel<64>" if re.search(r"heads_wide_kernel<(\(int\))?64\b", name) else "heads_wide_kernel<128>"
     m = re.search(r"(\w+_kernel)", name)
     return m.group(1) if m else name
 

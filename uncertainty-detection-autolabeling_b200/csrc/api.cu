@@ -137,6 +137,8 @@ static void free_head(udal_head_weights_dev& h) {
   cudaFree(h.fused_w);
   cudaFree(h.wide_w);
   cudaFree(h.wide_f);
+  cudaFree(h.l0_w);
+  cudaFree(h.l0_ep);
   h = udal_head_weights_dev();
 }
 

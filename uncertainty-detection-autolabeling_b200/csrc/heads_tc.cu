@@ -460,6 +460,9 @@ int udal_heads_fused_predict(udal_ctx* ctx, int head, const void* const* in, int
                              const float* bias, const udal_prenms_out* pre);
 int udal_heads_tc_use_ig = 1;  // 0: every layer through the per-tile kernel (debug / comparison)
 
+int udal_heads_l0_prepare(udal_ctx* ctx, int head);  // heads_wide.cu: tower layer 0 of the 64-channel heads
+int udal_heads_l0_layer(udal_ctx* ctx, int head, const float* const* feats, int B, void* const* out);
+extern int udal_heads_l0_persistent;
 int udal_heads_wide_ok(const udal_ctx* ctx);  // heads_wide.cu: 64 < fpn_num_filters <= 128
 int udal_heads_wide_prepare(udal_ctx* ctx, int head);
 int udal_heads_wide_sample(udal_ctx* ctx, const float* const* feats, int batch, const float* scale, float* const* cls_out,
@@ -558,6 +561,7 @@ int udal_heads_tc_prepare(udal_ctx* ctx, int head) {
     UDAL_CUDA(cudaStreamSynchronize(ctx->stream));
   }
   UDAL_CUDA(cudaStreamSynchronize(ctx->stream));
+  UDAL_TRY(udal_heads_l0_prepare(ctx, head));
   return UDAL_OK;
 }
 
@@ -634,6 +638,12 @@ static int run_tower_tc(udal_ctx* ctx, int head, const float* const* feats, int 
         p.wf[l] = wf_all + ((size_t)layer * L + l) * KF * KF;
         p.fb[l] = h.fold_bias + ((size_t)layer * L + l) * KF;
       }
+    }
+    if (udal_heads_tc_use_ig && udal_heads_l0_persistent && layer == 0) {
+      // fp32 BiFPN features -> bf16 layer-0 output: persistent kernel, depthwise on the CUDA cores, pointwise on tcgen05
+      UDAL_TRY(udal_heads_l0_layer(ctx, head, feats, B, p.out));
+      mark();
+      continue;
     }
     if (udal_heads_tc_use_ig && layer == 1) {
       // sample-invariant input: persistent kernel, one depthwise pass per image, T samples back to back

@@ -27,22 +27,35 @@
 
 namespace {
 
-constexpr int WF = 128;                                   // padded channel count
+constexpr int kWidePad = 128;                             // padded channel count of the wide heads
+constexpr int WF = kWidePad;                              // (host code and helper kernels; the head kernel has its own CH)
 constexpr int kWdBuilderWarps = 8, kWdEpiWarps = 8;
 constexpr int kWdThreads = 64 + 32 * (kWdBuilderWarps + kWdEpiWarps);
-constexpr int WD_STAGE = IG_ROWS * IG_BOXW * WF * 2;      // 46 080: halo tile, linear [18][10][128] bf16
-// shared memory map (offsets from a 1024-byte aligned base)
-constexpr int WD_A = 0;                                   // 2 x (2 atoms x [128 px][128 B]) depthwise output (UMMA A)
-constexpr int WD_B = WD_A + 2 * 32768;                    // 2 atoms x [128 n][128 B] pointwise weights (UMMA B)
-constexpr int WD_OUT = WD_B + 32768;                      // staging: bf16 2 atoms x [128][128 B], or fp32 2 x [128][34]
-constexpr int WD_IN = WD_OUT + 34816;                     // 2 x halo tile
-constexpr int WD_BAR = WD_IN + 2 * WD_STAGE;              // mbarriers + tmem slot
-constexpr int WD_EP = WD_BAR + 256;                      // [2][128] fp32 epilogue scale | bias of the current item's level
-constexpr int WD_SMEM = WD_EP + 1024 + 1024;
-static_assert(WD_STAGE % 1024 == 0 && WD_IN % 1024 == 0, "alignment");
 constexpr int WD_STG_STRIDE = 34;                         // floats per pixel row of the fp32 staging tile (32 + pad, even)
-static_assert(2 * 128 * WD_STG_STRIDE * 4 <= 34816, "fp32 staging of the predict epilogue");
-static_assert(WD_SMEM <= kIgSmemLimit, "shared-memory budget");
+// compile-time shape of one kernel variant: CH channels (64 | 128, in = out), input bf16 or fp32 (layer 0 of the
+// 64-channel towers reads the BiFPN features directly).  Shared memory map, offsets from a 1024-byte aligned base.
+template <int CH_, bool F32IN_>
+struct WdShape {
+  static constexpr int CH = CH_, ATOMS = CH_ / 64;
+  static constexpr bool F32IN = F32IN_;
+  static constexpr int PX_BYTES = CH * (F32IN ? 4 : 2);
+  static constexpr int STAGE = IG_ROWS * IG_BOXW * PX_BYTES;   // halo tile, linear [18][10][CH]
+  static constexpr int A_BYTES = ATOMS * 16384;                // ATOMS x [128 px][128 B] depthwise output (UMMA A)
+  static constexpr int B_BYTES = ATOMS * CH * 128;             // ATOMS x [CH n][128 B] pointwise weights (UMMA B)
+  static constexpr int A = 0;                                  // 2 x A_BYTES (double buffered)
+  static constexpr int B = A + 2 * A_BYTES;
+  static constexpr int OUT = B + B_BYTES;                      // staging: bf16 ATOMS x [128][128 B], or fp32 2 x [128][34]
+  static constexpr int OUT_BYTES = 2 * 128 * WD_STG_STRIDE * 4;
+  static constexpr int STAGES = CH == 64 ? 3 : 2;              // halo tile ring (HBM latency; 128 channels: no room for a third)
+  static constexpr int IN = OUT + OUT_BYTES;                   // STAGES x halo tile
+  static constexpr int BAR = IN + STAGES * STAGE;              // mbarriers + tmem slot
+  static constexpr int EP = BAR + 256;                         // [2][CH] fp32 epilogue scale | bias of the current item's level
+  static constexpr int SMEM = EP + 2 * CH * 4 + 1024;
+  static_assert(CH == 64 || CH == 128, "channel count");
+  static_assert(STAGE % 1024 == 0 && IN % 1024 == 0 && B % 1024 == 0 && OUT % 1024 == 0, "alignment");
+  static_assert(A_BYTES <= OUT_BYTES, "bf16 staging tile");
+  static_assert(SMEM <= kIgSmemLimit, "shared-memory budget");
+};
 
 struct WdParams {
   int num_levels, NB, items;             // NB = (sample, image) pairs written; items = sum_l tiles[l] * NB (level major)
@@ -68,23 +81,31 @@ struct WdMaps {
 __device__ __forceinline__ void wd_epi_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 __device__ __forceinline__ void wd_half_sync(int hc) { asm volatile("bar.sync %0, 128;" ::"r"(2 + hc) : "memory"); }
 
+template <int CH, bool F32IN>
 __global__ void __launch_bounds__(kWdThreads, 1) heads_wide_kernel(const __grid_constant__ WdMaps maps, const WdParams p) {
+  using S = WdShape<CH, F32IN>;
+  constexpr int WF = CH, WD_STAGE = S::STAGE, WD_A = S::A, WD_B = S::B, WD_OUT = S::OUT, WD_IN = S::IN, WD_BAR = S::BAR,
+                WD_EP = S::EP, A_BYTES = S::A_BYTES, B_BYTES = S::B_BYTES, PX_BYTES = S::PX_BYTES;
+  constexpr uint32_t kTmemCols = 2 * CH;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = s32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
   const uint32_t sb = s32(smem);
-  // barriers: in_full[2] @0  in_empty[2] @16  a_full[2] @32  a_empty[2] @48  tfull[2] @64  tempty[2] @80  bfull @96  slot @104
+  // barriers: in_full[4] @0  in_empty[4] @32  a_full[2] @64  a_empty[2] @80  tfull[2] @96  tempty[2] @112  bfull @128  slot @136
+  constexpr int STAGES = S::STAGES;
   const uint32_t bar0 = sb + WD_BAR;
-  const uint32_t in_full = bar0, in_empty = bar0 + 16, a_full = bar0 + 32, a_empty = bar0 + 48, tfull = bar0 + 64,
-                 tempty = bar0 + 80, bar_b = bar0 + 96;
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + WD_BAR + 104);
+  const uint32_t in_full = bar0, in_empty = bar0 + 32, a_full = bar0 + 64, a_empty = bar0 + 80, tfull = bar0 + 96,
+                 tempty = bar0 + 112, bar_b = bar0 + 128;
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + WD_BAR + 136);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int G = gridDim.x;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < STAGES; ++i) {
       bar_init(in_full + 8 * i, 1);
       bar_init(in_empty + 8 * i, kWdBuilderWarps);  // one arrival per builder warp
+    }
+    for (int i = 0; i < 2; ++i) {
       bar_init(a_full + 8 * i, kWdBuilderWarps);
       bar_init(a_empty + 8 * i, 1);
       bar_init(tfull + 8 * i, 1);
@@ -94,7 +115,7 @@ __global__ void __launch_bounds__(kWdThreads, 1) heads_wide_kernel(const __grid_
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(sb + WD_BAR + 104) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sb + WD_BAR + 136), "r"(kTmemCols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -105,19 +126,18 @@ __global__ void __launch_bounds__(kWdThreads, 1) heads_wide_kernel(const __grid_
   if (warp == 0) {
     // ===================== producer (warp-uniform loop, one elected lane issues) =====================
     if (ig_elect_one()) {
-      bar_expect_tx(bar_b, 32768);
+      bar_expect_tx(bar_b, B_BYTES);
       asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sb + WD_B),
-                   "l"(p.wimg), "r"(32768), "r"(bar_b)
+                   "l"(p.wimg), "r"(B_BYTES), "r"(bar_b)
                    : "memory");
     }
     __syncwarp();
-    int i = 0;
-    for (int item = blockIdx.x; item < p.items; item += G, ++i) {
+    int s = 0, ph = 0;
+    for (int item = blockIdx.x; item < p.items; item += G) {
       const IgItem w = ig_item(p, item);
-      const int s = i & 1;
       const int nb_in = w.nb % p.in_nb;
       if (ig_elect_one()) {
-        bar_wait(in_empty + 8 * s, ((i >> 1) & 1) ^ 1);
+        bar_wait(in_empty + 8 * s, ph ^ 1);
         bar_expect_tx(in_full + 8 * s, WD_STAGE);
         asm volatile(
             "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
@@ -126,6 +146,10 @@ __global__ void __launch_bounds__(kWdThreads, 1) heads_wide_kernel(const __grid_
             : "memory");
       }
       __syncwarp();
+      if (++s == STAGES) {
+        s = 0;
+        ph ^= 1;
+      }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
@@ -142,9 +166,8 @@ __global__ void __launch_bounds__(kWdThreads, 1) heads_wide_kernel(const __grid_
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
         for (int k = 0; k < WF / 16; ++k) {
-          const uint32_t koff = (uint32_t)((k >> 2) * 16384 + (k & 3) * 32);
-          const uint64_t adesc = ig_desc(sb + WD_A + ab * 32768 + koff, 1024, 0);
-          const uint64_t bdesc = ig_desc(sb + WD_B + koff, 1024, 0);
+          const uint64_t adesc = ig_desc(sb + WD_A + ab * A_BYTES + (uint32_t)((k >> 2) * 16384 + (k & 3) * 32), 1024, 0);
+          const uint64_t bdesc = ig_desc(sb + WD_B + (uint32_t)((k >> 2) * (CH * 128) + (k & 3) * 32), 1024, 0);
           ig_mma(d_tmem, adesc, bdesc, idesc, k ? 1u : 0u);
         }
         ig_commit(a_empty + 8 * ab);   // A buffer reusable once these MMAs retire
@@ -155,7 +178,11 @@ __global__ void __launch_bounds__(kWdThreads, 1) heads_wide_kernel(const __grid_
   } else if (warp < 2 + kWdBuilderWarps) {
     // ===================== builders: depthwise 3x3 -> A operand =====================
     const int tid = threadIdx.x - 64;
-    const int q4 = tid & 31, x = tid >> 5;  // channel quad (4 q4 .. 4 q4 + 3), tile column
+    // thread = channel quad (4 q4 .. 4 q4 + 3) x tile column; 128 channels: both row halves of the tile in turn,
+    // 64 channels: the two thread halves take one row half each
+    constexpr int QUADS = CH / 4;
+    const int q4 = tid & (QUADS - 1), x = (tid / QUADS) & 7;
+    const int half_lo = CH == 128 ? 0 : tid >> 7, half_hi = CH == 128 ? 2 : half_lo + 1;
     float2 wgt[9][2];
 #pragma unroll
     for (int tp = 0; tp < 9; ++tp) {
@@ -164,22 +191,22 @@ __global__ void __launch_bounds__(kWdThreads, 1) heads_wide_kernel(const __grid_
       wgt[tp][1] = make_float2(w4.z, w4.w);
     }
     const bool real = 4 * q4 < p.F;  // F % 4 == 0: a quad is entirely real or entirely padding
-    int i = 0;
+    int i = 0, s = 0, ph = 0;
     for (int item = blockIdx.x; item < p.items; item += G, ++i) {
       const IgItem w = ig_item(p, item);
-      const int s = i & 1, ab = i & 1;
+      const int ab = i & 1;
       float4 sc = make_float4(1.f, 1.f, 1.f, 1.f);
       if (p.in_scale[w.l] && real) sc = __ldg(reinterpret_cast<const float4*>(p.in_scale[w.l] + (size_t)w.nb * p.F) + q4);
       if (lane == 0) {
-        bar_wait(in_full + 8 * s, (i >> 1) & 1);          // halo tile landed
+        bar_wait(in_full + 8 * s, ph);                    // halo tile landed
         bar_wait(a_empty + 8 * ab, ((i >> 1) & 1) ^ 1);   // the MMAs of item i-2 are done with this A buffer
       }
       __syncwarp();
       const uint8_t* sIn = smem + WD_IN + s * WD_STAGE;
-      uint8_t* sA = smem + WD_A + ab * 32768 + (q4 >> 4) * 16384;
+      uint8_t* sA = smem + WD_A + ab * A_BYTES + (q4 >> 4) * 16384;
       const uint32_t chunk = (uint32_t)((q4 & 15) >> 1), sub = (uint32_t)(q4 & 1) * 8;
 #pragma unroll 1
-      for (int half = (p.debug & 1) ? 2 : 0; half < 2; ++half) {  // tile rows 8 half .. 8 half + 7 (halo rows 8 half .. 8 half + 9)
+      for (int half = (p.debug & 1) ? half_hi : half_lo; half < half_hi; ++half) {  // tile rows 8 half .. 8 half + 7 (halo rows 8 half .. 8 half + 9)
         float2 acc[8][2];  // packed pairs: the 9 x 4 FMAs per pixel issue as 18 FFMA2
 #pragma unroll
         for (int y = 0; y < 8; ++y) acc[y][0] = acc[y][1] = make_float2(0.f, 0.f);
@@ -187,9 +214,18 @@ __global__ void __launch_bounds__(kWdThreads, 1) heads_wide_kernel(const __grid_
         for (int r = 0; r < 10; ++r) {
 #pragma unroll
           for (int dx = 0; dx < 3; ++dx) {
-            const uint2 raw2 = *reinterpret_cast<const uint2*>(sIn + (size_t)((8 * half + r) * IG_BOXW + x + dx) * (WF * 2) + q4 * 8);
-            const float2 v01 = make_float2(__uint_as_float(raw2.x << 16), __uint_as_float(raw2.x & 0xffff0000u));
-            const float2 v23 = make_float2(__uint_as_float(raw2.y << 16), __uint_as_float(raw2.y & 0xffff0000u));
+            const uint8_t* px = sIn + (size_t)((8 * half + r) * IG_BOXW + x + dx) * PX_BYTES;
+            float2 v01, v23;
+            if constexpr (F32IN) {
+              // BiFPN features enter the fp32 depthwise accumulation unrounded (the A operand is rounded to bf16 once)
+              const float4 f = *reinterpret_cast<const float4*>(px + q4 * 16);
+              v01 = make_float2(f.x, f.y);
+              v23 = make_float2(f.z, f.w);
+            } else {
+              const uint2 raw2 = *reinterpret_cast<const uint2*>(px + q4 * 8);
+              v01 = make_float2(__uint_as_float(raw2.x << 16), __uint_as_float(raw2.x & 0xffff0000u));
+              v23 = make_float2(__uint_as_float(raw2.y << 16), __uint_as_float(raw2.y & 0xffff0000u));
+            }
 #pragma unroll
             for (int dy = 0; dy < 3; ++dy) {
               const int y = r - dy;
@@ -215,12 +251,17 @@ __global__ void __launch_bounds__(kWdThreads, 1) heads_wide_kernel(const __grid_
         bar_arrive(a_full + 8 * ab);
         bar_arrive(in_empty + 8 * s);
       }
+      if (++s == STAGES) {
+        s = 0;
+        ph ^= 1;
+      }
     }
   } else {
     // ===================== epilogue: 4 lane quarters x 2 column halves =====================
     const int ew = warp - 2 - kWdBuilderWarps;
     const int q = warp & 3;                 // TMEM lane quarter this warp may access
-    const int hc = ew >> 2;                 // column half: accumulator columns 64 hc .. 64 hc + 63
+    constexpr int HC = CH / 2, PASSES = HC / 32;  // columns per warp, in passes of 32
+    const int hc = ew >> 2;                 // column half: accumulator columns HC hc .. HC hc + HC - 1
     const int m = q * 32 + lane;            // GEMM row = pixel (m / 8, m % 8) of the tile
     const bool elected = ew == 0 && lane == 0;
     const uint32_t swz = (uint32_t)(m & 7);
@@ -235,18 +276,18 @@ __global__ void __launch_bounds__(kWdThreads, 1) heads_wide_kernel(const __grid_
       {
         const int et = threadIdx.x - 64 - 32 * kWdBuilderWarps;
         if (!p.predict) {
-          sEp[et] = 0.5f * __ldg(p.ep[w.l] + et);
-        } else if ((et & 127) < 64) {  // predict: each column-half group (own barrier) loads the 64 biases it reads
-          const int n = WF + hc * 64 + (et & 127);
+          if (et < 2 * CH) sEp[et] = 0.5f * __ldg(p.ep[w.l] + et);
+        } else if ((et & 127) < HC) {  // predict: each column-half group (own barrier) loads the biases it reads
+          const int n = WF + hc * HC + (et & 127);
           sEp[n] = __ldg(p.ep[w.l] + n);
         }
       }
-      const float4* eps = reinterpret_cast<const float4*>(sEp + hc * 64);
-      const float4* epb = reinterpret_cast<const float4*>(sEp + WF + hc * 64);
+      const float4* eps = reinterpret_cast<const float4*>(sEp + hc * HC);
+      const float4* epb = reinterpret_cast<const float4*>(sEp + WF + hc * HC);
       if (lane == 0) bar_wait(tfull + 8 * ab, (i >> 1) & 1);
       __syncwarp();
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * WF + hc * 64);
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * WF + hc * HC);
       if (p.debug & 2) {
         uint32_t r8[8];
         ig_ld8(taddr, r8);
@@ -260,19 +301,20 @@ __global__ void __launch_bounds__(kWdThreads, 1) heads_wide_kernel(const __grid_
         __syncwarp();
         wd_epi_sync();
 #pragma unroll
-        for (int pass = 0; pass < 2; ++pass) {
+        for (int pass = 0; pass < PASSES; ++pass) {
           uint32_t r[4][8];
 #pragma unroll
           for (int u = 0; u < 4; ++u) ig_ld8(taddr + pass * 32 + u * 8, r[u]);
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-          if (pass == 1) {
+          if (pass == PASSES - 1) {
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
             if (lane == 0) bar_arrive(tempty + 8 * ab);  // accumulator may be overwritten
           }
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
-            const int j = pass * 4 + u;  // 16-byte chunk (8 channels) inside the atom row
+            const int j = pass * 4 + u;                 // 8-channel group of this warp's columns (epilogue table index)
+            const int col = hc * HC + j * 8;            // first output channel of the group
             const float4 g0 = eps[2 * j], g1 = eps[2 * j + 1];
             const float4 f0 = epb[2 * j], f1 = epb[2 * j + 1];
             const float2 gs[4] = {make_float2(g0.x, g0.y), make_float2(g0.z, g0.w), make_float2(g1.x, g1.y), make_float2(g1.z, g1.w)};
@@ -290,14 +332,14 @@ __global__ void __launch_bounds__(kWdThreads, 1) heads_wide_kernel(const __grid_
             o.y = ig_pack(v[2], v[3]);
             o.z = ig_pack(v[4], v[5]);
             o.w = ig_pack(v[6], v[7]);
-            *reinterpret_cast<uint4*>(ob + hc * 16384 + m * 128 + (((uint32_t)j ^ swz) << 4)) = o;
+            *reinterpret_cast<uint4*>(ob + (col >> 6) * 16384 + m * 128 + (((uint32_t)((col & 63) >> 3) ^ swz) << 4)) = o;
           }
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // staging writes -> visible to TMA
         wd_epi_sync();
         if (elected) {
           ig_tma_store(&maps.out[w.l], s32(ob), 0, w.tx0, w.ty0, w.nb);
-          ig_tma_store(&maps.out[w.l], s32(ob) + 16384, 64, w.tx0, w.ty0, w.nb);
+          if (CH == 128) ig_tma_store(&maps.out[w.l], s32(ob) + 16384, 64, w.tx0, w.ty0, w.nb);
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
         __syncwarp();
@@ -307,13 +349,13 @@ __global__ void __launch_bounds__(kWdThreads, 1) heads_wide_kernel(const __grid_
         float* const stg = reinterpret_cast<float*>(ob) + hc * (128 * WD_STG_STRIDE);
         const int ht = threadIdx.x - 64 - 32 * kWdBuilderWarps - hc * 128;  // thread of the column-half group
 #pragma unroll 1
-        for (int pass = 0; pass < 2; ++pass) {
-          const int c0 = hc * 64 + pass * 32;  // first accumulator column of the pass
+        for (int pass = 0; pass < PASSES; ++pass) {
+          const int c0 = hc * HC + pass * 32;  // first accumulator column of the pass
           uint32_t r[4][8];
 #pragma unroll
           for (int u = 0; u < 4; ++u) ig_ld8(taddr + pass * 32 + u * 8, r[u]);
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-          if (pass == 1) {
+          if (pass == PASSES - 1) {
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
             if (lane == 0) bar_arrive(tempty + 8 * ab);
@@ -365,7 +407,7 @@ __global__ void __launch_bounds__(kWdThreads, 1) heads_wide_kernel(const __grid_
   __syncthreads();
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem_base) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
   }
 }
 
@@ -384,14 +426,15 @@ __global__ void wide_convert_kernel(const float* __restrict__ in, size_t n_px, i
 }
 
 // weight image of one pointwise matrix: wimg[atom = k / 64][n][k % 64] = bf16(w[k][n0 + n]) (n < cout, k < F), 128B swizzle
-__global__ void wide_weights_kernel(const float* __restrict__ w, int F, int ldw, int n0, int cout, __nv_bfloat16* __restrict__ wimg) {
+__global__ void wide_weights_kernel(const float* __restrict__ w, int F, int ldw, int n0, int cout, __nv_bfloat16* __restrict__ wimg,
+                                    int ch = WF) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= WF * WF) return;
-  const int k = i % WF, n = i / WF;
+  if (i >= ch * ch) return;
+  const int k = i % ch, n = i / ch;
   float v = 0.f;
   if (k < F && n < cout) v = w[(size_t)k * ldw + n0 + n];
   const int kk = k & 63;
-  const size_t byte = (size_t)(k >> 6) * 16384 + (size_t)n * 128 + (size_t)((((kk >> 3) ^ (n & 7)) << 4) + (kk & 7) * 2);
+  const size_t byte = (size_t)(k >> 6) * ((size_t)ch * 128) + (size_t)n * 128 + (size_t)((((kk >> 3) ^ (n & 7)) << 4) + (kk & 7) * 2);
   wimg[byte / 2] = __float2bfloat16_rn(v);
 }
 
@@ -405,16 +448,16 @@ __global__ void wide_dw_kernel(const float* __restrict__ src, int F, float* __re
 
 // ep[0][n] = scale, ep[1][n] = bias*scale + shift (tower) or ep = (1, bias) (predict), zero padded
 __global__ void wide_ep_kernel(const float* __restrict__ bias, const float* __restrict__ bn_scale, const float* __restrict__ bn_shift,
-                               int n0, int cout, float* __restrict__ ep) {
+                               int n0, int cout, float* __restrict__ ep, int ch = WF) {
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
-  if (n >= WF) return;
+  if (n >= ch) return;
   float s = 0.f, b = 0.f;
   if (n < cout) {
     s = bn_scale ? bn_scale[n0 + n] : 1.f;
     b = bn_scale ? fmaf(bias[n0 + n], bn_scale[n0 + n], bn_shift[n0 + n]) : bias[n0 + n];
   }
   ep[n] = s;
-  ep[WF + n] = b;
+  ep[ch + n] = b;
 }
 
 }  // namespace
@@ -468,9 +511,11 @@ int udal_heads_wide_prepare(udal_ctx* ctx, int head) {
   return UDAL_OK;
 }
 
+template <int CH, bool F32IN>
 static int launch_wide(udal_ctx* ctx, const void* const* in, int in_nb, int NB, const float* const* in_scale, const float* dw,
                        const void* wimg, const float* const* ep, int predict, int cout, int ch_off, int ch_total,
                        void* const* out) {
+  using S = WdShape<CH, F32IN>;
   EncodeTiledFn encode = get_encode();
   UDAL_REQUIRE(encode != nullptr, "cuTensorMapEncodeTiled is not available from this driver");
   const udal_config& c = ctx->cfg;
@@ -492,9 +537,10 @@ static int launch_wide(udal_ctx* ctx, const void* const* in, int in_nb, int NB, 
   int off = 0;
   for (int l = 0; l < c.num_levels; ++l) {
     const int H = c.level_h[l], W = c.level_w[l];
-    UDAL_TRY(encode_nhwc(encode, &maps.in[l], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, in[l], in_nb, H, W, WF, WF, IG_BOXW, IG_ROWS, false));
+    UDAL_TRY(encode_nhwc(encode, &maps.in[l], F32IN ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, F32IN ? 4 : 2,
+                         in[l], in_nb, H, W, CH, CH, IG_BOXW, IG_ROWS, false));
     if (!predict)
-      UDAL_TRY(encode_nhwc(encode, &maps.out[l], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, out[l], NB, H, W, WF, 64, IG_TW, IG_TH, true));
+      UDAL_TRY(encode_nhwc(encode, &maps.out[l], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, out[l], NB, H, W, CH, 64, IG_TW, IG_TH, true));
     p.H[l] = H;
     p.W[l] = W;
     p.tiles_x[l] = (W + IG_TW - 1) / IG_TW;
@@ -511,10 +557,50 @@ static int launch_wide(udal_ctx* ctx, const void* const* in, int in_nb, int NB, 
   for (int l = c.num_levels; l <= UDAL_MAX_LEVELS; ++l) p.item_off[l] = off;
   p.items = off;
   const int grid = udal_persistent_grid(ctx, p.items);
-  UDAL_CUDA(cudaFuncSetAttribute(heads_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WD_SMEM));
-  heads_wide_kernel<<<grid, kWdThreads, WD_SMEM, ctx->stream>>>(maps, p);
+  UDAL_CUDA(cudaFuncSetAttribute(heads_wide_kernel<CH, F32IN>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::SMEM));
+  heads_wide_kernel<CH, F32IN><<<grid, kWdThreads, S::SMEM, ctx->stream>>>(maps, p);
   UDAL_CHECK_LAUNCH(ctx);
   return UDAL_OK;
+}
+
+// ---- layer 0 of the 64-channel towers through the same kernel (CH = 64, fp32 BiFPN features in) ----
+int udal_heads_l0_persistent = 1;  // 0: layer 0 through the per-tile kernel of heads_tc.cu (debug / comparison)
+
+// pointwise image [64 n][64 k] bf16 and, per level, the epilogue table (BN scale | folded bias) of tower layer 0
+int udal_heads_l0_prepare(udal_ctx* ctx, int head) {
+  const udal_config& c = ctx->cfg;
+  udal_head_weights_dev& h = ctx->heads[head];
+  UDAL_REQUIRE(c.num_filters == KF, "layer-0 kernel: 64 channels");
+  const int L = c.num_levels;
+  if (h.l0_w) UDAL_CUDA(cudaFree(h.l0_w));
+  if (h.l0_ep) UDAL_CUDA(cudaFree(h.l0_ep));
+  h.l0_w = nullptr;
+  h.l0_ep = nullptr;
+  UDAL_CUDA(cudaMalloc(&h.l0_w, (size_t)KF * KF * 2));
+  UDAL_CUDA(cudaMalloc(&h.l0_ep, (size_t)L * 2 * KF * sizeof(float)));
+  wide_weights_kernel<<<(KF * KF + 255) / 256, 256, 0, ctx->stream>>>(h.pw, KF, KF, 0, KF, reinterpret_cast<__nv_bfloat16*>(h.l0_w), KF);
+  UDAL_CHECK_LAUNCH(ctx);
+  for (int l = 0; l < L; ++l) {
+    wide_ep_kernel<<<1, KF, 0, ctx->stream>>>(h.bias, h.bn_scale + (size_t)l * KF, h.bn_shift + (size_t)l * KF, 0, KF,
+                                              h.l0_ep + (size_t)l * 2 * KF, KF);
+    UDAL_CHECK_LAUNCH(ctx);
+  }
+  UDAL_CUDA(cudaStreamSynchronize(ctx->stream));
+  return UDAL_OK;
+}
+
+// tower layer 0: feats[l] fp32 [B,H_l,W_l,64] -> out[l] bf16 [B,H_l,W_l,64] = swish(BN(sepconv(bf16(feats)))), no dropout applied
+int udal_heads_l0_layer(udal_ctx* ctx, int head, const float* const* feats, int B, void* const* out) {
+  const udal_config& c = ctx->cfg;
+  const udal_head_weights_dev& h = ctx->heads[head];
+  UDAL_REQUIRE(h.l0_w && h.l0_ep, "layer-0 tables not built");
+  const void* in[UDAL_MAX_LEVELS];
+  const float* ep[UDAL_MAX_LEVELS];
+  for (int l = 0; l < c.num_levels; ++l) {
+    in[l] = feats[l];
+    ep[l] = h.l0_ep + (size_t)l * 2 * KF;
+  }
+  return launch_wide<64, true>(ctx, in, B, B, nullptr, h.dw, h.l0_w, ep, 0, KF, 0, KF, out);
 }
 
 // one head: R tower layers + the predict layer(s); feats16[l] = bf16 [B,H_l,W_l,128] features (wide_convert_kernel),
@@ -563,13 +649,13 @@ static int run_tower_wide(udal_ctx* ctx, int head, const __nv_bfloat16* const* f
     }
     mark();
     if (!predict) {
-      UDAL_TRY(launch_wide(ctx, in, in_nb, nb_out, (mc && layer >= 1) ? in_scale : nullptr, dwp + (size_t)layer * 9 * WF,
+      UDAL_TRY((launch_wide<kWidePad, false>)(ctx, in, in_nb, nb_out, (mc && layer >= 1) ? in_scale : nullptr, dwp + (size_t)layer * 9 * WF,
                            img + (size_t)layer * WF * WF, ep, 0, WF, 0, WF, out));
     } else {
       for (int q = 0; q < h.wide_chunks; ++q) {
         const int n0 = q * WF, nc = h.cout - n0 < WF ? h.cout - n0 : WF;
         for (int l = 0; l < L; ++l) ep[l] = ep_all + ((size_t)R * L + q) * 2 * WF;
-        UDAL_TRY(launch_wide(ctx, in, in_nb, nb_out, (mc && layer >= 1) ? in_scale : nullptr, dwp + (size_t)R * 9 * WF,
+        UDAL_TRY((launch_wide<kWidePad, false>)(ctx, in, in_nb, nb_out, (mc && layer >= 1) ? in_scale : nullptr, dwp + (size_t)R * 9 * WF,
                              img + (size_t)(R + q) * WF * WF, ep, 1, nc, n0, h.cout, out));
       }
     }
