@@ -59,6 +59,19 @@ int udal_scratch_get(udal_ctx* ctx, int slot, size_t bytes, void** out) {
   return UDAL_OK;
 }
 
+int udal_work_counters_reset(udal_ctx* ctx) {
+  if (!ctx->work_counters) UDAL_CUDA(cudaMalloc(&ctx->work_counters, UDAL_WORK_COUNTERS * sizeof(int)));
+  UDAL_CUDA(cudaMemsetAsync(ctx->work_counters, 0, UDAL_WORK_COUNTERS * sizeof(int), ctx->stream));
+  ctx->work_counter_next = 0;
+  return UDAL_OK;
+}
+
+int udal_work_counter(udal_ctx* ctx, int** out) {
+  UDAL_REQUIRE(ctx->work_counters && ctx->work_counter_next < UDAL_WORK_COUNTERS, "persistent-kernel work counters exhausted");
+  *out = ctx->work_counters + ctx->work_counter_next++;
+  return UDAL_OK;
+}
+
 extern "C" {
 
 const char* udal_last_error(void) { return g_err; }
@@ -150,6 +163,7 @@ int udal_destroy(udal_ctx* ctx) {
   for (auto& s : ctx->scratch) cudaFree(s.ptr);
   for (void* p : ctx->user_allocs) cudaFree(p);
   cudaFree(ctx->anchors);
+  cudaFree(ctx->work_counters);
   free_head(ctx->heads[0]);
   free_head(ctx->heads[1]);
   cudaEventDestroy(ctx->ev_start);

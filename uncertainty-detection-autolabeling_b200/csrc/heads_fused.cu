@@ -47,7 +47,8 @@ struct FuShape {
   static constexpr int BAR = OUT2 + OUT2_BYTES_;       // barriers + tmem slot (128 B)
   static constexpr int TBL = BAR + 128;                // 64 doubles: 2^(j/64) table of exp_fast
   static constexpr int BIAS = TBL + 512;               // [NPAD] fp32 predict bias
-  static constexpr int SMEM = BIAS + NPAD * 4 + 1024;
+  static constexpr int QUEUE = BIAS + NPAD * 4;         // item-index ring (IG_QRING ints)
+  static constexpr int SMEM = QUEUE + IG_QRING * 4 + 1024;
   static_assert(B_BYTES % 1024 == 0 && STAGES <= FU_MAX_STAGES && 2 * NPAD <= 256, "layout");
   static_assert(SMEM <= kIgSmemLimit, "shared-memory budget");
 };
@@ -67,6 +68,7 @@ struct FuParams {
   const void* wimg;                      // bf16 [9][NROWS][64] swizzled weight image of the predict layer
   const float* bias;                     // [NPAD]
   const float* anchors;                  // [N,4]
+  int* counter;                          // zeroed work-item counter of this launch (dynamic claiming, heads_umma.cuh)
   long long N;                           // anchors per image
   float* mean_logits;                    // class head outputs [NB,N,NC]
   float* std_logits;
@@ -134,6 +136,7 @@ __global__ void __launch_bounds__(kFuThreads, 1) heads_fused_kernel(const __grid
   using S = FuShapeOf<BOX, NC>;
   constexpr int FU_NPAD = S::NPAD, FU_NROWS = S::NROWS, FU_STAGES = S::STAGES, FU_B = S::B, FU_B_BYTES = S::B_BYTES,
                 FU_IN = S::IN, FU_OUT = S::OUT, FU_OUT2 = S::OUT2, FU_BAR = S::BAR, FU_TBL = S::TBL, FU_BIAS = S::BIAS;
+  volatile int* sQ = nullptr;  // item-index ring, set below
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = s32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
@@ -144,6 +147,7 @@ __global__ void __launch_bounds__(kFuThreads, 1) heads_fused_kernel(const __grid
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + FU_BAR + 104);
   double* sTbl = reinterpret_cast<double*>(smem + FU_TBL);
   float* sBias = reinterpret_cast<float*>(smem + FU_BIAS);
+  sQ = reinterpret_cast<volatile int*>(smem + S::QUEUE);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int T = p.T, G = gridDim.x;
 
@@ -180,11 +184,22 @@ __global__ void __launch_bounds__(kFuThreads, 1) heads_fused_kernel(const __grid
     }
     __syncwarp();
     int s = 0, ph = 0;
-    for (int item = blockIdx.x; item < p.items; item += G) {
+    for (int i = 0;; ++i) {
+      const int item = ig_claim(p.counter, p.items, lane);
+      if (item < 0) {  // end of the stream: an empty "sample" carries it to the MMA warp
+        if (ig_elect_one()) {
+          bar_wait(bar_empty + 8 * s, ph ^ 1);
+          sQ[i & (IG_QRING - 1)] = -1;
+          bar_arrive(bar_full + 8 * s);
+        }
+        __syncwarp();
+        break;
+      }
       const IgItem w = ig_item(p, item);
       for (int t = 0; t < T; ++t) {
         if (ig_elect_one()) {
           bar_wait(bar_empty + 8 * s, ph ^ 1);
+          if (t == 0) sQ[i & (IG_QRING - 1)] = item;  // published by the arrival on the first sample's full barrier
           bar_expect_tx(bar_full + 8 * s, IG_ROWS * IG_BOXW * 128);
           asm volatile(
               "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
@@ -205,7 +220,17 @@ __global__ void __launch_bounds__(kFuThreads, 1) heads_fused_kernel(const __grid
     if (lane == 0) bar_wait(bar_b, 0);
     __syncwarp();
     int j = 0, s = 0, ph = 0;
-    for (int item = blockIdx.x; item < p.items; item += G) {
+    for (int i = 0;; ++i) {
+      if (lane == 0) bar_wait(bar_full + 8 * s, ph);  // first sample of the item (or the end marker) landed
+      __syncwarp();
+      if (ig_queue_read(sQ, i) < 0) {
+        if (ig_elect_one()) {  // wake the epilogue: its next accumulator "arrives" empty
+          bar_wait(bar_tempty + 8 * (j & 1), ((j >> 1) & 1) ^ 1);
+          bar_arrive(bar_tfull + 8 * (j & 1));
+        }
+        __syncwarp();
+        break;
+      }
       for (int t = 0; t < T; ++t, ++j) {
         const int a = j & 1;
         const uint32_t in0 = sb + FU_IN + s * FU_STAGE;
@@ -245,7 +270,11 @@ __global__ void __launch_bounds__(kFuThreads, 1) heads_fused_kernel(const __grid
     float* const sOut = reinterpret_cast<float*>(smem + FU_OUT);
     float* const sOut2 = reinterpret_cast<float*>(smem + FU_OUT2);
     int j = 0;
-    for (int item = blockIdx.x; item < p.items; item += G) {
+    for (int i = 0;; ++i) {
+      if (lane == 0) bar_wait(bar_tfull + 8 * (j & 1), (j >> 1) & 1);  // first sample of the item (or the end marker)
+      __syncwarp();
+      const int item = ig_queue_read(sQ, i);
+      if (item < 0) break;
       const IgItem w = ig_item(p, item);
       const int H = p.H[w.l], W = p.W[w.l];
       const int oy = w.ty0 + (m >> 3), ox = w.tx0 + (m & 7);
@@ -266,8 +295,8 @@ __global__ void __launch_bounds__(kFuThreads, 1) heads_fused_kernel(const __grid
           if constexpr (NC > 8) {
             // 30 logits x (sum, first sample, squared deviations) already fill the register file: the accumulator is
             // read 8 columns at a time (the MMA of the next sample takes ~2000 cycles, the extra load latency hides)
-#pragma unroll
             static_assert(CH % 2 == 0, "packed pairs");
+#pragma unroll
             for (int u = 0; u < NLD; ++u) {
               uint32_t r8[8];
               ig_ld8(taddr + u * 8, r8);
@@ -597,6 +626,7 @@ int udal_heads_fused_predict(udal_ctx* ctx, int head, const void* const* in, int
     return encode_strided(encode, map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, base + (size_t)ctx->level_pix_off[l] * ch, gdim, gstr, ch,
                           IG_TW, IG_TH, false);
   };
+  UDAL_TRY(udal_work_counter(ctx, &p.counter));
   const int grid = udal_persistent_grid(ctx, p.items);
   if (head == UDAL_HEAD_CLASS) {
     UDAL_REQUIRE(pre->mean_logits && pre->std_logits && pre->scores && pre->classes, "fused class head: NULL output");

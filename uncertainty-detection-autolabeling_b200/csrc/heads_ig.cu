@@ -54,7 +54,7 @@ struct IgShape {
   static constexpr int SM_OUT = SM_IN + STAGES * STAGE_STRIDE;
   static constexpr int SM_BAR = SM_OUT + 2 * OUT_BYTES;
   static constexpr int SM_FBS = SM_BAR + 640;  // barriers (96 B) + 2 x 64 keep-scales
-  static constexpr int smem(int levels) { return SM_FBS + levels * 2 * NPAD * 4 + 1024; }
+  static constexpr int smem(int levels) { return SM_FBS + levels * 2 * NPAD * 4 + IG_QRING * 4 + 1024; }
   static_assert(B_BYTES % 1024 == 0 && OUT_BYTES % 1024 == 0, "swizzled regions must stay 1 KB aligned");
   static_assert(STAGES <= kIgMaxStages, "barrier slots");
 };
@@ -74,6 +74,7 @@ struct IgParams {
   int ch_off, ch_total;                  // predictions: this launch writes channels [ch_off, ch_off + Cout) of ch_total
   int tma_store;                         // predictions through the staging tile + TMA store (Cout % 4 == 0)
   int debug;                             // timing experiments only (wrong results): 1 = one tap, 2 = no epilogue math / stores, 4 = no TMA loads after the first ring fill
+  int* counter;                          // zeroed work-item counter of this launch (dynamic claiming, heads_umma.cuh)
 };
 
 struct IgMaps {
@@ -96,6 +97,7 @@ __global__ void __launch_bounds__(kIgThreads, 1) heads_ig_kernel(const __grid_co
   const uint32_t bar_full = bar0, bar_empty = bar0 + 24, bar_tfull = bar0 + 48, bar_tempty = bar0 + 64, bar_b = bar0 + 80;
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + S::SM_BAR + 88);
   float* sFb = reinterpret_cast<float*>(smem + S::SM_FBS);
+  volatile int* sQ = reinterpret_cast<volatile int*>(smem + S::SM_FBS + p.num_levels * 2 * NPAD * 4);  // item-index ring
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
@@ -143,13 +145,18 @@ __global__ void __launch_bounds__(kIgThreads, 1) heads_ig_kernel(const __grid_co
     }
     __syncwarp();
     int s = 0, ph = 0, n_loaded = 0;
-    for (int item = blockIdx.x; item < p.items; item += G) {
-      const IgItem w = ig_item(p, item);
+    for (int k = 0;; ++k) {
+      const int item = ig_claim(p.counter, p.items, lane);
+      const IgItem w = ig_item(p, item < 0 ? 0 : item);
       const uint32_t dst = sb + S::SM_IN + s * S::STAGE_STRIDE;
       const bool skip = (p.debug & 4) && n_loaded++ >= STAGES;
       if (ig_elect_one()) {
         bar_wait(bar_empty + 8 * s, ph ^ 1);  // stage free (first round passes immediately)
-        if (skip) {
+        sQ[k & (IG_QRING - 1)] = item;        // published by the arrival on the stage's full barrier
+        if (item < 0) {
+          sQ[(k + 1) & (IG_QRING - 1)] = -1;  // end of the stream, for both epilogue groups
+          bar_arrive(bar_full + 8 * s);
+        } else if (skip) {
           bar_arrive(bar_full + 8 * s);
         } else {
           bar_expect_tx(bar_full + 8 * s, IG_ROWS * IG_BOXW * 128);
@@ -161,6 +168,7 @@ __global__ void __launch_bounds__(kIgThreads, 1) heads_ig_kernel(const __grid_co
         }
       }
       __syncwarp();
+      if (item < 0) break;
       if (++s == STAGES) {
         s = 0;
         ph ^= 1;
@@ -175,14 +183,26 @@ __global__ void __launch_bounds__(kIgThreads, 1) heads_ig_kernel(const __grid_co
     constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NPAD >> 3) << 17) | ((128u >> 4) << 24);
     if (lane == 0) bar_wait(bar_b, 0);  // weights resident
     __syncwarp();
-    int it = 0, s = 0, ph = 0;
-    for (int item = blockIdx.x; item < p.items; item += G, ++it) {
+    int s = 0, ph = 0;
+    for (int it = 0;; ++it) {
       const int a = it & 1;
       const uint32_t in0 = sb + S::SM_IN + s * S::STAGE_STRIDE;
       const uint32_t d_tmem = tmem_base + (uint32_t)(a * NPAD);
-      if (ig_elect_one()) {  // only this lane polls the barriers: 32 pollers would crowd the epilogue's smem traffic
+      if (lane == 0) bar_wait(bar_full + 8 * s, ph);  // halo tile landed (one poller: 32 would crowd the epilogue's smem traffic)
+      __syncwarp();
+      if (ig_queue_read(sQ, it) < 0) {
+        // end of the stream: wake both epilogue groups (their next accumulator "arrives" empty)
+        if (ig_elect_one()) {
+          bar_wait(bar_tempty + 8 * a, ((it >> 1) & 1) ^ 1);
+          bar_arrive(bar_tfull + 8 * a);
+          bar_wait(bar_tempty + 8 * (a ^ 1), (((it + 1) >> 1) & 1) ^ 1);
+          bar_arrive(bar_tfull + 8 * (a ^ 1));
+        }
+        __syncwarp();
+        break;
+      }
+      if (ig_elect_one()) {
         bar_wait(bar_tempty + 8 * a, ((it >> 1) & 1) ^ 1);  // accumulator drained by its epilogue group
-        bar_wait(bar_full + 8 * s, ph);                      // halo tile landed
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
         for (int tap = 0; tap < 9; ++tap) {
@@ -214,10 +234,12 @@ __global__ void __launch_bounds__(kIgThreads, 1) heads_ig_kernel(const __grid_co
     const bool staged = !S::PREDICT || p.tma_store;
     uint8_t* const ob = smem + S::SM_OUT + g * S::OUT_BYTES;
     const uint32_t swz = (uint32_t)(m & 7);
-    int it = 0;
-    for (int item = blockIdx.x; item < p.items; item += G, ++it) {
-      if ((it & 1) != g) continue;
+    for (int it = g;; it += 2) {  // group g drains the items with it % 2 == g
       const int a = g;
+      if (lane == 0) bar_wait(bar_tfull + 8 * a, (it >> 1) & 1);  // one poller per warp
+      __syncwarp();
+      const int item = ig_queue_read(sQ, it);
+      if (item < 0) break;
       const IgItem w = ig_item(p, item);
       const int nb = w.nb;
       const float* ep_s = sFb + (2 * w.l) * NPAD;
@@ -231,8 +253,6 @@ __global__ void __launch_bounds__(kIgThreads, 1) heads_ig_kernel(const __grid_co
           reinterpret_cast<float4*>(sSc)[lane] = __ldg(sc + lane);
         }
       }
-      if (lane == 0) bar_wait(bar_tfull + 8 * a, (it >> 1) & 1);  // one poller per warp
-      __syncwarp();
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * NPAD);
       uint32_t r[NPAD / 8][8];
@@ -477,6 +497,7 @@ int udal_heads_ig_layer(udal_ctx* ctx, const void* const* in, int NB, const void
   p.Cout = cout;
   p.wimg = wimg;
   p.debug = udal_ig_debug;
+  UDAL_TRY(udal_work_counter(ctx, &p.counter));
   const int grid = udal_persistent_grid(ctx, p.items);
   if (!predict) return launch_ig<IgTower>(ctx, maps, p, grid);
   if (npad == 64) return launch_ig<IgPred64>(ctx, maps, p, grid);

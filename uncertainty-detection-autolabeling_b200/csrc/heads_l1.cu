@@ -33,7 +33,7 @@ constexpr int L1_A = 0;                          // 2 x [128][128 B] depthwise o
 constexpr int L1_BT = L1_A + 2 * 16384;          // 4 x [64][128 B] masked weights (UMMA B)
 constexpr int L1_OUT = L1_BT + 4 * 8192;         // 2 x [128][128 B] staging tiles (one per epilogue group)
 constexpr int L1_IN = L1_OUT + 2 * 16384;        // 2 x halo tile, linear [18][10][64] bf16
-constexpr int L1_BAR = L1_IN + 2 * L1_STAGE;     // mbarriers + tmem slot (256 B)
+constexpr int L1_BAR = L1_IN + 2 * L1_STAGE;     // mbarriers + tmem slot (168 B), item-index ring (64 B at +192)
 constexpr int L1_DW = L1_BAR + 256;              // [9][64] fp32 depthwise weights
 constexpr int L1_SC = L1_DW + 9 * KF * 4;        // 2 x [64] fp32 keep-scales of the tile being stored
 constexpr int L1_FB = L1_SC + 2 * KF * 4;        // [levels][64] fp32 folded bias (halved)
@@ -54,6 +54,7 @@ struct L1Params {
   const float* dw;                       // [9][64]
   int T, sc_stride;
   float inv_keep;                        // the non-zero value of in_scale
+  int* counter;                          // zeroed work-item counter of this launch (dynamic claiming, heads_umma.cuh)
 };
 
 struct L1Maps {
@@ -72,6 +73,7 @@ __global__ void __launch_bounds__(kL1Threads, 1) heads_l1_kernel(const __grid_co
   const uint32_t in_full = bar0, in_empty = bar0 + 16, a_full = bar0 + 32, a_empty = bar0 + 48, b_full = bar0 + 64,
                  tfull = bar0 + 96, tempty = bar0 + 128;
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + L1_BAR + 160);
+  volatile int* sQ = reinterpret_cast<volatile int*>(smem + L1_BAR + 192);  // item-index ring (IG_QRING ints)
   float* sDw = reinterpret_cast<float*>(smem + L1_DW);
   float* sFb = reinterpret_cast<float*>(smem + L1_FB);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -117,34 +119,54 @@ __global__ void __launch_bounds__(kL1Threads, 1) heads_l1_kernel(const __grid_co
 
   if (warp == 0) {
     // ===================== producer (warp-uniform loop, one elected lane issues) =====================
-    int i = 0;
-    for (int item = blockIdx.x; item < p.items; item += G, ++i) {
-      const IgItem w = ig_item(p, item);
+    for (int i = 0;; ++i) {
+      const int item = ig_claim(p.counter, p.items, lane);
+      const IgItem w = ig_item(p, item < 0 ? 0 : item);
       const int s = i & 1;
       if (ig_elect_one()) {
         bar_wait(in_empty + 8 * s, ((i >> 1) & 1) ^ 1);
-        bar_expect_tx(in_full + 8 * s, IG_ROWS * IG_BOXW * 128);
-        asm volatile(
-            "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-            ::"r"(sb + L1_IN + s * L1_STAGE), "l"(&maps.in[w.l]), "r"(in_full + 8 * s), "r"(0), "r"(w.tx0 - 1), "r"(w.ty0 - 1),
-            "r"(w.nb)
-            : "memory");
+        sQ[i & (IG_QRING - 1)] = item;  // published by the arrival on the stage's full barrier
+        if (item < 0) {
+          sQ[(i + 1) & (IG_QRING - 1)] = -1;  // end of the stream, for both epilogue groups
+          bar_arrive(in_full + 8 * s);
+        } else {
+          bar_expect_tx(in_full + 8 * s, IG_ROWS * IG_BOXW * 128);
+          asm volatile(
+              "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+              ::"r"(sb + L1_IN + s * L1_STAGE), "l"(&maps.in[w.l]), "r"(in_full + 8 * s), "r"(0), "r"(w.tx0 - 1), "r"(w.ty0 - 1),
+              "r"(w.nb)
+              : "memory");
+        }
       }
       __syncwarp();
+      if (item < 0) break;
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(64 >> 3) << 17) | ((128u >> 4) << 24);
-    int i = 0, j = 0;
-    for (int item = blockIdx.x; item < p.items; item += G, ++i) {
+    int j = 0;
+    for (int i = 0;; ++i) {
       const int ab = i & 1;
       const uint64_t adesc = ig_desc(sb + L1_A + ab * 16384, 1024, 0);
+      if (lane == 0) bar_wait(a_full + 8 * ab, (i >> 1) & 1);        // depthwise output of this item in place
+      __syncwarp();
+      if (ig_queue_read(sQ, i) < 0) {
+        // end of the stream (the builders arrived without an A tile): wake both epilogue groups
+        if (ig_elect_one()) {
+          for (int dj = 0; dj < 2; ++dj) {
+            const int q = (j + dj) & 3;
+            bar_wait(tempty + 8 * q, (((j + dj) >> 2) & 1) ^ 1);
+            bar_arrive(tfull + 8 * q);
+          }
+        }
+        __syncwarp();
+        break;
+      }
       for (int t = 0; t < T; ++t, ++j) {
         const int q = j & 3;
         const uint64_t bdesc = ig_desc(sb + L1_BT + q * 8192, 1024, 0);
         const uint32_t d_tmem = tmem_base + (uint32_t)(q * KF);
         if (ig_elect_one()) {
-          if (t == 0) bar_wait(a_full + 8 * ab, (i >> 1) & 1);       // depthwise output of this item in place
           bar_wait(b_full + 8 * q, (j >> 2) & 1);                    // masked weights of this sample in place
           bar_wait(tempty + 8 * q, ((j >> 2) & 1) ^ 1);              // accumulator drained
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -168,19 +190,24 @@ __global__ void __launch_bounds__(kL1Threads, 1) heads_l1_kernel(const __grid_co
       const float4 w4 = *reinterpret_cast<const float4*>(sDw + tp * KF + q4 * 4);
       wgt[tp][0] = w4.x; wgt[tp][1] = w4.y; wgt[tp][2] = w4.z; wgt[tp][3] = w4.w;
     }
-    int i = 0, j = 0;
-    for (int item = blockIdx.x; item < p.items; item += G, ++i) {
-      const IgItem w = ig_item(p, item);
+    int j = 0;
+    for (int i = 0;; ++i) {
       const int s = i & 1, ab = i & 1;
-      const float* isc = p.in_scale[w.l];
-      // keep-scales of sample 0 for this thread's k chunk: in flight during the depthwise pass
-      float4 m0 = __ldg(reinterpret_cast<const float4*>(isc + (size_t)w.nb * p.sc_stride + kc * 8));
-      float4 m1 = __ldg(reinterpret_cast<const float4*>(isc + (size_t)w.nb * p.sc_stride + kc * 8 + 4));
       if (lane == 0) {
         bar_wait(in_full + 8 * s, (i >> 1) & 1);          // halo tile landed
         bar_wait(a_empty + 8 * ab, ((i >> 1) & 1) ^ 1);   // the MMAs of item i-2 are done with this A buffer
       }
       __syncwarp();
+      const int item = ig_queue_read(sQ, i);
+      if (item < 0) {  // end of the stream: pass it on to the MMA warp through the A barrier
+        if (lane == 0) bar_arrive(a_full + 8 * ab);
+        break;
+      }
+      const IgItem w = ig_item(p, item);
+      const float* isc = p.in_scale[w.l];
+      // keep-scales of sample 0 for this thread's k chunk: in flight during the depthwise pass
+      float4 m0 = __ldg(reinterpret_cast<const float4*>(isc + (size_t)w.nb * p.sc_stride + kc * 8));
+      float4 m1 = __ldg(reinterpret_cast<const float4*>(isc + (size_t)w.nb * p.sc_stride + kc * 8 + 4));
       {
         const uint8_t* sIn = smem + L1_IN + s * L1_STAGE;
         uint8_t* sA = smem + L1_A + ab * 16384;
@@ -264,38 +291,36 @@ __global__ void __launch_bounds__(kL1Threads, 1) heads_l1_kernel(const __grid_co
     const bool elected = (ew & 7) == 0 && lane == 0;
     float* const sSc = reinterpret_cast<float*>(smem + L1_SC) + g * KF;
     const uint32_t swz = (uint32_t)(m & 7);
-    // keep-scales of the group's samples are fetched one sample ahead by 16 lanes of one warp: the global-load latency
-    // (the whole group would otherwise wait for it at its first barrier, every sample) hides under the previous sample
+    // keep-scales of the group's next sample of the same item are fetched one sample ahead by 16 lanes of one warp: the
+    // global-load latency (the whole group would otherwise wait for it at its first barrier) hides under the current sample
     const bool sc_loader = (ew & 7) == 1 && lane < KF / 4;
-    auto load_scales = [&](int ii, int tt) -> float4 {  // sample tt of this CTA's ii-th item
-      while (tt >= T) {
-        tt -= T;
-        ++ii;
-      }
-      const int it2 = blockIdx.x + ii * G;
-      if (it2 >= p.items) return make_float4(0.f, 0.f, 0.f, 0.f);
-      const IgItem w2 = ig_item(p, it2);
-      return __ldg(reinterpret_cast<const float4*>(p.out_scale[w2.l] + (size_t)(tt * p.NB + w2.nb) * p.sc_stride) + lane);
-    };
     float4 sc_next = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (sc_loader) sc_next = load_scales(0, g);  // the group's first sample: j = g
-    int i = 0, j = 0;
-    for (int item = blockIdx.x; item < p.items; item += G, ++i) {
-      const IgItem w = ig_item(p, item);
-      const float* fbv = sFb + w.l * KF + hc * 32;
-      for (int t = 0; t < T; ++t, ++j) {
-        if ((j & 1) != g) continue;
-        const int q = j & 3;
+    bool have_next = false;
+    int i = 0, t = g;  // sample j = g, g + 2, ... of this CTA's item stream is sample t of its i-th item
+    for (int j = g;; j += 2, t += 2) {
+      while (t >= T) {
+        t -= T;
+        ++i;
+        have_next = false;
+      }
+      const int q = j & 3;
+      if (lane == 0) bar_wait(tfull + 8 * q, (j >> 2) & 1);
+      __syncwarp();
+      const int item = ig_queue_read(sQ, i);
+      if (item < 0) break;
+      {
+        const IgItem w = ig_item(p, item);
+        const float* fbv = sFb + w.l * KF + hc * 32;
         const int nb = t * p.NB + w.nb;
         uint8_t* const ob = smem + L1_OUT + g * 16384;
         // this sample's keep-scales -> the group's slot (published by the first group barrier below; the
-        // previous tile's readers passed its second barrier); then the fetch for the group's next sample (j + 2)
+        // previous tile's readers passed its second barrier); then the fetch for sample t + 2 of the item
         if (sc_loader) {
-          reinterpret_cast<float4*>(sSc)[lane] = sc_next;
-          sc_next = load_scales(i, t + 2);
+          const float* row = p.out_scale[w.l] + (size_t)nb * p.sc_stride;
+          reinterpret_cast<float4*>(sSc)[lane] = have_next ? sc_next : __ldg(reinterpret_cast<const float4*>(row) + lane);
+          if (t + 2 < T) sc_next = __ldg(reinterpret_cast<const float4*>(row + (size_t)2 * p.NB * p.sc_stride) + lane);
         }
-        if (lane == 0) bar_wait(tfull + 8 * q, (j >> 2) & 1);
-        __syncwarp();
+        have_next = t + 2 < T;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(q * KF + hc * 32);
         uint32_t r[4][8];
@@ -398,6 +423,7 @@ int udal_heads_l1_layer(udal_ctx* ctx, const void* const* in, int NB, int T, con
   }
   for (int l = c.num_levels; l <= UDAL_MAX_LEVELS; ++l) p.item_off[l] = off;
   p.items = off;
+  UDAL_TRY(udal_work_counter(ctx, &p.counter));
   const int grid = udal_persistent_grid(ctx, p.items);
   UDAL_REQUIRE(c.num_levels <= kL1MaxLevels, "the tensor-core head sampler keeps the weights of at most %d pyramid levels "
                "resident (got %d) - use heads_mode fp32", kL1MaxLevels, c.num_levels);

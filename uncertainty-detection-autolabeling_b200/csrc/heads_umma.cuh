@@ -157,6 +157,19 @@ __device__ __forceinline__ IgItem ig_item(const P& p, int item) {
   return it;
 }
 
+// Dynamic work distribution of the persistent kernels: the producer warp claims item indices from a global counter
+// (a CTA that starts late - its SM was still busy with another stream's kernel - simply claims fewer) and publishes
+// them in a shared-memory ring; every other role reads item k from slot k % IG_QRING once the barrier that orders it
+// behind the producer has completed.  -1 ends the stream (written to two slots: both epilogue groups see it).
+constexpr int IG_QRING = 16;  // > deepest look-ahead between the producer and the epilogue (stages + accumulators)
+__device__ __forceinline__ int ig_claim(int* counter, int items, int lane) {  // whole warp, converged
+  int v = 0;
+  if (lane == 0) v = atomicAdd(counter, 1);
+  v = __shfl_sync(0xffffffffu, v, 0);
+  return v < items ? v : -1;
+}
+__device__ __forceinline__ int ig_queue_read(const volatile int* q, int k) { return q[k & (IG_QRING - 1)]; }
+
 __device__ __forceinline__ void ig_group_sync(int g) {  // the 128 threads of epilogue group g
   asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
 }

@@ -50,7 +50,8 @@ struct WdShape {
   static constexpr int IN = OUT + OUT_BYTES;                   // STAGES x halo tile
   static constexpr int BAR = IN + STAGES * STAGE;              // mbarriers + tmem slot
   static constexpr int EP = BAR + 256;                         // [2][CH] fp32 epilogue scale | bias of the current item's level
-  static constexpr int SMEM = EP + 2 * CH * 4 + 1024;
+  static constexpr int QUEUE = EP + 2 * CH * 4;                // item-index ring (IG_QRING ints)
+  static constexpr int SMEM = QUEUE + IG_QRING * 4 + 1024;
   static_assert(CH == 64 || CH == 128, "channel count");
   static_assert(STAGE % 1024 == 0 && IN % 1024 == 0 && B % 1024 == 0 && OUT % 1024 == 0, "alignment");
   static_assert(A_BYTES <= OUT_BYTES, "bf16 staging tile");
@@ -71,6 +72,7 @@ struct WdParams {
   void* out[UDAL_MAX_LEVELS];            // tower: [NB,H,W,128] bf16 (through the tensor maps); predict: [NB,H,W,ch_total] fp32
   int predict, Cout, ch_off, ch_total;   // predict: this launch writes channels [ch_off, ch_off + Cout)
   int debug;                             // timing experiments only (wrong results): 1 = no depthwise math, 2 = no epilogue math / stores
+  int* counter;                          // zeroed work-item counter of this launch (dynamic claiming, heads_umma.cuh)
 };
 
 struct WdMaps {
@@ -97,6 +99,7 @@ __global__ void __launch_bounds__(kWdThreads, 1) heads_wide_kernel(const __grid_
   const uint32_t in_full = bar0, in_empty = bar0 + 32, a_full = bar0 + 64, a_empty = bar0 + 80, tfull = bar0 + 96,
                  tempty = bar0 + 112, bar_b = bar0 + 128;
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + WD_BAR + 136);
+  volatile int* sQ = reinterpret_cast<volatile int*>(smem + S::QUEUE);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int G = gridDim.x;
 
@@ -133,19 +136,26 @@ __global__ void __launch_bounds__(kWdThreads, 1) heads_wide_kernel(const __grid_
     }
     __syncwarp();
     int s = 0, ph = 0;
-    for (int item = blockIdx.x; item < p.items; item += G) {
-      const IgItem w = ig_item(p, item);
+    for (int i = 0;; ++i) {
+      const int item = ig_claim(p.counter, p.items, lane);
+      const IgItem w = ig_item(p, item < 0 ? 0 : item);
       const int nb_in = w.nb % p.in_nb;
       if (ig_elect_one()) {
         bar_wait(in_empty + 8 * s, ph ^ 1);
-        bar_expect_tx(in_full + 8 * s, WD_STAGE);
-        asm volatile(
-            "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-            ::"r"(sb + WD_IN + s * WD_STAGE), "l"(&maps.in[w.l]), "r"(in_full + 8 * s), "r"(0), "r"(w.tx0 - 1), "r"(w.ty0 - 1),
-            "r"(nb_in)
-            : "memory");
+        sQ[i & (IG_QRING - 1)] = item;  // published by the arrival on the stage's full barrier; -1 ends the stream
+        if (item < 0) {
+          bar_arrive(in_full + 8 * s);
+        } else {
+          bar_expect_tx(in_full + 8 * s, WD_STAGE);
+          asm volatile(
+              "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+              ::"r"(sb + WD_IN + s * WD_STAGE), "l"(&maps.in[w.l]), "r"(in_full + 8 * s), "r"(0), "r"(w.tx0 - 1), "r"(w.ty0 - 1),
+              "r"(nb_in)
+              : "memory");
+        }
       }
       __syncwarp();
+      if (item < 0) break;
       if (++s == STAGES) {
         s = 0;
         ph ^= 1;
@@ -156,12 +166,20 @@ __global__ void __launch_bounds__(kWdThreads, 1) heads_wide_kernel(const __grid_
     constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(WF >> 3) << 17) | ((128u >> 4) << 24);
     if (lane == 0) bar_wait(bar_b, 0);  // weights resident
     __syncwarp();
-    int i = 0;
-    for (int item = blockIdx.x; item < p.items; item += G, ++i) {
+    for (int i = 0;; ++i) {
       const int ab = i & 1;
       const uint32_t d_tmem = tmem_base + (uint32_t)(ab * WF);
+      if (lane == 0) bar_wait(a_full + 8 * ab, (i >> 1) & 1);  // depthwise output of this item in place (or the end marker)
+      __syncwarp();
+      if (ig_queue_read(sQ, i) < 0) {
+        if (ig_elect_one()) {  // wake the epilogue: its next accumulator "arrives" empty
+          bar_wait(tempty + 8 * ab, ((i >> 1) & 1) ^ 1);
+          bar_arrive(tfull + 8 * ab);
+        }
+        __syncwarp();
+        break;
+      }
       if (ig_elect_one()) {
-        bar_wait(a_full + 8 * ab, (i >> 1) & 1);          // depthwise output of this item in place
         bar_wait(tempty + 8 * ab, ((i >> 1) & 1) ^ 1);    // accumulator drained
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
@@ -191,17 +209,22 @@ __global__ void __launch_bounds__(kWdThreads, 1) heads_wide_kernel(const __grid_
       wgt[tp][1] = make_float2(w4.z, w4.w);
     }
     const bool real = 4 * q4 < p.F;  // F % 4 == 0: a quad is entirely real or entirely padding
-    int i = 0, s = 0, ph = 0;
-    for (int item = blockIdx.x; item < p.items; item += G, ++i) {
-      const IgItem w = ig_item(p, item);
+    int s = 0, ph = 0;
+    for (int i = 0;; ++i) {
       const int ab = i & 1;
-      float4 sc = make_float4(1.f, 1.f, 1.f, 1.f);
-      if (p.in_scale[w.l] && real) sc = __ldg(reinterpret_cast<const float4*>(p.in_scale[w.l] + (size_t)w.nb * p.F) + q4);
       if (lane == 0) {
         bar_wait(in_full + 8 * s, ph);                    // halo tile landed
         bar_wait(a_empty + 8 * ab, ((i >> 1) & 1) ^ 1);   // the MMAs of item i-2 are done with this A buffer
       }
       __syncwarp();
+      const int item = ig_queue_read(sQ, i);
+      if (item < 0) {  // end of the stream: pass it on to the MMA warp through the A barrier
+        if (lane == 0) bar_arrive(a_full + 8 * ab);
+        break;
+      }
+      const IgItem w = ig_item(p, item);
+      float4 sc = make_float4(1.f, 1.f, 1.f, 1.f);
+      if (p.in_scale[w.l] && real) sc = __ldg(reinterpret_cast<const float4*>(p.in_scale[w.l] + (size_t)w.nb * p.F) + q4);
       const uint8_t* sIn = smem + WD_IN + s * WD_STAGE;
       uint8_t* sA = smem + WD_A + ab * A_BYTES + (q4 >> 4) * 16384;
       const uint32_t chunk = (uint32_t)((q4 & 15) >> 1), sub = (uint32_t)(q4 & 1) * 8;
@@ -266,10 +289,13 @@ __global__ void __launch_bounds__(kWdThreads, 1) heads_wide_kernel(const __grid_
     const bool elected = ew == 0 && lane == 0;
     const uint32_t swz = (uint32_t)(m & 7);
     uint8_t* const ob = smem + WD_OUT;
-    int i = 0;
-    for (int item = blockIdx.x; item < p.items; item += G, ++i) {
-      const IgItem w = ig_item(p, item);
+    for (int i = 0;; ++i) {
       const int ab = i & 1;
+      if (lane == 0) bar_wait(tfull + 8 * ab, (i >> 1) & 1);
+      __syncwarp();
+      const int item = ig_queue_read(sQ, i);
+      if (item < 0) break;
+      const IgItem w = ig_item(p, item);
       // this item's epilogue table -> shared memory (tower: halved, x*sigmoid(x) = h*tanh(h) + h with h = x/2); the
       // previous item's readers passed its last group barrier, the first barrier below publishes the table
       float* const sEp = reinterpret_cast<float*>(smem + WD_EP);
@@ -284,8 +310,6 @@ __global__ void __launch_bounds__(kWdThreads, 1) heads_wide_kernel(const __grid_
       }
       const float4* eps = reinterpret_cast<const float4*>(sEp + hc * HC);
       const float4* epb = reinterpret_cast<const float4*>(sEp + WF + hc * HC);
-      if (lane == 0) bar_wait(tfull + 8 * ab, (i >> 1) & 1);
-      __syncwarp();
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * WF + hc * HC);
       if (p.debug & 2) {
@@ -534,6 +558,7 @@ static int launch_wide(udal_ctx* ctx, const void* const* in, int in_nb, int NB, 
   p.ch_off = ch_off;
   p.ch_total = ch_total;
   p.debug = udal_wide_debug;
+  UDAL_TRY(udal_work_counter(ctx, &p.counter));
   int off = 0;
   for (int l = 0; l < c.num_levels; ++l) {
     const int H = c.level_h[l], W = c.level_w[l];

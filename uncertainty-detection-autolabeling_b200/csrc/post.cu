@@ -257,7 +257,8 @@ __global__ void __launch_bounds__(256) merge_per_class_kernel(const MergeParams 
 }  // namespace
 
 int udal_run_overlap = 1;  // 0: udal_run keeps its whole tail on the context's stream
-int udal_run_reserved_sms = 4;     // SMs the persistent head kernels of a pipelined udal_run leave to the post stream
+int udal_run_reserved_sms = 0;     // SMs the persistent head kernels of a pipelined udal_run leave to the post stream (0: none - the
+                                   // kernels claim their work items dynamically, a CTA whose SM is busy with the tail just claims fewer)
 int udal_run_prefilter_on_main = 0;
 int udal_run_debug_timeline = 0;   // development: print when the tail of every udal_run started / ended relative to its heads
 

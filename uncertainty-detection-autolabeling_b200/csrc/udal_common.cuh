@@ -73,6 +73,9 @@ struct udal_ctx {
   int (*between_heads)(udal_ctx*, void*) = nullptr;
   void* between_heads_arg = nullptr;
   std::vector<void*> user_allocs;
+  // work-item counters of the persistent head kernels (dynamic item claiming): one zeroed int per launch of a run
+  int* work_counters = nullptr;
+  int work_counter_next = 0;
   bool profile_layers = false;
   std::vector<cudaEvent_t> layer_events;  // pairs (start, stop) in launch order
 };
@@ -131,12 +134,16 @@ int udal_join(udal_ctx* ctx);
     if (s__ != UDAL_OK) return s__; \
   } while (0)
 
-// CTAs of a persistent (one CTA per SM) head kernel.  When udal_run calls arrive back to back (the previous
-// run's tail is still executing: throughput mode) a few SMs stay free for that top-k / NMS tail on the post
-// stream (udal_run_reserved_sms), which otherwise only gets the gaps between the head kernels.  A caller
-// that waits for every result (latency mode) gets all SMs and the faster shared-memory-staged NMS.
+// CTAs of a persistent (one CTA per SM) head kernel.  The kernels claim their work items from a global counter
+// (heads_umma.cuh), so the top-k / NMS tail of the previous udal_run on the post stream may occupy SMs at any time: a CTA
+// that starts late claims fewer items.  udal_run_reserved_sms > 0 additionally leaves SMs free for that tail when
+// udal_run calls arrive back to back (the static-striding kernels needed it; kept as a switch).
 extern int udal_run_reserved_sms;
 extern int udal_run_overlap;
+constexpr int UDAL_WORK_COUNTERS = 64;
+int udal_work_counters_reset(udal_ctx* ctx);        // zeroes the counters on the context's stream (start of a head-sampler run)
+int udal_work_counter(udal_ctx* ctx, int** out);    // the next zeroed counter
+
 static inline int udal_persistent_grid(const udal_ctx* ctx, int items) {
   int sms = UDAL_NUM_SMS;
   if (ctx->in_run && ctx->run_pipelined && udal_run_overlap && udal_run_reserved_sms > 0 &&
