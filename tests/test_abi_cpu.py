@@ -167,3 +167,23 @@ def test_synthetic_generators_match_the_oracle_copy():
     np.testing.assert_array_equal(syn.make_masks(4, 5, 3, 2, 64, 0.05, 0.1, seed=5), heads_ref.make_masks(4, 5, 3, 2, 64, 0.05, 0.1, seed=5))
     for x, y in zip(syn.make_features([(4, 6), (2, 3)], 2, 64, seed=11), heads_ref.make_features([(4, 6), (2, 3)], 2, 64, seed=11)):
         np.testing.assert_array_equal(x, y)
+
+
+def test_product_and_tools_do_not_import_the_oracle():
+    """oracle/ is test infrastructure: only tests/, __graft_entry__.smoke() and bench.py's CPU baseline legs may use it."""
+    import os
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pat = re.compile(r"^\s*(from\s+oracle\b|import\s+oracle\b)", re.M)
+    offenders = []
+    for sub in ("uncertainty-detection-autolabeling_b200", "tools"):
+        for dirpath, _, files in os.walk(os.path.join(root, sub)):
+            for f in files:
+                if f.endswith(".py") and pat.search(open(os.path.join(dirpath, f)).read()):
+                    offenders.append(os.path.join(sub, f))
+    assert not offenders, offenders
+    # bench.py: the oracle appears only inside the CPU arms (cpu_port_step / run_reference / the cpu_baseline leg)
+    src = open(os.path.join(root, "bench.py")).read()
+    gpu_arm = src[src.index("def run_gpu("):]
+    lines = [l for l in gpu_arm.splitlines() if pat.search(l)]
+    assert all("oracle_build" in l for l in lines), lines   # building the checker for the cpu_baseline leg is not using it
