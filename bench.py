@@ -329,8 +329,8 @@ def run_gpu(args):
     # the timed region; two contexts alternate so that the copies of step i+1 overlap the kernels of
     # step i (PipelinedSampler).  Timed with the host clock around fully synchronised work.
     host_feats = [pa.array for pa in pinned]
-    pipe = u.heads.PipelinedSampler(p, weights, device_id=local_rank, heads_mode=args.heads_mode, depth=2)
-    for _ in pipe.map([host_feats] * 4, [scales_host] * 4, seed=1):
+    pipe = u.heads.PipelinedSampler(p, weights, device_id=local_rank, heads_mode=args.heads_mode, depth=4)
+    for _ in pipe.map([host_feats] * 8, [scales_host] * 8, seed=1):  # warm-up: every context twice
         pass
     barrier()
     e2e_steps = max(24, args.steps)  # the first batch of a map() cannot hide its H2D copy: amortised over the run
@@ -430,7 +430,7 @@ def run_gpu(args):
         "clocks": clock_info,
         "e2e": {"value": world * batch / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms, "steps": e2e_steps,
-                "how": "PipelinedSampler.map: HeadSampler.detect(host arrays) on 2 contexts, H2D of step i+1 "
+                "how": "PipelinedSampler.map: HeadSampler.detect(host arrays) on 4 contexts, H2D of the next steps "
                        "overlaps the kernels of step i; host clock over fully synchronised work",
                 "blocking_ms_per_step": e2e_blocking_ms},
         "gpu_launches": int(launches),

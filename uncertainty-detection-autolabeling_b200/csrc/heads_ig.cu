@@ -112,6 +112,7 @@ __global__ void __launch_bounds__(kIgThreads, 1) heads_ig_kernel(const __grid_co
     bar_init(bar_b, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  if (threadIdx.x >= 64 && threadIdx.x < 64 + IG_QRING) sQ[threadIdx.x - 64] = -1;  // (slots are peeked ahead of their time)
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sb + S::SM_BAR + 88),
                  "r"(kTmemCols)
@@ -234,6 +235,8 @@ __global__ void __launch_bounds__(kIgThreads, 1) heads_ig_kernel(const __grid_co
     const bool staged = !S::PREDICT || p.tma_store;
     uint8_t* const ob = smem + S::SM_OUT + g * S::OUT_BYTES;
     const uint32_t swz = (uint32_t)(m & 7);
+    int pre_item = -1;  // item whose keep-scales were fetched ahead
+    float4 pre_sc = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int it = g;; it += 2) {  // group g drains the items with it % 2 == g
       const int a = g;
       if (lane == 0) bar_wait(bar_tfull + 8 * a, (it >> 1) & 1);  // one poller per warp
@@ -250,7 +253,16 @@ __global__ void __launch_bounds__(kIgThreads, 1) heads_ig_kernel(const __grid_co
       if constexpr (!S::PREDICT) {
         if (((warp - 2) & 3) == 1 && lane < KF / 4) {  // (predicated, no divergence)
           const float4* sc = reinterpret_cast<const float4*>(p.out_scale[w.l] + (size_t)nb * p.sc_stride);
-          reinterpret_cast<float4*>(sSc)[lane] = __ldg(sc + lane);
+          reinterpret_cast<float4*>(sSc)[lane] = item == pre_item ? pre_sc : __ldg(sc + lane);
+          // the group's next item (it + 2) is usually in the ring already (the producer runs a few items ahead): fetch its
+          // keep-scales now, verified against the ring when the item is really due (a stale slot only costs a wasted load)
+          pre_item = ig_queue_read(sQ, it + 2);
+          if (pre_item >= 0 && pre_item < p.items) {
+            const IgItem w2 = ig_item(p, pre_item);
+            pre_sc = __ldg(reinterpret_cast<const float4*>(p.out_scale[w2.l] + (size_t)w2.nb * p.sc_stride) + lane);
+          } else {
+            pre_item = -1;
+          }
         }
       }
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");

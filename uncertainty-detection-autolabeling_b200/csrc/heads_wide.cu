@@ -289,6 +289,7 @@ __global__ void __launch_bounds__(kWdThreads, 1) heads_wide_kernel(const __grid_
     const bool elected = ew == 0 && lane == 0;
     const uint32_t swz = (uint32_t)(m & 7);
     uint8_t* const ob = smem + WD_OUT;
+    int ep_level = -1;  // level whose epilogue table is in shared memory
     for (int i = 0;; ++i) {
       const int ab = i & 1;
       if (lane == 0) bar_wait(tfull + 8 * ab, (i >> 1) & 1);
@@ -299,7 +300,8 @@ __global__ void __launch_bounds__(kWdThreads, 1) heads_wide_kernel(const __grid_
       // this item's epilogue table -> shared memory (tower: halved, x*sigmoid(x) = h*tanh(h) + h with h = x/2); the
       // previous item's readers passed its last group barrier, the first barrier below publishes the table
       float* const sEp = reinterpret_cast<float*>(smem + WD_EP);
-      {
+      if (w.l != ep_level) {  // (items arrive level by level: a handful of reloads per CTA)
+        ep_level = w.l;
         const int et = threadIdx.x - 64 - 32 * kWdBuilderWarps;
         if (!p.predict) {
           if (et < 2 * CH) sEp[et] = 0.5f * __ldg(p.ep[w.l] + et);
