@@ -202,10 +202,43 @@ def run_reference(args):
 # -------------------------------------------------------------------------------------------------
 # GPU arm
 # -------------------------------------------------------------------------------------------------
+def bind_to_gpu_numa_node(local_rank):
+    """Best effort: run this rank (and first-touch its pinned staging buffers) on the CPU socket the GPU hangs off, so that
+    the H2D copies of the end-to-end leg read local memory.  Returns the node or None."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(local_rank)).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        bus = bus.lower()
+        if len(bus.split(":")[0]) == 8:  # NVML prints an 8-digit domain, sysfs uses 4
+            bus = bus[4:]
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bus).read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        allowed = os.sched_getaffinity(0)
+        cpus &= allowed
+        if cpus:
+            bind_to_gpu_numa_node.original = allowed
+            os.sched_setaffinity(0, cpus)
+            return node
+    except Exception:
+        pass
+    return None
+
+
+bind_to_gpu_numa_node.original = None
+
+
 def run_gpu(args):
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    numa_node = bind_to_gpu_numa_node(local_rank)
     dist = None
     if world > 1:
         import torch
@@ -432,7 +465,7 @@ def run_gpu(args):
                 "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms, "steps": e2e_steps,
                 "how": "PipelinedSampler.map: HeadSampler.detect(host arrays) on 4 contexts, H2D of the next steps "
                        "overlaps the kernels of step i; host clock over fully synchronised work",
-                "blocking_ms_per_step": e2e_blocking_ms},
+                "blocking_ms_per_step": e2e_blocking_ms, "numa_node": numa_node},
         "gpu_launches": int(launches),
         "roofline": {
             "kernel": dominant["kernel"], "what": dominant["what"], "bound": "hbm",
@@ -455,7 +488,9 @@ def run_gpu(args):
         import torch
         from oracle import build as oracle_build
         oracle_build.build()
-        cores = os.cpu_count() or 1
+        if bind_to_gpu_numa_node.original:  # the CPU baseline uses every core of the box again
+            os.sched_setaffinity(0, bind_to_gpu_numa_node.original)
+        cores = len(os.sched_getaffinity(0)) or 1
         torch.set_num_threads(cores)
         cpu_port_step(1, 0)
         n_img, t_cpu, seg = 0, 0.0, {}
