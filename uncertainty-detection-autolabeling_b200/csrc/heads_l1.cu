@@ -37,7 +37,9 @@ constexpr int L1_BAR = L1_IN + 2 * L1_STAGE;     // mbarriers + tmem slot (168 B
 constexpr int L1_DW = L1_BAR + 256;              // [9][64] fp32 depthwise weights
 constexpr int L1_SC = L1_DW + 9 * KF * 4;        // 2 x [64] fp32 keep-scales of the tile being stored
 constexpr int L1_FB = L1_SC + 2 * KF * 4;        // [levels][64] fp32 folded bias (halved)
-constexpr int L1_WC = (L1_FB + UDAL_MAX_LEVELS * KF * 4 + 1023) / 1024 * 1024;  // [levels][64][128 B] bf16 weights
+constexpr int L1_MSK = L1_FB + UDAL_MAX_LEVELS * KF * 4;  // 2 x [kL1MaxT samples][8] bytes: keep bits of the item's samples (per k chunk)
+constexpr int kL1MaxT = 64;
+constexpr int L1_WC = (L1_MSK + 2 * kL1MaxT * 8 + 1023) / 1024 * 1024;  // [levels][64][128 B] bf16 weights
 constexpr int l1_smem(int levels) { return L1_WC + levels * 8192 + 1024; }
 constexpr int kL1MaxLevels = UDAL_MAX_LEVELS;  // resident weight images: 8 KB per pyramid level
 static_assert(l1_smem(kL1MaxLevels) <= kIgSmemLimit, "shared-memory budget");
@@ -204,10 +206,20 @@ __global__ void __launch_bounds__(kL1Threads, 1) heads_l1_kernel(const __grid_co
         break;
       }
       const IgItem w = ig_item(p, item);
-      const float* isc = p.in_scale[w.l];
-      // keep-scales of sample 0 for this thread's k chunk: in flight during the depthwise pass
-      float4 m0 = __ldg(reinterpret_cast<const float4*>(isc + (size_t)w.nb * p.sc_stride + kc * 8));
-      float4 m1 = __ldg(reinterpret_cast<const float4*>(isc + (size_t)w.nb * p.sc_stride + kc * 8 + 4));
+      // keep bits of ALL samples of the item, one byte per (sample, 8-channel chunk), fetched now (one global-load latency
+      // per item, under the depthwise pass) - a fetch per sample sat in the serial chain B copy -> MMA -> epilogue
+      uint8_t* const sMsk = smem + L1_MSK + ab * (kL1MaxT * 8);
+      {
+        const float* isc = p.in_scale[w.l];
+        for (int t = tid >> 3; t < T; t += 16) {
+          const size_t row = ((size_t)t * p.NB + w.nb) * p.sc_stride + kc * 8;
+          const float4 m0 = __ldg(reinterpret_cast<const float4*>(isc + row));
+          const float4 m1 = __ldg(reinterpret_cast<const float4*>(isc + row + 4));
+          sMsk[t * 8 + kc] = (uint8_t)((m0.x != 0.f ? 1u : 0u) | (m0.y != 0.f ? 2u : 0u) | (m0.z != 0.f ? 4u : 0u) | (m0.w != 0.f ? 8u : 0u) |
+                                       (m1.x != 0.f ? 16u : 0u) | (m1.y != 0.f ? 32u : 0u) | (m1.z != 0.f ? 64u : 0u) |
+                                       (m1.w != 0.f ? 128u : 0u));
+        }
+      }
       {
         const uint8_t* sIn = smem + L1_IN + s * L1_STAGE;
         uint8_t* sA = smem + L1_A + ab * 16384;
@@ -251,20 +263,17 @@ __global__ void __launch_bounds__(kL1Threads, 1) heads_l1_kernel(const __grid_co
         bar_arrive(a_full + 8 * ab);
         bar_arrive(in_empty + 8 * s);
       }
+      asm volatile("bar.sync 5, 128;" ::: "memory");  // the builders' keep bits of this item are in place
       const uint8_t* sWc = smem + L1_WC + w.l * 8192;
       for (int t = 0; t < T; ++t, ++j) {
         const int q = j & 3;
         // bit masks of this thread's 8 channels: keep-scale is either 0 or 1/(1-rate)
+        const uint32_t kb = sMsk[t * 8 + kc];
         uint4 msk;
-        msk.x = (m0.x != 0.f ? 0x0000ffffu : 0u) | (m0.y != 0.f ? 0xffff0000u : 0u);
-        msk.y = (m0.z != 0.f ? 0x0000ffffu : 0u) | (m0.w != 0.f ? 0xffff0000u : 0u);
-        msk.z = (m1.x != 0.f ? 0x0000ffffu : 0u) | (m1.y != 0.f ? 0xffff0000u : 0u);
-        msk.w = (m1.z != 0.f ? 0x0000ffffu : 0u) | (m1.w != 0.f ? 0xffff0000u : 0u);
-        if (t + 1 < T) {  // next sample's scales
-          const size_t row = ((size_t)(t + 1) * p.NB + w.nb) * p.sc_stride + kc * 8;
-          m0 = __ldg(reinterpret_cast<const float4*>(isc + row));
-          m1 = __ldg(reinterpret_cast<const float4*>(isc + row + 4));
-        }
+        msk.x = (kb & 1u ? 0x0000ffffu : 0u) | (kb & 2u ? 0xffff0000u : 0u);
+        msk.y = (kb & 4u ? 0x0000ffffu : 0u) | (kb & 8u ? 0xffff0000u : 0u);
+        msk.z = (kb & 16u ? 0x0000ffffu : 0u) | (kb & 32u ? 0xffff0000u : 0u);
+        msk.w = (kb & 64u ? 0x0000ffffu : 0u) | (kb & 128u ? 0xffff0000u : 0u);
         if (lane == 0) bar_wait(tfull + 8 * q, ((j >> 2) & 1) ^ 1);  // the MMA of sample j-4 is done with this slot
         __syncwarp();
         uint8_t* sBt = smem + L1_BT + q * 8192;
@@ -396,6 +405,7 @@ int udal_heads_l1_layer(udal_ctx* ctx, const void* const* in, int NB, int T, con
   memset(&maps, 0, sizeof(maps));
   p.num_levels = c.num_levels;
   p.NB = NB;
+  UDAL_REQUIRE(T >= 1 && T <= kL1MaxT, "tensor-core heads: at most %d MC samples (got %d) - use heads_mode fp32", kL1MaxT, T);
   p.T = T;
   p.sc_stride = in_scale ? KF : 0;
   p.inv_keep = in_scale ? inv_keep : 1.0f;
