@@ -172,6 +172,32 @@ def test_heads_wide_tensor_core_vs_oracle(u, model, size, C, T, batch, la, rc, r
         np.testing.assert_array_equal(a, b)
 
 
+def test_layer0_kernels_agree(u):
+    """Tower layer 0 runs through heads_wide_kernel<64, fp32 in> (persistent, fp32 features unrounded); the per-tile
+    kernel it replaced stays selectable (udal_heads_l0_persistent = 0, rounds the features to bf16 first): both within the
+    bf16 tolerance of each other and of the oracle."""
+    import ctypes
+    p = _cfg(u, (128, 192), 8, 3, heads_mode="bf16")
+    eng = u.engine.get_engine(p)
+    L, batch = len(eng.level_hw), 2
+    w = heads_ref.init_head_weights(eng.F, eng.R, L, eng.A, 8, True, seed=4, randomize_bn=True)
+    feats = heads_ref.make_features(eng.level_hw, batch, eng.F, seed=2)
+    masks = heads_ref.make_masks(3, L, eng.R, batch, eng.F, 0.05, 0.05, seed=8)
+    sampler = u.heads.HeadSampler(p, w)
+    switch = ctypes.c_int.in_dll(eng.lib, "udal_heads_l0_persistent")
+    try:
+        switch.value = 0
+        old = sampler(feats, masks=masks)
+        switch.value = 1
+        new = sampler(feats, masks=masks)
+    finally:
+        switch.value = 1
+    rcls, rbox = heads_ref.heads_sample(feats, w, masks, 0.05, 0.05, 3)
+    for a, b, r in zip(old[0] + old[1], new[0] + new[1], rcls + rbox):
+        np.testing.assert_allclose(a, b, rtol=BF16_RTOL, atol=BF16_ATOL)
+        np.testing.assert_allclose(b, r, rtol=BF16_RTOL, atol=BF16_ATOL)
+
+
 def test_pipelined_sampler_matches_blocking_calls(u):
     p = _cfg(u, (64, 96), 7, 4, heads_mode="bf16")
     eng = u.engine.get_engine(p)
