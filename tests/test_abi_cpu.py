@@ -187,3 +187,25 @@ def test_product_and_tools_do_not_import_the_oracle():
     gpu_arm = src[src.index("def run_gpu("):]
     lines = [l for l in gpu_arm.splitlines() if pat.search(l)]
     assert all("oracle_build" in l for l in lines), lines   # building the checker for the cpu_baseline leg is not using it
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """bench.py --impl reference: ONE JSON line on stdout with the GPU arm's metric / unit / config keys, impl = reference,
+    a cpu_baseline describing the run and an e2e block without copies (runs the oracle port on 2 images per step)."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, timeout=600, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, out.stdout
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "mc_dropout_images_per_sec_effdet_d0_T10" and d["unit"] == "images/s"
+    assert d["higher_is_better"] is True and d["value"] > 0 and d["n_gpus"] == 1
+    assert d["config"]["workload"].startswith("EfficientDet-D0 1280x384") and d["config"]["T"] == 10
+    cb = d["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "sample" in cb
+    assert d["e2e"] == {"value": d["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
