@@ -260,11 +260,12 @@ def run_gpu(args):
     import udal_b200 as u
 
     p = workload_params(args.heads_mode)
-    eng = u.engine.get_engine(p, device_id=local_rank)
+    geom = u.engine.get_engine(p, device_id=local_rank)   # geometry only (the cached, weight-free engine)
+    weights = u.synthetic.init_head_weights(geom.F, geom.R, len(geom.level_hw), geom.A, geom.C, True, seed=2024)  # SURVEY 8d seeds
+    sampler = u.heads.HeadSampler(p, weights, device_id=local_rank)
+    eng = sampler.engine                                   # the sampler's own context holds the weights
     ctx = eng.ctx
     L = len(eng.level_hw)
-    weights = u.synthetic.init_head_weights(eng.F, eng.R, L, eng.A, eng.C, True, seed=2024)  # SURVEY 8d seeds
-    sampler = u.heads.HeadSampler(p, weights, device_id=local_rank)
     batch = args.batch
     rng = np.random.default_rng(1234 + rank)
     # host (pinned) and device copies of the synthetic BiFPN features

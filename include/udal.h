@@ -91,6 +91,13 @@ int udal_destroy(udal_ctx* ctx);
 /* use an external CUDA stream (cudaStream_t as void*); NULL restores the context's own stream */
 int udal_set_stream(udal_ctx* ctx, void* cuda_stream);
 int udal_sync(udal_ctx* ctx);
+/* the stream the context currently enqueues on (cudaStream_t as void*): what a DLPack producer is handed in
+ * __dlpack__(stream=...) */
+int udal_get_stream(udal_ctx* ctx, void** cuda_stream);
+/* orders all later work of the context after everything enqueued so far on producer_stream (a cudaStream_t, or the
+ * special handles 0 / 1 = legacy default stream, 2 = per-thread default stream): zero-copy inputs written by another
+ * framework's stream (the context's own streams are non-blocking and do not synchronise with the default stream) */
+int udal_wait_stream(udal_ctx* ctx, void* producer_stream);
 int udal_malloc(udal_ctx* ctx, size_t bytes, void** dev_ptr);
 int udal_free(udal_ctx* ctx, void* dev_ptr);
 int udal_host_alloc(size_t bytes, void** pinned_ptr);
@@ -271,6 +278,22 @@ int udal_concat_channels(udal_ctx* ctx, const float* a, int ca, const float* b, 
 int udal_gather_rows(udal_ctx* ctx, const void* src, int batch, int64_t n_rows, int width,
                      const int32_t* idx, int m, int mode, void* out);
 
+/* small device helpers behind the mirror's minor entry points (all pointers device memory):
+ * postprocess.py:69-72 (clip_boxes): out = clip(boxes [rows,4], 0, [H,W,H,W]) */
+int udal_clip_boxes(udal_ctx* ctx, const float* boxes, int64_t rows, float image_h, float image_w, float* out);
+/* postprocess.py:123-135 (topk_class_boxes, max-reduce branch): reduce_max / argmax (first maximum) over the last axis */
+int udal_max_reduce(udal_ctx* ctx, const float* x, int64_t rows, int c, float* max_out, int32_t* argmax_out);
+/* postprocess.py:104-105: indices = idx // num_classes, classes = idx % num_classes */
+int udal_divmod_i32(udal_ctx* ctx, const int32_t* idx, int64_t total, int d, int32_t* quot, int32_t* rem);
+/* postprocess.py:284 (tf.math.sigmoid) elementwise */
+int udal_sigmoid(udal_ctx* ctx, const float* x, int64_t total, float* y);
+
+/* utils_box.py:162-184 (decode_uncert, method "sample"): pred / sigma / anchors [n,4] -> mean and population std of
+ * the corners of n_samples decoded draws t + |sigma| z, in float64, rounded to fp32.  normals: device [n_samples,4,n]
+ * standard-normal draws (injected, parity) or NULL: Philox4x32-10 + Box-Muller in-kernel (counter s*n + i, key seed). */
+int udal_decode_sample(udal_ctx* ctx, const float* pred, const float* sigma, const float* anchors, int64_t n,
+                       int n_samples, const float* normals, uint64_t seed, float* coords, float* stds);
+
 /* heads + post-processing in one call: feats -> detections (variant by cfg.max_nms_inputs).
  * Replaces EfficientDetNet.call MC branch + postprocess_global / postprocess_per_class
  * (efficientdet_keras.py:999-1050, 1102-1116).  Asynchronous: outputs are valid after udal_sync (or any
@@ -281,6 +304,14 @@ int udal_gather_rows(udal_ctx* ctx, const void* src, int batch, int64_t n_rows, 
  * underneath the next udal_run.  Debug switches exported as ints: udal_run_fused, udal_run_overlap. */
 int udal_run(udal_ctx* ctx, const float* const* feats, int batch, const uint8_t* keep_masks,
              uint64_t seed, const float* image_scales, const udal_detections* out);
+
+/* The first half of udal_run on its own: feats -> per-anchor tensors (the max-reduce variant of pre_nms,
+ * postprocess.py:144-339, applied to the T head samples of efficientdet_keras.py:999-1050), through exactly the
+ * kernels udal_run launches for this configuration (fused predict + decode / MC moments where they cover it,
+ * predict layers + udal_decode_moments otherwise).  Needs cfg.max_nms_inputs == 0; with the fused kernels every
+ * pointer of `out` must be set.  The parity tests compare these tensors with the oracle anchor by anchor. */
+int udal_run_prenms(udal_ctx* ctx, const float* const* feats, int batch, const uint8_t* keep_masks,
+                    uint64_t seed, const udal_prenms_out* out);
 
 /* per-layer CUDA-event timing of the head sampler (bench.py roofline): enable, run
  * udal_heads_sample, then read ms[head * (R + 1) + layer]; *n = entries written (synchronises). */

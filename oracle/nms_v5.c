@@ -75,8 +75,14 @@ float udal_oracle_iou(const float* a, const float* b) {
   return inter / (area_a + area_b - inter);
 }
 
+/* 0 (default, what the CUDA kernels match): fp32(exp(fp64)), the correctly rounded value.
+ * 1: the C library's expf, i.e. what TF's std::exp(float) executes on a glibc host.  Only the
+ *    differential test (tests/test_oracle_extra.py) sets it, to put a number on the unpinned rounding. */
+int udal_oracle_weight_mode = 0;
+
 float udal_oracle_soft_weight(float scale, float iou) {
   float arg = (scale * iou) * iou;
+  if (udal_oracle_weight_mode == 1) return expf(arg);
   return (float)exp((double)arg);
 }
 

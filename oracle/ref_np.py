@@ -516,6 +516,13 @@ def postprocess_global(params, cls_outputs, box_outputs, image_scales=None):
     res = extract_uncertainties(params, cls_outputs, box_outputs)
     if res is None:
         raise TypeError("cannot unpack non-iterable NoneType object")
+    return global_from_pre_nms(params, res, image_scales)
+
+
+def global_from_pre_nms(params, res, image_scales=None):
+    """postprocess.py:497-621: the part of postprocess_global after extract_uncertainties (per-image NMS, clip,
+    image scales, output assembly), on its own so that the parity tests can apply it to per-anchor tensors
+    produced elsewhere (NMS keep-indices must be bit-exact GIVEN identical decoded scores and boxes)."""
     boxes, uncerts, scores, classes, classes_multi = res
     has_unc = bool(params["loss_attenuation"] or params["mc_dropout"])
     per_image = []

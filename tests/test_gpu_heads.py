@@ -206,7 +206,7 @@ def test_pipelined_sampler_matches_blocking_calls(u):
     batches = [heads_ref.make_features(eng.level_hw, batch, eng.F, seed=s) for s in range(5)]
     scales = [np.float32([1.0, 1.5])] * 5
     blocking = u.heads.HeadSampler(p, w)
-    ref = [blocking.detect(f, s, seed=100 + i) for i, (f, s) in enumerate(zip(batches, scales))]
+    ref = [blocking.detect(f, s, seed=u.heads.batch_seed(100, i)) for i, (f, s) in enumerate(zip(batches, scales))]
     pipe = u.heads.PipelinedSampler(p, w, depth=2)
     got = list(pipe.map(batches, scales, seed=100))
     assert len(got) == 5
@@ -306,3 +306,27 @@ def test_fused_predict_decode_matches_unfused(u, size, T, batch, C):
             np.testing.assert_allclose(got["boxes"][b, i, 8:12], ref["boxes"][b, k, 8:12], rtol=1e-3, atol=2e-4)  # MC std of corners
             np.testing.assert_allclose(got["classes"][b, i, 1:], ref["classes"][b, k, 1:], rtol=2e-4, atol=2e-6)  # MC logit std
     assert matched >= 0.95 * total, (matched, total)
+
+
+def test_two_samplers_with_different_weights_stay_independent(u):
+    """Every HeadSampler owns its context: same params, different checkpoints must not overwrite each other."""
+    p = _cfg(u, (64, 96), 7, 3)
+    L, batch = 5, 2
+    wa = heads_ref.init_head_weights(64, 3, L, 9, 7, True, seed=1, randomize_bn=True)
+    wb = heads_ref.init_head_weights(64, 3, L, 9, 7, True, seed=2, randomize_bn=True)
+    sa = u.heads.HeadSampler(p, wa)
+    feats = heads_ref.make_features(sa.engine.level_hw, batch, 64, seed=3)
+    masks = heads_ref.make_masks(3, L, 3, batch, 64, 0.05, 0.05, seed=4)
+    first = sa(feats, masks=masks)
+    sb = u.heads.HeadSampler(p, wb)          # must not touch sa's weights
+    other = sb(feats, masks=masks)
+    again = sa(feats, masks=masks)
+    assert sa.engine is not sb.engine
+    for x, y in zip(first[0] + first[1], again[0] + again[1]):
+        np.testing.assert_array_equal(x, y)
+    assert not np.array_equal(first[0][0], other[0][0])
+    # seed=None draws fresh masks on every call (the reference's stateful dropout), an explicit seed repeats
+    r1, r2 = sa(feats), sa(feats)
+    assert not np.array_equal(r1[0][0], r2[0][0])
+    s1, s2 = sa(feats, seed=5), sa(feats, seed=5)
+    np.testing.assert_array_equal(s1[0][0], s2[0][0])

@@ -69,6 +69,8 @@ SIGNATURES = {
     "udal_destroy": (ctypes.c_int, [_VP]),
     "udal_set_stream": (ctypes.c_int, [_VP, _VP]),
     "udal_sync": (ctypes.c_int, [_VP]),
+    "udal_get_stream": (ctypes.c_int, [_VP, _PP]),
+    "udal_wait_stream": (ctypes.c_int, [_VP, _VP]),
     "udal_malloc": (ctypes.c_int, [_VP, ctypes.c_size_t, _PP]),
     "udal_free": (ctypes.c_int, [_VP, _VP]),
     "udal_host_alloc": (ctypes.c_int, [ctypes.c_size_t, _PP]),
@@ -109,6 +111,12 @@ SIGNATURES = {
                                         ctypes.c_int, ctypes.c_int, _VP]),
     "udal_run": (ctypes.c_int, [_VP, _PP, ctypes.c_int, _VP, ctypes.c_uint64, _VP,
                                 ctypes.POINTER(Detections)]),
+    "udal_clip_boxes": (ctypes.c_int, [_VP, _VP, ctypes.c_int64, ctypes.c_float, ctypes.c_float, _VP]),
+    "udal_max_reduce": (ctypes.c_int, [_VP, _VP, ctypes.c_int64, ctypes.c_int, _VP, _VP]),
+    "udal_divmod_i32": (ctypes.c_int, [_VP, _VP, ctypes.c_int64, ctypes.c_int, _VP, _VP]),
+    "udal_sigmoid": (ctypes.c_int, [_VP, _VP, ctypes.c_int64, _VP]),
+    "udal_decode_sample": (ctypes.c_int, [_VP, _VP, _VP, _VP, ctypes.c_int64, ctypes.c_int, _VP, ctypes.c_uint64, _VP, _VP]),
+    "udal_run_prenms": (ctypes.c_int, [_VP, _PP, ctypes.c_int, _VP, ctypes.c_uint64, ctypes.POINTER(PreNmsOut)]),
     "udal_nms_np": (ctypes.c_int, [_VP, _VP, ctypes.c_int, ctypes.c_int, ctypes.c_float,
                                    ctypes.c_float, ctypes.c_float, _VP,
                                    ctypes.POINTER(ctypes.c_int32)]),

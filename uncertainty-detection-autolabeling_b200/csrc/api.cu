@@ -185,6 +185,26 @@ int udal_set_stream(udal_ctx* ctx, void* cuda_stream) {
   return UDAL_OK;
 }
 
+int udal_get_stream(udal_ctx* ctx, void** cuda_stream) {
+  UDAL_REQUIRE(ctx && cuda_stream, "NULL argument");
+  *cuda_stream = (void*)ctx->stream;
+  return UDAL_OK;
+}
+
+int udal_wait_stream(udal_ctx* ctx, void* producer_stream) {
+  UDAL_REQUIRE(ctx, "NULL ctx");
+  UDAL_CUDA(cudaSetDevice(ctx->cfg.device));
+  if ((cudaStream_t)producer_stream == ctx->stream) return UDAL_OK;
+  // a fresh event per call: the wait is consumed when it is enqueued, the event can be destroyed right away
+  cudaEvent_t ev;
+  UDAL_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  cudaError_t e = cudaEventRecord(ev, (cudaStream_t)producer_stream);
+  if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->stream, ev, 0);
+  cudaEventDestroy(ev);
+  UDAL_CUDA(e);
+  return UDAL_OK;
+}
+
 int udal_sync(udal_ctx* ctx) {
   UDAL_REQUIRE(ctx, "NULL ctx");
   UDAL_TRY(udal_join(ctx));

@@ -13,7 +13,7 @@
 namespace {
 
 constexpr int kT = 1024;
-constexpr int kMaxN = 8192;
+constexpr int kSmemN = 16384;  // sort keys + alive flags of up to this many boxes live in shared memory, more in global scratch
 
 enum { NP_HARD = 0, NP_DIOU = 1, NP_LINEAR = 2, NP_GAUSSIAN = 3, NP_SOFT_HARD = 4 };
 
@@ -30,11 +30,13 @@ __device__ __forceinline__ float inter_p1(float ax1, float ay1, float ax2, float
 
 // greedy family: hard / diou.  order[] = indices by score descending (ties: higher index first)
 __global__ void __launch_bounds__(kT) nms_np_greedy_kernel(const float* __restrict__ dets, int n, int diou, float thr,
+                                                           unsigned long long* __restrict__ gkeys,
                                                            float* __restrict__ kept, int* __restrict__ num_kept) {
-  extern __shared__ unsigned long long keys[];  // [p2] then alive bytes
+  extern __shared__ unsigned long long skeys[];  // [p2] then alive bytes (n <= kSmemN; larger inputs: gkeys, global)
   __shared__ int sh_p, sh_cnt;
   int p2 = 1;
   while (p2 < n) p2 <<= 1;
+  unsigned long long* keys = gkeys ? gkeys : skeys;
   unsigned char* alive = reinterpret_cast<unsigned char*>(keys + p2);
   const int tid = threadIdx.x;
   for (int i = tid; i < p2; i += kT) {
@@ -223,7 +225,7 @@ extern "C" int udal_nms_np(udal_ctx* ctx, const float* dets_host, int n, int met
   UDAL_REQUIRE(ctx && num_kept, "NULL argument");
   UDAL_TRY(udal_join(ctx));
   UDAL_REQUIRE(method >= NP_HARD && method <= NP_SOFT_HARD, "Unknown NMS method: %d", method);
-  UDAL_REQUIRE(n >= 0 && n <= kMaxN, "nms_np: %d boxes, the device kernels take at most %d per call", n, kMaxN);
+  UDAL_REQUIRE(n >= 0 && n <= (1 << 24), "nms_np: %d boxes", n);
   *num_kept = 0;
   if (n == 0) return UDAL_OK;
   UDAL_REQUIRE(dets_host && kept_host, "NULL argument");
@@ -237,10 +239,15 @@ extern "C" int udal_nms_np(udal_ctx* ctx, const float* dets_host, int n, int met
   if (method == NP_HARD || method == NP_DIOU) {
     int p2 = 1;
     while (p2 < n) p2 <<= 1;
-    const size_t smem = (size_t)p2 * 8 + (size_t)n + 16;
+    size_t smem = (size_t)p2 * 8 + (size_t)n + 16;
+    unsigned long long* gkeys = nullptr;
+    if (n > kSmemN) {  // the reference has no size limit: sort keys and alive flags in global scratch
+      UDAL_TRY(udal_scratch_get(ctx, SCR_NMS_A, smem, (void**)&gkeys));
+      smem = 0;
+    }
     if (smem > 48 * 1024)
       UDAL_CUDA(cudaFuncSetAttribute(nms_np_greedy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    nms_np_greedy_kernel<<<1, kT, smem, ctx->stream>>>(d_dets, n, method == NP_DIOU ? 1 : 0, iou_thresh, d_kept, d_cnt);
+    nms_np_greedy_kernel<<<1, kT, smem, ctx->stream>>>(d_dets, n, method == NP_DIOU ? 1 : 0, iou_thresh, gkeys, d_kept, d_cnt);
   } else {
     nms_np_soft_kernel<<<1, kT, 0, ctx->stream>>>(d_dets, n, method, iou_thresh, sigma, score_thresh, d_work, d_kept,
                                                   d_cnt);

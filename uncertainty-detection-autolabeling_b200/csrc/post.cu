@@ -89,7 +89,12 @@ __global__ void __launch_bounds__(256) class_partition_kernel(const int32_t* __r
   const int32_t* cls = classes + (size_t)b * k;
   for (int c = threadIdx.x; c < C; c += blockDim.x) cnt[c] = 0;
   __syncthreads();
-  for (int j = threadIdx.x; j < k; j += blockDim.x) atomicAdd(&cnt[cls[j]], 1);
+  // rows whose class id is outside [0, C) belong to no segment: the reference loops over range(num_classes)
+  // (postprocess.py:655-657) and never selects them
+  for (int j = threadIdx.x; j < k; j += blockDim.x) {
+    const int c = cls[j];
+    if (c >= 0 && c < C) atomicAdd(&cnt[c], 1);
+  }
   __syncthreads();
   if (threadIdx.x == 0) {
     int a = 0;
@@ -598,6 +603,81 @@ int udal_gather_rows(udal_ctx* ctx, const void* src, int batch, int64_t n_rows, 
   if (total == 0) return UDAL_OK;
   gather_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>((const uint32_t*)src, n_rows, width, idx,
                                                                                 m, mode, (uint32_t*)out, total);
+  UDAL_CHECK_LAUNCH(ctx);
+  return UDAL_OK;
+}
+
+// ---- elementwise helpers of the mirror's small entry points (clip_boxes, topk_class_boxes, pre_nms(topk=False)) ----
+__global__ void clip_boxes_kernel(const float* __restrict__ in, int64_t total, float h, float w, float* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  // tf.clip_by_value(boxes, [0], [H, W, H, W]) = minimum(maximum(x, 0), hi)
+  out[i] = fminf(fmaxf(in[i], 0.f), (i & 1) ? w : h);
+}
+
+int udal_clip_boxes(udal_ctx* ctx, const float* boxes, int64_t rows, float image_h, float image_w, float* out) {
+  UDAL_REQUIRE(ctx && boxes && out, "NULL argument");
+  UDAL_TRY(udal_join(ctx));
+  if (rows == 0) return UDAL_OK;
+  clip_boxes_kernel<<<(unsigned)((rows * 4 + 255) / 256), 256, 0, ctx->stream>>>(boxes, rows * 4, image_h, image_w, out);
+  UDAL_CHECK_LAUNCH(ctx);
+  return UDAL_OK;
+}
+
+__global__ void max_reduce_kernel(const float* __restrict__ x, int64_t rows, int c, float* __restrict__ mx,
+                                  int32_t* __restrict__ arg) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  const float* p = x + r * c;
+  float best = p[0];
+  int a = 0;
+  for (int j = 1; j < c; ++j)
+    if (p[j] > best) {  // tf.math.argmax: first maximum
+      best = p[j];
+      a = j;
+    }
+  mx[r] = best;
+  arg[r] = a;
+}
+
+int udal_max_reduce(udal_ctx* ctx, const float* x, int64_t rows, int c, float* max_out, int32_t* argmax_out) {
+  UDAL_REQUIRE(ctx && x && max_out && argmax_out && c > 0, "bad argument");
+  UDAL_TRY(udal_join(ctx));
+  if (rows == 0) return UDAL_OK;
+  max_reduce_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, ctx->stream>>>(x, rows, c, max_out, argmax_out);
+  UDAL_CHECK_LAUNCH(ctx);
+  return UDAL_OK;
+}
+
+__global__ void divmod_kernel(const int32_t* __restrict__ idx, int64_t total, int d, int32_t* __restrict__ q,
+                              int32_t* __restrict__ r) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int32_t v = idx[i];
+  q[i] = v / d;
+  r[i] = v % d;
+}
+
+int udal_divmod_i32(udal_ctx* ctx, const int32_t* idx, int64_t total, int d, int32_t* quot, int32_t* rem) {
+  UDAL_REQUIRE(ctx && idx && quot && rem && d > 0, "bad argument");
+  UDAL_TRY(udal_join(ctx));
+  if (total == 0) return UDAL_OK;
+  divmod_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(idx, total, d, quot, rem);
+  UDAL_CHECK_LAUNCH(ctx);
+  return UDAL_OK;
+}
+
+__global__ void sigmoid_kernel(const float* __restrict__ x, int64_t total, float* __restrict__ y) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  y[i] = (float)(1.0 / (1.0 + exp(-(double)x[i])));  // the oracle's sigmoid: fp32(1 / (1 + exp(-fp64(x))))
+}
+
+int udal_sigmoid(udal_ctx* ctx, const float* x, int64_t total, float* y) {
+  UDAL_REQUIRE(ctx && x && y, "NULL argument");
+  UDAL_TRY(udal_join(ctx));
+  if (total == 0) return UDAL_OK;
+  sigmoid_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(x, total, y);
   UDAL_CHECK_LAUNCH(ctx);
   return UDAL_OK;
 }

@@ -5,6 +5,57 @@ int udal_heads_fused_ok(const udal_ctx* ctx);
 int udal_run_global_fused(udal_ctx* ctx, const float* const* feats, int batch, const uint8_t* keep_masks, uint64_t seed,
                           const float* image_scales, const udal_detections* out);
 
+int udal_heads_sample_fused(udal_ctx* ctx, const float* const* feats, int batch, const uint8_t* keep_masks, uint64_t seed,
+                            const udal_prenms_out* pre);
+
+// per-level head outputs in one scratch block, every level starting on a 16-byte boundary (odd channel
+// counts such as 63 = 9 anchors x 7 classes would otherwise misalign the following levels)
+static int head_output_scratch(udal_ctx* ctx, int batch, float** cls, float** box) {
+  const udal_config& c = ctx->cfg;
+  const int L = c.num_levels, T = c.mc_samples;
+  const int ccls = c.anchors_per_loc * c.num_classes, cbox = udal_box_channels(ctx);
+  const size_t tc = (size_t)(c.cls_mc ? T : 1) * batch, tb = (size_t)(c.box_mc ? T : 1) * batch;
+  size_t off_cls[UDAL_MAX_LEVELS], off_box[UDAL_MAX_LEVELS], total = 0;
+  for (int l = 0; l < L; ++l) {
+    const size_t px = (size_t)c.level_h[l] * c.level_w[l];
+    off_cls[l] = total;
+    total += (tc * px * ccls + 3) & ~(size_t)3;
+  }
+  for (int l = 0; l < L; ++l) {
+    const size_t px = (size_t)c.level_h[l] * c.level_w[l];
+    off_box[l] = total;
+    total += (tb * px * cbox + 3) & ~(size_t)3;
+  }
+  float* buf;
+  UDAL_TRY(udal_scratch_get(ctx, SCR_PRE_A, total * sizeof(float), (void**)&buf));
+  for (int l = 0; l < L; ++l) {
+    cls[l] = buf + off_cls[l];
+    box[l] = buf + off_box[l];
+  }
+  return UDAL_OK;
+}
+
+// features -> per-anchor tensors (pre_nms of postprocess.py:144-339 in the max-reduce variant, starting at the BiFPN
+// outputs) through exactly the kernels udal_run launches for this configuration: fused predict + K2 where they cover
+// it, predict layers + decode_moments otherwise.  The parity tests compare these tensors with the oracle anchor by anchor.
+extern "C" int udal_run_prenms(udal_ctx* ctx, const float* const* feats, int batch, const uint8_t* keep_masks,
+                               uint64_t seed, const udal_prenms_out* out) {
+  UDAL_REQUIRE(ctx && feats && out, "NULL argument");
+  UDAL_CUDA(cudaSetDevice(ctx->cfg.device));
+  UDAL_TRY(udal_join(ctx));
+  UDAL_REQUIRE(ctx->cfg.max_nms_inputs == 0, "udal_run_prenms: the max-reduce variant (max_nms_inputs == 0)");
+  if (udal_heads_fused_ok(ctx)) {
+    UDAL_REQUIRE(out->mean_logits && out->std_logits && out->boxes && out->albox && out->mcbox && out->scores && out->classes,
+                 "udal_run_prenms: the fused kernels write every per-anchor tensor");
+    return udal_heads_sample_fused(ctx, feats, batch, keep_masks, seed, out);
+  }
+  float* cls[UDAL_MAX_LEVELS];
+  float* box[UDAL_MAX_LEVELS];
+  UDAL_TRY(head_output_scratch(ctx, batch, cls, box));
+  UDAL_TRY(udal_heads_sample(ctx, feats, batch, keep_masks, seed, cls, box));
+  return udal_launch_decode_moments(ctx, cls, box, batch, out);
+}
+
 extern "C" int udal_run(udal_ctx* ctx, const float* const* feats, int batch, const uint8_t* keep_masks,
                         uint64_t seed, const float* image_scales, const udal_detections* out) {
   UDAL_REQUIRE(ctx && feats && out, "NULL argument");
@@ -37,32 +88,9 @@ extern "C" int udal_run(udal_ctx* ctx, const float* const* feats, int batch, con
     ctx->run_bank = bank ^ 1;
     return udal_run_global_fused(ctx, feats, batch, keep_masks, seed, image_scales, out);
   }
-  const int L = c.num_levels, T = c.mc_samples;
-  const int ccls = c.anchors_per_loc * c.num_classes, cbox = udal_box_channels(ctx);
-  const size_t P = (size_t)ctx->num_pixels;
-  // per-level head outputs in one scratch block, every level starting on a 16-byte boundary (odd channel
-  // counts such as 63 = 9 anchors x 7 classes would otherwise misalign the following levels)
-  const size_t tc = (size_t)(c.cls_mc ? T : 1) * batch, tb = (size_t)(c.box_mc ? T : 1) * batch;
-  size_t off_cls[UDAL_MAX_LEVELS], off_box[UDAL_MAX_LEVELS], total = 0;
-  for (int l = 0; l < L; ++l) {
-    const size_t px = (size_t)c.level_h[l] * c.level_w[l];
-    off_cls[l] = total;
-    total += (tc * px * ccls + 3) & ~(size_t)3;
-  }
-  for (int l = 0; l < L; ++l) {
-    const size_t px = (size_t)c.level_h[l] * c.level_w[l];
-    off_box[l] = total;
-    total += (tb * px * cbox + 3) & ~(size_t)3;
-  }
-  (void)P;
-  float* buf;
-  UDAL_TRY(udal_scratch_get(ctx, SCR_PRE_A, total * sizeof(float), (void**)&buf));
   float* cls[UDAL_MAX_LEVELS];
   float* box[UDAL_MAX_LEVELS];
-  for (int l = 0; l < L; ++l) {
-    cls[l] = buf + off_cls[l];
-    box[l] = buf + off_box[l];
-  }
+  UDAL_TRY(head_output_scratch(ctx, batch, cls, box));
   UDAL_TRY(udal_heads_sample(ctx, feats, batch, keep_masks, seed, cls, box));
   const int bank = ctx->run_bank;
   if (ctx->post_pending[bank]) {

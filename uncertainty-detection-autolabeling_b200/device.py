@@ -86,7 +86,8 @@ class Context:
         return p.value
 
     def _release(self, ptr, nbytes):
-        # all work of a context is ordered on one stream, so a released block can be handed out again
+        # every entry point orders its work behind everything the context enqueued before (udal_join brings the
+        # post stream of udal_run back in), so a released block can be handed out again without a sync
         self._pool.setdefault(nbytes, []).append(ptr)
 
     def trim(self):
@@ -122,6 +123,16 @@ class Context:
 
     def sync(self):
         _lib.check(self.lib.udal_sync(self.handle))
+
+    def stream_handle(self):
+        p = ctypes.c_void_p()
+        _lib.check(self.lib.udal_get_stream(self.handle, ctypes.byref(p)))
+        return p.value or 0
+
+    def wait_stream(self, producer_stream):
+        """Order the context's later work after everything enqueued so far on ``producer_stream`` (int handle;
+        0 / 1 = legacy default stream, 2 = per-thread default stream)."""
+        _lib.check(self.lib.udal_wait_stream(self.handle, ctypes.c_void_p(producer_stream or 0)))
 
     def timer_start(self):
         _lib.check(self.lib.udal_timer_start(self.handle))
@@ -251,6 +262,9 @@ class DeviceArray:
     # -- zero-copy export ----------------------------------------------------------------------
     @property
     def __cuda_array_interface__(self):
+        # "stream": None tells the consumer that no synchronisation is needed - so make that true: results may
+        # still be pending on the context's streams (udal_run's tail runs on the post stream)
+        self.ctx.sync()
         return {"shape": self.shape, "typestr": self.dtype.str, "data": (self.ptr or 0, False),
                 "version": 3, "strides": None, "stream": None}
 
@@ -275,10 +289,14 @@ class DeviceArray:
 
 
 def _from_dlpack(ctx, obj):
+    # DLPack protocol: the consumer passes ITS stream; the producer makes that stream wait for the work that
+    # writes the tensor.  The context's streams are non-blocking, i.e. they do not implicitly follow the
+    # producer's default stream.  (A CUDA stream handle is never 0 here; 1 / 2 are the reserved default handles.)
     try:
+        cap = obj.__dlpack__(stream=ctx.stream_handle())
+    except (TypeError, ValueError, AssertionError):
         cap = obj.__dlpack__()
-    except TypeError:
-        cap = obj.__dlpack__(stream=None)
+        ctx.wait_stream(0)  # producer did not take a stream: order behind the legacy default stream
     if not _py.PyCapsule_IsValid(cap, b"dltensor"):
         raise ValueError("object did not return a 'dltensor' capsule")
     mptr = _py.PyCapsule_GetPointer(cap, b"dltensor")
@@ -324,6 +342,9 @@ def as_device(ctx, x, dtype=None):
                     raise ValueError("device array must be C-contiguous")
                 expect *= s
         arr = DeviceArray(ctx, cai["shape"], np.dtype(cai["typestr"]), ptr=cai["data"][0], base=x)
+        # stream ordering (CAI v3): an int names the producer's stream; None / absent (v2 producers such as torch) says
+        # nothing - order behind the legacy default stream, where such producers run unless told otherwise
+        ctx.wait_stream(int(cai.get("stream") or 0))
     elif hasattr(x, "__dlpack__") and not isinstance(x, np.ndarray):
         arr = _from_dlpack(ctx, x)
     else:

@@ -373,6 +373,29 @@ class Engine:
                                               device.ptr_array(box)))
         return cls, box
 
+    def run_prenms(self, feats, masks=None, seed=0):
+        """features -> per-anchor tensors (dict of DeviceArray) through the kernels ``run`` launches
+        (udal_run_prenms); max-reduce variant only."""
+        if not self.weights_set:
+            raise RuntimeError("head weights not set")
+        f, batch, _ = self.feats_input(feats)
+        m, mptr = self.masks_input(masks, batch)
+        n, c = self.N, self.C
+        out = {}
+        st = _lib.PreNmsOut()
+        for name, shape, dtype in (("mean_logits", (batch, n, c), np.float32), ("std_logits", (batch, n, c), np.float32),
+                                   ("boxes", (batch, n, 4), np.float32), ("albox", (batch, n, 4), np.float32),
+                                   ("mcbox", (batch, n, 4), np.float32), ("scores", (batch, n), np.float32),
+                                   ("classes", (batch, n), np.int32)):
+            if (name == "std_logits" and not self.cls_mc) or (name == "albox" and not self.la) or \
+                    (name == "mcbox" and not self.box_mc):
+                continue
+            out[name] = self.ctx.empty(shape, dtype)
+            setattr(st, name, out[name].ptr)
+        _lib.check(self.lib.udal_run_prenms(self.ctx.handle, device.ptr_array(f), batch, mptr,
+                                            ctypes.c_uint64(seed), ctypes.byref(st)))
+        return out
+
     def run(self, feats, image_scales=None, masks=None, seed=0):
         if not self.weights_set:
             raise RuntimeError("head weights not set")

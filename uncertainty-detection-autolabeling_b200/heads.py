@@ -6,9 +6,11 @@ configuration every shipped inference YAML uses): the backbone/BiFPN are then de
 their output is identical for all T passes.  With backbone dropout the features differ
 per pass, which this entry point does not model - it raises.
 """
+import os
+
 import numpy as np
 
-from . import device
+from . import device, utils
 from . import engine as _engine
 
 
@@ -18,26 +20,43 @@ class HeadSampler:
             raise ValueError("mc_dropoutrate > 0 (backbone MC dropout) changes the BiFPN features per "
                              "sample; the head sampler starts at the BiFPN outputs (head-only dropout)")
         self.params = params
-        self.engine = _engine.get_engine(params, device_id, heads_mode, instance=instance)
+        # every sampler owns its context: the head weights live in the context, so two samplers with the same
+        # params but different checkpoints (ensembles, model comparison, reloads) must never share one.  The
+        # config-keyed cache of engine.get_engine serves the weight-free postprocess.* entry points only.
+        if device_id is None:
+            device_id = params.get("device", 0) or 0
+        self.engine = _engine.Engine(params, device_id, heads_mode or params.get("heads_mode", "fp32"))
         self.engine.set_head_weights(weights)
+        # the reference draws fresh dropout masks on every call: seed=None continues a per-sampler random stream
+        self._seed_base = int.from_bytes(os.urandom(8), "little")
+        self._calls = 0
 
-    def __call__(self, fpn_feats, masks=None, seed=0):
+    def _seed(self, seed):
+        if seed is not None:
+            return int(seed) & ((1 << 64) - 1)
+        self._calls += 1
+        return utils.mix_seed(self._seed_base, self._calls)
+
+    def close(self):
+        self.engine.ctx.close()
+
+    def __call__(self, fpn_feats, masks=None, seed=None):
         """fpn_feats: list[L] of [B,H_l,W_l,F].  Returns (cls_outputs, box_outputs) with the
         structure of EfficientDetNet.call: list[L] of [T,B,H,W,A*C] and [T,B,H,W,8A] (no leading T
         for a head without MC dropout).  ``masks`` [T,2,L,R,B,F] uint8 injects keep masks (parity
         runs); otherwise Philox4x32-10 masks are drawn on the device from ``seed``."""
         host = not any(isinstance(x, device.DeviceArray) or hasattr(x, "__cuda_array_interface__") for x in fpn_feats)
-        cls, box = self.engine.heads_sample(list(fpn_feats), masks, seed)
+        cls, box = self.engine.heads_sample(list(fpn_feats), masks, self._seed(seed))
         if host:
             cls = [c.copy_to_host(sync=False) for c in cls]
             box = [b.copy_to_host(sync=False) for b in box]
             self.engine.ctx.sync()
         return cls, box
 
-    def detect(self, fpn_feats, image_scales=None, masks=None, seed=0):
+    def detect(self, fpn_feats, image_scales=None, masks=None, seed=None):
         """features -> detections in one device call (udal_run); tuple like postprocess_*."""
         host = not any(isinstance(x, device.DeviceArray) or hasattr(x, "__cuda_array_interface__") for x in fpn_feats)
-        bufs = self.engine.run(list(fpn_feats), image_scales, masks, seed)
+        bufs = self.engine.run(list(fpn_feats), image_scales, masks, self._seed(seed))
         out = [bufs["boxes"], bufs["scores"], bufs["classes"], bufs["valid"], bufs["logits"]]
         if host:
             out = [o.copy_to_host(sync=False) for o in out]
@@ -53,20 +72,30 @@ class PipelinedSampler:
 
     def __init__(self, params, weights, device_id=None, heads_mode=None, depth=2):
         self.samplers = [HeadSampler(params, weights, device_id, heads_mode, instance=i) for i in range(depth)]
+        self._seed_base = int.from_bytes(os.urandom(8), "little")
+        self._maps = 0
 
-    def map(self, batches, image_scales=None, seed=0):
+    def map(self, batches, image_scales=None, seed=None):
         import concurrent.futures as cf
 
         depth = len(self.samplers)
+        if seed is None:
+            self._maps += 1
+            seed = utils.mix_seed(self._seed_base, self._maps)
         with cf.ThreadPoolExecutor(max_workers=depth) as pool:
             pending = []
             for i, feats in enumerate(batches):
                 sc = None if image_scales is None else image_scales[i]
-                pending.append(pool.submit(self.samplers[i % depth].detect, feats, sc, None, seed + i))
+                pending.append(pool.submit(self.samplers[i % depth].detect, feats, sc, None, batch_seed(seed, i)))
                 if len(pending) >= depth:
                     yield pending.pop(0).result()
             for f in pending:
                 yield f.result()
+
+
+def batch_seed(seed, i):
+    """seed of batch / shard ``i`` of a call seeded with ``seed`` (see utils.mix_seed)"""
+    return utils.mix_seed(seed, i)
 
 
 def philox_keep_masks(shape, rate_class, rate_box, seed):

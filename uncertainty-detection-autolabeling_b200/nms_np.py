@@ -3,7 +3,7 @@
 nms_np.py:30-89 diou_nms | :92-129 hard_nms | :132-194 soft_nms | :197-220 nms | :223-278
 per_class_nms.  Same signatures and return values (NumPy in / NumPy out, like the reference, which
 calls these through ``tf.numpy_function``); the arithmetic - "+1" pixel convention, fp32, visiting
-order - runs on the GPU.  At most 8192 boxes per ``nms`` call (the reference feeds <= 5000).
+order - runs on the GPU.  Any number of boxes per ``nms`` call (up to 16384 sort in shared memory, more in global scratch; the reference feeds <= 5000).
 
 Tie order: ``argsort()[::-1]`` of the reference uses NumPy's unstable default sort; the device
 kernel orders equal scores by descending index (what a stable sort would give).

@@ -5,7 +5,7 @@ NumPy on the host (copied in, results copied out) or device arrays (``DeviceArra
 tensors via ``__cuda_array_interface__`` / DLPack - borrowed zero-copy, results stay on the device).
 
 Reference map (src/postprocess.py):
-  to_list :44-50 | merge_class_box_level_outputs :75-87 | topk_class_boxes :90-141 |
+  to_list :44-50 | batch_map_fn :53-66 | clip_boxes :69-72 | merge_class_box_level_outputs :75-87 | topk_class_boxes :90-141 |
   pre_nms :144-339 | nms :342-420 | extract_uncertainties :423-469 | postprocess_global :472-621 |
   per_class_nms :624-716 | postprocess_per_class :719-740 |
   generate_detections_from_nms_output :743-785 | generate_detections :788-871 |
@@ -35,6 +35,121 @@ def to_list(inputs):
     if isinstance(inputs, tuple):
         return list(inputs)
     return None
+
+
+def batch_map_fn(map_fn, inputs, *args):
+    """postprocess.py:53-66: apply ``map_fn`` per image and stack the results (host or device arrays)."""
+    first = inputs[0]
+    batch_size = len(first) if isinstance(first, (list, tuple)) else first.shape[0]
+    outputs = [map_fn([_row(x, i) for x in inputs]) for i in range(batch_size)]
+    return [_stack(list(y)) for y in zip(*outputs)]
+
+
+def _row(x, i):
+    return x.slice0(i, i + 1).reshape(x.shape[1:]) if isinstance(x, device.DeviceArray) else x[i]
+
+
+def _stack(items):
+    if not isinstance(items[0], device.DeviceArray):
+        return np.stack([np.asarray(v) for v in items])
+    ctx, a0 = items[0].ctx, items[0]
+    out = ctx.empty((len(items),) + a0.shape, a0.dtype)
+    for i, a in enumerate(items):
+        _lib.check(ctx.lib.udal_memcpy_d2d(ctx.handle, out.ptr + i * a0.nbytes, a.ptr, a0.nbytes))
+    return out
+
+
+def clip_boxes(boxes, image_size):
+    """postprocess.py:69-72: clip [..., 4] boxes (ymin, xmin, ymax, xmax) to the image."""
+    h, w = utils.parse_image_size(image_size)
+    host = not _is_dev(boxes)
+    eng = _any_engine()
+    b, _ = device.as_device(eng.ctx, boxes, np.float32)
+    if b.shape[-1] != 4:
+        raise ValueError("clip_boxes expects a trailing dimension of 4")
+    out = eng.ctx.empty(b.shape)
+    _lib.check(eng.lib.udal_clip_boxes(eng.ctx.handle, b.ptr, b.size // 4, float(h), float(w), out.ptr))
+    return out.numpy() if host else out
+
+
+def merge_class_box_level_outputs(params, cls_outputs, box_outputs):
+    """postprocess.py:75-87: per level [B,H,W,A*C] -> [B,H*W*A,C] and [B,H,W,4A] -> [B,H*W*A,4], levels concatenated
+    (anchor order = level, y, x, anchor).  A pure re-layout: device-to-device copies, no arithmetic."""
+    if params.get("data_format", "channels_last") == "channels_first":
+        raise ValueError("channels_first head outputs are not supported (NHWC only)")
+    nc = params["num_classes"]
+    nlev = params["max_level"] - params["min_level"] + 1
+    host = not any(_is_dev(x) for x in list(cls_outputs)[:nlev] + list(box_outputs)[:nlev])
+    if host:
+        cls = [np.asarray(cls_outputs[l]) for l in range(nlev)]
+        box = [np.asarray(box_outputs[l]) for l in range(nlev)]
+        b = cls[0].shape[0]
+        return (np.concatenate([c.reshape(b, -1, nc) for c in cls], 1),
+                np.concatenate([x.reshape(b, -1, 4) for x in box], 1))
+    eng = _any_engine()
+    outs = []
+    for levels, width in ((cls_outputs, nc), (box_outputs, 4)):
+        arrs = [device.as_device(eng.ctx, levels[l], np.float32)[0] for l in range(nlev)]
+        b = arrs[0].shape[0]
+        rows = [a.size // (b * width) for a in arrs]
+        merged = eng.ctx.empty((b, sum(rows), width))
+        for i in range(b):
+            off = 0
+            for a, r in zip(arrs, rows):
+                nbytes = r * width * 4
+                _lib.check(eng.lib.udal_memcpy_d2d(eng.ctx.handle, merged.ptr + (i * sum(rows) + off) * width * 4,
+                                                   a.ptr + i * nbytes, nbytes))
+                off += r
+        outs.append(merged)
+    return outs[0], outs[1]
+
+
+def topk_class_boxes(params, cls_outputs, box_outputs, uncerts=None):
+    """postprocess.py:90-141 on merged tensors: cls_outputs [B,N,C], box_outputs [B,N,4];
+    uncerts = [class [B,N,C] | None, box [B,N,4] | None, box [B,N,4] | None] is gathered in place.
+    top-k order is canonical (value descending, index ascending; the reference asks for sorted=False)."""
+    host = not (_is_dev(cls_outputs) or _is_dev(box_outputs))
+    eng = _any_engine()
+    ctx, lib = eng.ctx, eng.lib
+    cls, _ = device.as_device(ctx, cls_outputs, np.float32)
+    box, _ = device.as_device(ctx, box_outputs, np.float32)
+    b, n, c = cls.shape
+    if c != params["num_classes"]:
+        raise ValueError("cls_outputs must be [B,N,num_classes]")
+    k = int(params["nms_configs"].get("max_nms_inputs", 0) or 0)
+    if k > 0:
+        flat = ctx.empty((b, k), np.int32)
+        cls_topk = ctx.empty((b, k))
+        _lib.check(lib.udal_topk(ctx.handle, cls.ptr, b, n * c, k, flat.ptr, cls_topk.ptr))
+        indices, classes = ctx.empty((b, k), np.int32), ctx.empty((b, k), np.int32)
+        _lib.check(lib.udal_divmod_i32(ctx.handle, flat.ptr, b * k, c, indices.ptr, classes.ptr))
+        box_topk = ctx.empty((b, k, 4))
+        _lib.check(lib.udal_gather_rows(ctx.handle, box.ptr, b, n, 4, indices.ptr, k, 0, box_topk.ptr))
+        if uncerts is not None:
+            for i in range(len(uncerts)):
+                if uncerts[i] is None:
+                    continue
+                u, _ = device.as_device(ctx, uncerts[i], np.float32)
+                if i == 0:  # class uncertainty: by (anchor, class)
+                    g = ctx.empty((b, k))
+                    _lib.check(lib.udal_gather_rows(ctx.handle, u.ptr, b, n * c, 1, flat.ptr, k, 0, g.ptr))
+                else:       # box uncertainties: by anchor
+                    g = ctx.empty((b, k, 4))
+                    _lib.check(lib.udal_gather_rows(ctx.handle, u.ptr, b, n, 4, indices.ptr, k, 0, g.ptr))
+                uncerts[i] = g.numpy() if host else g
+    else:
+        cls_topk, classes = ctx.empty((b, n)), ctx.empty((b, n), np.int32)
+        _lib.check(lib.udal_max_reduce(ctx.handle, cls.ptr, b * n, c, cls_topk.ptr, classes.ptr))
+        box_topk = box
+        indices = np.tile(np.arange(n, dtype=np.int32)[None], (b, 1))
+        if not host:
+            indices = ctx.to_device(indices)
+    res = [cls_topk, box_topk, classes, indices]
+    if host:
+        res = [r.numpy() if isinstance(r, device.DeviceArray) else r for r in res]
+    if uncerts is not None:
+        return res[0], res[1], res[2], res[3], uncerts
+    return tuple(res)
 
 
 def _is_dev(x):
@@ -110,9 +225,11 @@ def pre_nms(params, cls_outputs, box_outputs, topk=True, uncerts=None):
     (extract_uncertainties): ``cls_outputs`` are the per-level MEAN logits, ``box_outputs`` the
     per-level box regressions (with a leading sample axis under box MC dropout) and ``uncerts`` =
     [per-level logit std | None, per-level sigma | None, None]."""
-    if not topk:
-        raise NotImplementedError("pre_nms(topk=False) has no caller in the reference; not offered")
     cls_outputs, box_outputs = to_list(cls_outputs), to_list(box_outputs)
+    if not topk:
+        # postprocess.py:276-282: no candidate selection - every anchor, every class; scores = sigmoid of all
+        # logits [B,N,C], classes = None.  Same decode as the max-reduce variant (which keeps all anchors too).
+        params = dict(params, nms_configs=dict(params["nms_configs"], max_nms_inputs=0))
     eng = _engine.get_engine(params, cls_mc=False)
     la = eng.la
     host = not any(_is_dev(x) for x in cls_outputs + box_outputs)
@@ -156,8 +273,13 @@ def pre_nms(params, cls_outputs, box_outputs, topk=True, uncerts=None):
                 if uncerts[i] is not None:
                     uncerts[i] = uncerts[i].numpy()
     boxes, scores, classes, multi = o["boxes"], o["scores"], o["classes"], o["mean_logits"]
+    if not topk:
+        scores = eng.ctx.empty(multi.shape)
+        _lib.check(eng.lib.udal_sigmoid(eng.ctx.handle, multi.ptr, multi.size, scores.ptr))
+        classes = None
     if host:
-        boxes, scores, classes, multi = boxes.numpy(), scores.numpy(), classes.numpy(), multi.numpy()
+        boxes, scores, multi = boxes.numpy(), scores.numpy(), multi.numpy()
+        classes = classes.numpy() if classes is not None else None
     out = [boxes, uncerts, scores, classes]
     if params["enable_softmax"]:
         out.append(multi)
@@ -180,6 +302,10 @@ def nms(params, boxes, scores, classes, padded, multiclass=None, uncerts1=None, 
 
     def gather(src, width, mode=0, dtype=np.float32):
         a, _ = device.as_device(eng.ctx, src, np.int32 if mode == 1 else np.float32)
+        if a.ndim <= 1:
+            width = 1  # [n] sources (top-k class uncertainties, 1-D multiclass): one value per row
+        if a.size != n * width:
+            raise ValueError("nms: a gathered tensor has %d values, expected %d rows x %d" % (a.size, n, width))
         out = eng.ctx.empty((m,) + ((width,) if a.ndim > 1 else ()), dtype)
         _lib.check(eng.lib.udal_gather_rows(eng.ctx.handle, a.ptr, 1, n, width, idx.ptr, m, mode, out.ptr))
         return out

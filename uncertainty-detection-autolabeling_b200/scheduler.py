@@ -72,10 +72,15 @@ class ImageScheduler:
         self.samplers = [heads.HeadSampler(params, weights, device_id=d, heads_mode=heads_mode)
                          for d in self.devices]
 
-    def detect(self, fpn_feats, image_scales=None, masks=None, seed=0):
+    def detect(self, fpn_feats, image_scales=None, masks=None, seed=None):
         """fpn_feats: list[L] of host arrays [B,H_l,W_l,F].  Returns the detection tuple of
         ``HeadSampler.detect`` for the whole batch, in input order."""
+        from . import heads, utils
+
         batch = fpn_feats[0].shape[0]
+        if seed is None:  # a fresh draw per call, like the reference's stateful dropout layers
+            import os
+            seed = int.from_bytes(os.urandom(8), "little")
         ranges = shard_ranges(batch, len(self.devices))
         results = [None] * len(self.devices)
         errors = []
@@ -88,7 +93,7 @@ class ImageScheduler:
                 sc = None if image_scales is None else np.asarray(image_scales)[start:stop]
                 mk = None if masks is None else np.ascontiguousarray(np.asarray(masks)[:, :, :, :, start:stop])
                 results[i] = self.samplers[i].detect(take_shard(fpn_feats, start, stop), sc, masks=mk,
-                                                     seed=seed + i)
+                                                     seed=heads.batch_seed(seed, i))
             except Exception as e:  # surfaced after the join
                 errors.append(e)
 

@@ -25,3 +25,13 @@ def get_feat_sizes(image_size, max_level):
         h, w = (h - 1) // 2 + 1, (w - 1) // 2 + 1
         sizes.append({"height": h, "width": w})
     return sizes
+
+
+def mix_seed(seed, stream):
+    """64-bit seed of sub-stream ``stream`` (a shard, a batch of a map) of ``seed``: splitmix64 of the pair, so that
+    callers stepping ``seed`` by one never collide with the sub-streams of a neighbouring call (seed + i would)."""
+    m = (1 << 64) - 1
+    z = (int(seed) * 0x9E3779B97F4A7C15 + (int(stream) + 1) * 0xD1B54A32D192ED03) & m
+    z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & m
+    z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & m
+    return z ^ (z >> 31)

@@ -12,6 +12,9 @@ def stack_mcpred(output):
     return [np.stack([np.asarray(x) for x in o], axis=0) for o in (o0, o1, o2, o3, o4)]
 
 
+_engines = {}  # (T, level sizes, device) -> cached engine: one CUDA context per shape, not one per call
+
+
 def get_mcuncert(output, device_id=0):
     """utils_extra.py:220-244: per level mean and population std over the leading (sample) axis,
     computed by the moments kernel (sequential fp32 sum / T, two-pass std).  Host arrays in/out
@@ -20,24 +23,25 @@ def get_mcuncert(output, device_id=0):
     levels = [np.asarray(x, np.float32) for x in (o0, o1, o2, o3, o4)]
     T, batch = levels[0].shape[0], levels[0].shape[1]
     sizes = [int(np.prod(x.shape[2:], dtype=np.int64)) for x in levels]
-    params = dict(_GENERIC, max_level=len(levels) - 1, loss_attenuation=False, mc_dropout=True,
-                  mc_classheadrate=0.5, mc_dropoutsamp=T, uncert_adjust_method="l-norm")
-    n_total = sum(sizes)
-    eng = _engine.Engine(params, device_id, level_hw=[(1, n) for n in sizes],
-                         anchors=np.zeros((n_total, 4), np.float32))
-    try:
-        cls = [eng.ctx.to_device(x.reshape(T, batch, 1, n, 1)) for x, n in zip(levels, sizes)]
-        box = [eng.ctx.zeros((batch, 1, n, 4)) for n in sizes]
-        out = eng.decode_moments(cls, box, batch, want=("mean_logits", "std_logits"))
-        m, s = out["mean_logits"].numpy(), out["std_logits"].numpy()
-        mean, std, off = [], [], 0
-        for x, n in zip(levels, sizes):
-            mean.append(m[:, off:off + n, 0].reshape(x.shape[1:]))
-            std.append(s[:, off:off + n, 0].reshape(x.shape[1:]))
-            off += n
-        return mean, std
-    finally:
-        eng.ctx.close()
+    key = (T, tuple(sizes), device_id)
+    eng = _engines.get(key)
+    if eng is None:
+        if len(_engines) >= 8:  # bounded: drop the oldest shape
+            _engines.pop(next(iter(_engines))).ctx.close()
+        params = dict(_GENERIC, max_level=len(levels) - 1, loss_attenuation=False, mc_dropout=True,
+                      mc_classheadrate=0.5, mc_dropoutsamp=T, uncert_adjust_method="l-norm")
+        eng = _engines[key] = _engine.Engine(params, device_id, level_hw=[(1, n) for n in sizes],
+                                             anchors=np.zeros((sum(sizes), 4), np.float32))
+    cls = [eng.ctx.to_device(x.reshape(T, batch, 1, n, 1)) for x, n in zip(levels, sizes)]
+    box = [eng.ctx.zeros((batch, 1, n, 4)) for n in sizes]
+    out = eng.decode_moments(cls, box, batch, want=("mean_logits", "std_logits"))
+    m, s = out["mean_logits"].numpy(), out["std_logits"].numpy()
+    mean, std, off = [], [], 0
+    for x, n in zip(levels, sizes):
+        mean.append(m[:, off:off + n, 0].reshape(x.shape[1:]))
+        std.append(s[:, off:off + n, 0].reshape(x.shape[1:]))
+        off += n
+    return mean, std
 
 
 def mc_eval(mc_model, images, config=None):
