@@ -46,7 +46,12 @@ enum { UDAL_DECODE_LNORM = 0, UDAL_DECODE_NFLOW = 1, UDAL_DECODE_FALSEDEC = 2 };
 /* NMS method, reference postprocess.py:373-388 */
 enum { UDAL_NMS_HARD = 0, UDAL_NMS_GAUSSIAN = 1 };
 /* head-GEMM arithmetic */
-enum { UDAL_HEADS_FP32 = 0, UDAL_HEADS_BF16_TC = 1 };
+enum {
+  UDAL_HEADS_FP32 = 0,    /* CUDA-core fp32 towers: the 1e-4 parity mode */
+  UDAL_HEADS_BF16_TC = 1, /* tcgen05, bf16 operands / activations (implicit-GEMM kernels) */
+  UDAL_HEADS_FP16_TC = 2  /* tcgen05 pointwise + packed-fp16 depthwise, fp16 operands / activations: the precision the
+                             reference's own GPU export runs in (mixed_float16, infer_lib.py:429-431); the benchmarked mode */
+};
 enum { UDAL_HEAD_CLASS = 0, UDAL_HEAD_BOX = 1 };
 
 /* The hot-path slice of the reference's params dict (hparams_config.py:183-370) plus geometry. */

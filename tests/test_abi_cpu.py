@@ -111,6 +111,12 @@ def test_anchor_table_matches_golden():
         np.testing.assert_array_equal(a.boxes[g[tag + "_rows"]], g[tag + "_vals"])
         np.testing.assert_array_equal(a.boxes.astype(np.float64).sum(0), g[tag + "_sum64"])
         assert a.get_anchors_per_location() == 9
+        # the table's raw pointer is uploaded to the device: it must be C-contiguous [N,4] fp32 at EVERY geometry (round 1
+        # uploaded a Fortran-ordered table for every level above ~100 px: NumPy's concatenate / astype kept the order of
+        # the transposed views)
+        t = u.engine.anchor_table(3, 7, 3, [1.0, 2.0, 0.5], 4.0, size)
+        assert t.flags["C_CONTIGUOUS"] and t.dtype == np.float32 and t.strides == (16, 4)
+        np.testing.assert_array_equal(np.frombuffer(t.tobytes(), np.float32).reshape(-1, 4), a.boxes)
     np.testing.assert_array_equal(
         u.anchors.Anchors(3, 5, 2, [1.0, [1.4, 0.7]], [4.0, 3.0, 5.0], 128).boxes, g["custom_128"])
 

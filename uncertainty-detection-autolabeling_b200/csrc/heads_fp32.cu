@@ -239,7 +239,7 @@ extern "C" int udal_set_head_weights(udal_ctx* ctx, int head, const float* dw, c
   // host sources are pageable: make sure the copies are done before the caller reuses them
   UDAL_CUDA(cudaStreamSynchronize(ctx->stream));
   h.set = true;
-  if (c.heads_mode == UDAL_HEADS_BF16_TC) UDAL_TRY(udal_heads_tc_prepare(ctx, head));
+  if (c.heads_mode != UDAL_HEADS_FP32) UDAL_TRY(udal_heads_tc_prepare(ctx, head));
   return UDAL_OK;
 }
 
@@ -335,7 +335,7 @@ static int heads_sample_impl(udal_ctx* ctx, const float* const* feats, int batch
   for (int l = 0; l < c.num_levels; ++l)
     UDAL_REQUIRE(feats[l] && (fused_pre || (cls_out[l] && box_out[l])), "level %d pointer is NULL", l);
   const int T = c.mc_samples, L = c.num_levels, R = c.repeats, F = c.num_filters;
-  if (c.heads_mode == UDAL_HEADS_BF16_TC) UDAL_TRY(udal_work_counters_reset(ctx));
+  if (c.heads_mode != UDAL_HEADS_FP32) UDAL_TRY(udal_work_counters_reset(ctx));
   const int64_t total = (int64_t)T * 2 * L * R * batch * F;
   float* scale_raw;
   UDAL_TRY(udal_scratch_get(ctx, SCR_HEADS_C, (size_t)total * 4 * 2, (void**)&scale_raw));
@@ -348,8 +348,8 @@ static int heads_sample_impl(udal_ctx* ctx, const float* const* feats, int batch
     scale_transpose_kernel<<<(int)((total + 255) / 256), 256, 0, ctx->stream>>>(scale_raw, scale, T, L, R, batch, F);
     UDAL_CHECK_LAUNCH(ctx);
   }
-  if (c.heads_mode == UDAL_HEADS_BF16_TC) return udal_heads_tc_sample(ctx, feats, batch, scale, cls_out, box_out, fused_pre);
-  UDAL_REQUIRE(!fused_pre, "the fused predict + decode kernels need heads_mode bf16");
+  if (c.heads_mode != UDAL_HEADS_FP32) return udal_heads_tc_sample(ctx, feats, batch, scale, cls_out, box_out, fused_pre);
+  UDAL_REQUIRE(!fused_pre, "the fused predict + decode kernels need a tensor-core heads mode (fp16 | bf16)");
   UDAL_TRY(run_tower_fp32(ctx, UDAL_HEAD_CLASS, feats, batch, scale, cls_out));
   UDAL_TRY(run_tower_fp32(ctx, UDAL_HEAD_BOX, feats, batch, scale, box_out));
   return UDAL_OK;

@@ -573,7 +573,7 @@ int udal_run_fused = 1;  // 0: udal_run always goes through predict layers + dec
 // true if the fused predict + decode kernels cover this configuration (the serving default)
 int udal_heads_fused_ok(const udal_ctx* ctx) {
   const udal_config& c = ctx->cfg;
-  return udal_run_fused && c.heads_mode == UDAL_HEADS_BF16_TC && c.repeats >= 2 && c.num_filters == KF && c.anchors_per_loc == 9 &&
+  return udal_run_fused && (c.heads_mode == UDAL_HEADS_BF16_TC || c.heads_mode == UDAL_HEADS_FP16_TC) && c.repeats >= 2 && c.num_filters == KF && c.anchors_per_loc == 9 &&
          (c.num_classes == 8 || c.num_classes == 7 || c.num_classes == 10) && c.loss_attenuation && c.decode_method == UDAL_DECODE_LNORM && c.cls_mc && c.box_mc &&
          c.max_nms_inputs == 0 && c.mc_samples >= 2;
 }

@@ -64,6 +64,8 @@ struct L1Maps {
   CUtensorMap out[UDAL_MAX_LEVELS];   // [T*NB,H,W,64] bf16, box {64,8,16,1}, 128B swizzle
 };
 
+// FP16: 16-bit format of the activations in / out and of the GEMM operands (false: bf16)
+template <bool FP16>
 __global__ void __launch_bounds__(kL1Threads, 1) heads_l1_kernel(const __grid_constant__ L1Maps maps, const L1Params p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = s32(smem_raw);
@@ -108,10 +110,10 @@ __global__ void __launch_bounds__(kL1Threads, 1) heads_l1_kernel(const __grid_co
     const float4* src = reinterpret_cast<const float4*>(p.wf[l] + (size_t)n * KF + c * 8);
     const float4 a = __ldg(src), b = __ldg(src + 1);
     uint4 v;
-    v.x = ig_pack(a.x * p.inv_keep, a.y * p.inv_keep);
-    v.y = ig_pack(a.z * p.inv_keep, a.w * p.inv_keep);
-    v.z = ig_pack(b.x * p.inv_keep, b.y * p.inv_keep);
-    v.w = ig_pack(b.z * p.inv_keep, b.w * p.inv_keep);
+    v.x = ig_pack16<FP16>(a.x * p.inv_keep, a.y * p.inv_keep);
+    v.y = ig_pack16<FP16>(a.z * p.inv_keep, a.w * p.inv_keep);
+    v.z = ig_pack16<FP16>(b.x * p.inv_keep, b.y * p.inv_keep);
+    v.w = ig_pack16<FP16>(b.z * p.inv_keep, b.w * p.inv_keep);
     *reinterpret_cast<uint4*>(smem + L1_WC + l * 8192 + n * 128 + ((c ^ (n & 7)) << 4)) = v;
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -145,7 +147,7 @@ __global__ void __launch_bounds__(kL1Threads, 1) heads_l1_kernel(const __grid_co
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(64 >> 3) << 17) | ((128u >> 4) << 24);
+    constexpr uint32_t idesc = ig_idesc<FP16>(64);
     int j = 0;
     for (int i = 0;; ++i) {
       const int ab = i & 1;
@@ -233,11 +235,8 @@ __global__ void __launch_bounds__(kL1Threads, 1) heads_l1_kernel(const __grid_co
 #pragma unroll
           for (int dx = 0; dx < 3; ++dx) {
             const uint2 raw2 = *reinterpret_cast<const uint2*>(sIn + (size_t)(r * IG_BOXW + x + dx) * 128 + q4 * 8);
-            float v[4];
-            v[0] = __uint_as_float(raw2.x << 16);
-            v[1] = __uint_as_float(raw2.x & 0xffff0000u);
-            v[2] = __uint_as_float(raw2.y << 16);
-            v[3] = __uint_as_float(raw2.y & 0xffff0000u);
+            const float2 v01 = ig_unpack16<FP16>(raw2.x), v23 = ig_unpack16<FP16>(raw2.y);
+            const float v[4] = {v01.x, v01.y, v23.x, v23.y};
 #pragma unroll
             for (int dy = 0; dy < 3; ++dy) {
               const int y = r - dy;
@@ -251,8 +250,8 @@ __global__ void __launch_bounds__(kL1Threads, 1) heads_l1_kernel(const __grid_co
             const int y = r - 2;
             const int m = y * IG_TW + x;
             uint2 o;
-            o.x = ig_pack(acc[y][0], acc[y][1]);
-            o.y = ig_pack(acc[y][2], acc[y][3]);
+            o.x = ig_pack16<FP16>(acc[y][0], acc[y][1]);
+            o.y = ig_pack16<FP16>(acc[y][2], acc[y][3]);
             *reinterpret_cast<uint2*>(sA + (size_t)m * 128 + (((q4 >> 1) ^ (m & 7)) << 4) + (q4 & 1) * 8) = o;
           }
         }
@@ -360,10 +359,10 @@ __global__ void __launch_bounds__(kL1Threads, 1) heads_l1_kernel(const __grid_co
             v[e + 1] = sw.y;
           }
           uint4 o;
-          o.x = ig_pack(v[0], v[1]);
-          o.y = ig_pack(v[2], v[3]);
-          o.z = ig_pack(v[4], v[5]);
-          o.w = ig_pack(v[6], v[7]);
+          o.x = ig_pack16<FP16>(v[0], v[1]);
+          o.y = ig_pack16<FP16>(v[2], v[3]);
+          o.z = ig_pack16<FP16>(v[4], v[5]);
+          o.w = ig_pack16<FP16>(v[6], v[7]);
           *reinterpret_cast<uint4*>(ob + m * 128 + (((uint32_t)(hc * 4 + u) ^ swz) << 4)) = o;
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -395,6 +394,8 @@ __global__ void __launch_bounds__(kL1Threads, 1) heads_l1_kernel(const __grid_co
 int udal_heads_l1_layer(udal_ctx* ctx, const void* const* in, int NB, int T, const float* dw, const float* const* wf,
                         const float* const* fb, const float* const* in_scale, const float* const* out_scale,
                         const float* ones, float inv_keep, void* const* out) {
+  const bool fp16 = ctx->cfg.heads_mode == UDAL_HEADS_FP16_TC;
+  const CUtensorMapDataType dt16 = fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
   EncodeTiledFn encode = get_encode();
   UDAL_REQUIRE(encode != nullptr, "cuTensorMapEncodeTiled is not available from this driver");
   UDAL_REQUIRE((in_scale == nullptr) == (out_scale == nullptr), "layer 1: both dropout scale tables or none");
@@ -413,10 +414,8 @@ int udal_heads_l1_layer(udal_ctx* ctx, const void* const* in, int NB, int T, con
   int off = 0;
   for (int l = 0; l < c.num_levels; ++l) {
     const int H = c.level_h[l], W = c.level_w[l];
-    UDAL_TRY(encode_nhwc(encode, &maps.in[l], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, in[l], NB, H, W, KF, KF, IG_BOXW, IG_ROWS,
-                         false));
-    UDAL_TRY(encode_nhwc(encode, &maps.out[l], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, out[l], T * NB, H, W, KF, KF, IG_TW, IG_TH,
-                         true));
+    UDAL_TRY(encode_nhwc(encode, &maps.in[l], dt16, 2, in[l], NB, H, W, KF, KF, IG_BOXW, IG_ROWS, false));
+    UDAL_TRY(encode_nhwc(encode, &maps.out[l], dt16, 2, out[l], T * NB, H, W, KF, KF, IG_TW, IG_TH, true));
     p.H[l] = H;
     p.W[l] = W;
     p.tiles_x[l] = (W + IG_TW - 1) / IG_TW;
@@ -438,8 +437,13 @@ int udal_heads_l1_layer(udal_ctx* ctx, const void* const* in, int NB, int T, con
   UDAL_REQUIRE(c.num_levels <= kL1MaxLevels, "the tensor-core head sampler keeps the weights of at most %d pyramid levels "
                "resident (got %d) - use heads_mode fp32", kL1MaxLevels, c.num_levels);
   const int smem = l1_smem(c.num_levels);
-  UDAL_CUDA(cudaFuncSetAttribute(heads_l1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  heads_l1_kernel<<<grid, kL1Threads, smem, ctx->stream>>>(maps, p);
+  if (fp16) {
+    UDAL_CUDA(cudaFuncSetAttribute(heads_l1_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    heads_l1_kernel<true><<<grid, kL1Threads, smem, ctx->stream>>>(maps, p);
+  } else {
+    UDAL_CUDA(cudaFuncSetAttribute(heads_l1_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    heads_l1_kernel<false><<<grid, kL1Threads, smem, ctx->stream>>>(maps, p);
+  }
   UDAL_CHECK_LAUNCH(ctx);
   return UDAL_OK;
 }

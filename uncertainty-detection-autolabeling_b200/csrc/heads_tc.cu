@@ -458,7 +458,12 @@ int udal_heads_l1_layer(udal_ctx* ctx, const void* const* in, int NB, int T, con
                         const float* ones, float inv_keep, void* const* out);
 int udal_heads_fused_predict(udal_ctx* ctx, int head, const void* const* in, int NB, int T, const void* wimg, int rows,
                              const float* bias, const udal_prenms_out* pre);
-int udal_heads_tc_use_ig = 1;  // 0: every layer through the per-tile kernel (debug / comparison)
+int udal_heads_tc_use_ig = 1;  // 0: every layer through the per-tile kernel (debug / comparison; bf16 mode only)
+// heads_dw.cu: fp16 mode, tower layers >= 2 and predict layers (depthwise on the CUDA cores, pointwise on tcgen05)
+int udal_heads_dw_prepare(udal_ctx* ctx, int head);
+int udal_heads_dw_layer(udal_ctx* ctx, int head, int layer, const void* const* in, int NB, const float* const* ep_scale,
+                        const float* const* ep_bias, const float* const* out_scale, void* const* out);
+int udal_heads_dw_fused_predict(udal_ctx* ctx, int head, const void* const* in, int NB, int T, const udal_prenms_out* pre);
 
 int udal_heads_l0_prepare(udal_ctx* ctx, int head);  // heads_wide.cu: tower layer 0 of the 64-channel heads
 int udal_heads_l0_layer(udal_ctx* ctx, int head, const float* const* feats, int B, void* const* out);
@@ -562,6 +567,7 @@ int udal_heads_tc_prepare(udal_ctx* ctx, int head) {
   }
   UDAL_CUDA(cudaStreamSynchronize(ctx->stream));
   UDAL_TRY(udal_heads_l0_prepare(ctx, head));
+  if (c.heads_mode == UDAL_HEADS_FP16_TC) UDAL_TRY(udal_heads_dw_prepare(ctx, head));
   return UDAL_OK;
 }
 
@@ -616,7 +622,8 @@ static int run_tower_tc(udal_ctx* ctx, int head, const float* const* feats, int 
     // layer 1 reads the sample-invariant layer-0 output: one CTA per (tile, image) loops the samples
     p.nt = (layer == 1 && mc) ? T : 1;
     const int grid_y = layer <= 1 ? B : NBt;
-    const bool use_ig = udal_heads_tc_use_ig && layer >= 2;
+    const bool fp16 = c.heads_mode == UDAL_HEADS_FP16_TC;
+    const bool use_ig = (udal_heads_tc_use_ig || fp16) && layer >= 2;
     for (int l = 0; l < L; ++l) {
       const size_t lvl = (size_t)ctx->level_pix_off[l] * KF;
       if (layer == 0) p.in[l] = feats[l];
@@ -639,13 +646,26 @@ static int run_tower_tc(udal_ctx* ctx, int head, const float* const* feats, int 
         p.fb[l] = h.fold_bias + ((size_t)layer * L + l) * KF;
       }
     }
-    if (udal_heads_tc_use_ig && udal_heads_l0_persistent && layer == 0) {
+    if (fp16 && layer >= 2) {
+      // fp16 mode: depthwise on the CUDA cores (packed fp16) + one K = 64 GEMM per tile on tcgen05 (heads_dw.cu)
+      if (predict && fused_pre) {
+        UDAL_REQUIRE(mc, "fused predict kernels: MC dropout on both heads");
+        UDAL_TRY(udal_heads_dw_fused_predict(ctx, head, p.in, B, T, fused_pre));
+      } else {
+        const float* ep_scale[UDAL_MAX_LEVELS];
+        for (int l = 0; l < L; ++l) ep_scale[l] = predict ? nullptr : h.bn_scale + ((size_t)layer * L + l) * KF;
+        UDAL_TRY(udal_heads_dw_layer(ctx, head, layer, p.in, NBt, ep_scale, p.fb, mc && !predict ? p.out_scale : nullptr, p.out));
+      }
+      mark();
+      continue;
+    }
+    if ((fp16 || (udal_heads_tc_use_ig && udal_heads_l0_persistent)) && layer == 0) {
       // fp32 BiFPN features -> bf16 layer-0 output: persistent kernel, depthwise on the CUDA cores, pointwise on tcgen05
       UDAL_TRY(udal_heads_l0_layer(ctx, head, feats, B, p.out));
       mark();
       continue;
     }
-    if (udal_heads_tc_use_ig && layer == 1) {
+    if ((udal_heads_tc_use_ig || fp16) && layer == 1) {
       // sample-invariant input: persistent kernel, one depthwise pass per image, T samples back to back
       const size_t tower_img = (size_t)9 * KF * KF, pred_img = (size_t)9 * npad_p * KF;
       const float* ones = reinterpret_cast<const float*>(reinterpret_cast<const __nv_bfloat16*>(h.ig_w) +

@@ -3,6 +3,7 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include "udal_common.cuh"
 
@@ -76,6 +77,31 @@ __device__ __forceinline__ uint32_t ig_pack(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
 }
+// 16-bit operand format of the tensor-core heads: bf16 (range of fp32, 8-bit significand) or fp16 (11-bit significand: 8x
+// smaller rounding error; what the reference's own GPU export computes in, mixed_float16, infer_lib.py:429-431)
+template <bool FP16>
+__device__ __forceinline__ uint32_t ig_pack16(float lo, float hi) {
+  if constexpr (FP16) {
+    const __half2 v = __floats2half2_rn(lo, hi);
+    return *reinterpret_cast<const uint32_t*>(&v);
+  } else {
+    return ig_pack(lo, hi);
+  }
+}
+template <bool FP16>
+__device__ __forceinline__ float2 ig_unpack16(uint32_t v) {
+  if constexpr (FP16) {
+    return __half22float2(*reinterpret_cast<const __half2*>(&v));
+  } else {
+    return make_float2(__uint_as_float(v << 16), __uint_as_float(v & 0xffff0000u));
+  }
+}
+// tcgen05 instruction descriptor, kind::f16: fp32 accumulate, A / B both bf16 (format 1) or fp16 (format 0), K-major, M = 128
+template <bool FP16>
+__host__ __device__ constexpr uint32_t ig_idesc(int n) {
+  return (1u << 4) | (FP16 ? 0u : ((1u << 7) | (1u << 10))) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24);
+}
+
 __device__ __forceinline__ float ig_swish_h(float h) {  // h = x / 2
   float t;
   asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
@@ -180,6 +206,76 @@ __device__ __forceinline__ void ig_tma_store(const CUtensorMap* map, uint32_t sr
   asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(map),
                "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
                : "memory");
+}
+
+// ---- depthwise 3x3 on the CUDA cores in packed fp16 (heads_dw.cu) ------------------------------------------------------
+// 128 builder threads turn one staged halo tile - linear [18][10] pixels x 64 channels fp16 (128 B per pixel) - into the A
+// operand of the pointwise GEMM: [128 px][64 ch] fp16, K-major, 128B swizzle.  thread = 8-channel group (one 16-byte chunk)
+// x column pair x row quarter: a 4-row x 2-column patch of outputs, fed by a sliding window over 6 x 4 input pixels (24
+// LDS.128 for 8 outputs - the 9-fold tap reuse happens in registers), 288 HFMA2 (two fp16 FMAs per lane and issue slot: twice
+// the fp32 rate).  fp16 accumulation of the 9 taps adds ~sqrt(9) * 2^-12 relative to a result that is rounded to fp16 (2^-12)
+// for the tensor core anyway.
+constexpr int kDwBuilderThreads = 128;
+struct DwWeights {
+  __half2 w[9][4];  // this thread's 8 channels of the 9 taps
+};
+__device__ __forceinline__ void dw_load_weights(const float* __restrict__ dw /* [9][64] fp32 */, int cg, DwWeights& W) {
+#pragma unroll
+  for (int tp = 0; tp < 9; ++tp) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(dw + tp * KF + cg * 8));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(dw + tp * KF + cg * 8 + 4));
+    W.w[tp][0] = __floats2half2_rn(a.x, a.y);
+    W.w[tp][1] = __floats2half2_rn(a.z, a.w);
+    W.w[tp][2] = __floats2half2_rn(b.x, b.y);
+    W.w[tp][3] = __floats2half2_rn(b.z, b.w);
+  }
+}
+// rows_valid: tile rows that lie inside the image (rows past it are never stored: their A rows stay as they are)
+__device__ __forceinline__ void dw_build_tile(const uint8_t* __restrict__ sIn, uint8_t* __restrict__ sA, const DwWeights& W, int btid,
+                                              int rows_valid) {
+  const int cg = btid & 7, x0 = 2 * ((btid >> 3) & 3), y0 = 4 * (btid >> 5);
+  if (y0 >= rows_valid) return;  // warp-uniform: a warp is one row quarter
+  __half2 acc[4][2][4];
+#pragma unroll
+  for (int y = 0; y < 4; ++y)
+#pragma unroll
+    for (int oc = 0; oc < 2; ++oc)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) acc[y][oc][q] = __floats2half2_rn(0.f, 0.f);
+#pragma unroll
+  for (int r = 0; r < 6; ++r) {
+    uint4 in[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+      in[c] = *reinterpret_cast<const uint4*>(sIn + (size_t)((y0 + r) * IG_BOXW + x0 + c) * 128 + cg * 16);
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy) {
+      const int y = r - dy;
+      if (y >= 0 && y < 4) {
+#pragma unroll
+        for (int oc = 0; oc < 2; ++oc)
+#pragma unroll
+          for (int dx = 0; dx < 3; ++dx) {
+            const __half2* v = reinterpret_cast<const __half2*>(&in[oc + dx]);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) acc[y][oc][q] = __hfma2(v[q], W.w[dy * 3 + dx][q], acc[y][oc][q]);
+          }
+      }
+    }
+    if (r >= 2) {
+      const int y = r - 2;
+#pragma unroll
+      for (int oc = 0; oc < 2; ++oc) {
+        const int m = (y0 + y) * IG_TW + x0 + oc;
+        uint4 o;
+        o.x = *reinterpret_cast<const uint32_t*>(&acc[y][oc][0]);
+        o.y = *reinterpret_cast<const uint32_t*>(&acc[y][oc][1]);
+        o.z = *reinterpret_cast<const uint32_t*>(&acc[y][oc][2]);
+        o.w = *reinterpret_cast<const uint32_t*>(&acc[y][oc][3]);
+        *reinterpret_cast<uint4*>(sA + (size_t)m * 128 + (((uint32_t)cg ^ (uint32_t)(m & 7)) << 4)) = o;
+      }
+    }
+  }
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,

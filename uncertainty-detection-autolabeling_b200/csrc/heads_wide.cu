@@ -83,7 +83,7 @@ struct WdMaps {
 __device__ __forceinline__ void wd_epi_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 __device__ __forceinline__ void wd_half_sync(int hc) { asm volatile("bar.sync %0, 128;" ::"r"(2 + hc) : "memory"); }
 
-template <int CH, bool F32IN>
+template <int CH, bool F32IN, bool FP16>
 __global__ void __launch_bounds__(kWdThreads, 1) heads_wide_kernel(const __grid_constant__ WdMaps maps, const WdParams p) {
   using S = WdShape<CH, F32IN>;
   constexpr int WF = CH, WD_STAGE = S::STAGE, WD_A = S::A, WD_B = S::B, WD_OUT = S::OUT, WD_IN = S::IN, WD_BAR = S::BAR,
@@ -163,7 +163,7 @@ __global__ void __launch_bounds__(kWdThreads, 1) heads_wide_kernel(const __grid_
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(WF >> 3) << 17) | ((128u >> 4) << 24);
+    constexpr uint32_t idesc = ig_idesc<FP16>(WF);
     if (lane == 0) bar_wait(bar_b, 0);  // weights resident
     __syncwarp();
     for (int i = 0;; ++i) {
@@ -246,8 +246,8 @@ __global__ void __launch_bounds__(kWdThreads, 1) heads_wide_kernel(const __grid_
               v23 = make_float2(f.z, f.w);
             } else {
               const uint2 raw2 = *reinterpret_cast<const uint2*>(px + q4 * 8);
-              v01 = make_float2(__uint_as_float(raw2.x << 16), __uint_as_float(raw2.x & 0xffff0000u));
-              v23 = make_float2(__uint_as_float(raw2.y << 16), __uint_as_float(raw2.y & 0xffff0000u));
+              v01 = ig_unpack16<FP16>(raw2.x);
+              v23 = ig_unpack16<FP16>(raw2.y);
             }
 #pragma unroll
             for (int dy = 0; dy < 3; ++dy) {
@@ -262,8 +262,8 @@ __global__ void __launch_bounds__(kWdThreads, 1) heads_wide_kernel(const __grid_
             const int y = r - 2;
             const int m = (8 * half + y) * IG_TW + x;
             uint2 o;
-            o.x = ig_pack(acc[y][0].x * sc.x, acc[y][0].y * sc.y);
-            o.y = ig_pack(acc[y][1].x * sc.z, acc[y][1].y * sc.w);
+            o.x = ig_pack16<FP16>(acc[y][0].x * sc.x, acc[y][0].y * sc.y);
+            o.y = ig_pack16<FP16>(acc[y][1].x * sc.z, acc[y][1].y * sc.w);
             *reinterpret_cast<uint2*>(sA + (size_t)m * 128 + ((chunk ^ (uint32_t)(m & 7)) << 4) + sub) = o;
           }
         }
@@ -354,10 +354,10 @@ __global__ void __launch_bounds__(kWdThreads, 1) heads_wide_kernel(const __grid_
               v[2 * e + 1] = sw.y;
             }
             uint4 o;
-            o.x = ig_pack(v[0], v[1]);
-            o.y = ig_pack(v[2], v[3]);
-            o.z = ig_pack(v[4], v[5]);
-            o.w = ig_pack(v[6], v[7]);
+            o.x = ig_pack16<FP16>(v[0], v[1]);
+            o.y = ig_pack16<FP16>(v[2], v[3]);
+            o.z = ig_pack16<FP16>(v[4], v[5]);
+            o.w = ig_pack16<FP16>(v[6], v[7]);
             *reinterpret_cast<uint4*>(ob + (col >> 6) * 16384 + m * 128 + (((uint32_t)((col & 63) >> 3) ^ swz) << 4)) = o;
           }
         }
@@ -438,6 +438,7 @@ __global__ void __launch_bounds__(kWdThreads, 1) heads_wide_kernel(const __grid_
 }
 
 // fp32 [n_px][F] features -> bf16 [n_px][128], zero past F
+template <bool FP16>
 __global__ void wide_convert_kernel(const float* __restrict__ in, size_t n_px, int F, __nv_bfloat16* __restrict__ out) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // one thread per 4 output channels
   if (i >= n_px * (WF / 4)) return;
@@ -446,12 +447,13 @@ __global__ void wide_convert_kernel(const float* __restrict__ in, size_t n_px, i
   float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
   if (c < F) v = __ldg(reinterpret_cast<const float4*>(in + px * F + c));
   uint2 o;
-  o.x = ig_pack(v.x, v.y);
-  o.y = ig_pack(v.z, v.w);
+  o.x = ig_pack16<FP16>(v.x, v.y);
+  o.y = ig_pack16<FP16>(v.z, v.w);
   *reinterpret_cast<uint2*>(out + px * WF + c) = o;
 }
 
 // weight image of one pointwise matrix: wimg[atom = k / 64][n][k % 64] = bf16(w[k][n0 + n]) (n < cout, k < F), 128B swizzle
+template <bool FP16>
 __global__ void wide_weights_kernel(const float* __restrict__ w, int F, int ldw, int n0, int cout, __nv_bfloat16* __restrict__ wimg,
                                     int ch = WF) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -461,7 +463,8 @@ __global__ void wide_weights_kernel(const float* __restrict__ w, int F, int ldw,
   if (k < F && n < cout) v = w[(size_t)k * ldw + n0 + n];
   const int kk = k & 63;
   const size_t byte = (size_t)(k >> 6) * ((size_t)ch * 128) + (size_t)n * 128 + (size_t)((((kk >> 3) ^ (n & 7)) << 4) + (kk & 7) * 2);
-  wimg[byte / 2] = __float2bfloat16_rn(v);
+  if constexpr (FP16) reinterpret_cast<__half*>(wimg)[byte / 2] = __float2half_rn(v);
+  else wimg[byte / 2] = __float2bfloat16_rn(v);
 }
 
 // dst[9][128] = src[9][F] zero padded
@@ -496,6 +499,7 @@ int udal_heads_wide_ok(const udal_ctx* ctx) { return ctx->cfg.num_filters > KF &
 // ep [R][L][2][128] + [chunks][2][128]
 int udal_heads_wide_prepare(udal_ctx* ctx, int head) {
   const udal_config& c = ctx->cfg;
+  const bool fp16 = c.heads_mode == UDAL_HEADS_FP16_TC;
   udal_head_weights_dev& h = ctx->heads[head];
   const int F = c.num_filters, R = c.repeats, L = c.num_levels;
   UDAL_REQUIRE(udal_heads_wide_ok(ctx) && F % 4 == 0, "wide tensor-core heads: fpn_num_filters %d not in (64, 128]", F);
@@ -514,7 +518,8 @@ int udal_heads_wide_prepare(udal_ctx* ctx, int head) {
   float* ep = h.wide_f + (size_t)(R + 1) * 9 * WF;
   const int tb = 256;
   for (int r = 0; r < R; ++r) {
-    wide_weights_kernel<<<(WF * WF + tb - 1) / tb, tb, 0, ctx->stream>>>(h.pw + (size_t)r * F * F, F, F, 0, F, img + (size_t)r * WF * WF);
+    if (fp16) wide_weights_kernel<true><<<(WF * WF + tb - 1) / tb, tb, 0, ctx->stream>>>(h.pw + (size_t)r * F * F, F, F, 0, F, img + (size_t)r * WF * WF);
+    else wide_weights_kernel<false><<<(WF * WF + tb - 1) / tb, tb, 0, ctx->stream>>>(h.pw + (size_t)r * F * F, F, F, 0, F, img + (size_t)r * WF * WF);
     UDAL_CHECK_LAUNCH(ctx);
     wide_dw_kernel<<<(9 * WF + tb - 1) / tb, tb, 0, ctx->stream>>>(h.dw + (size_t)r * 9 * F, F, dwp + (size_t)r * 9 * WF);
     UDAL_CHECK_LAUNCH(ctx);
@@ -528,7 +533,8 @@ int udal_heads_wide_prepare(udal_ctx* ctx, int head) {
   UDAL_CHECK_LAUNCH(ctx);
   for (int q = 0; q < chunks; ++q) {
     const int n0 = q * WF, nc = h.cout - n0 < WF ? h.cout - n0 : WF;
-    wide_weights_kernel<<<(WF * WF + tb - 1) / tb, tb, 0, ctx->stream>>>(h.pwp, F, h.cout, n0, nc, img + (size_t)(R + q) * WF * WF);
+    if (fp16) wide_weights_kernel<true><<<(WF * WF + tb - 1) / tb, tb, 0, ctx->stream>>>(h.pwp, F, h.cout, n0, nc, img + (size_t)(R + q) * WF * WF);
+    else wide_weights_kernel<false><<<(WF * WF + tb - 1) / tb, tb, 0, ctx->stream>>>(h.pwp, F, h.cout, n0, nc, img + (size_t)(R + q) * WF * WF);
     UDAL_CHECK_LAUNCH(ctx);
     wide_ep_kernel<<<1, WF, 0, ctx->stream>>>(h.bp, nullptr, nullptr, n0, nc, ep + ((size_t)R * L + q) * 2 * WF);
     UDAL_CHECK_LAUNCH(ctx);
@@ -537,8 +543,8 @@ int udal_heads_wide_prepare(udal_ctx* ctx, int head) {
   return UDAL_OK;
 }
 
-template <int CH, bool F32IN>
-static int launch_wide(udal_ctx* ctx, const void* const* in, int in_nb, int NB, const float* const* in_scale, const float* dw,
+template <int CH, bool F32IN, bool FP16>
+static int launch_wide_t(udal_ctx* ctx, const void* const* in, int in_nb, int NB, const float* const* in_scale, const float* dw,
                        const void* wimg, const float* const* ep, int predict, int cout, int ch_off, int ch_total,
                        void* const* out) {
   using S = WdShape<CH, F32IN>;
@@ -564,10 +570,11 @@ static int launch_wide(udal_ctx* ctx, const void* const* in, int in_nb, int NB, 
   int off = 0;
   for (int l = 0; l < c.num_levels; ++l) {
     const int H = c.level_h[l], W = c.level_w[l];
-    UDAL_TRY(encode_nhwc(encode, &maps.in[l], F32IN ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, F32IN ? 4 : 2,
+    constexpr CUtensorMapDataType dt16 = FP16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+    UDAL_TRY(encode_nhwc(encode, &maps.in[l], F32IN ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : dt16, F32IN ? 4 : 2,
                          in[l], in_nb, H, W, CH, CH, IG_BOXW, IG_ROWS, false));
     if (!predict)
-      UDAL_TRY(encode_nhwc(encode, &maps.out[l], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, out[l], NB, H, W, CH, 64, IG_TW, IG_TH, true));
+      UDAL_TRY(encode_nhwc(encode, &maps.out[l], dt16, 2, out[l], NB, H, W, CH, 64, IG_TW, IG_TH, true));
     p.H[l] = H;
     p.W[l] = W;
     p.tiles_x[l] = (W + IG_TW - 1) / IG_TW;
@@ -584,10 +591,20 @@ static int launch_wide(udal_ctx* ctx, const void* const* in, int in_nb, int NB, 
   for (int l = c.num_levels; l <= UDAL_MAX_LEVELS; ++l) p.item_off[l] = off;
   p.items = off;
   const int grid = udal_persistent_grid(ctx, p.items);
-  UDAL_CUDA(cudaFuncSetAttribute(heads_wide_kernel<CH, F32IN>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::SMEM));
-  heads_wide_kernel<CH, F32IN><<<grid, kWdThreads, S::SMEM, ctx->stream>>>(maps, p);
+  UDAL_CUDA(cudaFuncSetAttribute(heads_wide_kernel<CH, F32IN, FP16>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::SMEM));
+  heads_wide_kernel<CH, F32IN, FP16><<<grid, kWdThreads, S::SMEM, ctx->stream>>>(maps, p);
   UDAL_CHECK_LAUNCH(ctx);
   return UDAL_OK;
+}
+
+// 16-bit format by the context's heads mode
+template <int CH, bool F32IN>
+static int launch_wide(udal_ctx* ctx, const void* const* in, int in_nb, int NB, const float* const* in_scale, const float* dw,
+                       const void* wimg, const float* const* ep, int predict, int cout, int ch_off, int ch_total,
+                       void* const* out) {
+  if (ctx->cfg.heads_mode == UDAL_HEADS_FP16_TC)
+    return launch_wide_t<CH, F32IN, true>(ctx, in, in_nb, NB, in_scale, dw, wimg, ep, predict, cout, ch_off, ch_total, out);
+  return launch_wide_t<CH, F32IN, false>(ctx, in, in_nb, NB, in_scale, dw, wimg, ep, predict, cout, ch_off, ch_total, out);
 }
 
 // ---- layer 0 of the 64-channel towers through the same kernel (CH = 64, fp32 BiFPN features in) ----
@@ -605,7 +622,10 @@ int udal_heads_l0_prepare(udal_ctx* ctx, int head) {
   h.l0_ep = nullptr;
   UDAL_CUDA(cudaMalloc(&h.l0_w, (size_t)KF * KF * 2));
   UDAL_CUDA(cudaMalloc(&h.l0_ep, (size_t)L * 2 * KF * sizeof(float)));
-  wide_weights_kernel<<<(KF * KF + 255) / 256, 256, 0, ctx->stream>>>(h.pw, KF, KF, 0, KF, reinterpret_cast<__nv_bfloat16*>(h.l0_w), KF);
+  if (c.heads_mode == UDAL_HEADS_FP16_TC)
+    wide_weights_kernel<true><<<(KF * KF + 255) / 256, 256, 0, ctx->stream>>>(h.pw, KF, KF, 0, KF, reinterpret_cast<__nv_bfloat16*>(h.l0_w), KF);
+  else
+    wide_weights_kernel<false><<<(KF * KF + 255) / 256, 256, 0, ctx->stream>>>(h.pw, KF, KF, 0, KF, reinterpret_cast<__nv_bfloat16*>(h.l0_w), KF);
   UDAL_CHECK_LAUNCH(ctx);
   for (int l = 0; l < L; ++l) {
     wide_ep_kernel<<<1, KF, 0, ctx->stream>>>(h.bias, h.bn_scale + (size_t)l * KF, h.bn_shift + (size_t)l * KF, 0, KF,
@@ -704,7 +724,8 @@ int udal_heads_wide_sample(udal_ctx* ctx, const float* const* feats, int batch, 
     __nv_bfloat16* dst = f16 + (size_t)batch * ctx->level_pix_off[l] * WF;
     const size_t n_px = (size_t)batch * c.level_h[l] * c.level_w[l];
     const size_t nthr = n_px * (WF / 4);
-    wide_convert_kernel<<<(unsigned)((nthr + 255) / 256), 256, 0, ctx->stream>>>(feats[l], n_px, F, dst);
+    if (c.heads_mode == UDAL_HEADS_FP16_TC) wide_convert_kernel<true><<<(unsigned)((nthr + 255) / 256), 256, 0, ctx->stream>>>(feats[l], n_px, F, dst);
+    else wide_convert_kernel<false><<<(unsigned)((nthr + 255) / 256), 256, 0, ctx->stream>>>(feats[l], n_px, F, dst);
     UDAL_CHECK_LAUNCH(ctx);
     feats16[l] = dst;
   }

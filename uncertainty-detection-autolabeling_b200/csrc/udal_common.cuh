@@ -38,6 +38,10 @@ struct udal_head_weights_dev {
   int wide_chunks = 0;      // predict layer as chunks of <= 128 channels
   void* l0_w = nullptr;     // 64-channel towers, layer 0 through heads_wide_kernel<64, fp32 in>: bf16 [64 n][64 k] image
   float* l0_ep = nullptr;   // ... and its epilogue tables [L][2][64] (BN scale | folded bias)
+  // fp16 mode (heads_dw.cu): depthwise on the CUDA cores, pointwise on tcgen05
+  void* dwh_w = nullptr;    // fp16 images: tower layers 2..R-1 [64][64] | predict chunks [dwh_chunks][dwh_rows][64] | fused predict [dwh_frows][64]
+  float* dwh_f = nullptr;   // predict bias per chunk [dwh_chunks][dwh_rows] | fused bias [dwh_frows] | ones [96]
+  int dwh_chunks = 0, dwh_chunk = 0, dwh_rows = 0, dwh_frows = 0;
   void* ig_w = nullptr;  // implicit-GEMM weight images: [(R-2)*L tower layers >= 2][9][64][64] then predict [9][Npad][64], bf16
 };
 

@@ -61,7 +61,11 @@ def anchor_table(min_level, max_level, num_scales, aspect_ratios, anchor_scale, 
                 b = np.vstack((yv - half_y, xv - half_x, yv + half_y, xv + half_x))
                 boxes_level.append(np.expand_dims(np.swapaxes(b, 0, 1), axis=1))
         boxes_all.append(np.concatenate(boxes_level, axis=1).reshape([-1, 4]))
-    return np.vstack(boxes_all).astype(np.float32)
+    # C-contiguous [N,4]: the raw pointer of this array is uploaded.  (astype keeps the memory order of its input, and
+    # np.concatenate of the transposed per-aspect views above comes out Fortran-ordered for large levels - the device then
+    # read a scrambled table at every geometry above ~100 px, silently: round 1 never compared decoded boxes at those
+    # sizes with the oracle.  tests/test_abi_cpu.py pins the layout.)
+    return np.ascontiguousarray(np.vstack(boxes_all), dtype=np.float32)
 
 
 def _key(params, device_id, heads_mode):
@@ -155,7 +159,11 @@ class Engine:
         cfg.nms_variant_old = 1 if params.get("tf_nms_variant", "new") == "old" else 0
         cfg.max_nms_inputs = int(nms.get("max_nms_inputs", 0) or 0)
         cfg.max_output_size = int(nms.get("max_output_size", 100))
-        cfg.heads_mode = _lib.HEADS_BF16_TC if heads_mode in ("bf16", "bf16_tc") else _lib.HEADS_FP32
+        modes = {"fp32": _lib.HEADS_FP32, "bf16": _lib.HEADS_BF16_TC, "bf16_tc": _lib.HEADS_BF16_TC,
+                 "fp16": _lib.HEADS_FP16_TC, "fp16_tc": _lib.HEADS_FP16_TC}
+        if heads_mode not in modes:
+            raise ValueError("heads_mode must be one of fp32 | fp16 | bf16, got %r" % (heads_mode,))
+        cfg.heads_mode = modes[heads_mode]
         cfg.prefilter_k = int(params.get("nms_prefilter_k", 0) or 0)
         self.cfg = cfg
         self.ctx = device.Context(cfg)
@@ -169,6 +177,8 @@ class Engine:
         self.N = self.anchors_host.shape[0]
         self.P = sum(a * b for a, b in self.level_hw)
         assert self.N == self.P * self.A
+        self.anchors_host = np.ascontiguousarray(self.anchors_host, dtype=np.float32)
+        assert self.anchors_host.flags["C_CONTIGUOUS"] and self.anchors_host.shape == (self.N, 4)
         _lib.check(self.lib.udal_set_anchors(self.ctx.handle, self.anchors_host.ctypes.data, self.N))
         self.box_channels = 4 * self.A * (2 if self.la else 1)
         self.max_out = cfg.max_output_size
