@@ -34,23 +34,30 @@ def u():
     return udal_b200
 
 
-# asserted tolerances per heads mode, on the DECODED quantities (measured values: profiles/r2_parity_*.json)
-#   logit_abs        max |mean logit - oracle|                       (logit units)
-#   score_rel        max relative error of sigmoid(max_c mean logit)
-#   box_rel_anchor   max |corner - oracle| / anchor side              (fraction of the anchor size)
-#   box_px_p999      99.9-percentile corner error in pixels
-#   albox_rel        max relative error of the aleatoric std
-#   mcbox_abs_anchor max |mcbox - oracle| / anchor side
-#   mc_inflation     |mean(std_device) / mean(std_oracle) - 1| for mcbox and mcclass (16-bit noise adds to the MC std)
-#   argmax_agree     min fraction of anchors with the oracle's class
-#   matched          min fraction of the oracle's detections with an IoU >= 0.9 same-class device detection
+# asserted tolerances per heads mode, on the DECODED quantities.  Measured values (B200, profiles/r2_parity_*.json,
+# DESIGN.md 3): fp16 / bf16 at the bench geometry - logits 1.4e-3 / 8.4e-3, corners 0.18 / 1.15 px (99.9 %),
+# aleatoric std 0.7 % / 3.4 % (max), MC-std inflation < 3e-4 in both modes.
+#   logit_abs     max |mean logit - oracle|                                       (logit units)
+#   score_rel     max relative error of sigmoid(max_c mean logit)
+#   box_rel       |corner - oracle| / max(anchor side, oracle box side): 99.9 % quantile and max
+#   box_px_p999   99.9-percentile corner error in pixels
+#   albox_rel     max relative error of the aleatoric std
+#   mcbox_abs     |mcbox - oracle| / max(anchor side, oracle box side): 99.9 % quantile and max
+#   mcclass_abs   max |std of the logits over T - oracle|
+#   mc_inflation  |mean(std_device) / mean(std_oracle) - 1| for mcbox and mcclass: how much the 16-bit rounding noise
+#                 of the head GEMMs adds to the epistemic (MC) standard deviations
+#   argmax_agree  min fraction of anchors with the oracle's class (near-ties of two class logits may flip)
+#   matched       min fraction of the oracle's detections with an IoU >= 0.9 same-class device detection
 TOL = {
-    "bf16": dict(logit_abs=6e-2, score_rel=6e-2, box_rel_anchor=4e-2, box_px_p999=6.0, albox_rel=8e-2,
-                 mcbox_abs_anchor=1.5e-2, mcclass_abs=3e-2, mc_inflation=0.05, argmax_agree=0.97, matched=0.5),
-    "fp16": dict(logit_abs=1e-2, score_rel=1e-2, box_rel_anchor=6e-3, box_px_p999=1.0, albox_rel=1.2e-2,
-                 mcbox_abs_anchor=2.5e-3, mcclass_abs=5e-3, mc_inflation=0.01, argmax_agree=0.995, matched=0.8),
-    "fp32": dict(logit_abs=2e-4, score_rel=2e-4, box_rel_anchor=1e-4, box_px_p999=2e-2, albox_rel=2e-4,
-                 mcbox_abs_anchor=1e-4, mcclass_abs=1e-4, mc_inflation=1e-3, argmax_agree=0.9999, matched=0.97),
+    "bf16": dict(logit_abs=2e-2, score_rel=2e-2, box_rel_p999=2.5e-2, box_rel_max=0.3, box_px_p999=3.0, albox_rel=8e-2,
+                 mcbox_abs_p999=1.2e-2, mcbox_abs_max=0.3, mcclass_abs=6e-3, mc_inflation=2e-3, argmax_agree=0.99,
+                 matched=0.95),
+    "fp16": dict(logit_abs=4e-3, score_rel=4e-3, box_rel_p999=4e-3, box_rel_max=3e-2, box_px_p999=0.6, albox_rel=2e-2,
+                 mcbox_abs_p999=2.5e-3, mcbox_abs_max=3e-2, mcclass_abs=1.5e-3, mc_inflation=2e-3, argmax_agree=0.998,
+                 matched=0.97),
+    "fp32": dict(logit_abs=2e-4, score_rel=2e-4, box_rel_p999=1e-4, box_rel_max=1e-4, box_px_p999=2e-2, albox_rel=2e-4,
+                 mcbox_abs_p999=1e-4, mcbox_abs_max=1e-4, mcclass_abs=1e-4, mc_inflation=1e-3, argmax_agree=0.9999,
+                 matched=0.97),
 }
 
 
@@ -74,6 +81,8 @@ def per_anchor_stats(dev, ref, anchors):
     boxes, uncerts, scores, classes, multi = ref
     mcclass, albox, mcbox = uncerts
     side = np.stack([anchors[:, 2] - anchors[:, 0], anchors[:, 3] - anchors[:, 1]] * 2, -1)[None]  # [1,N,4]
+    bside = np.stack([boxes[..., 2] - boxes[..., 0], boxes[..., 3] - boxes[..., 1]] * 2, -1)      # oracle box sides
+    side = np.maximum(side, bside)   # the scale of the box: anchor size, or the decoded size where exp(th) made it larger
     d_box = np.abs(dev["boxes"].astype(np.float64) - boxes)
     st = {
         "anchors": int(anchors.shape[0]), "images": int(boxes.shape[0]),
@@ -81,12 +90,12 @@ def per_anchor_stats(dev, ref, anchors):
         "logit_abs_p999": float(np.quantile(np.abs(dev["mean_logits"] - multi), 0.999)),
         "score_rel_max": float((np.abs(dev["scores"] - scores) / scores).max()),
         "box_px_max": float(d_box.max()), "box_px_p999": float(np.quantile(d_box, 0.999)),
-        "box_rel_anchor_max": float((d_box / side).max()),
-        "box_rel_anchor_p999": float(np.quantile(d_box / side, 0.999)),
+        "box_rel_max": float((d_box / side).max()),
+        "box_rel_p999": float(np.quantile(d_box / side, 0.999)),
         "albox_rel_max": float((np.abs(dev["albox"] - albox) / albox).max()),
         "albox_rel_p999": float(np.quantile(np.abs(dev["albox"] - albox) / albox, 0.999)),
-        "mcbox_abs_anchor_max": float((np.abs(dev["mcbox"] - mcbox) / side).max()),
-        "mcbox_abs_anchor_p999": float(np.quantile(np.abs(dev["mcbox"] - mcbox) / side, 0.999)),
+        "mcbox_abs_max": float((np.abs(dev["mcbox"] - mcbox) / side).max()),
+        "mcbox_abs_p999": float(np.quantile(np.abs(dev["mcbox"] - mcbox) / side, 0.999)),
         "mcbox_rel_p50": float(np.median(np.abs(dev["mcbox"] - mcbox) / np.maximum(mcbox, 1e-12))),
         "mcbox_inflation": float(dev["mcbox"].astype(np.float64).mean() / mcbox.astype(np.float64).mean() - 1.0),
         "mcclass_abs_max": float(np.abs(dev["std_logits"] - mcclass).max()),
@@ -173,10 +182,12 @@ def test_benchmarked_path_vs_oracle(u, name, size, C, T, batch, mode):
     tol = TOL[mode]
     assert st["logit_abs_max"] <= tol["logit_abs"], st
     assert st["score_rel_max"] <= tol["score_rel"], st
-    assert st["box_rel_anchor_max"] <= tol["box_rel_anchor"], st
+    assert st["box_rel_p999"] <= tol["box_rel_p999"], st
+    assert st["box_rel_max"] <= tol["box_rel_max"], st
     assert st["box_px_p999"] <= tol["box_px_p999"], st
     assert st["albox_rel_max"] <= tol["albox_rel"], st
-    assert st["mcbox_abs_anchor_max"] <= tol["mcbox_abs_anchor"], st
+    assert st["mcbox_abs_p999"] <= tol["mcbox_abs_p999"], st
+    assert st["mcbox_abs_max"] <= tol["mcbox_abs_max"], st
     assert st["mcclass_abs_max"] <= tol["mcclass_abs"], st
     assert abs(st["mcbox_inflation"]) <= tol["mc_inflation"], st
     assert abs(st["mcclass_inflation"]) <= tol["mc_inflation"], st
@@ -203,10 +214,10 @@ def test_fp32_path_end_to_end_vs_oracle(u):
     tol = TOL["fp32"]
     assert st["logit_abs_max"] <= tol["logit_abs"], st
     assert st["score_rel_max"] <= tol["score_rel"], st
-    assert st["box_rel_anchor_max"] <= tol["box_rel_anchor"], st
+    assert st["box_rel_max"] <= tol["box_rel_max"], st
     assert st["albox_rel_max"] <= tol["albox_rel"], st
     # SURVEY hard part 1: two conv implementations differ by ~1e-6 relative per head output, i.e. ~3e-4 px after decode:
     # the epistemic std is compared relative to the box scale
-    assert st["mcbox_abs_anchor_max"] <= tol["mcbox_abs_anchor"], st
+    assert st["mcbox_abs_max"] <= tol["mcbox_abs_max"], st
     assert st["mcclass_abs_max"] <= tol["mcclass_abs"], st
     assert st["argmax_agree"] >= tol["argmax_agree"], st

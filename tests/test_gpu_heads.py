@@ -90,6 +90,11 @@ def test_end_to_end_features_to_detections(u):
 # within a few 1e-2 of the output scale (logit / box-regression units).
 BF16_ATOL = 6e-2
 BF16_RTOL = 3e-2
+# fp16 tensor-core mode (heads_dw.cu): fp16 operands / activations (11-bit significand), packed-fp16 depthwise
+# accumulation, fp32 GEMM accumulation: measured max abs error ~2e-3 (printed by the tests), asserted with margin
+FP16_ATOL = 8e-3
+FP16_RTOL = 4e-3
+TC_TOL = {"bf16": (BF16_RTOL, BF16_ATOL), "fp16": (FP16_RTOL, FP16_ATOL)}
 
 
 @pytest.mark.parametrize("size,C,T,batch,la,rc,rb", [
@@ -106,8 +111,10 @@ BF16_RTOL = 3e-2
     ((360, 640), 10, 4, 1, True, 0.05, 0.05),   # the same on the 1280x720 aspect (odd level sizes 45x80 ... 3x5)
     (128, 20, 2, 1, True, 0.05, 0.0),           # 180 class channels = 3 chunks of 60
 ])
-def test_heads_bf16_tensor_core_vs_oracle(u, size, C, T, batch, la, rc, rb):
-    p = _cfg(u, size, C, T, la, rc, rb, heads_mode="bf16")
+@pytest.mark.parametrize("mode", ["bf16", "fp16"])
+def test_heads_bf16_tensor_core_vs_oracle(u, size, C, T, batch, la, rc, rb, mode):
+    rtol, atol = TC_TOL[mode]
+    p = _cfg(u, size, C, T, la, rc, rb, heads_mode=mode)
     eng = u.engine.get_engine(p)
     L = len(eng.level_hw)
     w = heads_ref.init_head_weights(eng.F, eng.R, L, eng.A, C, la, seed=9, randomize_bn=True)
@@ -125,9 +132,9 @@ def test_heads_bf16_tensor_core_vs_oracle(u, size, C, T, batch, la, rc, rb):
         rb_l = rbox[l] if rb else rbox[l][0]
         assert cls[l].shape == rc_l.shape and box[l].shape == rb_l.shape
         worst = max(worst, float(np.abs(cls[l] - rc_l).max()), float(np.abs(box[l] - rb_l).max()))
-        np.testing.assert_allclose(cls[l], rc_l, rtol=BF16_RTOL, atol=BF16_ATOL)
-        np.testing.assert_allclose(box[l], rb_l, rtol=BF16_RTOL, atol=BF16_ATOL)
-    print("bf16 heads max abs err", worst)
+        np.testing.assert_allclose(cls[l], rc_l, rtol=rtol, atol=atol)
+        np.testing.assert_allclose(box[l], rb_l, rtol=rtol, atol=atol)
+    print(mode, "heads max abs err", worst)
 
 
 @pytest.mark.parametrize("model,size,C,T,batch,la,rc,rb", [
@@ -137,12 +144,14 @@ def test_heads_bf16_tensor_core_vs_oracle(u, size, C, T, batch, la, rc, rb):
     ("efficientdet-d2", (384, 640), 10, 5, 1, True, 0.05, 0.05),  # many work items per CTA: ring wrap-around, every phase
     ("efficientdet-d2", 64, 20, 2, 1, True, 0.05, 0.0),           # 180 class channels = 2 predict chunks of <= 128
 ])
-def test_heads_wide_tensor_core_vs_oracle(u, model, size, C, T, batch, la, rc, rb):
+@pytest.mark.parametrize("mode", ["bf16", "fp16"])
+def test_heads_wide_tensor_core_vs_oracle(u, model, size, C, T, batch, la, rc, rb, mode):
     """fpn_num_filters 88 / 112 (D1 / D2) on the tensor cores: channels zero-padded to 128, depthwise on the CUDA cores,
     pointwise on tcgen05 (heads_wide.cu).  Same bf16 tolerance as the 64-channel path."""
     p = u.hparams_config.get_detection_config(
         model, image_size=size, num_classes=C, enable_softmax=True, loss_attenuation=la,
-        mc_dropout=bool(rc or rb), mc_classheadrate=rc, mc_boxheadrate=rb, mc_dropoutsamp=T, heads_mode="bf16")
+        mc_dropout=bool(rc or rb), mc_classheadrate=rc, mc_boxheadrate=rb, mc_dropoutsamp=T, heads_mode=mode)
+    rtol, atol = TC_TOL[mode]
     eng = u.engine.get_engine(p)
     assert eng.F in (88, 112)
     L = len(eng.level_hw)
@@ -161,9 +170,9 @@ def test_heads_wide_tensor_core_vs_oracle(u, model, size, C, T, batch, la, rc, r
         rb_l = rbox[l] if rb else rbox[l][0]
         assert cls[l].shape == rc_l.shape and box[l].shape == rb_l.shape
         worst = max(worst, float(np.abs(cls[l] - rc_l).max()), float(np.abs(box[l] - rb_l).max()))
-        np.testing.assert_allclose(cls[l], rc_l, rtol=BF16_RTOL, atol=BF16_ATOL)
-        np.testing.assert_allclose(box[l], rb_l, rtol=BF16_RTOL, atol=BF16_ATOL)
-    print("wide bf16 heads max abs err", worst)
+        np.testing.assert_allclose(cls[l], rc_l, rtol=rtol, atol=atol)
+        np.testing.assert_allclose(box[l], rb_l, rtol=rtol, atol=atol)
+    print("wide", mode, "heads max abs err", worst)
     # features -> detections through udal_run (predict layers + decode_moments + NMS) equals the two-stage path
     scales = np.linspace(1.0, 1.5, batch).astype(np.float32)
     det = sampler.detect(feats, scales, masks=masks)
@@ -258,15 +267,18 @@ def test_run_tail_overlap_is_invisible(u):
     ((128, 192), 4, 3, 10),      # BDD100K label map: 90 logits per pixel, the N = 96 variant of the class kernel
     ((40, 200), 3, 2, 10),
     ((720, 1280), 3, 1, 10),     # BASELINE configs[2] geometry (non-integer strides: 720 -> 23 rows at level 5)
+    ((384, 1280), 4, 6, 8),      # 540 work items on 148 CTAs: several items per CTA (ring wrap-around, staging reuse)
+    ((192, 640), 10, 12, 7),
 ])
-def test_fused_predict_decode_matches_unfused(u, size, T, batch, C):
+@pytest.mark.parametrize("mode", ["bf16", "fp16"])
+def test_fused_predict_decode_matches_unfused(u, size, T, batch, C, mode):
     """Serving configuration (A=9, C=8, loss attenuation, l-norm, MC dropout on both heads): udal_run fuses
     the predict layers with the MC moments / decode.  Against predict layers + decode_moments on the
     same activations: mean logits and classes are bit-identical; the standard deviations come from a
     one-pass (shifted) variance and the box quantities from an fp32 decode - both ~1e-6 relative, i.e.
     well inside the 1e-4 contract of BASELINE.json (tolerances below)."""
     import ctypes
-    p = _cfg(u, size, C, T, heads_mode="bf16")
+    p = _cfg(u, size, C, T, heads_mode=mode)
     eng = u.engine.get_engine(p)
     L = len(eng.level_hw)
     w = heads_ref.init_head_weights(eng.F, eng.R, L, eng.A, C, True, seed=21, randomize_bn=True)
