@@ -123,7 +123,7 @@ def test_decode_uncert_vs_golden(u, method):
     np.testing.assert_array_equal(s, g["ka_std"])
     np.testing.assert_allclose(u.anchors.decode_box_outputs(g["t"], g["anchors"]), g["plain"], rtol=1e-6, atol=1e-5)
     with pytest.raises(ValueError):
-        u.utils_box.decode_uncert(g["t"], g["sigma"], g["anchors"], method="sample")
+        u.utils_box.decode_uncert(g["t"], g["sigma"], g["anchors"], method="no-such-method")
 
 
 def test_get_mcuncert_vs_golden(u):
@@ -226,6 +226,37 @@ def test_nms_v5_vs_oracle(u, method, variant, n, extent, prefilter):
         assert valid[s] == rv
         np.testing.assert_array_equal(idx[s], ri)
         np.testing.assert_array_equal(sc[s], rs)
+
+
+@pytest.mark.parametrize("method,variant", [("gaussian", "new"), ("gaussian", "old"), ("hard", "new")])
+@pytest.mark.parametrize("n,spread,prefilter", [(2500, 4.0, 0), (2500, 4.0, 256), (6000, 25.0, 0), (1500, 0.0, 128)])
+def test_nms_v5_dense_clusters_vs_oracle(u, method, variant, n, spread, prefilter):
+    """worst case of the lazy soft-NMS: every candidate overlaps every selection (one cluster of jittered boxes, or n
+    copies of ONE box with distinct / equal scores), with and without a truncating pre-filter (exact redo of the flagged
+    images), through the cooperative CTA kernels and through the round-1 one-warp kernels"""
+    import ctypes
+    eng, p = _nms_engine(u, method, variant, prefilter)
+    rng = np.random.default_rng(n + prefilter)
+    S = 2
+    ctr = np.float32([200.0, 300.0]) + rng.normal(0, spread, (S, n, 2)).astype(np.float32)
+    hw = rng.uniform(60, 90, (S, n, 2)).astype(np.float32) if spread > 0 else np.full((S, n, 2), 70.0, np.float32)
+    boxes = np.concatenate([ctr - hw / 2, ctr + hw / 2], -1).astype(np.float32)
+    scores = rng.uniform(0.05, 1.0, (S, n)).astype(np.float32)
+    scores[1, ::3] = 0.5      # many exact ties: decayed scores collide, the heap's index rule decides
+    sigma_tf, iou_thr, thr, max_out = ref_np.nms_thresholds(p["nms_configs"])
+    ref = [nms_ref.non_max_suppression_v5(boxes[s], scores[s], max_out, iou_thr, thr, sigma_tf, True, variant) for s in range(S)]
+    switch = ctypes.c_int.in_dll(eng.lib, "udal_nms_cta")
+    try:
+        for cta in (1, 0):
+            switch.value = cta
+            idx, sc, valid = (a.numpy() for a in eng.nms_v5(boxes, scores))
+            for s in range(S):
+                ri, rs, rv = ref[s]
+                assert valid[s] == rv, (cta, s)
+                np.testing.assert_array_equal(idx[s], ri)
+                np.testing.assert_array_equal(sc[s], rs)
+    finally:
+        switch.value = 1
 
 
 def test_nms_mirror_padded_and_unpadded(u):

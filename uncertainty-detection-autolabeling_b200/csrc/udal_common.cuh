@@ -223,6 +223,9 @@ int udal_nms_sorted(udal_ctx* ctx, const float* boxes, const float* scores, cons
 int udal_nms_full(udal_ctx* ctx, const float* boxes, const float* scores, int segments, int n,
                   const int32_t* flag, int32_t* sel_row, float* sel_scores, int32_t* valid);
 int udal_nms_prefilter_k(const udal_ctx* ctx, int n);
+extern int udal_nms_cta;
+int udal_nms_epoch(udal_ctx* ctx, const float* boxes, const float* scores, int segments, int n, int32_t* sel_idx,
+                   float* sel_scores, int32_t* valid);
 // top-K pre-filter of a global NMS (scratch of the context's current bank) and the selection that consumes it
 struct udal_nms_plan {
   int kk = 0, kq = 0;
