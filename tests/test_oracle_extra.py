@@ -129,3 +129,93 @@ def test_real_reference_when_tensorflow_is_importable():
     want = ref_np.postprocess_global(dict(p), cls, box, scales)
     for a, b in zip(got, want):
         np.testing.assert_allclose(np.asarray(a), b, rtol=1e-6, atol=1e-6)
+
+
+# ---------------------------------------------------------------------------------------------
+# the "epoch" formulation of the lazy soft-NMS heap used by csrc/nms_cta.cu, transcribed to NumPy and checked against
+# the heap of oracle/nms_v5.c (the CUDA kernel is checked against the same oracle in the -m gpu tests)
+# ---------------------------------------------------------------------------------------------
+def _epoch_nms(boxes, scores, max_out, iou_thr, thr, sigma, old):
+    f32 = np.float32
+    n = len(scores)
+    soft = sigma > 0
+    scale = f32(-0.5 / sigma) if soft else f32(0)
+
+    def iou(a, b):
+        a, b = np.ascontiguousarray(a, f32), np.ascontiguousarray(b, f32)
+        return f32(nms_ref.lib().udal_oracle_iou(a.ctypes.data, b.ctypes.data))
+
+    def step(s, u):
+        w = f32(np.exp(np.float64(f32(f32(scale * u) * u))))
+        if old:
+            if not (u <= iou_thr):
+                w = f32(0)
+            hard = u >= iou_thr
+        else:
+            if not (soft or u <= iou_thr):
+                w = f32(0)
+            hard = (not soft) and u > iou_thr
+        return f32(s * w), hard
+
+    def chain(s, j, frm, to, sel):
+        for q in range(frm, to - 1, -1):
+            s, hard = step(s, iou(boxes[j], boxes[sel[q]]))
+            if hard:
+                return s, True
+            if s <= thr:
+                break
+        return s, not (s > thr)
+
+    cur = np.where(scores > thr, scores, -np.inf).astype(f32)
+    beg = np.zeros(n, int)
+    sel, out = [], []
+    key = lambda s, i: (s, -i)
+    for e in range(max_out):
+        ev, best = {}, None
+        for j in range(n):                       # round 1: empty or one-step chains
+            if cur[j] == -np.inf or beg[j] < e - 1:
+                continue
+            v, dead = (cur[j], False) if beg[j] == e else chain(cur[j], j, e - 1, e - 1, sel)
+            ev[j] = -np.inf if dead else v
+            if not dead and (best is None or key(v, j) > best):
+                best = key(v, j)
+        m1 = best
+        for j in range(n):                       # round 2: pending chains that reach the round-1 maximum
+            if cur[j] == -np.inf or j in ev or (m1 is not None and key(cur[j], j) < m1):
+                continue
+            v, dead = chain(cur[j], j, e - 1, beg[j], sel)
+            ev[j] = -np.inf if dead else v
+            if not dead and (best is None or key(v, j) > best):
+                best = key(v, j)
+        if best is None:
+            break
+        win = -best[1]
+        for j, v in ev.items():                  # commit
+            if j == win:
+                sel.append(j)
+                out.append(v)
+                cur[j] = -np.inf
+            elif key(cur[j], j) > best:
+                cur[j] = v
+                beg[j] = e
+    return sel, np.asarray(out, f32)
+
+
+def test_epoch_formulation_of_the_lazy_heap_matches_nms_v5_c():
+    rng = np.random.default_rng(0)
+    for trial in range(25):
+        n = int(rng.integers(5, 90))
+        spread = rng.choice([0.0, 3.0, 20.0, 80.0])
+        ctr = np.float32([200, 300]) + rng.normal(0, spread, (n, 2)).astype(np.float32)
+        hw = rng.uniform(20, 90, (n, 2)).astype(np.float32) if rng.random() < 0.8 else np.full((n, 2), 70, np.float32)
+        boxes = np.concatenate([ctr - hw / 2, ctr + hw / 2], -1).astype(np.float32)
+        scores = rng.uniform(0.01, 1, n).astype(np.float32)
+        if rng.random() < 0.5:
+            scores[::3] = 0.5
+        for sigma, old, iou_thr, thr in [(0.25, False, 0.5, 0.001), (0.25, True, 0.5, 0.001), (0.0, False, 0.5, -np.inf),
+                                         (0.0, True, 0.3, 0.2), (0.1, False, 0.5, 0.2)]:
+            mo = int(rng.integers(1, 30))
+            ri, rs, _ = nms_ref.non_max_suppression_v5(boxes, scores, mo, iou_thr, thr, sigma, False, "old" if old else "new")
+            si, so = _epoch_nms(boxes, scores, mo, np.float32(iou_thr), np.float32(thr), sigma, old)
+            assert list(ri) == si, (trial, sigma, old)
+            np.testing.assert_array_equal(so, rs)

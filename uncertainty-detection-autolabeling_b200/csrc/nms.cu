@@ -610,7 +610,7 @@ int udal_launch_nms_v5(udal_ctx* ctx, const float* boxes, const float* scores, i
   }
   // default: one cooperative CTA per image (nms_cta.cu); udal_nms_cta = 0 keeps the round-1 path (top-k pre-filter +
   // one warp per image) for comparison
-  if (udal_nms_cta) return udal_nms_epoch(ctx, boxes, scores, segments, n, sel_idx, sel_scores, valid);
+  if (udal_nms_cta && max_out <= 128) return udal_nms_epoch(ctx, boxes, scores, segments, n, sel_idx, sel_scores, valid);
   udal_nms_plan plan;
   UDAL_TRY(udal_nms_prefilter(ctx, scores, segments, n, &plan));
   return udal_nms_select(ctx, boxes, scores, segments, n, plan, sel_idx, sel_scores, valid);

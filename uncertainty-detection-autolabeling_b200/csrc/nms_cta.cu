@@ -12,16 +12,25 @@
 //     they take their decayed score (or die at the threshold), their begin becomes e; everybody else is untouched.
 // (Proof sketch: keys only decrease; the heap pops in key order; a popped candidate re-enters with s' and is selected
 // on its next pop - empty pending range - unless something with a larger key is still ahead; the first key that
-// survives its own pop unchanged is the maximum of s'.)  One epoch is therefore: every thread evaluates the chains of
-// its candidates that can matter, a block-wide arg-max, a commit.  Candidates evaluated in the previous epoch have a
-// one-box chain ("hot"); a candidate whose current score is already behind the hot maximum cannot be popped and is
-// skipped, so the total IoU work stays bounded by (candidates x selections) and is in practice a small multiple of the
-// candidate count.  The fp32 product of the decay weights is taken in exactly the oracle's order: results are bit-exact.
+// survives its own pop unchanged is the maximum of s'.  tests/test_oracle_extra.py holds a NumPy transcription of this
+// formulation checked against the heap of nms_v5.c.)  One epoch:
+//   round 1  every live candidate tests its box against the newest selection (interval overlap: a few instructions) and
+//            records a non-trivial step (IoU != 0) in its 128-bit mask.  A candidate without pending non-trivial steps
+//            has s' = s for free; the candidates popped in the previous epoch have a one-step chain.  Block maximum m1
+//            of these keys = a lower bound of the winner's key.
+//   round 2  a candidate with pending non-trivial steps matters only if its CURRENT key reaches m1: those (typically
+//            two per epoch) run their chain over the flagged selections, newest first.  Block maximum m2.
+//   commit   the owner of max(m1, m2) appends its candidate to the selection; evaluated candidates whose current key
+//            precedes the winner's take their decayed score and begin = e.
+// The fp32 product of the decay weights is taken in exactly the oracle's order (steps at IoU 0 multiply by exactly 1):
+// results are bit-exact.
 //
-// Candidates: the K best scores of the image (in-CTA radix select over the ordered-uint keys, no sort needed - the
-// epoch loop never looks at an order), resident in shared memory.  The truncation is provably exact when every
-// selection scored above the best excluded candidate; otherwise the segment is flagged and redone over all N
-// candidates by the same loop with its state in global memory (nms_epoch_full_kernel, early exit when not flagged).
+// Candidates: the K best scores of the image, resident in shared memory (no sort: the epoch loop never looks at an
+// order).  The cut is found by an adaptive histogram select over the ordered-uint keys (bins spread over the key range
+// of the image, refined while the boundary bin is too full), any cut with at most K keys above it will do.  The
+// truncation is provably exact when every selection scored above the cut; otherwise the image is flagged and redone over
+// all N candidates by the same loop with its state in global memory (nms_epoch_full_kernel; no work when nothing is
+// flagged).
 //
 // Arithmetic = oracle/nms_v5.c: fp32 IoU without "+1", weight = fp32(exp(fp64((scale*u)*u))).
 #include <math_constants.h>
@@ -29,11 +38,15 @@
 #include "fast_math64.cuh"
 #include "udal_common.cuh"
 
+// development counters (udal_nms_debug = 1): cycles of image 0 - select, round 1, round 2, commit; round-2 evaluations
+__device__ unsigned long long g_nms_dbg[8];
+
 namespace {
 
 constexpr int kCtaThreads = 1024;
-constexpr int kCtaWarps = kCtaThreads / 32;
 constexpr int kHistBins = 2048;
+constexpr int kUnroll = 8;       // independent score loads per thread in the select passes
+constexpr int kFullSlots = 32;   // CTAs (= state slots) of the exact redo
 
 struct EpochParams {
   const float* boxes;    // [S,n,4]
@@ -45,10 +58,30 @@ struct EpochParams {
   float* sel_scores;     // [S,max_out]
   int32_t* valid;        // [S]
   int32_t* flag;         // [S] 1 = the truncated run is not provably exact (written by the CTA kernel, read by the full one)
-  // full variant: state in global memory, [S,n] each
-  float* g_cur;
-  float* g_sp;
-  uint32_t* g_meta;
+  int32_t* cursor;       // work cursor of the full kernel (zeroed by the CTA kernel's launch)
+  char* g_state;         // full variant: kFullSlots x n x kStateBytes
+  int debug;
+};
+
+// per-candidate state (structure of arrays over `cap` / n candidates)
+constexpr int kStateBytes = 16 + 4 + 4 + 4 + 4 + 4 + 16;
+struct State {
+  float4* box;      // normalised corners (min y, min x, max y, max x)
+  float* area;
+  float* cur;       // current heap score, -inf = not in the heap
+  float* sp;        // decayed score of this epoch's evaluation (-inf: dies when popped)
+  int32_t* idx;     // box index in the image (the heap's tie rule); null = j
+  uint32_t* meta;   // begin (bits 0-7) | newest non-trivial selection + 1 (bits 8-15) | epoch stamp of the evaluation + 1 (16-31)
+  uint32_t* mask;   // [4] per candidate: selections with a non-trivial step
+  __device__ void carve(char* base, size_t count, bool with_idx) {
+    box = reinterpret_cast<float4*>(base);
+    mask = reinterpret_cast<uint32_t*>(base + count * 16);
+    area = reinterpret_cast<float*>(base + count * 32);
+    cur = area + count;
+    sp = cur + count;
+    meta = reinterpret_cast<uint32_t*>(sp + count);
+    idx = with_idx ? reinterpret_cast<int32_t*>(meta + count) : nullptr;
+  }
 };
 
 __device__ __forceinline__ uint32_t ordered_key(float f) {  // monotone float -> uint
@@ -63,151 +96,298 @@ __device__ __forceinline__ unsigned long long heap_key(float s, int idx) {
   return ((unsigned long long)ordered_key(s) << 32) | (unsigned long long)(0xffffffffu - (uint32_t)idx);
 }
 
-__device__ __forceinline__ float iou_v5(const float4 a, const float4 b) {
-  const float ay0 = fminf(a.x, a.z), ax0 = fminf(a.y, a.w);
-  const float ay1 = fmaxf(a.x, a.z), ax1 = fmaxf(a.y, a.w);
-  const float by0 = fminf(b.x, b.z), bx0 = fminf(b.y, b.w);
-  const float by1 = fmaxf(b.x, b.z), bx1 = fmaxf(b.y, b.w);
-  const float area_a = __fmul_rn(__fsub_rn(ay1, ay0), __fsub_rn(ax1, ax0));
-  const float area_b = __fmul_rn(__fsub_rn(by1, by0), __fsub_rn(bx1, bx0));
+__device__ __forceinline__ float4 normalise(const float4 a, float& area) {
+  const float y0 = fminf(a.x, a.z), x0 = fminf(a.y, a.w), y1 = fmaxf(a.x, a.z), x1 = fmaxf(a.y, a.w);
+  area = __fmul_rn(__fsub_rn(y1, y0), __fsub_rn(x1, x0));
+  return make_float4(y0, x0, y1, x1);
+}
+// intersection area of two normalised boxes (0 when either area is not positive: the IoU is 0 then)
+__device__ __forceinline__ float intersection(const float4 a, float area_a, const float4 b, float area_b) {
   if (area_a <= 0.f || area_b <= 0.f) return 0.f;
-  const float iy0 = fmaxf(ay0, by0), ix0 = fmaxf(ax0, bx0);
-  const float iy1 = fminf(ay1, by1), ix1 = fminf(ax1, bx1);
-  const float ih = fmaxf(__fsub_rn(iy1, iy0), 0.f), iw = fmaxf(__fsub_rn(ix1, ix0), 0.f);
-  const float inter = __fmul_rn(ih, iw);
-  if (inter == 0.f) return 0.f;  // (= 0 / union: skips the division for the disjoint pairs, the common case)
+  const float ih = fmaxf(__fsub_rn(fminf(a.z, b.z), fmaxf(a.x, b.x)), 0.f);
+  const float iw = fmaxf(__fsub_rn(fminf(a.w, b.w), fmaxf(a.y, b.y)), 0.f);
+  return __fmul_rn(ih, iw);
+}
+__device__ __forceinline__ float iou_from(float inter, float area_a, float area_b) {
+  if (inter == 0.f) return 0.f;   // (= 0 / union)
   return __fdiv_rn(inter, __fsub_rn(__fadd_rn(area_a, area_b), inter));
 }
 
-// the oracle's decay chain of one candidate over the selections sel[from] .. sel[to] (newest first); returns the decayed
-// score, dead = the candidate leaves the heap when popped (hard suppression or score at / below the threshold)
-__device__ __forceinline__ float decay_chain(float s, const float4 box, int from, int to, const float4* sel_box,
-                                             const EpochParams& p, const double* tbl, bool& dead) {
+// the decay weight of one step of the oracle's loop at IoU u, and whether the step suppresses the candidate for good
+__device__ __forceinline__ float step_weight(float u, const EpochParams& p, const double* tbl, bool& hard) {
+  float w = (u == 0.f || p.scale == 0.f) ? 1.f : (float)exp_fast((double)__fmul_rn(__fmul_rn(p.scale, u), u), tbl);
+  if (p.variant_old) {
+    if (!(u <= p.iou_thr)) w = 0.f;
+    hard = u >= p.iou_thr;
+  } else {
+    if (!(p.soft || u <= p.iou_thr)) w = 0.f;
+    hard = !p.soft && u > p.iou_thr;
+  }
+  return w;
+}
+// one step of the oracle's decay loop: the candidate (score s) against a selected box at IoU u.  Returns true when the
+// loop ends here (hard suppression -> dead, or the score fell to the threshold)
+__device__ __forceinline__ bool decay_step(float& s, float u, const EpochParams& p, const double* tbl, bool& dead) {
+  bool hard;
+  const float w = step_weight(u, p, tbl, hard);
+  s = __fmul_rn(s, w);
+  if (hard) {
+    dead = true;
+    return true;
+  }
+  return s <= p.score_thr;
+}
+
+// bits [lo, hi) of a 128-bit mask, word w
+__device__ __forceinline__ uint32_t range_word(int w, int lo, int hi) {
+  const int a = max(lo - 32 * w, 0), b = min(hi - 32 * w, 32);
+  if (a >= b) return 0u;
+  const uint32_t upto_b = b == 32 ? 0xffffffffu : ((1u << b) - 1u);
+  return upto_b & ~((1u << a) - 1u);   // a < 32 here
+}
+
+// The oracle's decay chain of ONE candidate over its pending selections sel[e-1] .. sel[begin], newest first, computed by
+// the whole warp: only the selections flagged in the mask can change the score or trigger a rule; lane i takes the i-th
+// newest flagged selection (IoU, fp64 exp: the long-latency part, in parallel), then the fp32 product is taken in the
+// oracle's order.  All arguments are warp-uniform; every lane returns the same result.
+__device__ __forceinline__ float decay_chain_warp(float s, const float4 box, float area, uint32_t m0, uint32_t m1, uint32_t m2,
+                                                  uint32_t m3, int begin, int e, const float4* sel_box, const float* sel_area,
+                                                  const EpochParams& p, const double* tbl, bool& dead) {
+  const int lane = threadIdx.x & 31;
   dead = false;
-  for (int q = from; q >= to; --q) {
-    const float u = iou_v5(box, sel_box[q]);
-    if (u == 0.f && p.soft && !p.variant_old) continue;  // weight exactly 1, no hard rule in this mode
-    float w = (u == 0.f || p.scale == 0.f) ? 1.f : (float)exp_fast((double)__fmul_rn(__fmul_rn(p.scale, u), u), tbl);
-    bool hard;
-    if (p.variant_old) {
-      if (!(u <= p.iou_thr)) w = 0.f;
-      hard = u >= p.iou_thr;
-    } else {
-      if (!(p.soft || u <= p.iou_thr)) w = 0.f;
-      hard = !p.soft && u > p.iou_thr;
+  uint32_t words[4] = {m0 & range_word(0, begin, e), m1 & range_word(1, begin, e), m2 & range_word(2, begin, e),
+                       m3 & range_word(3, begin, e)};
+  int left = __popc(words[0]) + __popc(words[1]) + __popc(words[2]) + __popc(words[3]);
+  while (left > 0) {
+    // lane i: the i-th newest flagged selection still pending
+    int q = -1, skip = lane;
+#pragma unroll
+    for (int w = 3; w >= 0; --w) {
+      const int c = __popc(words[w]);
+      if (q < 0) {
+        if (skip < c) q = 32 * w + (int)__fns(words[w], 31, -(skip + 1));
+        else skip -= c;
+      }
     }
-    s = __fmul_rn(s, w);
-    if (hard) {
-      dead = true;
-      return s;
+    float wgt = 1.f;
+    bool hard = false;
+    if (q >= 0) {
+      const float a2 = sel_area[q];
+      wgt = step_weight(iou_from(intersection(box, area, sel_box[q], a2), area, a2), p, tbl, hard);
     }
-    if (s <= p.score_thr) break;
+    const int take = min(left, 32);
+    for (int i = 0; i < take; ++i) {
+      const float wi = __shfl_sync(0xffffffffu, wgt, i);
+      const int hi = __shfl_sync(0xffffffffu, (int)hard, i);
+      s = __fmul_rn(s, wi);
+      if (hi) {
+        dead = true;
+        return s;
+      }
+      if (s <= p.score_thr) {
+        dead = true;
+        return s;
+      }
+    }
+    left -= take;
+    if (left > 0) {  // drop the 32 newest bits that were just applied
+      int drop = 32;
+#pragma unroll
+      for (int w = 3; w >= 0; --w) {
+        const int c = __popc(words[w]);
+        if (drop >= c) {
+          drop -= c;
+          words[w] = 0;
+        } else if (drop > 0) {
+          const int pos = (int)__fns(words[w], 31, -drop);   // the drop-th newest bit of this word
+          words[w] &= (1u << pos) - 1u;
+          drop = 0;
+        }
+      }
+    }
   }
   if (!(s > p.score_thr)) dead = true;
   return s;
 }
 
-// block-wide maximum of a 64-bit key: warp reduction, one shared-memory atomic per warp
-__device__ __forceinline__ void block_max_push(unsigned long long key, unsigned long long* slot, int lane) {
+// maximum of a 64-bit key over the warp (two 32-bit redux steps)
+__device__ __forceinline__ unsigned long long warp_max(unsigned long long key) {
   const uint32_t hi = (uint32_t)(key >> 32);
   const uint32_t mhi = __reduce_max_sync(0xffffffffu, hi);
   const uint32_t lo = hi == mhi ? (uint32_t)key : 0u;
   const uint32_t mlo = __reduce_max_sync(0xffffffffu, lo);
-  if (lane == 0) {
-    const unsigned long long m = ((unsigned long long)mhi << 32) | mlo;
-    if (m) atomicMax(slot, m);
-  }
+  return ((unsigned long long)mhi << 32) | mlo;
+}
+// block-wide maximum: one slot per warp, a barrier, every warp reduces the 32 slots again (no atomics: a 64-bit shared
+// memory atomicMax is a CAS loop that 32 warps fight over)
+__device__ __forceinline__ unsigned long long block_max(unsigned long long key, unsigned long long* wslots) {
+  const unsigned long long m = warp_max(key);
+  if ((threadIdx.x & 31) == 0) wslots[threadIdx.x >> 5] = m;
+  __syncthreads();
+  return warp_max(wslots[threadIdx.x & 31]);
 }
 
-// meta word of a candidate: begin (low 16 bits) | epoch stamp of its last evaluation + 1 (high 16 bits)
-__device__ __forceinline__ int meta_begin(uint32_t m) { return (int)(m & 0xffffu); }
+__device__ __forceinline__ int meta_begin(uint32_t m) { return (int)(m & 0xffu); }
+__device__ __forceinline__ int meta_nt(uint32_t m) { return (int)((m >> 8) & 0xffu); }
 __device__ __forceinline__ int meta_stamp(uint32_t m) { return (int)(m >> 16); }
 
-// The epoch loop.  Candidate j: box bx[j], index ix ? ix[j] : j, current score cur[j] (-inf = not in the heap), meta[j],
-// sp[j] = decayed score of this epoch's evaluation.  Returns through shared variables: nsel, last selected key.
-// slots: 4 x u64 in shared memory (zeroed); sel_box: [max_out] in shared memory.
-template <bool GLOBAL>
-__device__ __forceinline__ void epoch_loop(const EpochParams& p, int cnt, const float4* __restrict__ bx, const int32_t* ix,
-                                           float* cur, float* sp, uint32_t* meta, float4* sel_box, unsigned long long* slots,
-                                           const double* tbl, int32_t* out_row, float* out_score, int& nsel_out,
-                                           float& last_out, bool& emptied_out) {
+// The epoch loop over `cnt` candidates.  wslots: 64 x u64 in shared memory; sel_box / sel_area: [max_out <= 128].
+__device__ __forceinline__ void epoch_loop(const EpochParams& p, int cnt, const State& st, float4* sel_box, float* sel_area,
+                                           unsigned long long* wslots, const double* tbl, int32_t* out_row, float* out_score,
+                                           int& nsel_out, float& last_out, bool& emptied_out) {
   const int tid = threadIdx.x, lane = tid & 31;
   int nsel = 0;
   float last = CUDART_INF_F;
   bool emptied = false;
+  // does a step at IoU 0 leave the candidate untouched?  (always, unless a non-positive IoU threshold makes it a hard rule)
+  const bool zero_trivial = p.variant_old ? (p.iou_thr > 0.f) : (p.soft || p.iou_thr >= 0.f);
   for (int e = 0; e < p.max_out; ++e) {
-    unsigned long long* slot1 = slots + 2 * (e & 1);
-    unsigned long long* slot2 = slot1 + 1;
-    // ---- round 1: candidates whose pending chain is empty or the newest selection only ----
+    float4 nb = make_float4(0.f, 0.f, 0.f, 0.f);
+    float narea = 0.f;
+    if (e > 0) {
+      nb = sel_box[e - 1];
+      narea = sel_area[e - 1];
+    }
+    const long long t0 = p.debug ? clock64() : 0;
+    // ---- round 1 ----
     unsigned long long best = 0;
+    int bestj = -1;
+    bool has_cold = false, mine = false;
     for (int j = tid; j < cnt; j += kCtaThreads) {
-      const float s = cur[j];
+      float s = st.cur[j];
       if (s == -CUDART_INF_F) continue;
-      const uint32_t m = meta[j];
+      uint32_t m = st.meta[j];
+      float inter = 0.f, area = 0.f;
+      if (e > 0) {
+        const float4 box = st.box[j];
+        area = st.area[j];
+        inter = intersection(box, area, nb, narea);
+        if (inter != 0.f || !zero_trivial) {
+          st.mask[4 * (size_t)j + ((e - 1) >> 5)] |= 1u << ((e - 1) & 31);
+          m = (m & 0xffff00ffu) | ((uint32_t)e << 8);
+          st.meta[j] = m;
+        }
+      }
       const int b = meta_begin(m);
-      if (b < e - 1) continue;  // cold
-      float v = s;
-      bool dead = false;
-      if (b == e - 1) v = decay_chain(s, bx[j], e - 1, e - 1, sel_box, p, tbl, dead);
-      sp[j] = dead ? -CUDART_INF_F : v;
-      meta[j] = (uint32_t)b | ((uint32_t)(e + 1) << 16);
-      if (!dead) {
-        const unsigned long long k = heap_key(v, ix ? ix[j] : j);
-        best = k > best ? k : best;
+      if (meta_nt(m) > b) {
+        if (b != e - 1) {        // pending non-trivial steps from earlier epochs: round 2, if it can matter at all
+          has_cold = true;
+          continue;
+        }
+        bool dead = false;       // popped in the previous epoch: one step, against the newest selection
+        decay_step(s, iou_from(inter, area, narea), p, tbl, dead);
+        if (!(s > p.score_thr)) dead = true;
+        st.sp[j] = dead ? -CUDART_INF_F : s;
+        st.meta[j] = (m & 0xffffu) | ((uint32_t)(e + 1) << 16);
+        mine = true;
+        if (dead) continue;
+      }
+      const unsigned long long k = heap_key(s, st.idx ? st.idx[j] : j);
+      if (k > best) {
+        best = k;
+        bestj = j;
       }
     }
-    block_max_push(best, slot1, lane);
-    __syncthreads();
-    const unsigned long long m1 = *slot1;
-    // ---- round 2: cold candidates that would be popped before the round-1 maximum ----
-    best = 0;
+    if (p.debug && blockIdx.x == 0) {   // round-1 loop alone: thread 0 and the slowest warp
+      const long long tl = clock64() - t0;
+      if (tid == 0) g_nms_dbg[6] += (unsigned long long)tl;
+      if (lane == 0) atomicMax(reinterpret_cast<unsigned int*>(wslots + 63), (unsigned int)tl);
+    }
+    const unsigned long long m1 = block_max(best, wslots);
+    const long long t1 = p.debug ? clock64() : 0;
+    if (p.debug && blockIdx.x == 0 && tid == 0) {
+      g_nms_dbg[7] += (unsigned long long)*reinterpret_cast<unsigned int*>(wslots + 63);
+      *reinterpret_cast<unsigned int*>(wslots + 63) = 0;
+    }
+    // ---- round 2: candidates with a pending chain that would be popped before the round-1 maximum; each is evaluated by
+    //      its whole warp (the owner's lanes are otherwise idle here) ----
     int worked = 0;
-    for (int j = tid; j < cnt; j += kCtaThreads) {
-      const float s = cur[j];
-      if (s == -CUDART_INF_F) continue;
-      const uint32_t m = meta[j];
-      if (meta_stamp(m) == e + 1) continue;  // evaluated in round 1
-      if (heap_key(s, ix ? ix[j] : j) < m1) continue;
-      bool dead;
-      const float v = decay_chain(s, bx[j], e - 1, meta_begin(m), sel_box, p, tbl, dead);
-      sp[j] = dead ? -CUDART_INF_F : v;
-      meta[j] = (m & 0xffffu) | ((uint32_t)(e + 1) << 16);
-      worked = 1;
-      if (!dead) {
-        const unsigned long long k = heap_key(v, ix ? ix[j] : j);
-        best = k > best ? k : best;
+    unsigned long long best2 = 0;
+    if (__any_sync(0xffffffffu, has_cold)) {
+      for (int j0 = tid - lane; j0 < cnt; j0 += kCtaThreads) {
+        const int j = j0 + lane;
+        bool need = false;
+        float s = 0.f;
+        uint32_t m = 0;
+        if (j < cnt && has_cold) {
+          s = st.cur[j];
+          if (s != -CUDART_INF_F) {
+            m = st.meta[j];
+            const int b = meta_begin(m);
+            need = meta_nt(m) > b && b != e - 1 && heap_key(s, st.idx ? st.idx[j] : j) >= m1;
+          }
+        }
+        uint32_t todo = __ballot_sync(0xffffffffu, need);
+        if (!todo) continue;
+        float4 box = make_float4(0.f, 0.f, 0.f, 0.f);
+        float area = 0.f;
+        uint4 mw = make_uint4(0u, 0u, 0u, 0u);
+        if (need) {
+          box = st.box[j];
+          area = st.area[j];
+          mw = *reinterpret_cast<const uint4*>(st.mask + 4 * (size_t)j);
+        }
+        while (todo) {
+          const int src = __ffs(todo) - 1;
+          todo &= todo - 1;
+          float4 bb;
+          bb.x = __shfl_sync(0xffffffffu, box.x, src);
+          bb.y = __shfl_sync(0xffffffffu, box.y, src);
+          bb.z = __shfl_sync(0xffffffffu, box.z, src);
+          bb.w = __shfl_sync(0xffffffffu, box.w, src);
+          const float ba = __shfl_sync(0xffffffffu, area, src);
+          const float bs = __shfl_sync(0xffffffffu, s, src);
+          const int bbeg = meta_begin(__shfl_sync(0xffffffffu, m, src));
+          const uint32_t w0 = __shfl_sync(0xffffffffu, mw.x, src), w1 = __shfl_sync(0xffffffffu, mw.y, src);
+          const uint32_t w2 = __shfl_sync(0xffffffffu, mw.z, src), w3 = __shfl_sync(0xffffffffu, mw.w, src);
+          bool dead;
+          const float v = decay_chain_warp(bs, bb, ba, w0, w1, w2, w3, bbeg, e, sel_box, sel_area, p, tbl, dead);
+          if (lane == src) {
+            st.sp[j] = dead ? -CUDART_INF_F : v;
+            st.meta[j] = (m & 0xffffu) | ((uint32_t)(e + 1) << 16);
+            worked = 1;
+            mine = true;
+            if (!dead) {
+              const unsigned long long k = heap_key(v, st.idx ? st.idx[j] : j);
+              if (k > best2) best2 = k;
+              if (k > best) {
+                best = k;
+                bestj = j;
+              }
+            }
+          }
+        }
       }
     }
     unsigned long long mk = m1;
     if (__syncthreads_or(worked)) {
-      block_max_push(best, slot2, lane);
-      __syncthreads();
-      const unsigned long long m2 = *slot2;
+      const unsigned long long m2 = block_max(best2, wslots + 32);
       mk = m2 > m1 ? m2 : m1;
     }
-    // ---- commit: everything evaluated whose current key precedes the winner's key was popped before it ----
-    const int win_idx = (int)(0xffffffffu - (uint32_t)mk);
-    for (int j = tid; j < cnt; j += kCtaThreads) {
-      const float s = cur[j];
-      if (s == -CUDART_INF_F) continue;
-      const uint32_t m = meta[j];
-      if (meta_stamp(m) != e + 1) continue;
-      const int idx = ix ? ix[j] : j;
-      if (mk != 0 && idx == win_idx) {  // the selection (its own evaluation left the score unchanged or it re-entered with sp)
-        const float v = sp[j];
-        sel_box[e] = bx[j];
-        out_row[e] = idx;
-        out_score[e] = v;
-        cur[j] = -CUDART_INF_F;
-      } else if (mk == 0 || heap_key(s, idx) > mk) {
-        cur[j] = sp[j];                        // (-inf when it died)
-        meta[j] = (uint32_t)e | (m & 0xffff0000u);
-      }
+    const long long t2 = p.debug ? clock64() : 0;
+    if (p.debug && blockIdx.x == 0 && worked) atomicAdd(&g_nms_dbg[4], 1ull);
+    // ---- commit ----
+    if (mk != 0 && best == mk) {  // this thread owns the winner (box indices are unique)
+      const int j = bestj;
+      const uint32_t m = st.meta[j];
+      const float v = meta_stamp(m) == e + 1 ? st.sp[j] : st.cur[j];
+      sel_box[e] = st.box[j];
+      sel_area[e] = st.area[j];
+      out_row[e] = st.idx ? st.idx[j] : j;
+      out_score[e] = v;
+      st.cur[j] = -CUDART_INF_F;
     }
-    if (tid == 0) {
-      // next epoch's slots (nobody touches them before the barrier below)
-      slots[2 * ((e + 1) & 1)] = 0;
-      slots[2 * ((e + 1) & 1) + 1] = 0;
+    if (mine) {  // evaluated candidates whose current key precedes the winner's were popped before it
+      for (int j = tid; j < cnt; j += kCtaThreads) {
+        const float s = st.cur[j];
+        if (s == -CUDART_INF_F) continue;
+        const uint32_t m = st.meta[j];
+        if (meta_stamp(m) != e + 1) continue;
+        if (mk == 0 || heap_key(s, st.idx ? st.idx[j] : j) > mk) {
+          st.cur[j] = st.sp[j];                     // (-inf when it died)
+          st.meta[j] = (m & 0xffffff00u) | (uint32_t)e;
+        }
+      }
     }
     if (mk == 0) {
       emptied = true;
@@ -216,6 +396,12 @@ __device__ __forceinline__ void epoch_loop(const EpochParams& p, int cnt, const 
     last = key_to_float((uint32_t)(mk >> 32));
     nsel = e + 1;
     __syncthreads();
+    if (p.debug && blockIdx.x == 0 && tid == 0) {
+      const long long t3 = clock64();
+      g_nms_dbg[1] += (unsigned long long)(t1 - t0);
+      g_nms_dbg[2] += (unsigned long long)(t2 - t1);
+      g_nms_dbg[3] += (unsigned long long)(t3 - t2);
+    }
   }
   nsel_out = nsel;
   last_out = last;
@@ -223,78 +409,118 @@ __device__ __forceinline__ void epoch_loop(const EpochParams& p, int cnt, const 
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// one CTA per image: select the `cap` best scores into shared memory, run the epoch loop, flag an unprovable truncation
+// one CTA per image: select the best scores (at most `cap`) into shared memory, run the epoch loop, flag an unprovable
+// truncation
 // ---------------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kCtaThreads, 1) nms_epoch_cta_kernel(const EpochParams p) {
   extern __shared__ __align__(16) uint8_t smem[];
   const int s = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n = p.n, cap = p.cap;
-  float4* s_box = reinterpret_cast<float4*>(smem);                       // [cap]
-  float4* sel_box = s_box + cap;                                         // [max_out]
-  float* s_cur = reinterpret_cast<float*>(sel_box + p.max_out);          // [cap]
-  float* s_sp = s_cur + cap;                                             // [cap]
-  int32_t* s_idx = reinterpret_cast<int32_t*>(s_sp + cap);               // [cap]
-  uint32_t* s_meta = reinterpret_cast<uint32_t*>(s_idx + cap);           // [cap]
-  uint32_t* s_hist = s_meta + cap;                                       // [kHistBins]
+  const size_t cap_al = ((size_t)cap + 3) & ~(size_t)3;   // keeps every array 16-byte aligned
+  State st;
+  st.carve(reinterpret_cast<char*>(smem), cap_al, true);
+  float4* sel_box = reinterpret_cast<float4*>(smem + cap_al * kStateBytes);        // [max_out]
+  float* sel_area = reinterpret_cast<float*>(sel_box + p.max_out);                 // [max_out]
+  uint32_t* s_hist = reinterpret_cast<uint32_t*>(sel_area + p.max_out);            // [kHistBins]
   __shared__ double s_tbl[64];
-  __shared__ unsigned long long s_slots[4];
-  __shared__ uint32_t s_prefix, s_need, s_count, s_above;
+  __shared__ unsigned long long s_slots[64];
+  if (threadIdx.x == 0) s_slots[63] = 0;
+  __shared__ uint32_t s_kmin, s_kmax, s_above, s_count, s_bin, s_acc;
   const float* scores = p.scores + (size_t)s * n;
   const float4* boxes = reinterpret_cast<const float4*>(p.boxes) + (size_t)s * n;
   int32_t* out_row = p.sel_row + (size_t)s * p.max_out;
   float* out_score = p.sel_scores + (size_t)s * p.max_out;
   const float thr = p.score_thr;
+  const long long t_start = p.debug ? clock64() : 0;
   if (tid < 64) s_tbl[tid] = kExp2Table[tid];
-  if (tid < 4) s_slots[tid] = 0;
   if (tid == 0) {
-    s_count = 0;
-    s_above = 0;
+    s_kmin = 0xffffffffu;
+    s_kmax = 0u;
+    s_above = 0u;
+    s_count = 0u;
+    if (s == 0 && p.cursor) *p.cursor = 0;
   }
   __syncthreads();
 
-  // ---- how many candidates are there at all ----
+  // ---- key range and number of the candidates ----
   {
+    uint32_t mn = 0xffffffffu, mx = 0u;
     int c = 0;
-    for (int j = tid; j < n; j += kCtaThreads) c += scores[j] > thr ? 1 : 0;
+    for (int base = 0; base < n; base += kUnroll * kCtaThreads) {   // (kUnroll loads in flight per thread: the pass is L2-latency bound)
+      float v[kUnroll];
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) {
+        const int j = base + u * kCtaThreads + tid;
+        v[u] = j < n ? scores[j] : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) {
+        const int j = base + u * kCtaThreads + tid;
+        if (j < n && v[u] > thr) {
+          const uint32_t k = ordered_key(v[u]);
+          mn = min(mn, k);
+          mx = max(mx, k);
+          ++c;
+        }
+      }
+    }
+    mn = __reduce_min_sync(0xffffffffu, mn);
+    mx = __reduce_max_sync(0xffffffffu, mx);
     c = __reduce_add_sync(0xffffffffu, c);
-    if (lane == 0 && c) atomicAdd(&s_above, (uint32_t)c);
+    if (lane == 0 && c) {
+      atomicMin(&s_kmin, mn);
+      atomicMax(&s_kmax, mx);
+      atomicAdd(&s_above, (uint32_t)c);
+    }
   }
   __syncthreads();
   const int above = (int)s_above;
-  // ---- radix select: key of the cap-th best candidate (3 passes: 11 + 11 + 10 bits) ----
-  uint32_t cut = 0;        // candidates are the scores with ordered key > cut (and > thr)
+  // ---- the cut: candidates = keys > cut, at most cap of them (adaptive histogram, refined while the boundary bin
+  //      holds more than a quarter of the capacity) ----
+  uint32_t cut = 0;
   bool truncated = false;
   if (above > cap) {
     truncated = true;
-    uint32_t prefix = 0, need = (uint32_t)cap + 1;  // the (cap + 1)-th best key is the best excluded one
-    for (int pass = 0; pass < 3; ++pass) {
-      const int sh = pass == 0 ? 21 : (pass == 1 ? 10 : 0), width = pass == 2 ? 10 : 11, bins = 1 << width;
-      for (int i = tid; i < bins; i += kCtaThreads) s_hist[i] = 0;
+    uint32_t lo = s_kmin, hi = s_kmax;   // inclusive key range still undecided
+    uint32_t taken = 0;                  // keys above `hi` (all accepted)
+    for (int level = 0; level < 4; ++level) {
+      const uint32_t span = hi - lo;
+      const int shift = max(0, 32 - __clz(span | 1u) - 11);   // (span >> shift) < 2048
+      for (int i = tid; i < kHistBins; i += kCtaThreads) s_hist[i] = 0;
       __syncthreads();
-      const uint32_t himask = pass == 0 ? 0u : (0xffffffffu << (sh + width));
-      for (int j0 = 0; j0 < n; j0 += kCtaThreads) {
-        const int j = j0 + tid;
-        bool ok = false;
-        uint32_t bin = 0;
-        if (j < n) {
-          const float sc = scores[j];
-          const uint32_t k = ordered_key(sc);
-          ok = sc > thr && (k & himask) == prefix;
-          bin = (k >> sh) & (uint32_t)(bins - 1);
+      {
+        uint32_t run_bin = 0xffffffffu, run = 0;   // per-thread run-length aggregation (ties / flat score maps)
+        for (int base = 0; base < n; base += kUnroll * kCtaThreads) {
+          float v[kUnroll];
+#pragma unroll
+          for (int u = 0; u < kUnroll; ++u) {
+            const int j = base + u * kCtaThreads + tid;
+            v[u] = j < n ? scores[j] : 0.f;
+          }
+#pragma unroll
+          for (int u = 0; u < kUnroll; ++u) {
+            const int j = base + u * kCtaThreads + tid;
+            const uint32_t k = ordered_key(v[u]);
+            if (j < n && v[u] > thr && k >= lo && k <= hi) {
+              const uint32_t bin = (k - lo) >> shift;
+              if (bin != run_bin) {
+                if (run) atomicAdd(&s_hist[run_bin], run);
+                run_bin = bin;
+                run = 0;
+              }
+              ++run;
+            }
+          }
         }
-        // warp-aggregated histogram update (the scores of a random-init head are nearly flat: most lanes hit one bin)
-        const uint32_t act = __ballot_sync(0xffffffffu, ok);
-        if (ok) {
-          const uint32_t peers = __match_any_sync(act, bin);
-          if ((int)(__ffs(peers) - 1) == lane) atomicAdd(&s_hist[bin], (uint32_t)__popc(peers));
-        }
+        if (run) atomicAdd(&s_hist[run_bin], run);
       }
       __syncthreads();
-      // warp 0: the bin that holds the need-th largest key among the matching ones
+      // warp 0: boundary bin = the first bin from the top at which the accepted count would exceed the capacity
       if (warp == 0) {
-        const int per = bins / 32;
+        const uint32_t room = (uint32_t)cap - taken;
+        constexpr int per = kHistBins / 32;
         uint32_t mine = 0;
-        for (int i = 0; i < per; ++i) mine += s_hist[bins - 1 - (lane * per + i)];
+        for (int i = 0; i < per; ++i) mine += s_hist[kHistBins - 1 - (lane * per + i)];
         uint32_t incl = mine;
 #pragma unroll
         for (int off = 1; off < 32; off <<= 1) {
@@ -302,14 +528,14 @@ __global__ void __launch_bounds__(kCtaThreads, 1) nms_epoch_cta_kernel(const Epo
           if (lane >= off) incl += o;
         }
         const uint32_t excl = incl - mine;
-        if (need > excl && need <= incl) {
+        if (excl <= room && incl > room) {
           uint32_t acc = excl;
           for (int i = 0; i < per; ++i) {
-            const int b = bins - 1 - (lane * per + i);
+            const int b = kHistBins - 1 - (lane * per + i);
             const uint32_t h = s_hist[b];
-            if (need <= acc + h) {
-              s_prefix = prefix | ((uint32_t)b << sh);
-              s_need = need - acc;
+            if (acc + h > room) {
+              s_bin = (uint32_t)b;
+              s_acc = acc;
               break;
             }
             acc += h;
@@ -317,42 +543,59 @@ __global__ void __launch_bounds__(kCtaThreads, 1) nms_epoch_cta_kernel(const Epo
         }
       }
       __syncthreads();
-      prefix = s_prefix;
-      need = s_need;
+      const uint32_t bin = s_bin, acc = s_acc;
       __syncthreads();
+      taken += acc;
+      const uint32_t bin_lo = lo + (bin << shift);
+      const uint32_t bin_hi = shift == 0 ? bin_lo : min(hi, bin_lo + ((1u << shift) - 1u));
+      cut = bin_hi;   // keys in and below the boundary bin are excluded
+      if (shift == 0 || taken * 4u >= (uint32_t)cap * 3u) break;
+      lo = bin_lo;
+      hi = bin_hi;
     }
-    cut = prefix;  // the best excluded key: candidates = keys > cut  (at most cap of them)
   }
   // ---- compaction into shared memory (any order: the epoch loop ties by box index) ----
-  for (int j0 = 0; j0 < n; j0 += kCtaThreads) {
-    const int j = j0 + tid;
-    bool ok = false;
-    float sc = 0.f;
-    if (j < n) {
-      sc = scores[j];
-      ok = sc > thr && (!truncated || ordered_key(sc) > cut);
+  for (int base = 0; base < n; base += kUnroll * kCtaThreads) {
+    float v[kUnroll];
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      const int j = base + u * kCtaThreads + tid;
+      v[u] = j < n ? scores[j] : 0.f;
     }
-    const uint32_t act = __ballot_sync(0xffffffffu, ok);
-    if (act) {
-      uint32_t base = 0;
-      if (lane == 0) base = atomicAdd(&s_count, (uint32_t)__popc(act));
-      base = __shfl_sync(0xffffffffu, base, 0);
-      if (ok) {
-        const int slot = (int)(base + (uint32_t)__popc(act & ((1u << lane) - 1u)));
-        s_box[slot] = boxes[j];
-        s_cur[slot] = sc;
-        s_idx[slot] = j;
-        s_meta[slot] = 0;
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      const int j = base + u * kCtaThreads + tid;
+      const float sc = v[u];
+      const bool ok = j < n && sc > thr && (!truncated || ordered_key(sc) > cut);
+      const uint32_t act = __ballot_sync(0xffffffffu, ok);
+      if (act) {
+        uint32_t slot0 = 0;
+        if (lane == 0) slot0 = atomicAdd(&s_count, (uint32_t)__popc(act));
+        slot0 = __shfl_sync(0xffffffffu, slot0, 0);
+        if (ok) {
+          const int slot = (int)(slot0 + (uint32_t)__popc(act & ((1u << lane) - 1u)));
+          float area;
+          st.box[slot] = normalise(boxes[j], area);
+          st.area[slot] = area;
+          st.cur[slot] = sc;
+          st.idx[slot] = j;
+          st.meta[slot] = 0;
+          reinterpret_cast<uint4*>(st.mask)[slot] = make_uint4(0u, 0u, 0u, 0u);
+        }
       }
     }
   }
   __syncthreads();
   const int cnt = (int)s_count;
+  if (p.debug && s == 0 && tid == 0) {
+    g_nms_dbg[0] += (unsigned long long)(clock64() - t_start);
+    g_nms_dbg[5] = (unsigned long long)cnt;
+  }
 
   int nsel;
   float last;
   bool emptied;
-  epoch_loop<false>(p, cnt, s_box, s_idx, s_cur, s_sp, s_meta, sel_box, s_slots, s_tbl, out_row, out_score, nsel, last, emptied);
+  epoch_loop(p, cnt, st, sel_box, sel_area, s_slots, s_tbl, out_row, out_score, nsel, last, emptied);
   __syncthreads();
   for (int i = nsel + tid; i < p.max_out; i += kCtaThreads) {
     out_row[i] = 0;
@@ -361,53 +604,80 @@ __global__ void __launch_bounds__(kCtaThreads, 1) nms_epoch_cta_kernel(const Epo
   if (tid == 0) {
     p.valid[s] = nsel;
     if (p.flag) {
+      // exact iff nothing excluded could have been popped: every selection scored above the cut (every excluded key is
+      // at or below it)
       const float nx = key_to_float(cut);
-      // exact iff nothing excluded could have been popped: every pop scored above the best excluded candidate
       p.flag[s] = (truncated && (emptied || nsel == 0 || !(last > nx))) ? 1 : 0;
     }
   }
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// exact redo of a flagged image over all n candidates: the same loop, state in global memory (L2 resident)
+// exact redo of the flagged images over all n candidates: the same loop, state in global memory (L2 resident).  A few
+// persistent CTAs (one state slot each) walk the flag array.
 // ---------------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kCtaThreads, 1) nms_epoch_full_kernel(const EpochParams p) {
   extern __shared__ __align__(16) uint8_t smem[];
-  const int s = blockIdx.x, tid = threadIdx.x;
-  if (p.flag && !p.flag[s]) return;
+  const int tid = threadIdx.x;
   const int n = p.n;
-  float4* sel_box = reinterpret_cast<float4*>(smem);  // [max_out]
+  float4* sel_box = reinterpret_cast<float4*>(smem);               // [max_out]
+  float* sel_area = reinterpret_cast<float*>(sel_box + p.max_out);  // [max_out]
   __shared__ double s_tbl[64];
-  __shared__ unsigned long long s_slots[4];
-  const float* scores = p.scores + (size_t)s * n;
-  const float4* boxes = reinterpret_cast<const float4*>(p.boxes) + (size_t)s * n;
-  float* cur = p.g_cur + (size_t)s * n;
-  float* sp = p.g_sp + (size_t)s * n;
-  uint32_t* meta = p.g_meta + (size_t)s * n;
-  int32_t* out_row = p.sel_row + (size_t)s * p.max_out;
-  float* out_score = p.sel_scores + (size_t)s * p.max_out;
+  __shared__ unsigned long long s_slots[64];
+  if (threadIdx.x == 0) s_slots[63] = 0;
+  __shared__ int s_seg;
   if (tid < 64) s_tbl[tid] = kExp2Table[tid];
-  if (tid < 4) s_slots[tid] = 0;
-  for (int j = tid; j < n; j += kCtaThreads) {
-    const float sc = scores[j];
-    cur[j] = sc > p.score_thr ? sc : -CUDART_INF_F;
-    meta[j] = 0;
+  State st;
+  const size_t n_al = ((size_t)n + 3) & ~(size_t)3;
+  st.carve(p.g_state + (size_t)blockIdx.x * n_al * kStateBytes, n_al, false);
+  for (;;) {
+    __syncthreads();
+    if (tid == 0) {
+      int s = atomicAdd(p.cursor, 1);
+      while (s < p.segments && !p.flag[s]) s = atomicAdd(p.cursor, 1);
+      s_seg = s;
+    }
+    __syncthreads();
+    const int s = s_seg;
+    if (s >= p.segments) break;
+    const float* scores = p.scores + (size_t)s * n;
+    const float4* boxes = reinterpret_cast<const float4*>(p.boxes) + (size_t)s * n;
+    int32_t* out_row = p.sel_row + (size_t)s * p.max_out;
+    float* out_score = p.sel_scores + (size_t)s * p.max_out;
+    for (int j = tid; j < n; j += kCtaThreads) {
+      const float sc = scores[j];
+      float area;
+      st.box[j] = normalise(boxes[j], area);
+      st.area[j] = area;
+      st.cur[j] = sc > p.score_thr ? sc : -CUDART_INF_F;
+      st.meta[j] = 0;
+      reinterpret_cast<uint4*>(st.mask)[j] = make_uint4(0u, 0u, 0u, 0u);
+    }
+    __syncthreads();
+    int nsel;
+    float last;
+    bool emptied;
+    epoch_loop(p, n, st, sel_box, sel_area, s_slots, s_tbl, out_row, out_score, nsel, last, emptied);
+    __syncthreads();
+    for (int i = nsel + tid; i < p.max_out; i += kCtaThreads) {
+      out_row[i] = 0;
+      out_score[i] = 0.f;
+    }
+    if (tid == 0) p.valid[s] = nsel;
   }
-  __syncthreads();
-  int nsel;
-  float last;
-  bool emptied;
-  epoch_loop<true>(p, n, boxes, nullptr, cur, sp, meta, sel_box, s_slots, s_tbl, out_row, out_score, nsel, last, emptied);
-  __syncthreads();
-  for (int i = nsel + tid; i < p.max_out; i += kCtaThreads) {
-    out_row[i] = 0;
-    out_score[i] = 0.f;
-  }
-  if (tid == 0) p.valid[s] = nsel;
 }
 
 }  // namespace
 
+int udal_nms_debug = 0;
+extern "C" int udal_nms_debug_read(unsigned long long* out8, int reset) {
+  if (cudaMemcpyFromSymbol(out8, g_nms_dbg, sizeof(g_nms_dbg)) != cudaSuccess) return -1;
+  if (reset) {
+    unsigned long long z[8] = {0};
+    if (cudaMemcpyToSymbol(g_nms_dbg, z, sizeof(z)) != cudaSuccess) return -1;
+  }
+  return 0;
+}
 int udal_nms_cta = 1;  // 0: global NMS through the top-k pre-filter + one-warp-per-image kernels of nms.cu (comparison path)
 
 // Global NMS-V5 over [S,n] boxes / scores (unsorted): one cooperative CTA per image + the exact redo of flagged images.
@@ -422,9 +692,10 @@ int udal_nms_epoch(udal_ctx* ctx, const float* boxes, const float* scores, int s
   p.segments = segments;
   p.n = n;
   p.max_out = c.max_output_size;
-  UDAL_REQUIRE(p.max_out < 65535, "max_output_size %d too large", p.max_out);
+  UDAL_REQUIRE(p.max_out <= 128, "udal_nms_epoch: max_output_size %d > 128", p.max_out);
   int cap = udal_nms_prefilter_k(ctx, n);
   if (cap < 1) cap = 1;
+  if (cap > 3072) cap = 3072;
   p.cap = cap;
   p.iou_thr = c.nms_iou_thresh;
   p.score_thr = c.nms_score_thresh;
@@ -434,26 +705,25 @@ int udal_nms_epoch(udal_ctx* ctx, const float* boxes, const float* scores, int s
   p.sel_row = sel_idx;
   p.sel_scores = sel_scores;
   p.valid = valid;
+  p.debug = udal_nms_debug;
   const bool may_truncate = cap < n;
   if (may_truncate) {
     char* scr;
-    const size_t per = (size_t)segments * n;
-    UDAL_TRY(udal_scratch_get(ctx, SCR_NMS_B, per * 12 + (size_t)segments * 4, (void**)&scr));
-    p.g_cur = (float*)scr;
-    p.g_sp = (float*)(scr + per * 4);
-    p.g_meta = (uint32_t*)(scr + per * 8);
-    p.flag = (int32_t*)(scr + per * 12);
+    const size_t state = (size_t)kFullSlots * (((size_t)n + 3) & ~(size_t)3) * kStateBytes;
+    UDAL_TRY(udal_scratch_get(ctx, SCR_NMS_B, state + (size_t)segments * 4 + 16, (void**)&scr));
+    p.g_state = scr;
+    p.flag = (int32_t*)(scr + state);
+    p.cursor = p.flag + segments;
   }
-  const size_t smem = (size_t)cap * 32 + (size_t)p.max_out * 16 + kHistBins * 4;
+  const size_t smem = (((size_t)cap + 3) & ~(size_t)3) * kStateBytes + (size_t)p.max_out * 20 + kHistBins * 4;
   UDAL_REQUIRE(smem <= 200 * 1024, "nms: %d candidates x max_output_size %d do not fit in shared memory", cap, p.max_out);
   UDAL_CUDA(cudaFuncSetAttribute(nms_epoch_cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   nms_epoch_cta_kernel<<<segments, kCtaThreads, smem, ctx->stream>>>(p);
   UDAL_CHECK_LAUNCH(ctx);
   if (may_truncate) {
-    const size_t smem2 = (size_t)p.max_out * 16;
-    if (smem2 > 40 * 1024)
-      UDAL_CUDA(cudaFuncSetAttribute(nms_epoch_full_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-    nms_epoch_full_kernel<<<segments, kCtaThreads, smem2, ctx->stream>>>(p);
+    const size_t smem2 = (size_t)p.max_out * 20;
+    const int grid = segments < kFullSlots ? segments : kFullSlots;
+    nms_epoch_full_kernel<<<grid, kCtaThreads, smem2, ctx->stream>>>(p);
     UDAL_CHECK_LAUNCH(ctx);
   }
   return UDAL_OK;
