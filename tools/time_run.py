@@ -10,7 +10,7 @@ import udal_b200 as u
 batch = 64
 p = u.hparams_config.get_detection_config(
     "efficientdet-d0", image_size=(384, 1280), num_classes=8, enable_softmax=True, loss_attenuation=True,
-    mc_dropout=True, mc_classheadrate=0.05, mc_boxheadrate=0.05, mc_dropoutsamp=10, heads_mode="bf16")
+    mc_dropout=True, mc_classheadrate=0.05, mc_boxheadrate=0.05, mc_dropoutsamp=10, heads_mode=sys.argv[1] if len(sys.argv) > 1 and not sys.argv[1].startswith("-") else "fp16")
 eng = u.engine.get_engine(p)
 L = len(eng.level_hw)
 eng.set_head_weights(u.synthetic.init_head_weights(eng.F, eng.R, L, eng.A, 8, True, seed=2024))
@@ -22,10 +22,12 @@ unst = ctypes.c_int.in_dll(eng.lib, "udal_nms_post_unstaged")
 rsv = ctypes.c_int.in_dll(eng.lib, "udal_run_reserved_sms")
 tl = ctypes.c_int.in_dll(eng.lib, "udal_run_debug_timeline")
 tl.value = 1 if "--timeline" in sys.argv else 0
-for f, un, rs in ((1, 0, 0), (1, 1, 4)):
+ovl = ctypes.c_int.in_dll(eng.lib, "udal_run_overlap")
+for f, un, rs, ov in ((1, 0, 0, 1), (1, 0, 0, 0), (1, 0, 8, 1)):
     fused.value = f
     unst.value = un
     rsv.value = rs
+    ovl.value = ov
     for i in range(3):
         eng.run(feats, scales, None, seed=i)
     eng.ctx.sync()
@@ -43,5 +45,5 @@ for f, un, rs in ((1, 0, 0), (1, 1, 4)):
     lib.udal_get_layer_times(eng.ctx.handle, ms8, 64, ctypes.byref(n8))
     lib.udal_profile_layers(eng.ctx.handle, 0)
     print("   pipelined layer ms %s sum %.3f" % ([round(ms8[i], 3) for i in range(n8.value)], sum(ms8[i] for i in range(n8.value))))
-    print("nms_post_unstaged=%d reserved=%d" % (un, rs), end="  ")
+    print("overlap=%d reserved=%d" % (ov, rs), end="  ")
     print("fused=%d  layer ms %s  sum %.3f  step %.3f ms" % (f, [round(x, 3) for x in t], sum(t), ms), flush=True)

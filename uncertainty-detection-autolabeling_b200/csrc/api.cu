@@ -3,6 +3,8 @@
 
 #include <algorithm>
 
+#include <chrono>
+
 #include "udal_common.cuh"
 
 static thread_local char g_err[1024] = "";
@@ -22,6 +24,21 @@ int udal_cuda_fail(cudaError_t e, const char* what, const char* file, int line) 
 static bool scratch_banked(int slot) {
   // the head sampler's slots are only ever touched on the context's own stream
   return !(slot == SCR_HEADS_A || slot == SCR_HEADS_B || slot == SCR_HEADS_C || slot == SCR_PRE_A || slot == SCR_LEVEL_PTRS);
+}
+
+int udal_host_trace = 0;
+void udal_host_trace_mark(const char* file, int line) {
+  static thread_local std::chrono::steady_clock::time_point last;
+  static thread_local const char* last_file = nullptr;
+  static thread_local int last_line = 0;
+  const auto now = std::chrono::steady_clock::now();
+  if (last_file) {
+    const double ms = std::chrono::duration<double, std::milli>(now - last).count();
+    if (ms > 0.3) fprintf(stderr, "host gap %.3f ms between %s:%d and %s:%d\n", ms, last_file, last_line, file, line);
+  }
+  last = now;
+  last_file = file;
+  last_line = line;
 }
 
 int udal_join(udal_ctx* ctx) {

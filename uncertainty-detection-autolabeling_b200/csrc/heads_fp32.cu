@@ -335,7 +335,9 @@ static int heads_sample_impl(udal_ctx* ctx, const float* const* feats, int batch
   for (int l = 0; l < c.num_levels; ++l)
     UDAL_REQUIRE(feats[l] && (fused_pre || (cls_out[l] && box_out[l])), "level %d pointer is NULL", l);
   const int T = c.mc_samples, L = c.num_levels, R = c.repeats, F = c.num_filters;
+  if (udal_host_trace) udal_host_trace_mark("heads_sample_impl entry", 0);
   if (c.heads_mode != UDAL_HEADS_FP32) UDAL_TRY(udal_work_counters_reset(ctx));
+  if (udal_host_trace) udal_host_trace_mark("after counters reset", 0);
   const int64_t total = (int64_t)T * 2 * L * R * batch * F;
   float* scale_raw;
   UDAL_TRY(udal_scratch_get(ctx, SCR_HEADS_C, (size_t)total * 4 * 2, (void**)&scale_raw));

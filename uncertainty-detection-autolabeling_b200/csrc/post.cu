@@ -367,6 +367,7 @@ static int global_tail(udal_ctx* ctx, const GlobalScratch& g, int batch, const f
   a.out = *out;
   assemble_global_kernel<<<batch, 128, 0, ctx->stream>>>(a);
   UDAL_CHECK_LAUNCH(ctx);
+  if (udal_host_trace) udal_host_trace_mark("tail enqueued", 0);
   if (tail_on_post) {
     UDAL_CUDA(cudaEventRecord(ctx->ev_post[bank], ctx->post_stream));
     ctx->post_pending[bank] = true;
@@ -375,6 +376,7 @@ static int global_tail(udal_ctx* ctx, const GlobalScratch& g, int batch, const f
       dbg_valid[bank] = true;
     }
   }
+  if (udal_host_trace) udal_host_trace_mark("udal_run end", 0);
   return UDAL_OK;
 }
 

@@ -59,7 +59,9 @@ extern "C" int udal_run_prenms(udal_ctx* ctx, const float* const* feats, int bat
 extern "C" int udal_run(udal_ctx* ctx, const float* const* feats, int batch, const uint8_t* keep_masks,
                         uint64_t seed, const float* image_scales, const udal_detections* out) {
   UDAL_REQUIRE(ctx && feats && out, "NULL argument");
+  if (udal_host_trace) udal_host_trace_mark("udal_run entry", 0);
   UDAL_CUDA(cudaSetDevice(ctx->cfg.device));
+  if (udal_host_trace) udal_host_trace_mark("udal_run after cudaSetDevice", 0);
   // Pipelining across calls: the tail of the previous run (top-k / NMS / assemble) may still be in flight
   // on the post stream.  This run's heads start right away; its decode kernel writes scratch bank
   // `run_bank`, whose previous user (two runs ago) is waited for first.
@@ -86,6 +88,7 @@ extern "C" int udal_run(udal_ctx* ctx, const float* const* feats, int batch, con
     }
     ctx->scratch_bank = bank;
     ctx->run_bank = bank ^ 1;
+    if (udal_host_trace) udal_host_trace_mark("udal_run after bank wait", bank);
     return udal_run_global_fused(ctx, feats, batch, keep_masks, seed, image_scales, out);
   }
   float* cls[UDAL_MAX_LEVELS];

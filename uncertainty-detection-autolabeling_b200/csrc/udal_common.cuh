@@ -118,9 +118,15 @@ int udal_join(udal_ctx* ctx);
     if (e__ != cudaSuccess) return udal_cuda_fail(e__, #call, __FILE__, __LINE__); \
   } while (0)
 
+// development (udal_host_trace = 1): reports host-side gaps > 0.3 ms between consecutive kernel launches (a launch or an
+// API call in between that blocked on the device)
+extern int udal_host_trace;
+void udal_host_trace_mark(const char* file, int line);
+
 #define UDAL_CHECK_LAUNCH(ctx)                    \
   do {                                            \
     (ctx)->launches++;                            \
+    if (udal_host_trace) udal_host_trace_mark(__FILE__, __LINE__); \
     UDAL_CUDA(cudaGetLastError());                \
   } while (0)
 

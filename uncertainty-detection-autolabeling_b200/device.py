@@ -326,6 +326,12 @@ def _from_dlpack(ctx, obj):
     return DeviceArray(ctx, shape, dtype, ptr=(t.data or 0) + t.byte_offset, base=owner)
 
 
+def is_device_array(x):
+    """DeviceArray or a foreign CUDA-array-interface producer.  Never touches a DeviceArray's own
+    ``__cuda_array_interface__``: that property synchronises the context before it answers."""
+    return isinstance(x, DeviceArray) or hasattr(x, "__cuda_array_interface__")
+
+
 def as_device(ctx, x, dtype=None):
     """-> (DeviceArray, was_host).  Host arrays are copied, device arrays are borrowed."""
     if isinstance(x, DeviceArray):

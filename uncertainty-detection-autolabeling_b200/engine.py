@@ -216,10 +216,10 @@ class Engine:
     def scales_input(self, image_scales, batch):
         if image_scales is None:
             return None, 0
-        a, _ = device.as_device(self.ctx, np.asarray(image_scales, np.float32)
-                                if not hasattr(image_scales, "__cuda_array_interface__")
-                                and not isinstance(image_scales, device.DeviceArray)
-                                else image_scales, np.float32)
+        # (isinstance first: reading a DeviceArray's __cuda_array_interface__ synchronises the context - the property
+        # promises finished data to foreign consumers - and would serialise back-to-back udal_run calls)
+        a, _ = device.as_device(self.ctx, image_scales if device.is_device_array(image_scales)
+                                else np.asarray(image_scales, np.float32), np.float32)
         if a.size != batch:
             raise ValueError("image_scales must have one entry per image")
         return a, a.ptr
@@ -365,8 +365,7 @@ class Engine:
     def masks_input(self, masks, batch):
         if masks is None:
             return None, 0
-        m, _ = device.as_device(self.ctx, masks if hasattr(masks, "__cuda_array_interface__") or
-                                isinstance(masks, device.DeviceArray) else np.asarray(masks, np.uint8), np.uint8)
+        m, _ = device.as_device(self.ctx, masks if device.is_device_array(masks) else np.asarray(masks, np.uint8), np.uint8)
         want = (self.T, 2, len(self.level_hw), self.R, batch, self.F)
         if m.shape != want:
             raise ValueError("keep masks: expected %s, got %s" % (want, m.shape))
