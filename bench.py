@@ -429,21 +429,40 @@ def run_gpu(args, cfg):
     # step i (PipelinedSampler).  Timed with the host clock around fully synchronised work.
     host_feats = [pa.array for pa in pinned]
     e2e_blocking_ms = None
+    e2e_f32 = None
+    feat16 = args.feature_dtype == "f16" or (args.feature_dtype == "auto" and mode == "fp16" and eng.F == 64)
     e2e_steps = max(24, args.steps)
     if not cfg["autolabel"]:
         depth = 4 if cfg["tag"] == "configs[1]" else 2
-        pipe = u.heads.PipelinedSampler(p, weights, device_id=local_rank, heads_mode=mode, depth=depth)
-        for _ in pipe.map([host_feats] * (2 * depth), [scales_host] * (2 * depth), seed=1):  # warm-up: every context twice
-            pass
-        barrier()
-        t0 = time.perf_counter()
-        for det in pipe.map([host_feats] * e2e_steps, [scales_host] * e2e_steps, seed=3000):
-            pass
-        e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
-        barrier()
-        e2e_ms = max_over_ranks(e2e_ms)
-        for s in pipe.samplers:
-            s.close()
+
+        def measure_e2e(feats_h):
+            pipe = u.heads.PipelinedSampler(p, weights, device_id=local_rank, heads_mode=mode, depth=depth)
+            for _ in pipe.map([feats_h] * (2 * depth), [scales_host] * (2 * depth), seed=1):  # warm-up: every context twice
+                pass
+            barrier()
+            t0 = time.perf_counter()
+            for det in pipe.map([feats_h] * e2e_steps, [scales_host] * e2e_steps, seed=3000):
+                pass
+            ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
+            barrier()
+            for s in pipe.samplers:
+                s.close()
+            return max_over_ranks(ms)
+
+        if feat16:
+            # the feature maps cross the boundary as fp16 (udal_set_feature_format; what the reference's mixed_float16 GPU
+            # graphs hand over): pinned fp16 copies of the same synthetic maps, made outside the timed region
+            pinned16 = [u.device.PinnedArray(pa.shape, np.float16) for pa in pinned]
+            for a, b in zip(pinned16, pinned):
+                a.array[...] = b.array.astype(np.float16)
+            host_feats16 = [pa.array for pa in pinned16]
+            e2e_ms = measure_e2e(host_feats16)
+            e2e_f32 = dict(value=world * batch / (measure_e2e(host_feats) / 1e3), unit=UNIT, h2d_bytes_per_step=h2d,
+                           note="the same measurement with fp32 feature maps at the boundary")
+            h2d = sum(pa.nbytes for pa in pinned16) + scales_host.nbytes
+            host_feats = host_feats16
+        else:
+            e2e_ms = measure_e2e(host_feats)
         # un-pipelined reference point: one blocking call per step
         sampler.detect(host_feats, scales_host, seed=1)
         ctx.timer_start()
@@ -528,10 +547,12 @@ def run_gpu(args, cfg):
         return row
 
     kernels = [kernel_row(i, ms, fused_run) for i, ms in enumerate(layer_ms if mode != "fp32" else [])]
-    kernels.append({"kernel": "topk_* + nms_v5_sorted_kernel", "what": "score pre-filter + global soft-NMS",
+    kernels.append({"kernel": "nms_epoch_cta_kernel (+ nms_epoch_full_kernel for flagged images)",
+                    "what": "in-CTA score select + global soft-NMS, one cooperative CTA per image",
                     "ms": nms_ms, "bound": "latency", "us_per_image": 1e3 * nms_ms / batch,
                     "worst_case_ms": nms_worst_ms,
-                    "worst_case": "%d mutually overlapping candidates per image (every pop decays and re-inserts)" % wc_n})
+                    "worst_case": "%d mutually overlapping candidates per image (every pop decays and re-inserts; every image is "
+                                  "flagged and redone exactly over all candidates)" % wc_n})
     standalone = [kernel_row(i, ms, False) for i, ms in enumerate(layer_ms_unfused if fused_run else [])
                   if i % (eng.R + 1) == eng.R]
     dec_gbs = work["decode_bytes"] / (decode_ms / 1e3) / 1e9
@@ -600,6 +621,10 @@ def run_gpu(args, cfg):
                         "the kernels of step i; host clock over fully synchronised work") if not cfg["autolabel"] else
                        "per batch: features H2D -> udal_run -> auto-label pass -> decisions D2H; host clock",
                 "blocking_ms_per_step": e2e_blocking_ms, "h2d_GBs": h2d / (e2e_ms / 1e3) / 1e9,
+                "feature_dtype": "f16" if (feat16 and not cfg["autolabel"]) else "f32",
+                "feature_note": ("feature maps cross the boundary as fp16 (udal_set_feature_format; the reference's mixed_float16 "
+                                 "exports): half the upload; fp32 maps: see fp32_features") if (feat16 and not cfg["autolabel"]) else None,
+                "fp32_features": e2e_f32,
                 "numa_node": numa_node, "numa": numa_why},
         "gpu_launches": int(launches),
         "roofline": roof,
@@ -646,6 +671,9 @@ def main():
     ap.add_argument("--heads-mode", default=os.environ.get("UDAL_HEADS_MODE", "fp16"),
                     help="fp16 (tcgen05 + packed-fp16 depthwise, default) | bf16 (tcgen05 implicit GEMM) | fp32 (CUDA-core parity mode)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--feature-dtype", default="auto", choices=["auto", "f32", "f16"],
+                    help="element type of the feature maps in the end-to-end (host buffer) measurement; auto = f16 with the fp16 "
+                         "tensor-core heads (64 filters), f32 otherwise.  The device-resident `value` always reads fp32 maps")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     cfg = CONFIGS[args.config]

@@ -96,6 +96,13 @@ int udal_destroy(udal_ctx* ctx);
 /* use an external CUDA stream (cudaStream_t as void*); NULL restores the context's own stream */
 int udal_set_stream(udal_ctx* ctx, void* cuda_stream);
 int udal_sync(udal_ctx* ctx);
+/* element type of the BiFPN feature maps handed to udal_heads_sample / udal_run / udal_run_prenms (their `feats` pointers are
+ * typed float for the default): UDAL_FEAT_F16 = IEEE half [B,H_l,W_l,F], what the reference's GPU graphs produce under the
+ * `mixed_precision` / mixed_float16 policy (src/hparams_config.py `mixed_precision`, src/utils_keras.py:142-160).  Needs
+ * heads_mode UDAL_HEADS_FP16_TC and F = 64: the layer-0 kernel stages the fp16 tiles with TMA directly (half the bytes over
+ * PCIe and HBM).  Sticky until changed. */
+enum { UDAL_FEAT_F32 = 0, UDAL_FEAT_F16 = 1 };
+int udal_set_feature_format(udal_ctx* ctx, int format);
 /* the stream the context currently enqueues on (cudaStream_t as void*): what a DLPack producer is handed in
  * __dlpack__(stream=...) */
 int udal_get_stream(udal_ctx* ctx, void** cuda_stream);

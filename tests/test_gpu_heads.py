@@ -256,6 +256,40 @@ def test_run_tail_overlap_is_invisible(u):
             np.testing.assert_array_equal(a[k], b[k])
 
 
+def test_fp16_feature_maps_at_the_boundary(u):
+    """udal_set_feature_format(UDAL_FEAT_F16): fp16 BiFPN maps (the reference's mixed_float16 exports) go straight into the
+    layer-0 kernel.  On features that are exactly representable in fp16 the fp32-input and the fp16-input path run the same
+    arithmetic (fp32 depthwise accumulation of the converted values): every result is bit-identical."""
+    p = _cfg(u, (128, 192), 8, 4, heads_mode="fp16")
+    L, batch = 5, 3
+    w = heads_ref.init_head_weights(64, 3, L, 9, 8, True, randomize_bn=True)
+    s32 = u.heads.HeadSampler(p, w)
+    s16 = u.heads.HeadSampler(p, w)
+    eng = s32.engine
+    f16 = [f.astype(np.float16) for f in heads_ref.make_features(eng.level_hw, batch, eng.F, seed=3)]
+    f32 = [f.astype(np.float32) for f in f16]
+    masks = heads_ref.make_masks(eng.T, L, eng.R, batch, eng.F, 0.05, 0.05, seed=7)
+    scales = np.float32([1.0, 1.5, 0.75])
+    c32, b32 = s32(f32, masks=masks)
+    c16, b16 = s16(f16, masks=masks)
+    for a, b in zip(c32 + b32, c16 + b16):
+        np.testing.assert_array_equal(a, b)
+    d32 = s32.detect(f32, scales, masks=masks)
+    d16 = s16.detect([s16.engine.ctx.to_device(f) for f in f16], scales, masks=masks)   # device-resident fp16 maps
+    for a, b in zip(d32, d16):
+        np.testing.assert_array_equal(np.asarray(a), b.numpy())
+    # the same sampler may alternate between the two formats
+    d32b = s16.detect(f32, scales, masks=masks)
+    for a, b in zip(d32, d32b):
+        np.testing.assert_array_equal(a, b)
+    with pytest.raises(TypeError):
+        s16.detect(f16[:1] + f32[1:], scales, masks=masks)
+    # other heads modes read fp32 maps only
+    pb = _cfg(u, (128, 192), 8, 4, heads_mode="bf16")
+    with pytest.raises(ValueError, match="fp16 feature maps"):
+        u.heads.HeadSampler(pb, w).detect(f16, scales, masks=masks)
+
+
 def test_run_back_to_back_does_not_block_the_host(u):
     """udal_run is asynchronous: a call issued behind another one must return long before the device has finished the
     first (a hidden synchronisation between calls - round 2 had one in the Python input handling - costs the whole

@@ -28,6 +28,10 @@ def family(name):
         return "heads_fused_kernel<box>"
     if "heads_ig_kernel" in name:
         return "heads_ig_kernel<predict>" if re.search(r"IgShape<[^>]*(\(bool\)1|true)>", name) else "heads_ig_kernel<tower>"
+    if "heads_dwf_kernel" in name:
+        return "heads_dwf_kernel<class>" if re.search(r"heads_dwf_kernel<(\(bool\))?(0|false)\b", name) else "heads_dwf_kernel<box>"
+    if "heads_dw_kernel" in name:
+        return "heads_dw_kernel<predict>" if re.search(r"DwShape<[^>]*(\(bool\)1|true|, 1)>", name) else "heads_dw_kernel<tower>"
     if "heads_wide_kernel" in name:
         return "heads_wide_kernel<64>" if re.search(r"heads_wide_kernel<(\(int\))?64\b", name) else "heads_wide_kernel<128>"
     m = re.search(r"(\w+_kernel)", name)
@@ -64,6 +68,15 @@ def main():
             cur = {}
         for k, v in traffic.items():
             cur[k] = sum(v) / len(v)
+        # per kernel FUNCTION (what bench.py's roofline.traffic looks up): mean over its launches
+        fn = {}
+        for k, v in traffic.items():
+            fn.setdefault(k.split("<")[0], []).extend(v)
+        for k, v in fn.items():
+            cur.setdefault(k, sum(v) / len(v)) if "<" in "".join(x for x in traffic if x.split("<")[0] == k) else None
+            cur[k] = sum(v) / len(v)
+        if "--step" in sys.argv:   # the capture holds exactly the launches of one udal_run
+            cur["step_total"] = sum(sum(v) for v in traffic.values())
         json.dump(cur, open(path, "w"), indent=1)
         print({k: round(sum(v) / len(v) / 1e9, 3) for k, v in traffic.items()}, "GB per launch ->", path)
 

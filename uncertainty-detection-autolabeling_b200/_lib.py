@@ -16,6 +16,7 @@ OK, ERR_INVALID, ERR_CUDA, ERR_STATE, ERR_NOMEM = 0, -1, -2, -3, -4
 DECODE_METHODS = {"l-norm": 0, "n-flow": 1, "falsedec": 2}
 NMS_HARD, NMS_GAUSSIAN = 0, 1
 HEADS_FP32, HEADS_BF16_TC, HEADS_FP16_TC = 0, 1, 2
+FEAT_F32, FEAT_F16 = 0, 1
 HEAD_CLASS, HEAD_BOX = 0, 1
 
 
@@ -69,6 +70,7 @@ SIGNATURES = {
     "udal_destroy": (ctypes.c_int, [_VP]),
     "udal_set_stream": (ctypes.c_int, [_VP, _VP]),
     "udal_sync": (ctypes.c_int, [_VP]),
+    "udal_set_feature_format": (ctypes.c_int, [_VP, ctypes.c_int]),
     "udal_get_stream": (ctypes.c_int, [_VP, _PP]),
     "udal_wait_stream": (ctypes.c_int, [_VP, _VP]),
     "udal_malloc": (ctypes.c_int, [_VP, ctypes.c_size_t, _PP]),

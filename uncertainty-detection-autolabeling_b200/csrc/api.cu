@@ -202,6 +202,16 @@ int udal_set_stream(udal_ctx* ctx, void* cuda_stream) {
   return UDAL_OK;
 }
 
+int udal_set_feature_format(udal_ctx* ctx, int format) {
+  UDAL_REQUIRE(ctx, "NULL ctx");
+  UDAL_REQUIRE(format == UDAL_FEAT_F32 || format == UDAL_FEAT_F16, "unknown feature format %d", format);
+  if (format == UDAL_FEAT_F16)
+    UDAL_REQUIRE(ctx->cfg.heads_mode == UDAL_HEADS_FP16_TC && ctx->cfg.num_filters == 64,
+                 "fp16 feature maps: heads_mode fp16 and fpn_num_filters 64 (the tensor-core layer-0 kernel reads them directly)");
+  ctx->feat_f16 = format == UDAL_FEAT_F16;
+  return UDAL_OK;
+}
+
 int udal_get_stream(udal_ctx* ctx, void** cuda_stream) {
   UDAL_REQUIRE(ctx && cuda_stream, "NULL argument");
   *cuda_stream = (void*)ctx->stream;

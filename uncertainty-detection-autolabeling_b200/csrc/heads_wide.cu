@@ -53,7 +53,7 @@ struct WdShape {
   static constexpr int QUEUE = EP + 2 * CH * 4;                // item-index ring (IG_QRING ints)
   static constexpr int SMEM = QUEUE + IG_QRING * 4 + 1024;
   static_assert(CH == 64 || CH == 128, "channel count");
-  static_assert(STAGE % 1024 == 0 && IN % 1024 == 0 && B % 1024 == 0 && OUT % 1024 == 0, "alignment");
+  static_assert(STAGE % 128 == 0 && IN % 1024 == 0 && B % 1024 == 0 && OUT % 1024 == 0, "alignment");   // (the halo tile is linear: no swizzle atom)
   static_assert(A_BYTES <= OUT_BYTES, "bf16 staging tile");
   static_assert(SMEM <= kIgSmemLimit, "shared-memory budget");
 };
@@ -636,7 +636,9 @@ int udal_heads_l0_prepare(udal_ctx* ctx, int head) {
   return UDAL_OK;
 }
 
-// tower layer 0: feats[l] fp32 [B,H_l,W_l,64] -> out[l] bf16 [B,H_l,W_l,64] = swish(BN(sepconv(bf16(feats)))), no dropout applied
+// tower layer 0: feats[l] fp32 [B,H_l,W_l,64] -> out[l] bf16 [B,H_l,W_l,64] = swish(BN(sepconv(bf16(feats)))), no dropout applied.
+// With udal_set_feature_format(ctx, UDAL_FEAT_F16) the feature maps are fp16 [B,H_l,W_l,64] (what the reference's GPU exports
+// produce under mixed_float16, efficientdet_keras.py / hparams_config.py `mixed_precision`): half the bytes over PCIe and HBM.
 int udal_heads_l0_layer(udal_ctx* ctx, int head, const float* const* feats, int B, void* const* out) {
   const udal_config& c = ctx->cfg;
   const udal_head_weights_dev& h = ctx->heads[head];
@@ -646,6 +648,10 @@ int udal_heads_l0_layer(udal_ctx* ctx, int head, const float* const* feats, int 
   for (int l = 0; l < c.num_levels; ++l) {
     in[l] = feats[l];
     ep[l] = h.l0_ep + (size_t)l * 2 * KF;
+  }
+  if (ctx->feat_f16) {
+    UDAL_REQUIRE(c.heads_mode == UDAL_HEADS_FP16_TC, "fp16 feature maps need heads_mode fp16");
+    return launch_wide_t<64, false, true>(ctx, in, B, B, nullptr, h.dw, h.l0_w, ep, 0, KF, 0, KF, out);
   }
   return launch_wide<64, true>(ctx, in, B, B, nullptr, h.dw, h.l0_w, ep, 0, KF, 0, KF, out);
 }

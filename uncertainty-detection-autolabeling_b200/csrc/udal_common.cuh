@@ -80,6 +80,7 @@ struct udal_ctx {
   // work-item counters of the persistent head kernels (dynamic item claiming): one zeroed int per launch of a run
   int* work_counters = nullptr;
   int work_counter_next = 0;
+  bool feat_f16 = false;         // udal_set_feature_format: the feats pointers of udal_run / udal_heads_sample are fp16
   bool profile_layers = false;
   std::vector<cudaEvent_t> layer_events;  // pairs (start, stop) in launch order
 };

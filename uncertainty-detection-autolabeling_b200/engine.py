@@ -184,6 +184,7 @@ class Engine:
         self.max_out = cfg.max_output_size
         self.k = cfg.max_nms_inputs
         self.weights_set = False
+        self._feat_format = _lib.FEAT_F32
 
     # ---- inputs ----------------------------------------------------------------------------
     def level_inputs(self, outputs, channels, mc):
@@ -342,9 +343,17 @@ class Engine:
         self.weights_set = True
 
     def feats_input(self, feats):
+        """BiFPN feature maps -> device arrays.  float32 (default) or, with heads_mode fp16 and 64 filters, float16 - all
+        levels alike; the context is told which (udal_set_feature_format)."""
         arrs, any_host, batch = [], False, None
+        first = feats[0]
+        dt = np.dtype(getattr(first, "dtype", np.float32))
+        if dt != np.float16:
+            dt = np.dtype(np.float32)
         for l, x in enumerate(feats):
-            a, was_host = device.as_device(self.ctx, x, np.float32)
+            if dt == np.float16 and np.dtype(getattr(x, "dtype", np.float32)) != np.float16:
+                raise TypeError("feature levels must share one dtype (float16 or float32)")
+            a, was_host = device.as_device(self.ctx, x, dt)
             lh, lw = self.level_hw[l]
             if a.ndim != 4 or a.shape[1:] != (lh, lw, self.F):
                 raise ValueError("feature level %d: expected [B,%d,%d,%d], got %s" % (l, lh, lw, self.F, a.shape))
@@ -353,6 +362,10 @@ class Engine:
                 raise ValueError("levels disagree on the batch size")
             any_host |= was_host
             arrs.append(a)
+        fmt = _lib.FEAT_F16 if dt == np.float16 else _lib.FEAT_F32
+        if fmt != self._feat_format:
+            _lib.check(self.lib.udal_set_feature_format(self.ctx.handle, fmt))
+            self._feat_format = fmt
         return arrs, batch, any_host
 
     def head_output_buffers(self, batch):
