@@ -436,8 +436,8 @@ def run_gpu(args, cfg):
         depth = 4 if cfg["tag"] == "configs[1]" else 2
 
         def measure_e2e(feats_h):
-            pipe = u.heads.PipelinedSampler(p, weights, device_id=local_rank, heads_mode=mode, depth=depth)
-            for _ in pipe.map([feats_h] * (2 * depth), [scales_host] * (2 * depth), seed=1):  # warm-up: every context twice
+            pipe = u.heads.StreamingSampler(p, weights, device_id=local_rank, heads_mode=mode, depth=3)
+            for _ in pipe.map([feats_h] * 6, [scales_host] * 6, seed=1):  # warm-up: every staging slot twice
                 pass
             barrier()
             t0 = time.perf_counter()
@@ -445,8 +445,7 @@ def run_gpu(args, cfg):
                 pass
             ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
             barrier()
-            for s in pipe.samplers:
-                s.close()
+            pipe.close()
             return max_over_ranks(ms)
 
         if feat16:
@@ -617,8 +616,9 @@ def run_gpu(args, cfg):
         "clocks": clock_info,
         "e2e": {"value": world * batch / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms, "steps": e2e_steps,
-                "how": ("PipelinedSampler.map: HeadSampler.detect(host arrays) on several contexts, H2D of the next steps overlaps "
-                        "the kernels of step i; host clock over fully synchronised work") if not cfg["autolabel"] else
+                "how": ("StreamingSampler.map(host batches): per step the feature maps go pinned host -> device on a copy stream "
+                        "(3 staging slots), udal_run, detections device -> pinned host behind the run's NMS tail, NumPy results "
+                        "yielded in order; host clock over the whole loop, fully synchronised at both ends") if not cfg["autolabel"] else
                        "per batch: features H2D -> udal_run -> auto-label pass -> decisions D2H; host clock",
                 "blocking_ms_per_step": e2e_blocking_ms, "h2d_GBs": h2d / (e2e_ms / 1e3) / 1e9,
                 "feature_dtype": "f16" if (feat16 and not cfg["autolabel"]) else "f32",

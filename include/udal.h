@@ -103,6 +103,26 @@ int udal_sync(udal_ctx* ctx);
  * PCIe and HBM).  Sticky until changed. */
 enum { UDAL_FEAT_F32 = 0, UDAL_FEAT_F16 = 1 };
 int udal_set_feature_format(udal_ctx* ctx, int format);
+/* ---- streaming front end ------------------------------------------------------------------
+ * Keeps the GPU-side sequence of back-to-back udal_run calls (heads of run i+1 over the NMS tail of run i) when inputs
+ * come from HOST buffers: uploads run on a copy stream into one of UDAL_STAGE_SLOTS caller-owned device buffer sets,
+ * results are fetched behind the tail of their own run without joining it into the context's stream.
+ *   udal_stage_begin(slot)      the copy stream waits until the run that last consumed `slot` is through its inputs
+ *   udal_stage_h2d(...)         cudaMemcpyAsync on the copy stream (pinned host memory for a truly asynchronous copy)
+ *   udal_stage_end(slot)        marks the slot's uploads
+ *   udal_stage_acquire(slot)    the context's stream waits for them             (before udal_run)
+ *   udal_stage_release(slot)    records "inputs consumed" on the context's stream (after udal_run)
+ *   udal_fetch_d2h(...)         device -> host copy ordered behind the results of the last udal_run / postprocess call
+ *   udal_fetch_mark(slot) / udal_fetch_wait(slot)   completion of the fetches enqueued so far / the host waits for it */
+#define UDAL_STAGE_SLOTS 4
+int udal_stage_begin(udal_ctx* ctx, int slot);
+int udal_stage_h2d(udal_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes);
+int udal_stage_end(udal_ctx* ctx, int slot);
+int udal_stage_acquire(udal_ctx* ctx, int slot);
+int udal_stage_release(udal_ctx* ctx, int slot);
+int udal_fetch_d2h(udal_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes);
+int udal_fetch_mark(udal_ctx* ctx, int slot);
+int udal_fetch_wait(udal_ctx* ctx, int slot);
 /* the stream the context currently enqueues on (cudaStream_t as void*): what a DLPack producer is handed in
  * __dlpack__(stream=...) */
 int udal_get_stream(udal_ctx* ctx, void** cuda_stream);

@@ -290,6 +290,27 @@ def test_fp16_feature_maps_at_the_boundary(u):
         u.heads.HeadSampler(pb, w).detect(f16, scales, masks=masks)
 
 
+def test_streaming_sampler_matches_blocking_calls(u):
+    """StreamingSampler (copy stream + staging slots + fetch behind the tail) returns, batch by batch, exactly what one
+    blocking HeadSampler.detect per batch returns - fp32 and fp16 feature maps, more batches than slots."""
+    p = _cfg(u, (128, 192), 8, 4, heads_mode="fp16")
+    L = 5
+    w = heads_ref.init_head_weights(64, 3, L, 9, 8, True, randomize_bn=True)
+    ref = u.heads.HeadSampler(p, w)
+    st = u.heads.StreamingSampler(p, w, depth=3)
+    hw = ref.engine.level_hw
+    for dt in (np.float32, np.float16):
+        batches = [[f.astype(dt) for f in heads_ref.make_features(hw, 2, 64, seed=10 + i)] for i in range(8)]
+        scales = [np.float32([1.0, 1.0 + 0.1 * i]) for i in range(8)]
+        got = list(st.map(batches, scales, seed=77))
+        assert len(got) == 8
+        for i, g in enumerate(got):
+            r = ref.detect(batches[i], scales[i], seed=u.heads.batch_seed(77, i))
+            for a, b in zip(r, g):
+                np.testing.assert_array_equal(a, b)
+    st.close()
+
+
 def test_run_back_to_back_does_not_block_the_host(u):
     """udal_run is asynchronous: a call issued behind another one must return long before the device has finished the
     first (a hidden synchronisation between calls - round 2 had one in the Python input handling - costs the whole

@@ -17,6 +17,7 @@ DECODE_METHODS = {"l-norm": 0, "n-flow": 1, "falsedec": 2}
 NMS_HARD, NMS_GAUSSIAN = 0, 1
 HEADS_FP32, HEADS_BF16_TC, HEADS_FP16_TC = 0, 1, 2
 FEAT_F32, FEAT_F16 = 0, 1
+STAGE_SLOTS = 4
 HEAD_CLASS, HEAD_BOX = 0, 1
 
 
@@ -71,6 +72,14 @@ SIGNATURES = {
     "udal_set_stream": (ctypes.c_int, [_VP, _VP]),
     "udal_sync": (ctypes.c_int, [_VP]),
     "udal_set_feature_format": (ctypes.c_int, [_VP, ctypes.c_int]),
+    "udal_stage_begin": (ctypes.c_int, [_VP, ctypes.c_int]),
+    "udal_stage_h2d": (ctypes.c_int, [_VP, _VP, _VP, ctypes.c_size_t]),
+    "udal_stage_end": (ctypes.c_int, [_VP, ctypes.c_int]),
+    "udal_stage_acquire": (ctypes.c_int, [_VP, ctypes.c_int]),
+    "udal_stage_release": (ctypes.c_int, [_VP, ctypes.c_int]),
+    "udal_fetch_d2h": (ctypes.c_int, [_VP, _VP, _VP, ctypes.c_size_t]),
+    "udal_fetch_mark": (ctypes.c_int, [_VP, ctypes.c_int]),
+    "udal_fetch_wait": (ctypes.c_int, [_VP, ctypes.c_int]),
     "udal_get_stream": (ctypes.c_int, [_VP, _PP]),
     "udal_wait_stream": (ctypes.c_int, [_VP, _VP]),
     "udal_malloc": (ctypes.c_int, [_VP, ctypes.c_size_t, _PP]),

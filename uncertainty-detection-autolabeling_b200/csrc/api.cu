@@ -53,6 +53,7 @@ int udal_join(udal_ctx* ctx) {
     }
   ctx->scratch_bank = 0;
   ctx->run_bank = 0;
+  ctx->last_tail_stream = nullptr;   // everything is ordered on the context's stream again
   return UDAL_OK;
 }
 
@@ -136,6 +137,12 @@ int udal_create(const udal_config* cfg, udal_ctx** out) {
   ctx->num_anchors = off * cfg->anchors_per_loc;
   cudaError_t e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->post_stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
+  for (int i = 0; i < UDAL_STAGE_SLOTS && e == cudaSuccess; ++i) {
+    e = cudaEventCreateWithFlags(&ctx->ev_staged[i], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_consumed[i], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_fetched[i], cudaEventDisableTiming);
+  }
   if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev_start);
   if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev_stop);
   for (int b = 0; b < 2 && e == cudaSuccess; ++b) {
@@ -177,6 +184,15 @@ int udal_destroy(udal_ctx* ctx) {
   cudaSetDevice(ctx->cfg.device);
   cudaStreamSynchronize(ctx->stream);
   if (ctx->post_stream) cudaStreamSynchronize(ctx->post_stream);
+  if (ctx->copy_stream) {
+    cudaStreamSynchronize(ctx->copy_stream);
+    cudaStreamDestroy(ctx->copy_stream);
+  }
+  for (int i = 0; i < UDAL_STAGE_SLOTS; ++i) {
+    if (ctx->ev_staged[i]) cudaEventDestroy(ctx->ev_staged[i]);
+    if (ctx->ev_consumed[i]) cudaEventDestroy(ctx->ev_consumed[i]);
+    if (ctx->ev_fetched[i]) cudaEventDestroy(ctx->ev_fetched[i]);
+  }
   for (auto& s : ctx->scratch) cudaFree(s.ptr);
   for (void* p : ctx->user_allocs) cudaFree(p);
   cudaFree(ctx->anchors);
@@ -199,6 +215,62 @@ int udal_set_stream(udal_ctx* ctx, void* cuda_stream) {
   UDAL_REQUIRE(ctx, "NULL ctx");
   UDAL_TRY(udal_join(ctx));
   ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+  return UDAL_OK;
+}
+
+#define UDAL_SLOT_OK(slot) UDAL_REQUIRE(ctx && (slot) >= 0 && (slot) < UDAL_STAGE_SLOTS, "bad staging slot %d", (slot))
+
+int udal_stage_begin(udal_ctx* ctx, int slot) {
+  UDAL_SLOT_OK(slot);
+  UDAL_CUDA(cudaSetDevice(ctx->cfg.device));
+  if (ctx->consumed_pending[slot]) {
+    UDAL_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_consumed[slot], 0));
+    ctx->consumed_pending[slot] = false;
+  }
+  return UDAL_OK;
+}
+
+int udal_stage_h2d(udal_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes) {
+  UDAL_REQUIRE(ctx && (bytes == 0 || (dst_dev && src_host)), "NULL argument");
+  if (bytes) UDAL_CUDA(cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
+  return UDAL_OK;
+}
+
+int udal_stage_end(udal_ctx* ctx, int slot) {
+  UDAL_SLOT_OK(slot);
+  UDAL_CUDA(cudaEventRecord(ctx->ev_staged[slot], ctx->copy_stream));
+  return UDAL_OK;
+}
+
+int udal_stage_acquire(udal_ctx* ctx, int slot) {
+  UDAL_SLOT_OK(slot);
+  UDAL_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_staged[slot], 0));
+  return UDAL_OK;
+}
+
+int udal_stage_release(udal_ctx* ctx, int slot) {
+  UDAL_SLOT_OK(slot);
+  UDAL_CUDA(cudaEventRecord(ctx->ev_consumed[slot], ctx->stream));
+  ctx->consumed_pending[slot] = true;
+  return UDAL_OK;
+}
+
+int udal_fetch_d2h(udal_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes) {
+  UDAL_REQUIRE(ctx && (bytes == 0 || (dst_host && src_dev)), "NULL argument");
+  cudaStream_t st = ctx->last_tail_stream ? ctx->last_tail_stream : ctx->stream;
+  if (bytes) UDAL_CUDA(cudaMemcpyAsync(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost, st));
+  return UDAL_OK;
+}
+
+int udal_fetch_mark(udal_ctx* ctx, int slot) {
+  UDAL_SLOT_OK(slot);
+  UDAL_CUDA(cudaEventRecord(ctx->ev_fetched[slot], ctx->last_tail_stream ? ctx->last_tail_stream : ctx->stream));
+  return UDAL_OK;
+}
+
+int udal_fetch_wait(udal_ctx* ctx, int slot) {
+  UDAL_SLOT_OK(slot);
+  UDAL_CUDA(cudaEventSynchronize(ctx->ev_fetched[slot]));
   return UDAL_OK;
 }
 

@@ -368,6 +368,7 @@ static int global_tail(udal_ctx* ctx, const GlobalScratch& g, int batch, const f
   assemble_global_kernel<<<batch, 128, 0, ctx->stream>>>(a);
   UDAL_CHECK_LAUNCH(ctx);
   if (udal_host_trace) udal_host_trace_mark("tail enqueued", 0);
+  ctx->last_tail_stream = tail_on_post ? ctx->post_stream : nullptr;
   if (tail_on_post) {
     UDAL_CUDA(cudaEventRecord(ctx->ev_post[bank], ctx->post_stream));
     ctx->post_pending[bank] = true;

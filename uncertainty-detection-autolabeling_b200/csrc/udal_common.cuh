@@ -80,6 +80,11 @@ struct udal_ctx {
   // work-item counters of the persistent head kernels (dynamic item claiming): one zeroed int per launch of a run
   int* work_counters = nullptr;
   int work_counter_next = 0;
+  // streaming front end (udal_stage_* / udal_fetch_*): uploads on a copy stream, results fetched behind the run's tail
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_staged[UDAL_STAGE_SLOTS] = {}, ev_consumed[UDAL_STAGE_SLOTS] = {}, ev_fetched[UDAL_STAGE_SLOTS] = {};
+  bool consumed_pending[UDAL_STAGE_SLOTS] = {};
+  cudaStream_t last_tail_stream = nullptr;   // where the last udal_run / postprocess call left its results (null: ctx->stream)
   bool feat_f16 = false;         // udal_set_feature_format: the feats pointers of udal_run / udal_heads_sample are fp16
   bool profile_layers = false;
   std::vector<cudaEvent_t> layer_events;  // pairs (start, stop) in launch order

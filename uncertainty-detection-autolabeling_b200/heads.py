@@ -10,7 +10,7 @@ import os
 
 import numpy as np
 
-from . import device, utils
+from . import device, utils, _lib
 from . import engine as _engine
 
 
@@ -91,6 +91,88 @@ class PipelinedSampler:
                     yield pending.pop(0).result()
             for f in pending:
                 yield f.result()
+
+
+class StreamingSampler:
+    """Throughput front end for host-resident batches on ONE context: the GPU runs exactly the sequence of back-to-back
+    ``udal_run`` calls (heads of batch i+1 over the NMS tail of batch i), the feature maps of the next batches are uploaded
+    on a copy stream into ``depth`` device buffer sets meanwhile, and the detections of a batch are fetched into pinned
+    host memory right behind its own tail (udal_stage_* / udal_fetch_* of include/udal.h).  ``map(batches)`` yields the
+    detection tuples (NumPy) in input order, ``depth - 1`` batches behind the submission.
+
+    Host arrays should live in pinned memory (device.PinnedArray) for the uploads to be asynchronous; float32 maps or -
+    fp16 heads - float16 maps (the reference's mixed_float16 exports)."""
+
+    def __init__(self, params, weights, device_id=None, heads_mode=None, depth=3):
+        if not 2 <= depth <= _lib.STAGE_SLOTS:
+            raise ValueError("depth must be 2..%d" % _lib.STAGE_SLOTS)
+        self.sampler = HeadSampler(params, weights, device_id, heads_mode)
+        self.engine = self.sampler.engine
+        self.depth = depth
+        self._slots = [None] * depth      # per slot: dict(key=(batch, dtype), feats=[DeviceArray], scales=DeviceArray, host={name: PinnedArray})
+        self._seed_base = int.from_bytes(os.urandom(8), "little")
+        self._maps = 0
+
+    def close(self):
+        self._slots = [None] * self.depth
+        self.sampler.close()
+
+    def _slot(self, i, batch, dtype):
+        eng = self.engine
+        sl = self._slots[i]
+        if sl is None or sl["key"] != (batch, dtype):
+            sl = dict(key=(batch, dtype),
+                      feats=[eng.ctx.empty((batch, h, w, eng.F), dtype) for h, w in eng.level_hw],
+                      scales=eng.ctx.empty((batch,), np.float32), scales_host=device.PinnedArray((batch,), np.float32), host=None)
+            self._slots[i] = sl
+        return sl
+
+    def map(self, batches, image_scales=None, seed=None):
+        eng, lib, h = self.engine, self.engine.lib, self.engine.ctx.handle
+        if seed is None:
+            self._maps += 1
+            seed = utils.mix_seed(self._seed_base, self._maps)
+        pending = []
+
+        def finish(slot):
+            _lib.check(lib.udal_fetch_wait(h, slot))
+            host = self._slots[slot]["host"]
+            return tuple(np.array(host[k].array, copy=True) for k in ("boxes", "scores", "classes", "valid", "logits"))
+
+        for i, feats in enumerate(batches):
+            slot = i % self.depth
+            if len(pending) >= self.depth:      # the slot's previous results must be out of its pinned buffers
+                yield finish(pending.pop(0))
+            feats = [np.ascontiguousarray(f) for f in feats]
+            dt = np.dtype(np.float16) if feats[0].dtype == np.float16 else np.dtype(np.float32)
+            batch = feats[0].shape[0]
+            sl = self._slot(slot, batch, dt)
+            # ---- upload on the copy stream ----
+            _lib.check(lib.udal_stage_begin(h, slot))
+            for dst, src in zip(sl["feats"], feats):
+                if src.dtype != dt or src.shape != dst.shape:
+                    raise ValueError("feature maps: expected %s %s, got %s %s" % (dt, dst.shape, src.dtype, src.shape))
+                _lib.check(lib.udal_stage_h2d(h, dst.ptr, src.ctypes.data, dst.nbytes))
+            sc = None
+            if image_scales is not None:
+                sl["scales_host"].array[...] = np.asarray(image_scales[i], np.float32)
+                _lib.check(lib.udal_stage_h2d(h, sl["scales"].ptr, sl["scales_host"].ptr, sl["scales"].nbytes))
+                sc = sl["scales"]
+            _lib.check(lib.udal_stage_end(h, slot))
+            # ---- the run, ordered behind its uploads; its inputs are free again once the heads are through ----
+            _lib.check(lib.udal_stage_acquire(h, slot))
+            bufs = eng.run(sl["feats"], sc, None, batch_seed(seed, i))
+            _lib.check(lib.udal_stage_release(h, slot))
+            # ---- results -> pinned host memory, behind this run's tail ----
+            if sl["host"] is None or any(sl["host"][k].shape != bufs[k].shape for k in bufs):
+                sl["host"] = {k: device.PinnedArray(v.shape, v.dtype) for k, v in bufs.items()}
+            for k, v in bufs.items():
+                _lib.check(lib.udal_fetch_d2h(h, sl["host"][k].ptr, v.ptr, v.nbytes))
+            _lib.check(lib.udal_fetch_mark(h, slot))
+            sl["bufs"] = bufs                   # keep the device buffers alive until the fetch has run
+            pending.append(slot)
+        while pending:
+            yield finish(pending.pop(0))
 
 
 def batch_seed(seed, i):
