@@ -289,6 +289,8 @@ def run_gpu(args, cfg):
     p = workload_params(cfg, mode)
     geom = u.engine.get_engine(p, device_id=local_rank)   # geometry only (the cached, weight-free engine)
     weights = u.synthetic.init_head_weights(geom.F, geom.R, len(geom.level_hw), geom.A, geom.C, True, seed=2024)  # SURVEY 8d seeds
+    if cfg["autolabel"]:
+        u.synthetic.autolabel_variant(weights)   # scores around min_score: the decision rule takes both branches
     sampler = u.heads.HeadSampler(p, weights, device_id=local_rank)
     eng = sampler.engine                                   # the sampler's own context holds the weights
     ctx = eng.ctx
@@ -296,8 +298,9 @@ def run_gpu(args, cfg):
     rng = np.random.default_rng(1234 + rank)
     # host (pinned) and device copies of the synthetic BiFPN features
     pinned = [u.device.PinnedArray((batch, h, w, eng.F)) for h, w in eng.level_hw]
+    amp = u.synthetic.autolabel_amplitudes(batch)[:, None, None, None] if cfg["autolabel"] else np.float32(1.0)
     for pa in pinned:
-        pa.array[...] = rng.standard_normal(pa.shape, dtype=np.float32)
+        pa.array[...] = rng.standard_normal(pa.shape, dtype=np.float32) * amp
     feats_dev = [ctx.to_device(pa.array) for pa in pinned]
     scales_host = np.ones(batch, np.float32)
     scales_dev = ctx.to_device(scales_host)
@@ -430,6 +433,7 @@ def run_gpu(args, cfg):
     host_feats = [pa.array for pa in pinned]
     e2e_blocking_ms = None
     e2e_f32 = None
+    auto_fraction = None
     feat16 = args.feature_dtype == "f16" or (args.feature_dtype == "auto" and mode == "fp16" and eng.F == 64)
     e2e_steps = max(24, args.steps)
     if not cfg["autolabel"]:
@@ -476,10 +480,12 @@ def run_gpu(args, cfg):
             return o["auto_label"].numpy()
         host_step(0)
         barrier()
+        decisions = []
         t0 = time.perf_counter()
         for i in range(e2e_steps):
-            host_step(i)
+            decisions.append(host_step(i))
         e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
+        auto_fraction = float(np.mean(np.concatenate(decisions)))
         barrier()
         e2e_ms = max_over_ranks(e2e_ms)
         d2h = batch  # one decision byte per image
@@ -614,6 +620,7 @@ def run_gpu(args, cfg):
         "p50_ms_per_step": float(np.median(step_ms)),
         "wall_s_timed_region": wall_s,
         "clocks": clock_info,
+        "auto_labelled_fraction": auto_fraction,
         "e2e": {"value": world * batch / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms, "steps": e2e_steps,
                 "how": ("StreamingSampler.map(host batches): per step the feature maps go pinned host -> device on a copy stream "

@@ -311,6 +311,29 @@ def test_streaming_sampler_matches_blocking_calls(u):
     st.close()
 
 
+def test_image_scheduler_shards_and_gathers(u):
+    """ImageScheduler (single process, one host thread + context per device; north_star item 4): the batch is sharded in
+    contiguous chunks, every shard runs udal_run on its own context, detections come back to the host in input order.
+    Runs on whatever is visible - with one GPU both shards land on it (two contexts), which exercises the same code."""
+    p = _cfg(u, (128, 192), 8, 4, heads_mode="fp16")
+    w = heads_ref.init_head_weights(64, 3, 5, 9, 8, True, randomize_bn=True)
+    n = u._lib.device_count()
+    devices = list(range(n)) if n > 1 else [0, 0]
+    sched = u.scheduler.ImageScheduler(p, w, devices=devices)
+    hw = sched.samplers[0].engine.level_hw
+    batch = 2 * len(devices) + 1                      # ragged: the last shard is shorter
+    feats = heads_ref.make_features(hw, batch, 64, seed=5)
+    scales = np.linspace(1.0, 2.0, batch).astype(np.float32)
+    got = sched.detect(feats, scales, seed=123)
+    assert got[0].shape[0] == batch and got[3].shape == (batch,)
+    ref = u.heads.HeadSampler(p, w)
+    for i, (a, b) in enumerate(u.scheduler.shard_ranges(batch, len(devices))):
+        if b > a:
+            r = ref.detect([f[a:b] for f in feats], scales[a:b], seed=u.heads.batch_seed(123, i))
+            for x, y in zip(r, got):
+                np.testing.assert_array_equal(x, y[a:b])
+
+
 def test_run_back_to_back_does_not_block_the_host(u):
     """udal_run is asynchronous: a call issued behind another one must return long before the device has finished the
     first (a hidden synchronisation between calls - round 2 had one in the Python input handling - costs the whole

@@ -22,6 +22,9 @@ ap.add_argument("--images", type=int, default=512)
 ap.add_argument("--batch", type=int, default=16)
 ap.add_argument("--heads-mode", default="bf16")
 ap.add_argument("--out", default=None)
+ap.add_argument("--class-bias", type=float, default=None,
+                help="class-predict bias of the synthetic head (default: udal_b200.synthetic.AUTOLABEL_CLASS_BIAS; the reference "
+                     "initialiser -log(99) puts every score near 0.01, far below min_score 0.4: no detection would ever be examined)")
 args = ap.parse_args()
 
 C, T = 10, 30
@@ -29,22 +32,31 @@ p = u.hparams_config.get_detection_config(
     "efficientdet-d2", image_size=(768, 768), num_classes=C, enable_softmax=True, loss_attenuation=True,
     mc_dropout=True, mc_classheadrate=0.05, mc_boxheadrate=0.05, mc_dropoutsamp=T, heads_mode=args.heads_mode)
 eng = u.engine.get_engine(p)
-eng.set_head_weights(u.synthetic.init_head_weights(eng.F, eng.R, len(eng.level_hw), eng.A, C, True, seed=2024))
+weights = u.synthetic.init_head_weights(eng.F, eng.R, len(eng.level_hw), eng.A, C, True, seed=2024)
+u.synthetic.autolabel_variant(weights, args.class_bias)
+eng.set_head_weights(weights)
 rng = np.random.default_rng(1234)
-feats = [eng.ctx.to_device(rng.standard_normal((args.batch, h, w, eng.F), dtype=np.float32)) for h, w in eng.level_hw]
+amp = u.synthetic.autolabel_amplitudes(args.batch)
+feats = [eng.ctx.to_device(rng.standard_normal((args.batch, h, w, eng.F), dtype=np.float32) * amp[:, None, None, None])
+         for h, w in eng.level_hw]
 scales = eng.ctx.to_device(np.ones(args.batch, np.float32))
 labeler = u.autolabel.AutoLabeler(dict(num_classes=C, thr_sel_uncert=["ENT", "ALBOX"], calib_method_box=None, min_score=0.4),
                                   opt_params=[0.5, 0.5], opt_thrs=[0.5])
 
 
-def step(seed):
+best = []
+
+
+def step(seed, stats=False):
     det = eng.run(feats, scales, None, seed=seed)
     out = labeler.decide((det["boxes"], det["scores"], det["classes"], det["valid"], det["logits"]))
+    if stats:
+        best.append(det["scores"].numpy().max(axis=1))
     return out["auto_label"].numpy()   # D2H of the decisions (synchronises)
 
 
 for i in range(2):
-    step(i)
+    step(i, stats=True)
 n_steps = (args.images + args.batch - 1) // args.batch
 labels = []
 eng.ctx.sync()
@@ -57,7 +69,12 @@ n = n_steps * args.batch
 res = {"config": "BASELINE configs[4]: EfficientDet-D2 768x768, C=10, T=30, auto-label threshold pass", "heads_mode": args.heads_mode,
        "images": n, "batch": args.batch, "seconds": sec, "images_per_s_per_gpu": n / sec,
        "projected_s_for_4096_images_on_8_gpus": 4096 / 8 / (n / sec), "anchors": eng.N,
-       "auto_labelled_fraction": float(np.mean(np.concatenate(labels))), "scratch_GB": eng.ctx.scratch_bytes() / 1e9}
+       "auto_labelled_fraction": float(np.mean(np.concatenate(labels))), "scratch_GB": eng.ctx.scratch_bytes() / 1e9,
+       "class_bias": float(weights["class"]["bp"][0]),
+       "best_score_per_image_quantiles": [float(q) for q in np.quantile(np.concatenate(best), [0, 0.25, 0.5, 0.75, 1.0])],
+       "synthetic_note": "per-image feature amplitude 0.6 .. 1.4 and a class-predict bias that puts the median image's best score at "
+                         "min_score, so that the decision rule (all opt_uncert of the detections with score > min_score < thr) "
+                         "takes both branches"}
 print(json.dumps(res))
 if args.out:
     json.dump(res, open(args.out, "w"), indent=1)

@@ -80,3 +80,23 @@ def make_masks(num_samples, num_levels, repeats, batch, num_filters, rate_class,
 def make_features(level_shapes, batch, num_filters, seed=1234):
     rng = np.random.default_rng(seed)
     return [rng.standard_normal((batch, h, w, num_filters)).astype(np.float32) for h, w in level_shapes]
+
+
+# ---- BASELINE configs[4] (auto-label threshold pass) --------------------------------------------------------------
+# With the reference initialiser (class-predict bias -log(99)) every score of a random-init head sits near 0.01, far
+# below the synthetic min_score 0.4 of SURVEY 8d: no detection is ever examined and the decision rule
+# (src/infer_model.py:742-764) says "auto-label" for every image.  The measured pass therefore shifts the class-predict
+# bias so that the median image's best score lands at min_score, and gives the images different feature amplitudes:
+# roughly half of them then carry detections above min_score (high entropy -> "examine"), the rest do not.
+AUTOLABEL_CLASS_BIAS = -1.3   # measured on B200: best score per image 0.26 .. 0.46 (median 0.35) at -1.5
+
+
+def autolabel_variant(weights, class_bias=None):
+    """in place: class-predict bias of the synthetic head for the auto-label pass"""
+    weights["class"]["bp"][...] = AUTOLABEL_CLASS_BIAS if class_bias is None else class_bias
+    return weights
+
+
+def autolabel_amplitudes(batch):
+    """per-image amplitude of the synthetic BiFPN features of the auto-label pass"""
+    return np.linspace(0.6, 1.4, batch).astype(np.float32)
