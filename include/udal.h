@@ -222,6 +222,28 @@ int udal_prenms_topk(udal_ctx* ctx, const float* const* cls, const float* const*
 int udal_nms_v5(udal_ctx* ctx, const float* boxes, const float* scores, int segments, int n,
                 int32_t* sel_idx, float* sel_scores, int32_t* valid);
 
+/* ---- BiFPN primitives (efficientdet_keras.py:51-350, 766-847) ---------------------------------
+ * The node graph (fpn_configs.bifpn_config) is host logic - bifpn.py mirrors FNode / FPNCell / FPNCells on top of
+ * these three calls.  All tensors device fp32 NHWC.
+ * udal_conv1x1_bn : ResampleFeatureMap._maybe_apply_1x1 (305-311): in [NB,H,W,Cin] @ w [Cin,F] + bias [F], then
+ *                   v * bn_scale + bn_shift when the tables are given (apply_bn_for_resampling).
+ * udal_bifpn_fuse : FNode.call / fuse_features (86-125, 166-173): out [NB,H,W,F] = act(sum_i weight_i *
+ *                   resample_i(in[i] [NB,in_h[i],in_w[i],F])); resampling by size as ResampleFeatureMap.call (313-350):
+ *                   larger source = max (pool_avg: average) pooling with stride s = (in-1)/out+1, window s+1, SAME
+ *                   padding; smaller = nearest neighbour; mode UDAL_FUSE_* with edge weights wsm[i] (scalar, or [F]
+ *                   with per_channel); act != 0 applies swish to the fused value (OpAfterCombine, 229-236, activates
+ *                   before its conv when conv_bn_act_pattern is off - the reference default).
+ * udal_sepconv_bn : OpAfterCombine's SeparableConv2D + BN (200-236): depthwise 3x3 SAME [9][F] -> pointwise [F][Cout]
+ *                   + bias -> act (UDAL_ACT_*). */
+enum { UDAL_FUSE_SUM = 0, UDAL_FUSE_FASTATTN = 1, UDAL_FUSE_ATTN = 2 };
+enum { UDAL_ACT_NONE = 0, UDAL_ACT_BN_SWISH = 1, UDAL_ACT_BN = 2 };
+int udal_conv1x1_bn(udal_ctx* ctx, const float* in, int NB, int H, int W, int Cin, const float* w, const float* bias,
+                    const float* bn_scale, const float* bn_shift, int F, float* out);
+int udal_bifpn_fuse(udal_ctx* ctx, int n, const float* const* in, const int* in_h, const int* in_w, const float* const* wsm,
+                    int mode, int per_channel, int pool_avg, int NB, int H, int W, int F, int act, float* out);
+int udal_sepconv_bn(udal_ctx* ctx, const float* in, int NB, int H, int W, int F, int Cout, const float* dw, const float* pw,
+                    const float* bias, const float* bn_scale, const float* bn_shift, int act, float* out);
+
 /* ---- fused post-processing -------------------------------------------------------------- */
 /* postprocess.py:472-621 (postprocess_global), serving variant.  image_scales: device [B] or
  * NULL.  Outputs (device): boxes [B,max_out,4*(1+has_al+has_mc)] = box|albox|mcbox,

@@ -18,6 +18,8 @@ NMS_HARD, NMS_GAUSSIAN = 0, 1
 HEADS_FP32, HEADS_BF16_TC, HEADS_FP16_TC = 0, 1, 2
 FEAT_F32, FEAT_F16 = 0, 1
 STAGE_SLOTS = 4
+FUSE_SUM, FUSE_FASTATTN, FUSE_ATTN = 0, 1, 2
+ACT_NONE, ACT_BN_SWISH, ACT_BN = 0, 1, 2
 HEAD_CLASS, HEAD_BOX = 0, 1
 
 
@@ -72,6 +74,12 @@ SIGNATURES = {
     "udal_set_stream": (ctypes.c_int, [_VP, _VP]),
     "udal_sync": (ctypes.c_int, [_VP]),
     "udal_set_feature_format": (ctypes.c_int, [_VP, ctypes.c_int]),
+    "udal_conv1x1_bn": (ctypes.c_int, [_VP, _VP, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, _VP, _VP, _VP, _VP,
+                                       ctypes.c_int, _VP]),
+    "udal_bifpn_fuse": (ctypes.c_int, [_VP, ctypes.c_int, _VP, _VP, _VP, _VP, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                       ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, _VP]),
+    "udal_sepconv_bn": (ctypes.c_int, [_VP, _VP, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, _VP, _VP,
+                                       _VP, _VP, _VP, ctypes.c_int, _VP]),
     "udal_stage_begin": (ctypes.c_int, [_VP, ctypes.c_int]),
     "udal_stage_h2d": (ctypes.c_int, [_VP, _VP, _VP, ctypes.c_size_t]),
     "udal_stage_end": (ctypes.c_int, [_VP, ctypes.c_int]),

@@ -14,7 +14,7 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libudal.so")
 SOURCES = ["api.cu", "decode_moments.cu", "topk.cu", "nms.cu", "nms_cta.cu", "post.cu", "heads_fp32.cu",
-           "heads_tc.cu", "heads_ig.cu", "heads_dw.cu", "heads_l1.cu", "heads_fused.cu", "heads_wide.cu", "run.cu", "nms_np.cu", "autolabel.cu", "decode_sample.cu"]
+           "heads_tc.cu", "heads_ig.cu", "heads_dw.cu", "heads_l1.cu", "heads_fused.cu", "heads_wide.cu", "run.cu", "nms_np.cu", "autolabel.cu", "decode_sample.cu", "bifpn.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-I", os.path.join(ROOT, "include"),

@@ -1,0 +1,212 @@
+// BiFPN (the producer of the hot path's input): device primitives of FPNCells.
+//
+// Replaces (reference src/efficientdet_keras.py): ResampleFeatureMap 238-350 (1x1 conv + BN when the channel count
+// differs, max / average pooling with TF "SAME" padding, nearest-neighbour up-sampling), FNode.fuse_features 86-125
+// (fastattn / attn / sum and their per-channel variants) and OpAfterCombine 176-236 (swish -> separable 3x3 conv ->
+// BN).  The graph itself (which node reads which, fpn_configs.bifpn_config) is host logic and lives in bifpn.py, as it
+// does in the reference.  fp32 throughout on the CUDA cores: this row is a functional producer for the heads, not a
+// tuned kernel set; the separable conv reuses the fp32 tower kernel of heads_fp32.cu.
+//
+//   udal_conv1x1_bn   [NB,H,W,Cin] -> [NB,H,W,F]: x @ w + b, then BN (scale, shift) when given
+//   udal_bifpn_fuse   out = act( sum_i weight_i * resample_i(in_i) ), resample_i chosen by the source / target sizes:
+//                     same size - copy; larger source - pooling window (stride s = (in-1)/out+1, size s+1, SAME padding:
+//                     pad_before = total/2, padded cells never win a max and do not count in an average);
+//                     smaller source - nearest neighbour, src = min(floor(dst * (float)in / out), in - 1)
+//                     (tf.compat.v1.image.resize_nearest_neighbor, align_corners = False)
+//   udal_sepconv_bn   depthwise 3x3 SAME -> pointwise + bias -> BN               (heads_fp32.cu kernel)
+#include "udal_common.cuh"
+
+int udal_sepconv_fp32_launch(udal_ctx* ctx, const float* in, int NB, int H, int W, int F, int Cout, const float* dw,
+                             const float* pw, const float* bias, const float* bn_scale, const float* bn_shift, int act,
+                             float* out);
+
+namespace {
+
+__device__ __forceinline__ float swish_f(float x) { return __fdiv_rn(x, 1.f + expf(-x)); }
+
+__global__ void conv1x1_bn_kernel(const float* __restrict__ in, const float* __restrict__ w, const float* __restrict__ bias,
+                                  const float* __restrict__ bn_scale, const float* __restrict__ bn_shift, int64_t pixels,
+                                  int Cin, int F, float* __restrict__ out) {
+  // block = 8 pixels x F outputs (F <= 512 handled by the stride loop); the pixel rows are staged in shared memory
+  extern __shared__ float s_in[];  // [8][Cin]
+  const int64_t p0 = (int64_t)blockIdx.x * 8;
+  const int npx = (int)min((int64_t)8, pixels - p0);
+  for (int e = threadIdx.x; e < npx * Cin; e += blockDim.x) s_in[e] = __ldg(in + p0 * Cin + e);
+  __syncthreads();
+  for (int f = threadIdx.x; f < F; f += blockDim.x) {
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+    for (int k = 0; k < Cin; ++k) {
+      const float wk = __ldg(w + (size_t)k * F + f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] = fmaf(i < npx ? s_in[i * Cin + k] : 0.f, wk, acc[i]);
+    }
+    const float b = bias ? __ldg(bias + f) : 0.f;
+    const float sc = bn_scale ? __ldg(bn_scale + f) : 1.f, sh = bn_scale ? __ldg(bn_shift + f) : 0.f;
+    for (int i = 0; i < npx; ++i) {
+      float v = acc[i] + b;
+      if (bn_scale) v = fmaf(v, sc, sh);
+      out[(p0 + i) * F + f] = v;
+    }
+  }
+}
+
+struct FuseParams {
+  int n;                       // inputs (1..3)
+  const float* in[3];          // [NB, h_i, w_i, F]
+  int h[3], w[3];
+  const float* wsm[3];         // edge weight of input i: scalar or [F] (per_channel); null for "sum"
+  int mode;                    // UDAL_FUSE_*
+  int per_channel;
+  int pool_avg;
+  int NB, H, W, F;
+  int act;                     // 1: swish on the fused value (OpAfterCombine applies it before its conv)
+  float* out;                  // [NB,H,W,F]
+};
+
+__device__ __forceinline__ float resample_at(const float* __restrict__ src, int h, int w, int H, int W, int y, int x, int F,
+                                             int f, int pool_avg) {
+  if (h == H && w == W) return __ldg(src + ((size_t)y * w + x) * F + f);
+  if (h > H && w > W) {
+    // pooling, TF "SAME": out = ceil(in / s) must equal the target (checked on the host)
+    const int sy = (h - 1) / H + 1, sx = (w - 1) / W + 1, ky = sy + 1, kx = sx + 1;
+    const int pad_y = max((H - 1) * sy + ky - h, 0) / 2, pad_x = max((W - 1) * sx + kx - w, 0) / 2;
+    const int y0 = y * sy - pad_y, x0 = x * sx - pad_x;
+    float best = -3.402823466e38f, sum = 0.f;
+    int cnt = 0;
+    for (int dy = 0; dy < ky; ++dy) {
+      const int yy = y0 + dy;
+      if (yy < 0 || yy >= h) continue;
+      for (int dx = 0; dx < kx; ++dx) {
+        const int xx = x0 + dx;
+        if (xx < 0 || xx >= w) continue;
+        const float v = __ldg(src + ((size_t)yy * w + xx) * F + f);
+        best = fmaxf(best, v);
+        sum += v;
+        ++cnt;
+      }
+    }
+    return pool_avg ? __fdiv_rn(sum, (float)cnt) : best;
+  }
+  // nearest neighbour (h <= H and w <= W)
+  const float sy = (float)h / (float)H, sx = (float)w / (float)W;
+  const int yy = min((int)floorf((float)y * sy), h - 1), xx = min((int)floorf((float)x * sx), w - 1);
+  return __ldg(src + ((size_t)yy * w + xx) * F + f);
+}
+
+__global__ void bifpn_fuse_kernel(const FuseParams p) {
+  const int64_t total = (int64_t)p.NB * p.H * p.W * p.F;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int f = (int)(i % p.F);
+  int64_t r = i / p.F;
+  const int x = (int)(r % p.W);
+  r /= p.W;
+  const int y = (int)(r % p.H);
+  const int nb = (int)(r / p.H);
+  float v[3], ew[3];
+  for (int k = 0; k < p.n; ++k) {
+    v[k] = resample_at(p.in[k] + (size_t)nb * p.h[k] * p.w[k] * p.F, p.h[k], p.w[k], p.H, p.W, y, x, p.F, f, p.pool_avg);
+    ew[k] = p.wsm[k] ? __ldg(p.wsm[k] + (p.per_channel ? f : 0)) : 1.f;
+  }
+  float acc;
+  if (p.mode == UDAL_FUSE_FASTATTN) {
+    // nodes[i] * relu(w_i) / (sum_j relu(w_j) + 0.0001), then add_n (left to right)
+    float ws = 0.f;
+    for (int k = 0; k < p.n; ++k) {
+      ew[k] = fmaxf(ew[k], 0.f);
+      ws = k == 0 ? ew[0] : __fadd_rn(ws, ew[k]);
+    }
+    const float den = __fadd_rn(ws, 0.0001f);
+    acc = __fdiv_rn(__fmul_rn(v[0], ew[0]), den);
+    for (int k = 1; k < p.n; ++k) acc = __fadd_rn(acc, __fdiv_rn(__fmul_rn(v[k], ew[k]), den));
+  } else if (p.mode == UDAL_FUSE_ATTN) {
+    // softmax over the edge weights, reduce_sum(nodes * w)
+    float mx = ew[0];
+    for (int k = 1; k < p.n; ++k) mx = fmaxf(mx, ew[k]);
+    float e[3], se = 0.f;
+    for (int k = 0; k < p.n; ++k) {
+      e[k] = expf(ew[k] - mx);
+      se += e[k];
+    }
+    acc = __fmul_rn(v[0], __fdiv_rn(e[0], se));
+    for (int k = 1; k < p.n; ++k) acc = __fadd_rn(acc, __fmul_rn(v[k], __fdiv_rn(e[k], se)));
+  } else {
+    acc = v[0];
+    for (int k = 1; k < p.n; ++k) acc = __fadd_rn(acc, v[k]);
+  }
+  p.out[i] = p.act ? swish_f(acc) : acc;
+}
+
+}  // namespace
+
+extern "C" {
+
+int udal_conv1x1_bn(udal_ctx* ctx, const float* in, int NB, int H, int W, int Cin, const float* w, const float* bias,
+                    const float* bn_scale, const float* bn_shift, int F, float* out) {
+  UDAL_REQUIRE(ctx && in && w && out, "NULL argument");
+  UDAL_REQUIRE(NB > 0 && H > 0 && W > 0 && Cin > 0 && F > 0, "udal_conv1x1_bn: bad sizes");
+  UDAL_REQUIRE((bn_scale == nullptr) == (bn_shift == nullptr), "udal_conv1x1_bn: BN scale and shift go together");
+  UDAL_REQUIRE((size_t)8 * Cin * sizeof(float) <= 48 * 1024, "udal_conv1x1_bn: %d input channels", Cin);
+  UDAL_TRY(udal_join(ctx));
+  const int64_t pixels = (int64_t)NB * H * W;
+  const int threads = F >= 128 ? 128 : 64;
+  conv1x1_bn_kernel<<<(unsigned)((pixels + 7) / 8), threads, (size_t)8 * Cin * sizeof(float), ctx->stream>>>(
+      in, w, bias, bn_scale, bn_shift, pixels, Cin, F, out);
+  UDAL_CHECK_LAUNCH(ctx);
+  return UDAL_OK;
+}
+
+int udal_bifpn_fuse(udal_ctx* ctx, int n, const float* const* in, const int* in_h, const int* in_w, const float* const* wsm,
+                    int mode, int per_channel, int pool_avg, int NB, int H, int W, int F, int act, float* out) {
+  UDAL_REQUIRE(ctx && in && in_h && in_w && out, "NULL argument");
+  UDAL_REQUIRE(n >= 1 && n <= 3, "udal_bifpn_fuse: %d inputs (1..3)", n);
+  UDAL_REQUIRE(mode == UDAL_FUSE_SUM || mode == UDAL_FUSE_FASTATTN || mode == UDAL_FUSE_ATTN, "unknown weight_method %d", mode);
+  UDAL_REQUIRE(NB > 0 && H > 0 && W > 0 && F > 0, "udal_bifpn_fuse: bad sizes");
+  FuseParams p;
+  memset(&p, 0, sizeof(p));
+  p.n = n;
+  for (int k = 0; k < n; ++k) {
+    UDAL_REQUIRE(in[k], "udal_bifpn_fuse: input %d is NULL", k);
+    const int h = in_h[k], w = in_w[k];
+    const bool same = h == H && w == W, down = h > H && w > W, up = h <= H && w <= W;
+    // efficientdet_keras.py:345-349
+    UDAL_REQUIRE(same || down || up, "Incompatible Resampling : feat shape %dx%d target_shape: %dx%d", h, w, H, W);
+    if (down) {
+      const int sy = (h - 1) / H + 1, sx = (w - 1) / W + 1;
+      UDAL_REQUIRE((h + sy - 1) / sy == H && (w + sx - 1) / sx == W,
+                   "pooling %dx%d with stride %dx%d does not give the target %dx%d", h, w, sy, sx, H, W);
+    }
+    p.in[k] = in[k];
+    p.h[k] = h;
+    p.w[k] = w;
+    p.wsm[k] = (wsm && mode != UDAL_FUSE_SUM) ? wsm[k] : nullptr;
+    UDAL_REQUIRE(mode == UDAL_FUSE_SUM || p.wsm[k], "udal_bifpn_fuse: edge weight %d is NULL", k);
+  }
+  p.mode = mode;
+  p.per_channel = per_channel;
+  p.pool_avg = pool_avg;
+  p.NB = NB;
+  p.H = H;
+  p.W = W;
+  p.F = F;
+  p.act = act;
+  p.out = out;
+  UDAL_TRY(udal_join(ctx));
+  const int64_t total = (int64_t)NB * H * W * F;
+  bifpn_fuse_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(p);
+  UDAL_CHECK_LAUNCH(ctx);
+  return UDAL_OK;
+}
+
+int udal_sepconv_bn(udal_ctx* ctx, const float* in, int NB, int H, int W, int F, int Cout, const float* dw, const float* pw,
+                    const float* bias, const float* bn_scale, const float* bn_shift, int act, float* out) {
+  UDAL_REQUIRE(ctx && in && dw && pw && bias && out, "NULL argument");
+  UDAL_REQUIRE(NB > 0 && H > 0 && W > 0 && F > 0 && Cout > 0, "udal_sepconv_bn: bad sizes");
+  UDAL_REQUIRE(act == UDAL_ACT_NONE || (bn_scale && bn_shift), "udal_sepconv_bn: BN tables missing");
+  UDAL_TRY(udal_join(ctx));
+  return udal_sepconv_fp32_launch(ctx, in, NB, H, W, F, Cout, dw, pw, bias, bn_scale, bn_shift, act, out);
+}
+
+}  // extern "C"

@@ -35,7 +35,7 @@ struct LayerParams {
   const float* bias;  // [Cout]
   int F, Cout, batch;
   int in_per_sample;  // 1: input indexed by nb (= t*B+b); 0: by b = nb % batch
-  int act;            // 1: BN + swish, 0: linear (predict)
+  int act;            // 1: BN + swish, 0: linear (predict), 2: BN only (BiFPN op_after_combine: the activation precedes the conv)
 };
 
 __device__ __forceinline__ float swish(float x) { return __fdiv_rn(x, 1.f + expf(-x)); }
@@ -126,13 +126,50 @@ __global__ void __launch_bounds__(kThreads) sepconv_layer_kernel(const LayerPara
         float v = acc[i][j] + __ldg(p.bias + n);
         if (p.act) {
           v = fmaf(v, __ldg(p.bn_scale[l] + n), __ldg(p.bn_shift[l] + n));
-          v = swish(v);
+          if (p.act == 1) v = swish(v);
         }
         out[((size_t)y * W + x) * p.Cout + n] = v;
       }
     }
   }
 }
+
+}  // namespace
+
+// one separable conv layer on a single feature map (BiFPN, bifpn.cu): depthwise 3x3 SAME -> pointwise + bias -> act
+int udal_sepconv_fp32_launch(udal_ctx* ctx, const float* in, int NB, int H, int W, int F, int Cout, const float* dw,
+                             const float* pw, const float* bias, const float* bn_scale, const float* bn_shift, int act,
+                             float* out) {
+  LayerParams p;
+  memset(&p, 0, sizeof(p));
+  p.num_levels = 1;
+  p.h[0] = H;
+  p.w[0] = W;
+  p.tiles_x[0] = (W + TW - 1) / TW;
+  const int tiles = p.tiles_x[0] * ((H + TH - 1) / TH);
+  for (int l = 1; l <= UDAL_MAX_LEVELS; ++l) p.tile_off[l] = tiles;
+  p.in[0] = in;
+  p.out[0] = out;
+  p.bn_scale[0] = bn_scale;
+  p.bn_shift[0] = bn_shift;
+  p.dw = dw;
+  p.pw = pw;
+  p.bias = bias;
+  p.F = F;
+  p.Cout = Cout;
+  p.batch = NB;
+  p.in_per_sample = 1;
+  p.act = act;
+  const size_t smem = ((size_t)F * IN_STRIDE + (size_t)F * TPX + (size_t)F * NCHUNK) * sizeof(float);
+  UDAL_REQUIRE(smem <= 227 * 1024, "separable conv with %d channels needs %zu bytes of shared memory", F, smem);
+  UDAL_REQUIRE(NB <= 65535, "separable conv: %d images per launch", NB);
+  UDAL_CUDA(cudaFuncSetAttribute(sepconv_layer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  sepconv_layer_kernel<<<dim3(tiles, NB), kThreads, smem, ctx->stream>>>(p);
+  UDAL_CHECK_LAUNCH(ctx);
+  return UDAL_OK;
+}
+
+namespace {
 
 // ---- dropout scales ---------------------------------------------------------------------------
 // scale[t][head][l][r][b][f] = keep ? 1/(1-rate) : 0   (SpatialDropout2D, noise shape [B,1,1,F])

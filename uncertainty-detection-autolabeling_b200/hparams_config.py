@@ -30,6 +30,9 @@ def default_detection_configs():
         min_level=3, max_level=7, num_scales=3, aspect_ratios=[1.0, 2.0, 0.5], anchor_scale=4.0,
         box_class_repeats=3, fpn_num_filters=64, separable_conv=True, act_type="swish",
         survival_prob=None,
+        # BiFPN (hparams_config.py:322-328, 344-346)
+        fpn_cell_repeats=3, apply_bn_for_resampling=True, conv_after_downsample=False, conv_bn_act_pattern=False,
+        fpn_name=None, fpn_weight_method=None, fpn_config=None,
         # nms (hparams_config.py:332-340)
         nms_configs=dict(method="gaussian", iou_thresh=None, score_thresh=0.0, sigma=None,
                          pyfunc=False, max_nms_inputs=0, max_output_size=100),
@@ -42,7 +45,10 @@ def get_detection_config(model_name="efficientdet-d0", **overrides):
     """Config dict for a model name plus overrides (``nms_configs`` merges key-wise)."""
     p = default_detection_configs()
     size, filters, _, repeats = MODEL_TABLE[model_name]
-    p.update(name=model_name, image_size=size, fpn_num_filters=filters, box_class_repeats=repeats)
+    _, _, cells, _ = MODEL_TABLE[model_name]
+    p.update(name=model_name, image_size=size, fpn_num_filters=filters, box_class_repeats=repeats, fpn_cell_repeats=cells)
+    if model_name in ("efficientdet-d6", "efficientdet-d7"):
+        p["fpn_weight_method"] = "sum"  # hparams_config.py:429,439
     overrides = copy.deepcopy(overrides)
     nms = overrides.pop("nms_configs", None)
     p.update(overrides)

@@ -100,3 +100,42 @@ def autolabel_variant(weights, class_bias=None):
 def autolabel_amplitudes(batch):
     """per-image amplitude of the synthetic BiFPN features of the auto-label pass"""
     return np.linspace(0.6, 1.4, batch).astype(np.float32)
+
+
+# ---- BiFPN (SURVEY 8(f)3) --------------------------------------------------------------------------------------------
+def init_bifpn_weights(num_filters, cell_repeats, in_channels, nodes, weight_method="fastattn", seed=77, randomize=True):
+    """Random FPNCells weights in the layout of ``bifpn.FPNCells``.  ``in_channels``: channel count of every input level of the
+    FIRST cell (e.g. EfficientNet-B0: [40, 112, 320, F, F]); ``nodes``: fpn_configs.bifpn_config(...)["nodes"].  The
+    reference initialises the edge weights with ones and BN with identity statistics; ``randomize`` draws non-trivial
+    values so that every term is exercised."""
+    rng = np.random.default_rng(seed)
+    f = num_filters
+    per_channel = weight_method.startswith("channel_")
+
+    def bn():
+        if not randomize:
+            return {"gamma": np.ones(f, np.float32), "beta": np.zeros(f, np.float32), "mean": np.zeros(f, np.float32),
+                    "var": np.ones(f, np.float32)}
+        return {"gamma": rng.uniform(0.5, 1.5, f).astype(np.float32), "beta": rng.normal(0, 0.2, f).astype(np.float32),
+                "mean": rng.normal(0, 0.2, f).astype(np.float32), "var": rng.uniform(0.5, 1.5, f).astype(np.float32)}
+
+    cells = []
+    for c in range(cell_repeats):
+        chans = list(in_channels) if c == 0 else [f] * len(in_channels)
+        fnodes = []
+        for node in nodes:
+            res, wsm = [], []
+            for off in node["inputs_offsets"]:
+                cin = chans[off] if off < len(chans) else f
+                if cin != f:
+                    res.append({"w": _trunc_normal(rng, (cin, f), math.sqrt(1.0 / cin)),
+                                "b": (rng.normal(0, 0.1, f) if randomize else np.zeros(f)).astype(np.float32), "bn": bn()})
+                else:
+                    res.append(None)
+                shape = (f,) if per_channel else ()
+                wsm.append((rng.uniform(-0.3, 1.5, shape) if randomize else np.ones(shape)).astype(np.float32))
+            fnodes.append({"resample": res, "wsm": None if weight_method == "sum" else wsm,
+                           "dw": _trunc_normal(rng, (3, 3, f), math.sqrt(1.0 / 9.0)), "pw": _trunc_normal(rng, (f, f), math.sqrt(1.0 / f)),
+                           "b": (rng.normal(0, 0.1, f) if randomize else np.zeros(f)).astype(np.float32), "bn": bn()})
+        cells.append({"fnodes": fnodes})
+    return {"cells": cells}
