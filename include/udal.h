@@ -49,8 +49,11 @@ enum { UDAL_NMS_HARD = 0, UDAL_NMS_GAUSSIAN = 1 };
 enum {
   UDAL_HEADS_FP32 = 0,    /* CUDA-core fp32 towers: the 1e-4 parity mode */
   UDAL_HEADS_BF16_TC = 1, /* tcgen05, bf16 operands / activations (implicit-GEMM kernels) */
-  UDAL_HEADS_FP16_TC = 2  /* tcgen05 pointwise + packed-fp16 depthwise, fp16 operands / activations: the precision the
+  UDAL_HEADS_FP16_TC = 2, /* tcgen05 pointwise + packed-fp16 depthwise, fp16 operands / activations: the precision the
                              reference's own GPU export runs in (mixed_float16, infer_lib.py:429-431); the benchmarked mode */
+  UDAL_HEADS_FP32X3_TC = 3 /* fp32-accurate on the tensor cores (64-channel towers): fp32 depthwise on the CUDA cores, the
+                              pointwise GEMM as three fp16 tcgen05 passes over (hi, lo) operand pairs with fp32 accumulation,
+                              fp32 activations: the 1e-4 contract of UDAL_HEADS_FP32 at several times its speed */
 };
 enum { UDAL_HEAD_CLASS = 0, UDAL_HEAD_BOX = 1 };
 

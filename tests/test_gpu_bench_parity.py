@@ -195,11 +195,15 @@ def test_benchmarked_path_vs_oracle(u, name, size, C, T, batch, mode):
     assert st["matched_fraction"] >= tol["matched"], st
 
 
-def test_fp32_path_end_to_end_vs_oracle(u):
-    """heads_mode fp32 (CUDA-core towers + fp64 decode): the 1e-4 contract of BASELINE.json on every decoded quantity,
-    per anchor, on a mid-size geometry (the fp32 towers are slow by design)."""
-    size, C, T, batch = (192, 320), 8, 6, 2
-    p = _params(u, size, C, T, "fp32")
+@pytest.mark.parametrize("mode,size,C,T,batch", [
+    ("fp32", (192, 320), 8, 6, 2),          # CUDA-core towers: slow by design, a mid-size geometry
+    ("fp32x3", (192, 320), 8, 6, 2),        # the same contract on the tensor cores (three fp16 passes over hi / lo operands)
+    ("fp32x3", (384, 1280), 8, 10, 1),      # ... at the bench geometry
+    ("fp32x3", (720, 1280), 10, 20, 1),     # ... and BASELINE configs[2] (90 logits: two predict chunks)
+])
+def test_fp32_path_end_to_end_vs_oracle(u, mode, size, C, T, batch):
+    """heads_mode fp32 / fp32x3 (+ fp64 decode): the 1e-4 contract of BASELINE.json on every decoded quantity, per anchor."""
+    p = _params(u, size, C, T, mode)
     eng = u.engine.get_engine(p)
     L = len(eng.level_hw)
     w = heads_ref.init_head_weights(eng.F, eng.R, L, eng.A, C, True, seed=2024, randomize_bn=True)
@@ -210,6 +214,11 @@ def test_fp32_path_end_to_end_vs_oracle(u):
     rcls, rbox = heads_ref.heads_sample(feats, w, masks, 0.05, 0.05, T)
     pre = ref_np.extract_uncertainties(p, rcls, rbox)
     st = per_anchor_stats(dev, pre, eng.anchors_host)
+    st.update(mode=mode, size=list(size), T=T, C=C)
+    out_dir = os.path.join(ROOT, "gpurun_out")
+    if os.path.isdir(out_dir):
+        with open(os.path.join(out_dir, "parity_%s_%dx%d.json" % (mode, size[0], size[1])), "w") as f:
+            json.dump(st, f, indent=1)
     print(json.dumps(st))
     tol = TOL["fp32"]
     assert st["logit_abs_max"] <= tol["logit_abs"], st

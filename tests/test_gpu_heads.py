@@ -256,6 +256,28 @@ def test_run_tail_overlap_is_invisible(u):
             np.testing.assert_array_equal(a[k], b[k])
 
 
+@pytest.mark.parametrize("size,C,T,batch,la,rc,rb", [
+    ((64, 96), 7, 4, 2, True, 0.05, 0.05),
+    ((40, 200), 10, 2, 3, True, 0.0, 0.2),   # ragged level sizes, class head deterministic, 90 logits = two predict chunks
+    ((128, 192), 8, 3, 2, False, 0.3, 0.0),  # box head deterministic and without sigma: 36 channels
+    ((384, 640), 8, 5, 1, True, 0.05, 0.05),
+])
+def test_heads_fp32x3_tensor_core_vs_oracle(u, size, C, T, batch, la, rc, rb):
+    """heads_mode fp32x3: pointwise GEMMs as three fp16 tensor-core passes over (hi, lo) operand pairs - the tolerance of
+    the CUDA-core fp32 towers (two fp32 conv implementations differ by summation order alone)"""
+    p = _cfg(u, size, C, T, la=la, rc=rc, rb=rb, heads_mode="fp32x3")
+    eng = u.engine.get_engine(p)
+    L = len(eng.level_hw)
+    w = heads_ref.init_head_weights(eng.F, eng.R, L, eng.A, C, la, randomize_bn=True)
+    feats = heads_ref.make_features(eng.level_hw, batch, eng.F)
+    masks = heads_ref.make_masks(T, L, eng.R, batch, eng.F, rc, rb)
+    cls, box = u.heads.HeadSampler(p, w)(feats, masks=masks)
+    rcls, rbox = heads_ref.heads_sample(feats, w, masks, rc, rb, T)
+    for a, b in zip(cls + box, rcls + rbox):
+        assert a.shape == b.shape
+        np.testing.assert_allclose(a, b, rtol=2e-4, atol=2e-4)
+
+
 def test_fp16_feature_maps_at_the_boundary(u):
     """udal_set_feature_format(UDAL_FEAT_F16): fp16 BiFPN maps (the reference's mixed_float16 exports) go straight into the
     layer-0 kernel.  On features that are exactly representable in fp16 the fp32-input and the fp16-input path run the same

@@ -15,7 +15,7 @@ ABI_VERSION = 1
 OK, ERR_INVALID, ERR_CUDA, ERR_STATE, ERR_NOMEM = 0, -1, -2, -3, -4
 DECODE_METHODS = {"l-norm": 0, "n-flow": 1, "falsedec": 2}
 NMS_HARD, NMS_GAUSSIAN = 0, 1
-HEADS_FP32, HEADS_BF16_TC, HEADS_FP16_TC = 0, 1, 2
+HEADS_FP32, HEADS_BF16_TC, HEADS_FP16_TC, HEADS_FP32X3_TC = 0, 1, 2, 3
 FEAT_F32, FEAT_F16 = 0, 1
 STAGE_SLOTS = 4
 FUSE_SUM, FUSE_FASTATTN, FUSE_ATTN = 0, 1, 2

@@ -175,6 +175,8 @@ static void free_head(udal_head_weights_dev& h) {
   cudaFree(h.wide_w);
   cudaFree(h.wide_f);
   cudaFree(h.l0_w);
+  cudaFree(h.x3_w);
+  cudaFree(h.x3_f);
   cudaFree(h.l0_ep);
   h = udal_head_weights_dev();
 }

@@ -234,6 +234,9 @@ int upload(udal_ctx* ctx, float** dst, const float* src, size_t n) {
 }  // namespace
 
 int udal_heads_tc_prepare(udal_ctx* ctx, int head);  // heads_tc.cu
+int udal_heads_x3_prepare(udal_ctx* ctx, int head);  // heads_wide.cu
+int udal_heads_x3_sample(udal_ctx* ctx, const float* const* feats, int batch, const float* scale, float* const* cls_out,
+                         float* const* box_out);
 int udal_heads_tc_sample(udal_ctx* ctx, const float* const* feats, int batch, const float* scale, float* const* cls_out,
                          float* const* box_out, const udal_prenms_out* fused_pre);
 
@@ -276,7 +279,8 @@ extern "C" int udal_set_head_weights(udal_ctx* ctx, int head, const float* dw, c
   // host sources are pageable: make sure the copies are done before the caller reuses them
   UDAL_CUDA(cudaStreamSynchronize(ctx->stream));
   h.set = true;
-  if (c.heads_mode != UDAL_HEADS_FP32) UDAL_TRY(udal_heads_tc_prepare(ctx, head));
+  if (c.heads_mode == UDAL_HEADS_FP32X3_TC) UDAL_TRY(udal_heads_x3_prepare(ctx, head));
+  else if (c.heads_mode != UDAL_HEADS_FP32) UDAL_TRY(udal_heads_tc_prepare(ctx, head));
   return UDAL_OK;
 }
 
@@ -386,6 +390,10 @@ static int heads_sample_impl(udal_ctx* ctx, const float* const* feats, int batch
     UDAL_CHECK_LAUNCH(ctx);
     scale_transpose_kernel<<<(int)((total + 255) / 256), 256, 0, ctx->stream>>>(scale_raw, scale, T, L, R, batch, F);
     UDAL_CHECK_LAUNCH(ctx);
+  }
+  if (c.heads_mode == UDAL_HEADS_FP32X3_TC) {
+    UDAL_REQUIRE(!fused_pre, "the fused predict + decode kernels need heads_mode fp16 | bf16");
+    return udal_heads_x3_sample(ctx, feats, batch, scale, cls_out, box_out);
   }
   if (c.heads_mode != UDAL_HEADS_FP32) return udal_heads_tc_sample(ctx, feats, batch, scale, cls_out, box_out, fused_pre);
   UDAL_REQUIRE(!fused_pre, "the fused predict + decode kernels need a tensor-core heads mode (fp16 | bf16)");

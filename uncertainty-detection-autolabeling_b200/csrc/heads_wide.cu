@@ -34,19 +34,25 @@ constexpr int kWdThreads = 64 + 32 * (kWdBuilderWarps + kWdEpiWarps);
 constexpr int WD_STG_STRIDE = 34;                         // floats per pixel row of the fp32 staging tile (32 + pad, even)
 // compile-time shape of one kernel variant: CH channels (64 | 128, in = out), input bf16 or fp32 (layer 0 of the
 // 64-channel towers reads the BiFPN features directly).  Shared memory map, offsets from a 1024-byte aligned base.
-template <int CH_, bool F32IN_>
+// X3 (fp32-accurate mode, 64 channels): both GEMM operands as fp16 pairs hi + lo (x = hi + lo to ~2^-22), the product
+// as three tensor-core passes into one fp32 accumulator: A_hi B_hi + A_hi B_lo + A_lo B_hi (the dropped lo x lo term is
+// ~2^-22 relative); activations stay fp32 in HBM.
+template <int CH_, bool F32IN_, bool X3_ = false>
 struct WdShape {
   static constexpr int CH = CH_, ATOMS = CH_ / 64;
-  static constexpr bool F32IN = F32IN_;
+  static constexpr bool F32IN = F32IN_, X3 = X3_;
   static constexpr int PX_BYTES = CH * (F32IN ? 4 : 2);
   static constexpr int STAGE = IG_ROWS * IG_BOXW * PX_BYTES;   // halo tile, linear [18][10][CH]
-  static constexpr int A_BYTES = ATOMS * 16384;                // ATOMS x [128 px][128 B] depthwise output (UMMA A)
-  static constexpr int B_BYTES = ATOMS * CH * 128;             // ATOMS x [CH n][128 B] pointwise weights (UMMA B)
+  static constexpr int A_TILE = ATOMS * 16384;                 // ATOMS x [128 px][128 B] depthwise output (UMMA A)
+  static constexpr int A_BYTES = A_TILE * (X3 ? 2 : 1);        // X3: hi tile, lo tile
+  static constexpr int B_IMG = ATOMS * CH * 128;               // ATOMS x [CH n][128 B] pointwise weights (UMMA B)
+  static constexpr int B_BYTES = B_IMG * (X3 ? 2 : 1);         // X3: hi image, lo image
   static constexpr int A = 0;                                  // 2 x A_BYTES (double buffered)
   static constexpr int B = A + 2 * A_BYTES;
   static constexpr int OUT = B + B_BYTES;                      // staging: bf16 ATOMS x [128][128 B], or fp32 2 x [128][34]
   static constexpr int OUT_BYTES = 2 * 128 * WD_STG_STRIDE * 4;
-  static constexpr int STAGES = CH == 64 ? 3 : 2;              // halo tile ring (HBM latency; 128 channels: no room for a third)
+  static constexpr int STAGES = (CH == 64 && !X3) ? 3 : 2;     // halo tile ring (HBM latency; 128 channels / X3: no room for a third)
+  static_assert(!X3 || (CH == 64 && F32IN), "the fp32-accurate mode: 64 channels, fp32 activations");
   static constexpr int IN = OUT + OUT_BYTES;                   // STAGES x halo tile
   static constexpr int BAR = IN + STAGES * STAGE;              // mbarriers + tmem slot
   static constexpr int EP = BAR + 256;                         // [2][CH] fp32 epilogue scale | bias of the current item's level
@@ -54,7 +60,7 @@ struct WdShape {
   static constexpr int SMEM = QUEUE + IG_QRING * 4 + 1024;
   static_assert(CH == 64 || CH == 128, "channel count");
   static_assert(STAGE % 128 == 0 && IN % 1024 == 0 && B % 1024 == 0 && OUT % 1024 == 0, "alignment");   // (the halo tile is linear: no swizzle atom)
-  static_assert(A_BYTES <= OUT_BYTES, "bf16 staging tile");
+  static_assert(A_TILE <= OUT_BYTES, "bf16 staging tile");
   static_assert(SMEM <= kIgSmemLimit, "shared-memory budget");
 };
 
@@ -71,6 +77,7 @@ struct WdParams {
   const void* wimg;                      // bf16 2 atoms x [128 n][64 k], 128B swizzle
   void* out[UDAL_MAX_LEVELS];            // tower: [NB,H,W,128] bf16 (through the tensor maps); predict: [NB,H,W,ch_total] fp32
   int predict, Cout, ch_off, ch_total;   // predict: this launch writes channels [ch_off, ch_off + Cout)
+  int act;                               // fp32-out path (predict = 1): 1 = epilogue scale, bias and an accurate swish (X3 tower layers)
   int debug;                             // timing experiments only (wrong results): 1 = no depthwise math, 2 = no epilogue math / stores
   int* counter;                          // zeroed work-item counter of this launch (dynamic claiming, heads_umma.cuh)
 };
@@ -83,9 +90,16 @@ struct WdMaps {
 __device__ __forceinline__ void wd_epi_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 __device__ __forceinline__ void wd_half_sync(int hc) { asm volatile("bar.sync %0, 128;" ::"r"(2 + hc) : "memory"); }
 
-template <int CH, bool F32IN, bool FP16>
+__device__ __forceinline__ float wd_swish_accurate(float x) {  // x * sigmoid(x), ~4e-7 relative (ex2 / rcp approximations)
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-1.4426950408889634f * x));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.f + e));
+  return x * r;
+}
+
+template <int CH, bool F32IN, bool FP16, bool X3 = false>
 __global__ void __launch_bounds__(kWdThreads, 1) heads_wide_kernel(const __grid_constant__ WdMaps maps, const WdParams p) {
-  using S = WdShape<CH, F32IN>;
+  using S = WdShape<CH, F32IN, X3>;
   constexpr int WF = CH, WD_STAGE = S::STAGE, WD_A = S::A, WD_B = S::B, WD_OUT = S::OUT, WD_IN = S::IN, WD_BAR = S::BAR,
                 WD_EP = S::EP, A_BYTES = S::A_BYTES, B_BYTES = S::B_BYTES, PX_BYTES = S::PX_BYTES;
   constexpr uint32_t kTmemCols = 2 * CH;
@@ -182,11 +196,23 @@ __global__ void __launch_bounds__(kWdThreads, 1) heads_wide_kernel(const __grid_
       if (ig_elect_one()) {
         bar_wait(tempty + 8 * ab, ((i >> 1) & 1) ^ 1);    // accumulator drained
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if constexpr (X3) {
+          // A_hi B_hi + A_hi B_lo + A_lo B_hi, smallest terms last
 #pragma unroll
-        for (int k = 0; k < WF / 16; ++k) {
-          const uint64_t adesc = ig_desc(sb + WD_A + ab * A_BYTES + (uint32_t)((k >> 2) * 16384 + (k & 3) * 32), 1024, 0);
-          const uint64_t bdesc = ig_desc(sb + WD_B + (uint32_t)((k >> 2) * (CH * 128) + (k & 3) * 32), 1024, 0);
-          ig_mma(d_tmem, adesc, bdesc, idesc, k ? 1u : 0u);
+          for (int g = 0; g < 3; ++g)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const uint64_t adesc = ig_desc(sb + WD_A + ab * A_BYTES + (uint32_t)((g == 2 ? S::A_TILE : 0) + k * 32), 1024, 0);
+              const uint64_t bdesc = ig_desc(sb + WD_B + (uint32_t)((g == 1 ? S::B_IMG : 0) + k * 32), 1024, 0);
+              ig_mma(d_tmem, adesc, bdesc, idesc, (g | k) ? 1u : 0u);
+            }
+        } else {
+#pragma unroll
+          for (int k = 0; k < WF / 16; ++k) {
+            const uint64_t adesc = ig_desc(sb + WD_A + ab * A_BYTES + (uint32_t)((k >> 2) * 16384 + (k & 3) * 32), 1024, 0);
+            const uint64_t bdesc = ig_desc(sb + WD_B + (uint32_t)((k >> 2) * (CH * 128) + (k & 3) * 32), 1024, 0);
+            ig_mma(d_tmem, adesc, bdesc, idesc, k ? 1u : 0u);
+          }
         }
         ig_commit(a_empty + 8 * ab);   // A buffer reusable once these MMAs retire
         ig_commit(tfull + 8 * ab);     // accumulator ready
@@ -261,10 +287,19 @@ __global__ void __launch_bounds__(kWdThreads, 1) heads_wide_kernel(const __grid_
           if (r >= 2) {
             const int y = r - 2;
             const int m = (8 * half + y) * IG_TW + x;
+            const float v0 = acc[y][0].x * sc.x, v1 = acc[y][0].y * sc.y, v2 = acc[y][1].x * sc.z, v3 = acc[y][1].y * sc.w;
             uint2 o;
-            o.x = ig_pack16<FP16>(acc[y][0].x * sc.x, acc[y][0].y * sc.y);
-            o.y = ig_pack16<FP16>(acc[y][1].x * sc.z, acc[y][1].y * sc.w);
-            *reinterpret_cast<uint2*>(sA + (size_t)m * 128 + ((chunk ^ (uint32_t)(m & 7)) << 4) + sub) = o;
+            o.x = ig_pack16<FP16>(v0, v1);
+            o.y = ig_pack16<FP16>(v2, v3);
+            uint8_t* const dstA = sA + (size_t)m * 128 + ((chunk ^ (uint32_t)(m & 7)) << 4) + sub;
+            *reinterpret_cast<uint2*>(dstA) = o;
+            if constexpr (X3) {  // the part of the value the 16-bit operand lost, as a second operand tile
+              const float2 h01 = ig_unpack16<FP16>(o.x), h23 = ig_unpack16<FP16>(o.y);
+              uint2 lo;
+              lo.x = ig_pack16<FP16>(v0 - h01.x, v1 - h01.y);
+              lo.y = ig_pack16<FP16>(v2 - h23.x, v3 - h23.y);
+              *reinterpret_cast<uint2*>(dstA + S::A_TILE) = lo;
+            }
           }
         }
       }
@@ -308,6 +343,7 @@ __global__ void __launch_bounds__(kWdThreads, 1) heads_wide_kernel(const __grid_
         } else if ((et & 127) < HC) {  // predict: each column-half group (own barrier) loads the biases it reads
           const int n = WF + hc * HC + (et & 127);
           sEp[n] = __ldg(p.ep[w.l] + n);
+          if (p.act) sEp[n - WF] = __ldg(p.ep[w.l] + n - WF);
         }
       }
       const float4* eps = reinterpret_cast<const float4*>(sEp + hc * HC);
@@ -391,10 +427,20 @@ __global__ void __launch_bounds__(kWdThreads, 1) heads_wide_kernel(const __grid_
           for (int u = 0; u < 4; ++u) {
             const float4 f0 = epb[pass * 8 + 2 * u], f1 = epb[pass * 8 + 2 * u + 1];
             const float fb[8] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w};
+            if (p.act) {  // tower layer of the fp32-accurate mode: BN scale, folded bias, swish
+              const float4 g0 = eps[pass * 8 + 2 * u], g1 = eps[pass * 8 + 2 * u + 1];
+              const float gs[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
 #pragma unroll
-            for (int e = 0; e < 8; e += 2)
-              *reinterpret_cast<float2*>(stg + m * WD_STG_STRIDE + u * 8 + e) =
-                  make_float2(__fadd_rn(__uint_as_float(r[u][e]), fb[e]), __fadd_rn(__uint_as_float(r[u][e + 1]), fb[e + 1]));
+              for (int e = 0; e < 8; e += 2)
+                *reinterpret_cast<float2*>(stg + m * WD_STG_STRIDE + u * 8 + e) =
+                    make_float2(wd_swish_accurate(fmaf(__uint_as_float(r[u][e]), gs[e], fb[e])),
+                                wd_swish_accurate(fmaf(__uint_as_float(r[u][e + 1]), gs[e + 1], fb[e + 1])));
+            } else {
+#pragma unroll
+              for (int e = 0; e < 8; e += 2)
+                *reinterpret_cast<float2*>(stg + m * WD_STG_STRIDE + u * 8 + e) =
+                    make_float2(__fadd_rn(__uint_as_float(r[u][e]), fb[e]), __fadd_rn(__uint_as_float(r[u][e + 1]), fb[e + 1]));
+            }
           }
           wd_half_sync(hc);
           const int nch = min(32, p.Cout - c0);  // channels of this pass that exist
@@ -543,11 +589,11 @@ int udal_heads_wide_prepare(udal_ctx* ctx, int head) {
   return UDAL_OK;
 }
 
-template <int CH, bool F32IN, bool FP16>
+template <int CH, bool F32IN, bool FP16, bool X3 = false>
 static int launch_wide_t(udal_ctx* ctx, const void* const* in, int in_nb, int NB, const float* const* in_scale, const float* dw,
                        const void* wimg, const float* const* ep, int predict, int cout, int ch_off, int ch_total,
-                       void* const* out) {
-  using S = WdShape<CH, F32IN>;
+                       void* const* out, int act = 0) {
+  using S = WdShape<CH, F32IN, X3>;
   EncodeTiledFn encode = get_encode();
   UDAL_REQUIRE(encode != nullptr, "cuTensorMapEncodeTiled is not available from this driver");
   const udal_config& c = ctx->cfg;
@@ -565,6 +611,7 @@ static int launch_wide_t(udal_ctx* ctx, const void* const* in, int in_nb, int NB
   p.Cout = cout;
   p.ch_off = ch_off;
   p.ch_total = ch_total;
+  p.act = act;
   p.debug = udal_wide_debug;
   UDAL_TRY(udal_work_counter(ctx, &p.counter));
   int off = 0;
@@ -591,8 +638,8 @@ static int launch_wide_t(udal_ctx* ctx, const void* const* in, int in_nb, int NB
   for (int l = c.num_levels; l <= UDAL_MAX_LEVELS; ++l) p.item_off[l] = off;
   p.items = off;
   const int grid = udal_persistent_grid(ctx, p.items);
-  UDAL_CUDA(cudaFuncSetAttribute(heads_wide_kernel<CH, F32IN, FP16>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::SMEM));
-  heads_wide_kernel<CH, F32IN, FP16><<<grid, kWdThreads, S::SMEM, ctx->stream>>>(maps, p);
+  UDAL_CUDA(cudaFuncSetAttribute(heads_wide_kernel<CH, F32IN, FP16, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::SMEM));
+  heads_wide_kernel<CH, F32IN, FP16, X3><<<grid, kWdThreads, S::SMEM, ctx->stream>>>(maps, p);
   UDAL_CHECK_LAUNCH(ctx);
   return UDAL_OK;
 }
@@ -737,5 +784,131 @@ int udal_heads_wide_sample(udal_ctx* ctx, const float* const* feats, int batch, 
   }
   UDAL_TRY(run_tower_wide(ctx, UDAL_HEAD_CLASS, feats16, batch, scale, cls_out));
   UDAL_TRY(run_tower_wide(ctx, UDAL_HEAD_BOX, feats16, batch, scale, box_out));
+  return UDAL_OK;
+}
+
+// =====================================================================================================================
+// fp32-accurate tensor-core mode (UDAL_HEADS_FP32X3_TC; 64-channel towers): every layer through heads_wide_kernel<64, fp32
+// in, fp16 operands, X3> - depthwise in fp32 on the CUDA cores, the pointwise GEMM as three fp16 tensor-core passes over
+// (hi, lo) operand pairs, fp32 accumulation, accurate swish, fp32 activations in HBM.  The 1e-4 parity contract of the
+// CUDA-core fp32 towers (heads_fp32.cu) at a multiple of their speed; predict layers write the [T,...] outputs, K2 is the
+// stand-alone decode_moments kernel.
+// =====================================================================================================================
+namespace {
+
+// hi / lo fp16 images of one pointwise matrix: [2][64 n][64 k], 128B swizzle; lo = fp16(w - fp32(fp16(w)))
+__global__ void x3_weights_kernel(const float* __restrict__ w, int ldw, int n0, int cout, __half* __restrict__ wimg) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= KF * KF) return;
+  const int k = i % KF, n = i / KF;
+  const float v = n < cout ? w[(size_t)k * ldw + n0 + n] : 0.f;
+  const __half hi = __float2half_rn(v);
+  const __half lo = __float2half_rn(v - __half2float(hi));
+  const size_t e = ((size_t)n * 128 + (size_t)((((k >> 3) ^ (n & 7)) << 4) + (k & 7) * 2)) / 2;
+  wimg[e] = hi;
+  wimg[(size_t)KF * KF + e] = lo;
+}
+
+}  // namespace
+
+int udal_heads_x3_prepare(udal_ctx* ctx, int head) {
+  const udal_config& c = ctx->cfg;
+  udal_head_weights_dev& h = ctx->heads[head];
+  UDAL_REQUIRE(c.num_filters == KF, "heads_mode fp32x3: fpn_num_filters 64 (EfficientDet-D0) only, got %d", c.num_filters);
+  const int R = c.repeats, L = c.num_levels;
+  const int chunks = (h.cout + KF - 1) / KF;
+  h.x3_chunks = chunks;
+  if (h.x3_w) UDAL_CUDA(cudaFree(h.x3_w));
+  if (h.x3_f) UDAL_CUDA(cudaFree(h.x3_f));
+  h.x3_w = nullptr;
+  h.x3_f = nullptr;
+  UDAL_CUDA(cudaMalloc(&h.x3_w, (size_t)(R + chunks) * 2 * KF * KF * sizeof(__half)));
+  UDAL_CUDA(cudaMalloc(&h.x3_f, ((size_t)R * L + chunks) * 2 * KF * sizeof(float)));
+  __half* img = reinterpret_cast<__half*>(h.x3_w);
+  for (int r = 0; r < R; ++r) {
+    x3_weights_kernel<<<(KF * KF + 255) / 256, 256, 0, ctx->stream>>>(h.pw + (size_t)r * KF * KF, KF, 0, KF, img + (size_t)r * 2 * KF * KF);
+    UDAL_CHECK_LAUNCH(ctx);
+    for (int l = 0; l < L; ++l) {
+      const size_t o = (size_t)r * L + l;
+      wide_ep_kernel<<<1, KF, 0, ctx->stream>>>(h.bias + (size_t)r * KF, h.bn_scale + o * KF, h.bn_shift + o * KF, 0, KF, h.x3_f + o * 2 * KF, KF);
+      UDAL_CHECK_LAUNCH(ctx);
+    }
+  }
+  for (int q = 0; q < chunks; ++q) {
+    const int n0 = q * KF, nc = h.cout - n0 < KF ? h.cout - n0 : KF;
+    x3_weights_kernel<<<(KF * KF + 255) / 256, 256, 0, ctx->stream>>>(h.pwp, h.cout, n0, nc, img + (size_t)(R + q) * 2 * KF * KF);
+    UDAL_CHECK_LAUNCH(ctx);
+    wide_ep_kernel<<<1, KF, 0, ctx->stream>>>(h.bp, nullptr, nullptr, n0, nc, h.x3_f + ((size_t)R * L + q) * 2 * KF, KF);
+    UDAL_CHECK_LAUNCH(ctx);
+  }
+  UDAL_CUDA(cudaStreamSynchronize(ctx->stream));
+  return UDAL_OK;
+}
+
+static int run_tower_x3(udal_ctx* ctx, int head, const float* const* feats, int batch, const float* scale_all, float* const* outs) {
+  const udal_config& c = ctx->cfg;
+  const udal_head_weights_dev& h = ctx->heads[head];
+  UDAL_REQUIRE(h.x3_w && h.x3_f, "fp32x3 tables not built");
+  const int R = c.repeats, L = c.num_levels, T = c.mc_samples, B = batch;
+  const bool mc = head == UDAL_HEAD_CLASS ? c.cls_mc != 0 : c.box_mc != 0;
+  const int NBt = mc ? T * B : B;
+  const size_t P = (size_t)ctx->num_pixels;
+  float *a0, *pp;
+  UDAL_TRY(udal_scratch_get(ctx, SCR_HEADS_A, (size_t)B * P * KF * 4, (void**)&a0));
+  UDAL_TRY(udal_scratch_get(ctx, SCR_HEADS_B, 2 * (size_t)NBt * P * KF * 4, (void**)&pp));
+  const __half* img = reinterpret_cast<const __half*>(h.x3_w);
+  auto mark = [&]() {
+    if (!ctx->profile_layers) return;
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) == cudaSuccess) {
+      cudaEventRecord(e, ctx->stream);
+      ctx->layer_events.push_back(e);
+    }
+  };
+  for (int layer = 0; layer <= R; ++layer) {
+    const bool predict = layer == R;
+    const void* in[UDAL_MAX_LEVELS];
+    void* out[UDAL_MAX_LEVELS];
+    const float* in_scale[UDAL_MAX_LEVELS];
+    const float* ep[UDAL_MAX_LEVELS];
+    const int nb_out = layer == 0 ? B : NBt;
+    const int in_nb = layer <= 1 ? B : NBt;
+    for (int l = 0; l < L; ++l) {
+      const size_t lvl = (size_t)ctx->level_pix_off[l] * KF;
+      if (layer == 0) in[l] = feats[l];
+      else if (layer == 1) in[l] = a0 + (size_t)B * lvl;
+      else in[l] = pp + (size_t)((layer - 1) & 1) * NBt * P * KF + (size_t)NBt * lvl;
+      if (predict) out[l] = outs[l];
+      else if (layer == 0) out[l] = a0 + (size_t)B * lvl;
+      else out[l] = pp + (size_t)(layer & 1) * NBt * P * KF + (size_t)NBt * lvl;
+      // SpatialDropout2D of the producer layer (layer - 1), applied to the depthwise output (it commutes)
+      in_scale[l] = (mc && layer >= 1) ? scale_all + (((size_t)head * L + l) * R + (layer - 1)) * (size_t)NBt * KF : nullptr;
+      ep[l] = predict ? nullptr : h.x3_f + ((size_t)layer * L + l) * 2 * KF;
+    }
+    mark();
+    const float* const* sc = (mc && layer >= 1) ? in_scale : nullptr;
+    if (!predict) {
+      // fp32 out through the staged row path (predict = 1) with BN + swish (act = 1)
+      UDAL_TRY((launch_wide_t<64, true, true, true>)(ctx, in, in_nb, nb_out, sc, h.dw + (size_t)layer * 9 * KF,
+                                                     img + (size_t)layer * 2 * KF * KF, ep, 1, KF, 0, KF, out, 1));
+    } else {
+      for (int q = 0; q < h.x3_chunks; ++q) {
+        const int n0 = q * KF, nc = h.cout - n0 < KF ? h.cout - n0 : KF;
+        for (int l = 0; l < L; ++l) ep[l] = h.x3_f + ((size_t)R * L + q) * 2 * KF;
+        UDAL_TRY((launch_wide_t<64, true, true, true>)(ctx, in, in_nb, nb_out, sc, h.dwp, img + (size_t)(R + q) * 2 * KF * KF, ep, 1, nc,
+                                                       n0, h.cout, out, 0));
+      }
+    }
+    mark();
+  }
+  return UDAL_OK;
+}
+
+int udal_heads_x3_sample(udal_ctx* ctx, const float* const* feats, int batch, const float* scale, float* const* cls_out,
+                         float* const* box_out) {
+  for (int l = 0; l < ctx->cfg.num_levels; ++l)
+    UDAL_REQUIRE(((uintptr_t)feats[l] & 15) == 0, "level %d: feature pointers must be 16-byte aligned", l);
+  UDAL_TRY(run_tower_x3(ctx, UDAL_HEAD_CLASS, feats, batch, scale, cls_out));
+  UDAL_TRY(run_tower_x3(ctx, UDAL_HEAD_BOX, feats, batch, scale, box_out));
   return UDAL_OK;
 }

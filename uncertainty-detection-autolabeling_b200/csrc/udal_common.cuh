@@ -36,6 +36,10 @@ struct udal_head_weights_dev {
   void* wide_w = nullptr;   // bf16 pointwise images [R + wide_chunks][2 atoms][128 n][64 k]
   float* wide_f = nullptr;  // depthwise [R + 1][9][128], then epilogue (scale | bias) [R][L][2][128] + [wide_chunks][2][128]
   int wide_chunks = 0;      // predict layer as chunks of <= 128 channels
+  // fp32-accurate tensor-core mode (heads_wide.cu, X3): fp16 (hi, lo) images [R + x3_chunks][2][64][64], epilogue tables
+  void* x3_w = nullptr;
+  float* x3_f = nullptr;
+  int x3_chunks = 0;
   void* l0_w = nullptr;     // 64-channel towers, layer 0 through heads_wide_kernel<64, fp32 in>: bf16 [64 n][64 k] image
   float* l0_ep = nullptr;   // ... and its epilogue tables [L][2][64] (BN scale | folded bias)
   // fp16 mode (heads_dw.cu): depthwise on the CUDA cores, pointwise on tcgen05

@@ -160,9 +160,10 @@ class Engine:
         cfg.max_nms_inputs = int(nms.get("max_nms_inputs", 0) or 0)
         cfg.max_output_size = int(nms.get("max_output_size", 100))
         modes = {"fp32": _lib.HEADS_FP32, "bf16": _lib.HEADS_BF16_TC, "bf16_tc": _lib.HEADS_BF16_TC,
-                 "fp16": _lib.HEADS_FP16_TC, "fp16_tc": _lib.HEADS_FP16_TC}
+                 "fp16": _lib.HEADS_FP16_TC, "fp16_tc": _lib.HEADS_FP16_TC, "fp32x3": _lib.HEADS_FP32X3_TC,
+                 "fp32_tc": _lib.HEADS_FP32X3_TC}
         if heads_mode not in modes:
-            raise ValueError("heads_mode must be one of fp32 | fp16 | bf16, got %r" % (heads_mode,))
+            raise ValueError("heads_mode must be one of fp32 | fp32x3 | fp16 | bf16, got %r" % (heads_mode,))
         cfg.heads_mode = modes[heads_mode]
         cfg.prefilter_k = int(params.get("nms_prefilter_k", 0) or 0)
         self.cfg = cfg
