@@ -606,7 +606,7 @@ def run_gpu(args, cfg):
     line = {
         "metric": cfg["metric"], "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": {"fp32": "f32", "bf16": "bf16", "fp16": "f16"}[mode], "data": "synthetic",
+        "vs_baseline": None, "dtype": {"fp32": "f32", "fp32x3": "f32 (3 x fp16 tensor-core passes)", "bf16": "bf16", "fp16": "f16"}[mode], "data": "synthetic",
         "config": {
             "workload": cfg["workload"],
             "batch_per_gpu": batch, "num_classes": cfg["C"], "T": cfg["T"], "anchors": eng.N,

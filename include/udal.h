@@ -133,6 +133,10 @@ int udal_get_stream(udal_ctx* ctx, void** cuda_stream);
  * special handles 0 / 1 = legacy default stream, 2 = per-thread default stream): zero-copy inputs written by another
  * framework's stream (the context's own streams are non-blocking and do not synchronise with the default stream) */
 int udal_wait_stream(udal_ctx* ctx, void* producer_stream);
+/* the same between two contexts: all later work of `ctx` after everything `producer` has enqueued so far (its udal_run
+ * tails included).  Device arrays of one context handed to an entry point of another one (a sampler's detections into the
+ * auto-label pass of a different context) are ordered this way by the Python layer. */
+int udal_wait_context(udal_ctx* ctx, udal_ctx* producer);
 int udal_malloc(udal_ctx* ctx, size_t bytes, void** dev_ptr);
 int udal_free(udal_ctx* ctx, void* dev_ptr);
 int udal_host_alloc(size_t bytes, void** pinned_ptr);

@@ -120,3 +120,38 @@ def test_autolabel_on_device_detections_and_errors():
         u.autolabel.AutoLabeler(dict(num_classes=C, calib_method_box="bogus"), [0.5, 0.5], [0.5])
     with pytest.raises(ValueError):
         u.autolabel.AutoLabeler(dict(num_classes=C, calib_method_box="iso_percoo"), [0.5, 0.5], [0.5], tables=[])
+
+
+@pytest.mark.gpu
+def test_autolabel_behind_a_sampler_of_another_context():
+    """detections left on the device by one context's udal_run (tail on its post stream) feed the auto-label pass: the
+    pass must see finished data (round 2 found it reading the buffers before the producer's tail had run) - decisions
+    equal the pass on host copies, repeatedly, with runs queued back to back"""
+    import udal_b200 as u
+    from oracle import heads_ref
+    C = 8
+    p = u.hparams_config.get_detection_config("efficientdet-d0", image_size=(256, 384), num_classes=C, enable_softmax=True,
+                                              loss_attenuation=True, mc_dropout=True, mc_classheadrate=0.05,
+                                              mc_boxheadrate=0.05, mc_dropoutsamp=6, heads_mode="fp16")
+    w = heads_ref.init_head_weights(64, 3, 5, 9, C, True)
+    w["class"]["bp"][...] = -1.0
+    sampler = u.heads.HeadSampler(p, w)
+    eng = sampler.engine
+    batch = 8
+    labeler = u.autolabel.AutoLabeler(dict(num_classes=C, thr_sel_uncert=["ENT", "ALBOX"], calib_method_box=None, min_score=0.3),
+                                      opt_params=[0.5, 0.5], opt_thrs=[0.5])
+    other = u.engine.get_engine(p)          # a second context: device arrays of `eng` handed to it are ordered behind eng
+    assert other.ctx is not eng.ctx
+    for trial in range(4):
+        feats = [eng.ctx.to_device(f * np.linspace(0.5, 1.5, batch, dtype=np.float32)[:, None, None, None])
+                 for f in heads_ref.make_features(eng.level_hw, batch, 64, seed=trial)]
+        det = eng.run(feats, None, None, seed=trial)
+        tup = (det["boxes"], det["scores"], det["classes"], det["valid"], det["logits"])
+        dev = labeler.decide(tup)                              # in the producer's context
+        sig = other.ctx.empty(det["logits"].shape)
+        u._lib.check(other.lib.udal_sigmoid(other.ctx.handle, u.device.as_device(other.ctx, det["logits"], np.float32)[0].ptr,
+                                            det["logits"].size, sig.ptr))          # cross-context consumer
+        host = labeler.decide(tuple(x.numpy() for x in tup))
+        np.testing.assert_array_equal(dev["auto_label"].numpy(), host["auto_label"])
+        np.testing.assert_allclose(dev["opt_uncert"].numpy(), host["opt_uncert"], rtol=1e-6)
+        np.testing.assert_allclose(sig.numpy(), 1.0 / (1.0 + np.exp(-det["logits"].numpy().astype(np.float64))), rtol=1e-5)

@@ -90,6 +90,7 @@ SIGNATURES = {
     "udal_fetch_wait": (ctypes.c_int, [_VP, ctypes.c_int]),
     "udal_get_stream": (ctypes.c_int, [_VP, _PP]),
     "udal_wait_stream": (ctypes.c_int, [_VP, _VP]),
+    "udal_wait_context": (ctypes.c_int, [_VP, _VP]),
     "udal_malloc": (ctypes.c_int, [_VP, ctypes.c_size_t, _PP]),
     "udal_free": (ctypes.c_int, [_VP, _VP]),
     "udal_host_alloc": (ctypes.c_int, [ctypes.c_size_t, _PP]),

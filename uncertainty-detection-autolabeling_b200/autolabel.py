@@ -110,7 +110,9 @@ class AutoLabeler:
         boxes, scores, classes, _valid, logits = detections
         host = not _post._is_dev(boxes)
         eng = _post._any_engine()
-        ctx = eng.ctx
+        # device inputs: work in THEIR context (same streams as the producer - no cross-context ordering, and a timer on
+        # that context sees the pass); host inputs: any cached context
+        ctx = boxes.ctx if isinstance(boxes, device.DeviceArray) else eng.ctx
         bx, _ = device.as_device(ctx, boxes, np.float32)
         sc, _ = device.as_device(ctx, scores, np.float32)
         cl, _ = device.as_device(ctx, classes, np.float32)

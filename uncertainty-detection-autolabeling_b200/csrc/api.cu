@@ -306,6 +306,21 @@ int udal_wait_stream(udal_ctx* ctx, void* producer_stream) {
   return UDAL_OK;
 }
 
+int udal_wait_context(udal_ctx* ctx, udal_ctx* producer) {
+  UDAL_REQUIRE(ctx && producer, "NULL ctx");
+  if (ctx == producer) return UDAL_OK;
+  // everything the producer has enqueued - its udal_run tails included - before anything this context enqueues from now on
+  UDAL_TRY(udal_join(producer));
+  cudaEvent_t ev;
+  UDAL_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  cudaError_t e = cudaEventRecord(ev, producer->stream);
+  if (e == cudaSuccess) e = cudaSetDevice(ctx->cfg.device);
+  if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->stream, ev, 0);
+  cudaEventDestroy(ev);
+  UDAL_CUDA(e);
+  return UDAL_OK;
+}
+
 int udal_sync(udal_ctx* ctx) {
   UDAL_REQUIRE(ctx, "NULL ctx");
   UDAL_TRY(udal_join(ctx));

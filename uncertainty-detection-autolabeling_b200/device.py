@@ -134,6 +134,11 @@ class Context:
         0 / 1 = legacy default stream, 2 = per-thread default stream)."""
         _lib.check(self.lib.udal_wait_stream(self.handle, ctypes.c_void_p(producer_stream or 0)))
 
+    def wait_context(self, producer):
+        """orders all later work of this context behind everything ``producer`` (another Context) has enqueued"""
+        if producer is not self and producer.handle:
+            _lib.check(self.lib.udal_wait_context(self.handle, producer.handle))
+
     def timer_start(self):
         _lib.check(self.lib.udal_timer_start(self.handle))
 
@@ -337,6 +342,8 @@ def as_device(ctx, x, dtype=None):
     if isinstance(x, DeviceArray):
         if dtype is not None and x.dtype != np.dtype(dtype):
             raise TypeError("expected %s, got %s" % (np.dtype(dtype), x.dtype))
+        if x.ctx is not ctx:   # produced by another context (own streams): order this context behind it
+            ctx.wait_context(x.ctx)
         return x, False
     cai = getattr(x, "__cuda_array_interface__", None)
     if cai is not None:

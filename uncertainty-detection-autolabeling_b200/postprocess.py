@@ -252,7 +252,9 @@ def pre_nms(params, cls_outputs, box_outputs, topk=True, uncerts=None):
     if uncerts is not None and uncerts[0] is not None:
         # level merge of the logit std (postprocess.py:177-178) = the moments kernel with T = 1
         std_levels, _, _ = eng.level_inputs(to_list(uncerts[0]), eng.A * eng.C, False)
-        dummy = [eng.ctx.zeros((batch, h, w, eng.box_channels)) for h, w in eng.level_hw]
+        # (the kernel reads the box head's full [T,B,...] extent even when only the logit moments are wanted)
+        lead = (eng.T,) if eng.box_mc else ()
+        dummy = [eng.ctx.zeros(lead + (batch, h, w, eng.box_channels)) for h, w in eng.level_hw]
         std_merged = eng.decode_moments(std_levels, dummy, batch, want=("mean_logits",))["mean_logits"]
     if eng.k > 0:
         o = eng.prenms_topk(cls, box, batch)
