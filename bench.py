@@ -522,8 +522,11 @@ def run_gpu(args, cfg):
     # ---- per-kernel rooflines: algorithmic work of the layer / CUDA-event time of its launch ----
     traffic = ncu_traffic()
     wide = eng.F != 64
-    fused_run = bool(mode != "fp32" and lib_int(eng, "udal_run_fused") and eng.C in (7, 8, 10) and eng.A == 9 and not wide)
-    if mode == "fp16":
+    fused_run = bool(mode not in ("fp32", "fp32x3") and lib_int(eng, "udal_run_fused") and eng.C in (7, 8, 10) and eng.A == 9 and not wide)
+    if mode == "fp32x3":
+        x3 = "heads_wide_kernel<64,f32in,fp16 x 3>"
+        names = {0: x3, 1: x3, "tower": x3, "predict": x3, "fused": x3 + " %s"}
+    elif mode == "fp16":
         names = {0: "heads_wide_kernel<64,f32in>", 1: "heads_l1_kernel", "tower": "heads_dw_kernel<tower>",
                  "predict": "heads_dw_kernel<predict>", "fused": "heads_dwf_kernel<%s>"}
     else:
