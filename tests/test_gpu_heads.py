@@ -280,6 +280,39 @@ def test_heads_fp32x3_tensor_core_vs_oracle(u, size, C, T, batch, la, rc, rb):
         np.testing.assert_allclose(a, b, rtol=2e-4, atol=2e-4)
 
 
+@pytest.mark.parametrize("size,T,batch,C", [
+    ((128, 192), 4, 3, 8),
+    ((40, 200), 3, 2, 7),         # ragged levels (5x25 ... 1x2): tiles hanging over every border
+    ((384, 1280), 10, 1, 8),      # the bench geometry
+    ((720, 1280), 5, 1, 10),      # odd level sizes, 90 logits
+])
+def test_tower_layer_fused_into_the_predict_kernels(u, size, T, batch, C):
+    """fp16 udal_run: the last tower layer inside the fused predict + K2 kernels (its output never reaches HBM) computes
+    exactly what its stand-alone kernel computes - same fp16 depthwise order, same GEMM, same epilogue - so every per-anchor
+    tensor and every detection is bit-identical between udal_heads_l2_fused = 1 and 0."""
+    import ctypes
+    p = _cfg(u, size, C, T, heads_mode="fp16")
+    eng = u.engine.get_engine(p)
+    L = len(eng.level_hw)
+    eng.set_head_weights(heads_ref.init_head_weights(eng.F, eng.R, L, eng.A, C, True, randomize_bn=True))
+    feats = [eng.ctx.to_device(f) for f in heads_ref.make_features(eng.level_hw, batch, eng.F, seed=9)]
+    masks = heads_ref.make_masks(T, L, eng.R, batch, eng.F, 0.05, 0.05, seed=4)
+    scales = eng.ctx.to_device(np.linspace(1.0, 1.5, batch).astype(np.float32))
+    sw = ctypes.c_int.in_dll(eng.lib, "udal_heads_l2_fused")
+    res = {}
+    try:
+        for v in (1, 0):
+            sw.value = v
+            pre = {k: a.numpy() for k, a in eng.run_prenms(feats, masks, seed=0).items()}
+            det = {k: a.numpy() for k, a in eng.run(feats, scales, masks, seed=0).items()}
+            res[v] = (pre, det)
+    finally:
+        sw.value = 1
+    for part in (0, 1):
+        for k in res[1][part]:
+            np.testing.assert_array_equal(res[1][part][k], res[0][part][k], err_msg=k)
+
+
 def test_fp16_feature_maps_at_the_boundary(u):
     """udal_set_feature_format(UDAL_FEAT_F16): fp16 BiFPN maps (the reference's mixed_float16 exports) go straight into the
     layer-0 kernel.  On features that are exactly representable in fp16 the fp32-input and the fp16-input path run the same

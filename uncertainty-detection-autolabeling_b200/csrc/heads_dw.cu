@@ -472,6 +472,7 @@ int dw_fill_geometry(udal_ctx* ctx, P& p, int NB) {
 constexpr int kDfThreads = 640;
 constexpr int kDfFirstBuilderWarp = 4, kDfFirstEpiWarp = 8;
 constexpr int kDfRegsIssue = 40, kDfRegsBuild = 104, kDfRegsEpi = 112;  // 128 x (40 + 104 + 3 x 112) = 640 x 96: the launch allocation
+constexpr int kDfRegsBuild2 = 104;   // (setmaxnreg can only redistribute the CTA's launch allocation, 640 x 96: a larger request would wait forever)
 template <int N>
 __device__ __forceinline__ void df_reg_inc() {
   asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N));
@@ -480,28 +481,43 @@ template <int N>
 __device__ __forceinline__ void df_reg_dec() {
   asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));
 }
-// compile-time shape of one kernel variant (offsets from a 1024-byte aligned base)
-template <int NPAD_, int STAGES_, int OUT_BYTES_, int OUT2_BYTES_>
+// compile-time shape of one kernel variant (offsets from a 1024-byte aligned base).  L2 = the last tower layer runs inside
+// the kernel as well: its input halo tile is 20 x 12 pixels, its output never leaves shared memory.
+constexpr int DF2_ROWS = IG_ROWS + 2, DF2_BOXW = IG_BOXW + 2;      // 20 x 12 pixel halo tile of the fused tower layer
+constexpr int DF2_IN_BYTES = DF2_ROWS * DF2_BOXW * 128;            // 30 720
+constexpr int DF2_MID_PX = IG_ROWS * IG_BOXW;                      // 180 pixels of tower-layer output feed one predict tile
+template <int NPAD_, int STAGES_, int OUT_BYTES_, int OUT2_BYTES_, bool L2_ = false>
 struct DfShape {
-  static constexpr int NPAD = NPAD_, STAGES = STAGES_;
+  static constexpr int NPAD = NPAD_, STAGES = L2_ ? 2 : STAGES_;
+  static constexpr bool L2 = L2_;
   static constexpr int B = 0;
   static constexpr int B_BYTES = (NPAD * 128 + 1023) / 1024 * 1024;
-  static constexpr int A = B + B_BYTES;                // 2 x [128][128 B]
-  static constexpr int IN = A + 2 * 16384;
-  static constexpr int OUT = IN + STAGES * DW_IN_STRIDE;  // class: [128 px][9 NC] fp32; box: boxes | albox, 2 x [128 px][36]
+  static constexpr int B2 = B + B_BYTES;               // L2: [64][128 B] tower pointwise image
+  static constexpr int A = B2 + (L2 ? 8192 : 0);       // 2 x [128][128 B]
+  static constexpr int A2 = A + 2 * 16384;             // L2: [256][128 B] depthwise output of the tower layer (180 rows used)
+  static constexpr int MID = A2 + (L2 ? 32768 : 0);    // L2: [18][10][128 B] tower-layer output = the predict layer's halo tile
+  static constexpr int IN = MID + (L2 ? DW_IN_STRIDE : 0);
+  static constexpr int IN_STRIDE = L2 ? DF2_IN_BYTES : DW_IN_STRIDE;
+  static constexpr int IN_BYTES = L2 ? DF2_IN_BYTES : DW_IN_BYTES;
+  static constexpr int OUT = IN + STAGES * IN_STRIDE;  // class: [128 px][9 NC] fp32; box: boxes | albox, 2 x [128 px][36]
   static constexpr int OUT2 = OUT + OUT_BYTES_;        // class: scores [128][9] fp32, classes [128][9] i32; box: mcbox [128][36]
-  static constexpr int BAR = OUT2 + OUT2_BYTES_;       // barriers + tmem slot (192 B)
-  static constexpr int BIAS = BAR + 192;               // [NPAD] fp32 predict bias
+  static constexpr int BAR = OUT2 + OUT2_BYTES_;       // barriers + tmem slot (256 B)
+  static constexpr int BIAS = BAR + 256;               // [NPAD] fp32 predict bias
   static constexpr int QUEUE = BIAS + NPAD * 4;        // item-index ring (IG_QRING ints)
-  static constexpr int SMEM = QUEUE + IG_QRING * 4 + 1024;
+  static constexpr int EP2 = QUEUE + IG_QRING * 4;     // L2: [2][64] halved BN scale | folded bias of the current level, then [64] keep-scales
+  static constexpr int DWW = EP2 + (L2 ? 3 * KF * 4 : 0);   // L2: depthwise weights [9][64] fp16 of the tower layer
+  static constexpr int SMEM = DWW + (L2 ? 2 * 9 * KF * 2 : 0) + 1024;   // (tower layer's, then the predict layer's)
   static_assert(STAGES <= 4 && 2 * NPAD <= 256, "layout");
+  static_assert(DF2_IN_BYTES % 1024 == 0 && A % 1024 == 0 && A2 % 1024 == 0 && IN % 128 == 0, "alignment");
   static_assert(SMEM <= kIgSmemLimit, "shared-memory budget");
 };
 // A = 9 anchors: 63 / 72 logits (7 / 8 classes) and the 72 box + sigma channels share one shape; 10 classes (BDD100K) = 90 logits
-using DfShape72 = DfShape<80, 4, 128 * 72 * 4, 128 * 36 * 4>;
-using DfShape96 = DfShape<96, 4, 128 * 90 * 4, 128 * 9 * 8>;
-template <bool BOX, int NC>
-using DfShapeOf = typename std::conditional<(BOX || NC <= 8), DfShape72, DfShape96>::type;
+template <bool L2>
+using DfShape72 = DfShape<80, 4, 128 * 72 * 4, 128 * 36 * 4, L2>;
+template <bool L2>
+using DfShape96 = DfShape<96, 4, 128 * 90 * 4, 128 * 9 * 8, L2>;
+template <bool BOX, int NC, bool L2 = false>
+using DfShapeOf = typename std::conditional<(BOX || NC <= 8), DfShape72<L2>, DfShape96<L2>>::type;
 
 struct DfParams {
   int num_levels, NB, T, items;          // NB = images; items = sum_l tiles[l] * NB (level major)
@@ -522,6 +538,12 @@ struct DfParams {
   float* boxes;                          // box head outputs [NB,N,4]
   float* albox;
   float* mcbox;
+  // L2 variant: the last tower layer (its input = maps.m, box {64,12,20,1})
+  const float* dw2;                      // [9][64] fp32 depthwise weights of the tower layer
+  const void* wimg2;                     // fp16 [64][64] swizzled image of its pointwise weights
+  const float* ep2_scale[UDAL_MAX_LEVELS];  // [64] per-level BN scale
+  const float* ep2_bias[UDAL_MAX_LEVELS];   // [64] folded bias
+  const float* keep2[UDAL_MAX_LEVELS];      // [T*NB][64] keep-scale of the tower layer's own SpatialDropout2D
 };
 
 struct DfMaps {
@@ -572,19 +594,93 @@ __device__ __forceinline__ void df_ld4(uint32_t taddr, uint32_t (&r)[4]) {
                : "memory");
 }
 
-// NC = classes per anchor of the class head (7: KITTI map of the reference YAMLs, 8, 10: BDD100K); the box head ignores it
-template <bool BOX, int NC>
+// ---- L2 variant helpers: the last tower layer inside the fused predict kernel -------------------------------------------
+__device__ __forceinline__ void df2_builder_sync() { asm volatile("bar.sync 2, 128;" ::: "memory"); }  // the 4 builder warps
+
+// depthwise 3x3 of the tower layer over the 18 x 10 positions that feed one predict tile: halo tile sIn [20][12] px x 64 ch
+// fp16 (linear) -> A operand sA2 [256][128 B] (row m = y * 10 + x, rows 180.. unused), K-major, 128B swizzle.  45 units of
+// 2 x 2 outputs x 8 channel groups over 128 threads = 3 passes; a unit reads a 4 x 4 pixel window row by row.
+__device__ __forceinline__ void df2_build_tile(const uint8_t* __restrict__ sIn, uint8_t* __restrict__ sA2,
+                                               const uint8_t* __restrict__ sW /* [9][64] fp16 */, int btid) {
+  const int cg = btid & 7;
+  __half2 W[9][4];
+#pragma unroll
+  for (int tp = 0; tp < 9; ++tp) {
+    const uint4 w4 = *reinterpret_cast<const uint4*>(sW + tp * 128 + cg * 16);
+    W[tp][0] = *reinterpret_cast<const __half2*>(&w4.x);
+    W[tp][1] = *reinterpret_cast<const __half2*>(&w4.y);
+    W[tp][2] = *reinterpret_cast<const __half2*>(&w4.z);
+    W[tp][3] = *reinterpret_cast<const __half2*>(&w4.w);
+  }
+#pragma unroll 1
+  for (int pass = 0; pass < 3; ++pass) {
+    const int u = pass * 16 + (btid >> 3);
+    if (u >= 45) continue;
+    const int y0 = 2 * (u / 5), x0 = 2 * (u % 5);
+    __half2 acc[2][2][4];
+#pragma unroll
+    for (int oy = 0; oy < 2; ++oy)
+#pragma unroll
+      for (int ox = 0; ox < 2; ++ox)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) acc[oy][ox][q] = __floats2half2_rn(0.f, 0.f);
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      uint4 in[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        in[c] = *reinterpret_cast<const uint4*>(sIn + (size_t)((y0 + r) * DF2_BOXW + x0 + c) * 128 + cg * 16);
+#pragma unroll
+      for (int dy = 0; dy < 3; ++dy) {
+        const int oy = r - dy;
+        if (oy >= 0 && oy < 2) {
+#pragma unroll
+          for (int ox = 0; ox < 2; ++ox)
+#pragma unroll
+            for (int dx = 0; dx < 3; ++dx) {
+              const __half2* v = reinterpret_cast<const __half2*>(&in[ox + dx]);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) acc[oy][ox][q] = __hfma2(v[q], W[dy * 3 + dx][q], acc[oy][ox][q]);
+            }
+        }
+      }
+      if (r >= 2) {
+        const int oy = r - 2;
+#pragma unroll
+        for (int ox = 0; ox < 2; ++ox) {
+          const int m = (y0 + oy) * IG_BOXW + x0 + ox;
+          uint4 o;
+          o.x = *reinterpret_cast<const uint32_t*>(&acc[oy][ox][0]);
+          o.y = *reinterpret_cast<const uint32_t*>(&acc[oy][ox][1]);
+          o.z = *reinterpret_cast<const uint32_t*>(&acc[oy][ox][2]);
+          o.w = *reinterpret_cast<const uint32_t*>(&acc[oy][ox][3]);
+          *reinterpret_cast<uint4*>(sA2 + (size_t)m * 128 + (((uint32_t)cg ^ (uint32_t)(m & 7)) << 4)) = o;
+        }
+      }
+    }
+  }
+}
+
+// NC = classes per anchor of the class head (7: KITTI map of the reference YAMLs, 8, 10: BDD100K); the box head ignores it.
+// L2: the last tower layer runs inside the kernel - per (tile, sample): TMA 20 x 12 halo tile of the layer's INPUT ->
+// builders: depthwise over 18 x 10 (df2_build_tile) -> 2 x 4 MMAs (M = 128 each) into TMEM columns 256.. -> builders: BN +
+// swish + keep-scale -> fp16 tile [18][10] in shared memory, zero outside the image (= the SAME padding the predict layer's
+// depthwise conv sees) -> dw_build_tile -> the predict GEMM -> statistics.  The tower layer's output never reaches HBM.
+template <bool BOX, int NC, bool L2 = false>
 __global__ void __launch_bounds__(kDfThreads, 1) heads_dwf_kernel(const __grid_constant__ DfMaps maps, const DfParams p) {
-  using S = DfShapeOf<BOX, NC>;
+  using S = DfShapeOf<BOX, NC, L2>;
   constexpr int NPAD = S::NPAD, STAGES = S::STAGES;
+  constexpr uint32_t kD2Col = 256;   // TMEM columns of the tower layer's accumulators (L2)
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = s32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
   const uint32_t sb = s32(smem);
   // barriers: in_full[4] @0  in_empty[4] @32  a_full[2] @64  a_empty[2] @80  tfull[2] @96  tempty[2] @112  bfull @128  slot @136
+  //           L2: a2_full @144  a2_empty @152  d2_full @160  d2_empty @168
   const uint32_t bar0 = sb + S::BAR;
   const uint32_t in_full = bar0, in_empty = bar0 + 32, a_full = bar0 + 64, a_empty = bar0 + 80, bar_tfull = bar0 + 96,
-                 bar_tempty = bar0 + 112, bar_b = bar0 + 128;
+                 bar_tempty = bar0 + 112, bar_b = bar0 + 128, a2_full = bar0 + 144, a2_empty = bar0 + 152, d2_full = bar0 + 160,
+                 d2_empty = bar0 + 168;
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + S::BAR + 136);
   float* sBias = reinterpret_cast<float*>(smem + S::BIAS);
   volatile int* sQ = reinterpret_cast<volatile int*>(smem + S::QUEUE);
@@ -603,13 +699,30 @@ __global__ void __launch_bounds__(kDfThreads, 1) heads_dwf_kernel(const __grid_c
       bar_init(bar_tempty + 8 * i, 12);   // one arrival per epilogue warp
     }
     bar_init(bar_b, 1);
+    if constexpr (L2) {
+      bar_init(a2_full, kDwBuilderWarps);
+      bar_init(a2_empty, 1);
+      bar_init(d2_full, 1);
+      bar_init(d2_empty, kDwBuilderWarps);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(sb + S::BAR + 136) : "memory");
+    if constexpr (L2)
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(sb + S::BAR + 136) : "memory");
+    else
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(sb + S::BAR + 136) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   if (threadIdx.x < NPAD) sBias[threadIdx.x] = __ldg(p.bias + threadIdx.x);
+  if constexpr (L2) {
+    // tower-layer depthwise weights as fp16 (the BN tables are loaded per level by the builders)
+    __half* sW2 = reinterpret_cast<__half*>(smem + S::DWW);
+    for (int e = threadIdx.x; e < 9 * KF; e += kDfThreads) {
+      sW2[e] = __float2half_rn(__ldg(p.dw2 + e));
+      sW2[9 * KF + e] = __float2half_rn(__ldg(p.dw + e));
+    }
+  }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -621,12 +734,17 @@ __global__ void __launch_bounds__(kDfThreads, 1) heads_dwf_kernel(const __grid_c
     // ===================== producer =====================
     df_reg_dec<kDfRegsIssue>();
     if (ig_elect_one()) {
-      bar_expect_tx(bar_b, NPAD * 128);
+      bar_expect_tx(bar_b, NPAD * 128 + (L2 ? 8192 : 0));
       asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sb + S::B),
                    "l"(p.wimg), "r"(NPAD * 128), "r"(bar_b)
                    : "memory");
+      if constexpr (L2)
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sb + S::B2),
+                     "l"(p.wimg2), "r"(8192), "r"(bar_b)
+                     : "memory");
     }
     __syncwarp();
+    constexpr int kHalo = L2 ? 2 : 1;
     int s = 0, ph = 0;
     for (int i = 0;; ++i) {
       const int item = ig_claim(p.counter, p.items, lane);
@@ -644,11 +762,11 @@ __global__ void __launch_bounds__(kDfThreads, 1) heads_dwf_kernel(const __grid_c
         if (ig_elect_one()) {
           bar_wait(in_empty + 8 * s, ph ^ 1);
           if (t == 0) sQ[i & (IG_QRING - 1)] = item;  // published by the arrival on the first sample's full barrier
-          bar_expect_tx(in_full + 8 * s, DW_IN_BYTES);
+          bar_expect_tx(in_full + 8 * s, S::IN_BYTES);
           asm volatile(
               "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-              ::"r"(sb + S::IN + s * DW_IN_STRIDE), "l"(&maps.m[w.l]), "r"(in_full + 8 * s), "r"(0), "r"(w.tx0 - 1), "r"(w.ty0 - 1),
-              "r"(t * p.NB + w.nb)
+              ::"r"(sb + S::IN + s * S::IN_STRIDE), "l"(&maps.m[w.l]), "r"(in_full + 8 * s), "r"(0), "r"(w.tx0 - kHalo),
+              "r"(w.ty0 - kHalo), "r"(t * p.NB + w.nb)
               : "memory");
         }
         __syncwarp();
@@ -664,43 +782,228 @@ __global__ void __launch_bounds__(kDfThreads, 1) heads_dwf_kernel(const __grid_c
     constexpr uint32_t idesc = ig_idesc<true>(NPAD);
     if (lane == 0) bar_wait(bar_b, 0);
     __syncwarp();
+    // the predict GEMM of sample j (A buffer / accumulator j & 1)
+    auto predict_mma = [&](int j) {
+      const int a = j & 1;
+      if (lane == 0) bar_wait(a_full + 8 * a, (j >> 1) & 1);
+      __syncwarp();
+      if (ig_elect_one()) {
+        bar_wait(bar_tempty + 8 * a, ((j >> 1) & 1) ^ 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint64_t adesc = ig_desc(sb + S::A + a * 16384, 1024, 0);
+        const uint64_t bdesc = ig_desc(sb + S::B, 1024, 0);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(a * NPAD);
+#pragma unroll
+        for (int k = 0; k < KF / 16; ++k) ig_mma(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, k ? 1u : 0u);
+        ig_commit(a_empty + 8 * a);
+        ig_commit(bar_tfull + 8 * a);
+      }
+      __syncwarp();
+    };
     int j = 0;
     bool done = false;
     for (int i = 0; !done; ++i) {
       for (int t = 0; t < T; ++t, ++j) {
-        const int a = j & 1;
-        if (lane == 0) bar_wait(a_full + 8 * a, (j >> 1) & 1);  // the builders' A tile of this sample (or the end marker)
-        __syncwarp();
-        if (t == 0 && ig_queue_read(sQ, i) < 0) {
-          if (ig_elect_one()) {  // wake the epilogue: its next accumulator "arrives" empty
-            bar_wait(bar_tempty + 8 * a, ((j >> 1) & 1) ^ 1);
-            bar_arrive(bar_tfull + 8 * a);
+        if constexpr (L2) {
+          // the tower layer's GEMM of sample j, then the predict GEMM of sample j - 1 (the builders produce in this order)
+          if (lane == 0) bar_wait(a2_full, j & 1);
+          __syncwarp();
+          if (t == 0 && ig_queue_read(sQ, i) < 0) {
+            done = true;
+            break;
+          }
+          if (ig_elect_one()) {
+            bar_wait(d2_empty, (j & 1) ^ 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            constexpr uint32_t idesc2 = ig_idesc<true>(KF);
+            const uint64_t bdesc = ig_desc(sb + S::B2, 1024, 0);
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+              const uint64_t adesc = ig_desc(sb + S::A2 + half * 16384, 1024, 0);
+#pragma unroll
+              for (int k = 0; k < KF / 16; ++k)
+                ig_mma(tmem_base + kD2Col + (uint32_t)(half * KF), adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc2, k ? 1u : 0u);
+            }
+            ig_commit(a2_empty);
+            ig_commit(d2_full);
           }
           __syncwarp();
-          done = true;
-          break;
-        }
-        if (ig_elect_one()) {
-          bar_wait(bar_tempty + 8 * a, ((j >> 1) & 1) ^ 1);
-          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint64_t adesc = ig_desc(sb + S::A + a * 16384, 1024, 0);
-          const uint64_t bdesc = ig_desc(sb + S::B, 1024, 0);
-          const uint32_t d_tmem = tmem_base + (uint32_t)(a * NPAD);
+          if (j > 0) predict_mma(j - 1);
+        } else {
+          const int a = j & 1;
+          if (lane == 0) bar_wait(a_full + 8 * a, (j >> 1) & 1);  // the builders' A tile of this sample (or the end marker)
+          __syncwarp();
+          if (t == 0 && ig_queue_read(sQ, i) < 0) {
+            if (ig_elect_one()) {  // wake the epilogue: its next accumulator "arrives" empty
+              bar_wait(bar_tempty + 8 * a, ((j >> 1) & 1) ^ 1);
+              bar_arrive(bar_tfull + 8 * a);
+            }
+            __syncwarp();
+            done = true;
+            break;
+          }
+          if (ig_elect_one()) {
+            bar_wait(bar_tempty + 8 * a, ((j >> 1) & 1) ^ 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint64_t adesc = ig_desc(sb + S::A + a * 16384, 1024, 0);
+            const uint64_t bdesc = ig_desc(sb + S::B, 1024, 0);
+            const uint32_t d_tmem = tmem_base + (uint32_t)(a * NPAD);
 #pragma unroll
-          for (int k = 0; k < KF / 16; ++k) ig_mma(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, k ? 1u : 0u);
-          ig_commit(a_empty + 8 * a);
-          ig_commit(bar_tfull + 8 * a);
+            for (int k = 0; k < KF / 16; ++k) ig_mma(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, k ? 1u : 0u);
+            ig_commit(a_empty + 8 * a);
+            ig_commit(bar_tfull + 8 * a);
+          }
+          __syncwarp();
         }
-        __syncwarp();
       }
+    }
+    if constexpr (L2) {
+      // j = the number of samples issued to the tower GEMM: the last predict GEMM is still due, then the end marker
+      if (j > 0) predict_mma(j - 1);
+      const int a = j & 1;
+      if (ig_elect_one()) {
+        bar_wait(bar_tempty + 8 * a, ((j >> 1) & 1) ^ 1);
+        bar_arrive(bar_tfull + 8 * a);
+      }
+      __syncwarp();
     }
   } else if (warp < kDfFirstBuilderWarp) {
     // warps 2-3: no role (they fill the issue-only warpgroup and donate their registers)
     df_reg_dec<kDfRegsIssue>();
   } else if (warp < kDfFirstEpiWarp) {
     // ===================== builders =====================
-    df_reg_inc<kDfRegsBuild>();
+    if constexpr (L2) df_reg_inc<kDfRegsBuild2>();
+    else df_reg_inc<kDfRegsBuild>();
     const int btid = threadIdx.x - 32 * kDfFirstBuilderWarp;
+    if constexpr (L2) {
+      const int q = warp & 3;              // TMEM lane quarter (builder warps 4..7 -> 0..3)
+      float* const sEp2 = reinterpret_cast<float*>(smem + S::EP2);
+      float* const sSc = sEp2 + 2 * KF;
+      uint8_t* const sMid = smem + S::MID;
+      int ep_level = -1;   // level whose BN tables are in shared memory (items arrive level by level)
+      // tower-layer epilogue of sample jj (item w, sample t) into the mid tile, then the predict layer's depthwise pass
+      auto mid_and_predict = [&](int jj, const IgItem& w, int t) {
+        const int H = p.H[w.l], Wd = p.W[w.l];
+        // keep-scales of this (sample, image); the barrier also orders the previous predict pass's reads of the mid tile
+        if (btid < KF / 4)
+          reinterpret_cast<float4*>(sSc)[btid] =
+              __ldg(reinterpret_cast<const float4*>(p.keep2[w.l] + (size_t)(t * p.NB + w.nb) * KF) + btid);
+        if (w.l != ep_level) {   // halved: x * sigmoid(x) = h * tanh(h) + h with h = x / 2
+          ep_level = w.l;
+          sEp2[btid] = 0.5f * __ldg((btid < KF ? p.ep2_scale[w.l] : p.ep2_bias[w.l]) + (btid & (KF - 1)));
+        }
+        if (lane == 0) bar_wait(d2_full, jj & 1);
+        __syncwarp();
+        df2_builder_sync();
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const float* ep_s = sEp2;
+        const float* ep_b = ep_s + KF;
+#pragma unroll 1
+        for (int half = 0; half < 2; ++half) {
+          const int m = half * 128 + q * 32 + lane;              // row of the tower GEMM = pixel (m / 10, m % 10) of the mid tile
+          if (half * 128 + q * 32 >= DF2_MID_PX) break;          // warp-uniform: rows 192.. do not exist
+          uint32_t r[KF / 8][8];
+          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + kD2Col + (uint32_t)(half * KF);
+#pragma unroll
+          for (int jc = 0; jc < KF / 8; ++jc) ig_ld8(taddr + jc * 8, r[jc]);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          if (m < DF2_MID_PX) {
+            const int py = m / IG_BOXW, px = m - py * IG_BOXW;
+            const int gy = w.ty0 - 1 + py, gx = w.tx0 - 1 + px;
+            const bool inside = gy >= 0 && gy < H && gx >= 0 && gx < Wd;
+            uint4* dst = reinterpret_cast<uint4*>(sMid + (size_t)m * 128);
+#pragma unroll
+            for (int jc = 0; jc < KF / 8; ++jc) {
+              uint4 o = make_uint4(0u, 0u, 0u, 0u);
+              if (inside) {
+                const float4 f0 = *reinterpret_cast<const float4*>(ep_b + jc * 8), f1 = *reinterpret_cast<const float4*>(ep_b + jc * 8 + 4);
+                const float4 g0 = *reinterpret_cast<const float4*>(ep_s + jc * 8), g1 = *reinterpret_cast<const float4*>(ep_s + jc * 8 + 4);
+                const float4 s0 = *reinterpret_cast<const float4*>(sSc + jc * 8), s1 = *reinterpret_cast<const float4*>(sSc + jc * 8 + 4);
+                const float fbv[8] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w};
+                const float gsv[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+                const float scl[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+                float v[8];
+#pragma unroll
+                for (int e = 0; e < 8; e += 2) {
+                  const float2 h = ig_fma2(make_float2(__uint_as_float(r[jc][e]), __uint_as_float(r[jc][e + 1])), make_float2(gsv[e], gsv[e + 1]),
+                                           make_float2(fbv[e], fbv[e + 1]));
+                  const float2 sw = ig_mul2(ig_fma2(h, make_float2(ig_tanh(h.x), ig_tanh(h.y)), h), make_float2(scl[e], scl[e + 1]));
+                  v[e] = sw.x;
+                  v[e + 1] = sw.y;
+                }
+                o.x = ig_pack16<true>(v[0], v[1]);
+                o.y = ig_pack16<true>(v[2], v[3]);
+                o.z = ig_pack16<true>(v[4], v[5]);
+                o.w = ig_pack16<true>(v[6], v[7]);
+              }
+              dst[jc] = o;
+            }
+          }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) bar_arrive(d2_empty);     // the tower accumulators may be overwritten
+        df2_builder_sync();                      // mid tile complete
+        const int ab = jj & 1;
+        if (lane == 0) bar_wait(a_empty + 8 * ab, ((jj >> 1) & 1) ^ 1);
+        __syncwarp();
+        {
+          DwWeights W3;   // (from shared memory, so that the 36 registers are live during this pass only)
+          const uint8_t* sW3 = smem + S::DWW + 9 * KF * 2;
+#pragma unroll
+          for (int tp = 0; tp < 9; ++tp) {
+            const uint4 w4 = *reinterpret_cast<const uint4*>(sW3 + tp * 128 + (btid & 7) * 16);
+            W3.w[tp][0] = *reinterpret_cast<const __half2*>(&w4.x);
+            W3.w[tp][1] = *reinterpret_cast<const __half2*>(&w4.y);
+            W3.w[tp][2] = *reinterpret_cast<const __half2*>(&w4.z);
+            W3.w[tp][3] = *reinterpret_cast<const __half2*>(&w4.w);
+          }
+          dw_build_tile(sMid, smem + S::A + ab * 16384, W3, btid, min(IG_TH, H - w.ty0));
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) bar_arrive(a_full + 8 * ab);
+      };
+      int s = 0, ph = 0, j = 0;
+      bool done = false, have_prev = false;
+      IgItem prev_w = {0, 0, 0, 0};
+      int prev_t = 0;
+      for (int i = 0; !done; ++i) {
+        IgItem w = {0, 0, 0, 0};
+        for (int t = 0; t < T; ++t, ++j) {
+          if (lane == 0) {
+            bar_wait(in_full + 8 * s, ph);
+            bar_wait(a2_empty, (j & 1) ^ 1);
+          }
+          __syncwarp();
+          if (t == 0) {
+            const int item = ig_queue_read(sQ, i);
+            if (item < 0) {
+              done = true;
+              break;
+            }
+            w = ig_item(p, item);
+          }
+          df2_build_tile(smem + S::IN + s * S::IN_STRIDE, smem + S::A2, smem + S::DWW, btid);
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) {
+            bar_arrive(a2_full);
+            bar_arrive(in_empty + 8 * s);
+          }
+          if (++s == STAGES) {
+            s = 0;
+            ph ^= 1;
+          }
+          if (have_prev) mid_and_predict(j - 1, prev_w, prev_t);
+          prev_w = w;
+          prev_t = t;
+          have_prev = true;
+        }
+      }
+      if (have_prev) mid_and_predict(j - 1, prev_w, prev_t);   // flush the pipeline, then pass the end marker on
+      if (lane == 0) bar_arrive(a2_full);
+    } else {
     DwWeights W;
     dw_load_weights(p.dw, btid & 7, W);
     int s = 0, ph = 0, j = 0;
@@ -736,6 +1039,7 @@ __global__ void __launch_bounds__(kDfThreads, 1) heads_dwf_kernel(const __grid_c
           ph ^= 1;
         }
       }
+    }
     }
   } else {
     // ===================== epilogue: thread = (pixel, anchors 3 cg .. 3 cg + 2) =====================
@@ -1042,15 +1346,18 @@ __global__ void __launch_bounds__(kDfThreads, 1) heads_dwf_kernel(const __grid_c
   __syncthreads();
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem_base) : "memory");
+    if constexpr (L2)
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem_base) : "memory");
   }
 }
 
-template <bool BOX, int NC>
+template <bool BOX, int NC, bool L2 = false>
 int launch_dwf(udal_ctx* ctx, const DfMaps& maps, const DfParams& p, int grid) {
-  using S = DfShapeOf<BOX, NC>;
-  UDAL_CUDA(cudaFuncSetAttribute(heads_dwf_kernel<BOX, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::SMEM));
-  heads_dwf_kernel<BOX, NC><<<grid, kDfThreads, S::SMEM, ctx->stream>>>(maps, p);
+  using S = DfShapeOf<BOX, NC, L2>;
+  UDAL_CUDA(cudaFuncSetAttribute(heads_dwf_kernel<BOX, NC, L2>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::SMEM));
+  heads_dwf_kernel<BOX, NC, L2><<<grid, kDfThreads, S::SMEM, ctx->stream>>>(maps, p);
   UDAL_CHECK_LAUNCH(ctx);
   return UDAL_OK;
 }
@@ -1172,7 +1479,27 @@ int udal_heads_dw_layer(udal_ctx* ctx, int head, int layer, const void* const* i
 
 // predict layer of one head fused with the MC moments (class) / decode + MC moments (box): in[l] = last tower layer output
 // [T*NB,H_l,W_l,64] fp16; writes the per-anchor tensors of `pre` that belong to the head.
+struct DfL2Args {            // the last tower layer fused in (null: `in` is that layer's output)
+  int layer;                 // its index (R - 1)
+  const float* const* ep_scale;   // [L] -> [64] BN scale
+  const float* const* ep_bias;    // [L] -> [64] folded bias
+  const float* const* keep;       // [L] -> [T*NB][64] keep-scale of its own dropout
+};
+static int dw_fused_predict_impl(udal_ctx* ctx, int head, const void* const* in, int NB, int T, const udal_prenms_out* pre,
+                                 const DfL2Args* l2);
 int udal_heads_dw_fused_predict(udal_ctx* ctx, int head, const void* const* in, int NB, int T, const udal_prenms_out* pre) {
+  return dw_fused_predict_impl(ctx, head, in, NB, T, pre, nullptr);
+}
+// in[l] = the INPUT of tower layer `layer` = R - 1 ([T*NB,H_l,W_l,64] fp16, dropout applied); that layer, the predict layer and
+// K2 run in one kernel
+int udal_heads_dw_fused_l2(udal_ctx* ctx, int head, int layer, const void* const* in, int NB, int T, const float* const* ep_scale,
+                           const float* const* ep_bias, const float* const* keep, const udal_prenms_out* pre) {
+  UDAL_REQUIRE(layer == ctx->cfg.repeats - 1 && layer >= 2, "fused tower layer: the last one (>= 2)");
+  DfL2Args a = {layer, ep_scale, ep_bias, keep};
+  return dw_fused_predict_impl(ctx, head, in, NB, T, pre, &a);
+}
+static int dw_fused_predict_impl(udal_ctx* ctx, int head, const void* const* in, int NB, int T, const udal_prenms_out* pre,
+                                 const DfL2Args* l2) {
   EncodeTiledFn encode = get_encode();
   UDAL_REQUIRE(encode != nullptr, "cuTensorMapEncodeTiled is not available from this driver");
   UDAL_REQUIRE(ctx->anchors_set, "anchor table not set");
@@ -1187,8 +1514,17 @@ int udal_heads_dw_fused_predict(udal_ctx* ctx, int head, const void* const* in, 
   UDAL_TRY(dw_fill_geometry(ctx, p, NB));
   p.T = T;
   for (int l = 0; l < c.num_levels; ++l)
-    UDAL_TRY(encode_nhwc(encode, &maps.m[l], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, in[l], T * NB, c.level_h[l], c.level_w[l], KF, KF, IG_BOXW,
-                         IG_ROWS, false));
+    UDAL_TRY(encode_nhwc(encode, &maps.m[l], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, in[l], T * NB, c.level_h[l], c.level_w[l], KF, KF,
+                         l2 ? DF2_BOXW : IG_BOXW, l2 ? DF2_ROWS : IG_ROWS, false));
+  if (l2) {
+    p.dw2 = h.dw + (size_t)l2->layer * 9 * KF;
+    p.wimg2 = reinterpret_cast<const __half*>(h.dwh_w) + (size_t)(l2->layer - 2) * KF * KF;
+    for (int l = 0; l < c.num_levels; ++l) {
+      p.ep2_scale[l] = l2->ep_scale[l];
+      p.ep2_bias[l] = l2->ep_bias[l];
+      p.keep2[l] = l2->keep[l];
+    }
+  }
   for (int l = 0; l <= UDAL_MAX_LEVELS; ++l) p.pix_off[l] = (int)ctx->level_pix_off[l < c.num_levels ? l : c.num_levels];
   p.dw = h.dwp;
   p.wimg = reinterpret_cast<const __half*>(h.dwh_w) + (size_t)(R - 2) * KF * KF + (size_t)h.dwh_chunks * h.dwh_rows * KF;
@@ -1217,14 +1553,14 @@ int udal_heads_dw_fused_predict(udal_ctx* ctx, int head, const void* const* in, 
         UDAL_TRY(out_map(&maps.o[0][l], pre->mean_logits, l, 72));
         UDAL_TRY(out_map(&maps.o[1][l], pre->std_logits, l, 72));
       }
-      return launch_dwf<false, 8>(ctx, maps, p, grid);
+      return l2 ? launch_dwf<false, 8, true>(ctx, maps, p, grid) : launch_dwf<false, 8>(ctx, maps, p, grid);
     }
     if (c.num_classes == 7) {
       UDAL_REQUIRE(h.dwh_frows == 80, "fused class head: weight image");
-      return launch_dwf<false, 7>(ctx, maps, p, grid);
+      return l2 ? launch_dwf<false, 7, true>(ctx, maps, p, grid) : launch_dwf<false, 7>(ctx, maps, p, grid);
     }
     UDAL_REQUIRE(c.num_classes == 10 && h.dwh_frows == 96, "fused class head: %d classes not covered", c.num_classes);
-    return launch_dwf<false, 10>(ctx, maps, p, grid);
+    return l2 ? launch_dwf<false, 10, true>(ctx, maps, p, grid) : launch_dwf<false, 10>(ctx, maps, p, grid);
   }
   UDAL_REQUIRE(pre->boxes && pre->albox && pre->mcbox, "fused box head: NULL output");
   UDAL_REQUIRE(h.cout == 72 && h.dwh_frows == 80, "fused box head: 8A = 72 channels");
@@ -1236,5 +1572,5 @@ int udal_heads_dw_fused_predict(udal_ctx* ctx, int head, const void* const* in, 
     UDAL_TRY(out_map(&maps.o[1][l], pre->albox, l, 36));
     UDAL_TRY(out_map(&maps.o[2][l], pre->mcbox, l, 36));
   }
-  return launch_dwf<true, 8>(ctx, maps, p, grid);
+  return l2 ? launch_dwf<true, 8, true>(ctx, maps, p, grid) : launch_dwf<true, 8>(ctx, maps, p, grid);
 }

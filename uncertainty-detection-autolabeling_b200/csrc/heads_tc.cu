@@ -464,6 +464,14 @@ int udal_heads_dw_prepare(udal_ctx* ctx, int head);
 int udal_heads_dw_layer(udal_ctx* ctx, int head, int layer, const void* const* in, int NB, const float* const* ep_scale,
                         const float* const* ep_bias, const float* const* out_scale, void* const* out);
 int udal_heads_dw_fused_predict(udal_ctx* ctx, int head, const void* const* in, int NB, int T, const udal_prenms_out* pre);
+int udal_heads_dw_fused_l2(udal_ctx* ctx, int head, int layer, const void* const* in, int NB, int T, const float* const* ep_scale,
+                           const float* const* ep_bias, const float* const* keep, const udal_prenms_out* pre);
+// fp16 mode, udal_run: 1 = the last tower layer runs inside the fused predict kernels (heads_dwf_kernel<.., L2>: its output
+// never reaches HBM; bit-identical results, tests/test_gpu_heads.py).  Measured on B200 (bench shape): 2.03 / 2.10 ms per head
+// against 0.43 + 0.53 / 0.43 + 0.65 ms for the two kernels - the four builder warps (one per scheduler) then carry both
+// depthwise passes and the tower epilogue as one dependent chain at ~0.2 IPC while the 12 statistics warps wait (ncu source view,
+// DESIGN.md 6).  Off by default until that work is spread over the statistics warps.
+int udal_heads_l2_fused = 0;
 
 int udal_heads_l0_prepare(udal_ctx* ctx, int head);  // heads_wide.cu: tower layer 0 of the 64-channel heads
 int udal_heads_l0_layer(udal_ctx* ctx, int head, const float* const* feats, int B, void* const* out);
@@ -609,6 +617,9 @@ static int run_tower_tc(udal_ctx* ctx, int head, const float* const* feats, int 
       ctx->layer_events.push_back(e);
     }
   };
+  const void* l2_in[UDAL_MAX_LEVELS];
+  const float *l2_scale[UDAL_MAX_LEVELS], *l2_bias[UDAL_MAX_LEVELS], *l2_keep[UDAL_MAX_LEVELS];
+  bool l2_pending = false;
   for (int layer = 0; layer <= R; ++layer) {
     const bool predict = layer == R;
     mark();
@@ -648,9 +659,22 @@ static int run_tower_tc(udal_ctx* ctx, int head, const float* const* feats, int 
     }
     if (fp16 && layer >= 2) {
       // fp16 mode: depthwise on the CUDA cores (packed fp16) + one K = 64 GEMM per tile on tcgen05 (heads_dw.cu)
+      if (fused_pre && udal_heads_l2_fused && mc && layer == R - 1) {
+        // the last tower layer runs inside the fused predict kernel: remember its input and tables, launch nothing
+        for (int l = 0; l < L; ++l) {
+          l2_in[l] = p.in[l];
+          l2_scale[l] = h.bn_scale + ((size_t)layer * L + l) * KF;
+          l2_bias[l] = p.fb[l];
+          l2_keep[l] = p.out_scale[l];
+        }
+        l2_pending = true;
+        mark();   // (a zero-length layer in the profile)
+        continue;
+      }
       if (predict && fused_pre) {
         UDAL_REQUIRE(mc, "fused predict kernels: MC dropout on both heads");
-        UDAL_TRY(udal_heads_dw_fused_predict(ctx, head, p.in, B, T, fused_pre));
+        if (l2_pending) UDAL_TRY(udal_heads_dw_fused_l2(ctx, head, R - 1, l2_in, B, T, l2_scale, l2_bias, l2_keep, fused_pre));
+        else UDAL_TRY(udal_heads_dw_fused_predict(ctx, head, p.in, B, T, fused_pre));
       } else {
         const float* ep_scale[UDAL_MAX_LEVELS];
         for (int l = 0; l < L; ++l) ep_scale[l] = predict ? nullptr : h.bn_scale + ((size_t)layer * L + l) * KF;
