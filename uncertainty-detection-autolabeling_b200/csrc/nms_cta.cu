@@ -408,6 +408,210 @@ __device__ __forceinline__ void epoch_loop(const EpochParams& p, int cnt, const 
   emptied_out = emptied;
 }
 
+// Per-warp slots of the block-wide arg-max: the warp's best key and the box that goes with it, so that after ONE barrier every
+// thread knows the winner AND its box (the next epoch's "newest selection") without a second barrier.
+struct WinSlots {
+  unsigned long long key[2][2][32];   // [epoch parity][round][warp]
+  float4 box[2][2][32];
+  float area[2][2][32];
+  uint32_t cold[2][32];               // the warp still has candidates with a pending chain
+};
+
+// The same loop with the candidate state in REGISTERS (the shared-memory kernel: at most CPT x 1024 candidates, thread t owns
+// candidates t, t + 1024, ..): no address arithmetic and no shared-memory traffic per candidate and epoch, two barriers per epoch
+// (the memory-based loop above: ~125 instructions per candidate and epoch and four barriers - tools/time_nms.py).
+template <int CPT>
+__device__ __forceinline__ void epoch_loop_regs(const EpochParams& p, int cnt, const State& st, float4* sel_box, float* sel_area,
+                                                WinSlots* ws, const double* tbl, int32_t* out_row, float* out_score,
+                                                int& nsel_out, float& last_out, bool& emptied_out) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  float4 box[CPT];
+  float area[CPT], cur[CPT], sp[CPT];
+  int idx[CPT], beg[CPT], nt[CPT];
+  uint32_t m0[CPT], m1w[CPT], m2[CPT], m3[CPT];
+#pragma unroll
+  for (int c = 0; c < CPT; ++c) {
+    const int j = tid + c * kCtaThreads;
+    const bool have = j < cnt;
+    box[c] = have ? st.box[j] : make_float4(0.f, 0.f, 0.f, 0.f);
+    area[c] = have ? st.area[j] : 0.f;
+    cur[c] = have ? st.cur[j] : -CUDART_INF_F;
+    idx[c] = have ? st.idx[j] : 0x7fffffff;
+    sp[c] = 0.f;
+    beg[c] = nt[c] = 0;
+    m0[c] = m1w[c] = m2[c] = m3[c] = 0u;
+  }
+  int nsel = 0;
+  float last = CUDART_INF_F;
+  bool emptied = false;
+  const bool zero_trivial = p.variant_old ? (p.iou_thr > 0.f) : (p.soft || p.iou_thr >= 0.f);
+  float4 nb = make_float4(0.f, 0.f, 0.f, 0.f);   // the newest selection (normalised box, area): carried in registers
+  float narea = 0.f;
+  // publishes the warp's best (key, box) in its slot
+  auto publish = [&](unsigned long long best, int bestc, int par, int round) {
+    const unsigned long long wm = warp_max(best);
+    if (best == wm && wm != 0) {   // exactly one lane (box indices are unique)
+      float4 bx = box[0];
+      float ar = area[0];
+#pragma unroll
+      for (int c = 1; c < CPT; ++c)
+        if (bestc == c) {
+          bx = box[c];
+          ar = area[c];
+        }
+      ws->box[par][round][warp] = bx;
+      ws->area[par][round][warp] = ar;
+    }
+    if (lane == 0) ws->key[par][round][warp] = wm;
+  };
+  for (int e = 0; e < p.max_out; ++e) {
+    const int par = e & 1;
+    const uint32_t newbit = e > 0 ? 1u << ((e - 1) & 31) : 0u;
+    const int neww = (e - 1) >> 5;
+    const long long t0 = p.debug ? clock64() : 0;
+    // ---- round 1 ----
+    unsigned long long best = 0;
+    int bestc = -1;
+    uint32_t evaluated = 0, cold = 0;
+#pragma unroll
+    for (int c = 0; c < CPT; ++c) {
+      float s = cur[c];
+      if (s == -CUDART_INF_F) continue;
+      float inter = 0.f;
+      if (e > 0) {
+        inter = intersection(box[c], area[c], nb, narea);
+        if (inter != 0.f || !zero_trivial) {
+          m0[c] |= neww == 0 ? newbit : 0u;
+          m1w[c] |= neww == 1 ? newbit : 0u;
+          m2[c] |= neww == 2 ? newbit : 0u;
+          m3[c] |= neww == 3 ? newbit : 0u;
+          nt[c] = e;
+        }
+      }
+      if (nt[c] > beg[c]) {
+        if (beg[c] != e - 1) {
+          cold |= 1u << c;
+          continue;
+        }
+        bool dead = false;
+        decay_step(s, iou_from(inter, area[c], narea), p, tbl, dead);
+        if (!(s > p.score_thr)) dead = true;
+        sp[c] = dead ? -CUDART_INF_F : s;
+        evaluated |= 1u << c;
+        if (dead) continue;
+      }
+      const unsigned long long k = heap_key(s, idx[c]);
+      if (k > best) {
+        best = k;
+        bestc = c;
+      }
+    }
+    publish(best, bestc, par, 0);
+    {
+      const uint32_t anyc = __ballot_sync(0xffffffffu, cold != 0u);
+      if (lane == 0) ws->cold[par][warp] = anyc;
+    }
+    if (p.debug && blockIdx.x == 0 && tid == 0) g_nms_dbg[6] += (unsigned long long)(clock64() - t0);
+    __syncthreads();
+    const unsigned long long k1 = ws->key[par][0][lane];
+    const unsigned long long mm1 = warp_max(k1);
+    const bool any_cold = __ballot_sync(0xffffffffu, ws->cold[par][lane] != 0u) != 0u;
+    const long long t1 = p.debug ? clock64() : 0;
+    // ---- round 2 ----
+    unsigned long long mk = mm1;
+    int wround = 0;
+    uint32_t wwarp = __ffs(__ballot_sync(0xffffffffu, k1 == mm1)) - 1;
+    if (any_cold) {
+      unsigned long long best2 = 0;
+      int best2c = -1;
+      if (__any_sync(0xffffffffu, cold != 0u)) {   // (warp-uniform)
+#pragma unroll
+        for (int c = 0; c < CPT; ++c) {
+          const bool need = ((cold >> c) & 1u) && heap_key(cur[c], idx[c]) >= mm1;
+          uint32_t todo = __ballot_sync(0xffffffffu, need);
+          while (todo) {
+            const int src = __ffs(todo) - 1;
+            todo &= todo - 1;
+            float4 bb;
+            bb.x = __shfl_sync(0xffffffffu, box[c].x, src);
+            bb.y = __shfl_sync(0xffffffffu, box[c].y, src);
+            bb.z = __shfl_sync(0xffffffffu, box[c].z, src);
+            bb.w = __shfl_sync(0xffffffffu, box[c].w, src);
+            const float ba = __shfl_sync(0xffffffffu, area[c], src);
+            const float bs = __shfl_sync(0xffffffffu, cur[c], src);
+            const int bbeg = __shfl_sync(0xffffffffu, beg[c], src);
+            const uint32_t w0 = __shfl_sync(0xffffffffu, m0[c], src), w1 = __shfl_sync(0xffffffffu, m1w[c], src);
+            const uint32_t w2 = __shfl_sync(0xffffffffu, m2[c], src), w3 = __shfl_sync(0xffffffffu, m3[c], src);
+            bool dead;
+            const float v = decay_chain_warp(bs, bb, ba, w0, w1, w2, w3, bbeg, e, sel_box, sel_area, p, tbl, dead);
+            if (lane == src) {
+              sp[c] = dead ? -CUDART_INF_F : v;
+              evaluated |= 1u << c;
+              if (p.debug && blockIdx.x == 0) atomicAdd(&g_nms_dbg[4], 1ull);
+              if (!dead) {
+                const unsigned long long k = heap_key(v, idx[c]);
+                if (k > best2) {
+                  best2 = k;
+                  best2c = c;
+                }
+                if (k > best) {
+                  best = k;
+                  bestc = c;
+                }
+              }
+            }
+          }
+        }
+      }
+      publish(best2, best2c, par, 1);
+      __syncthreads();
+      const unsigned long long k2 = ws->key[par][1][lane];
+      const unsigned long long mm2 = warp_max(k2);
+      if (mm2 > mm1) {
+        mk = mm2;
+        wround = 1;
+        wwarp = __ffs(__ballot_sync(0xffffffffu, k2 == mm2)) - 1;
+      }
+    }
+    const long long t2 = p.debug ? clock64() : 0;
+    if (mk == 0) {
+      emptied = true;
+      break;
+    }
+    // ---- commit: the winner's box is the next epoch's newest selection, for everybody, straight from its warp's slot ----
+    nb = ws->box[par][wround][wwarp];
+    narea = ws->area[par][wround][wwarp];
+    const bool winner = best == mk;   // this thread owns the selection (box indices are unique)
+#pragma unroll
+    for (int c = 0; c < CPT; ++c) {
+      if (cur[c] == -CUDART_INF_F) continue;
+      const bool ev = (evaluated >> c) & 1u;
+      if (winner && bestc == c) {
+        sel_box[e] = box[c];      // (read by later epochs' chains: ordered by the next epoch's first barrier)
+        sel_area[e] = area[c];
+        out_row[e] = idx[c];
+        out_score[e] = ev ? sp[c] : cur[c];
+        cur[c] = -CUDART_INF_F;
+      } else if (ev && heap_key(cur[c], idx[c]) > mk) {
+        cur[c] = sp[c];   // popped before the winner: its decayed score (-inf when it died), looked at up to here
+        beg[c] = e;
+      }
+    }
+    last = key_to_float((uint32_t)(mk >> 32));
+    nsel = e + 1;
+    if (p.debug && blockIdx.x == 0 && tid == 0) {
+      const long long t3 = clock64();
+      g_nms_dbg[1] += (unsigned long long)(t1 - t0);
+      g_nms_dbg[2] += (unsigned long long)(t2 - t1);
+      g_nms_dbg[3] += (unsigned long long)(t3 - t2);
+    }
+  }
+  // (emptied with everything evaluated: every evaluated candidate died - nothing left to commit)
+  nsel_out = nsel;
+  last_out = last;
+  emptied_out = emptied;
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 // one CTA per image: select the best scores (at most `cap`) into shared memory, run the epoch loop, flag an unprovable
 // truncation
@@ -595,7 +799,17 @@ __global__ void __launch_bounds__(kCtaThreads, 1) nms_epoch_cta_kernel(const Epo
   int nsel;
   float last;
   bool emptied;
-  epoch_loop(p, cnt, st, sel_box, sel_area, s_slots, s_tbl, out_row, out_score, nsel, last, emptied);
+  __shared__ WinSlots s_win;
+  if (cnt <= kCtaThreads) epoch_loop_regs<1>(p, cnt, st, sel_box, sel_area, &s_win, s_tbl, out_row, out_score, nsel, last, emptied);
+  else if (cnt <= 2 * kCtaThreads) epoch_loop_regs<2>(p, cnt, st, sel_box, sel_area, &s_win, s_tbl, out_row, out_score, nsel, last, emptied);
+  else {  // (more candidates than two per thread: state stays in shared memory)
+    for (int j = tid; j < cnt; j += kCtaThreads) {
+      st.meta[j] = 0;
+      reinterpret_cast<uint4*>(st.mask)[j] = make_uint4(0u, 0u, 0u, 0u);
+    }
+    __syncthreads();
+    epoch_loop(p, cnt, st, sel_box, sel_area, s_slots, s_tbl, out_row, out_score, nsel, last, emptied);
+  }
   __syncthreads();
   for (int i = nsel + tid; i < p.max_out; i += kCtaThreads) {
     out_row[i] = 0;
