@@ -329,6 +329,14 @@ int udal_autolabel(udal_ctx* ctx, const float* boxes, int box_stride, int albox_
                    int max_out, const udal_autolabel_params* prm, float* entropy, float* calib_albox,
                    float* rel_albox, float* opt_uncert, int32_t* decision);
 
+/* utils_class.py:116-187 (CalibrateClass._perform_class_calib, no MC class uncertainty): calibrated class probabilities and
+ * their entropy for `rows` detections.  method UDAL_CLASSCAL_*: temperature scaling with one temperature (temps[1]) or one per
+ * class (temps[C]); isotonic regression on the softmax probabilities with one table or one per class (knots tx / ty, table t =
+ * [off[t], off[t+1]); sklearn IsotonicRegression.predict, out_of_bounds="clip"), renormalised.  All pointers device. */
+enum { UDAL_CLASSCAL_TS_ALL = 0, UDAL_CLASSCAL_TS_PERCLS = 1, UDAL_CLASSCAL_ISO_ALL = 2, UDAL_CLASSCAL_ISO_PERCLS = 3 };
+int udal_calibrate_class(udal_ctx* ctx, const float* logits, long long rows, int C, int method, const float* temps,
+                         const float* tx, const float* ty, const int32_t* off, float* probab, float* entropy);
+
 /* layout helpers used by the Python mirror (device pointers):
  * out[r] = a[r] ++ b[r] for r < rows (tf.concat on the last axis) */
 int udal_concat_channels(udal_ctx* ctx, const float* a, int ca, const float* b, int cb,

@@ -99,3 +99,25 @@ def autolabel_image(boxes, albox, scores, classes, logits, num_classes, w_entrop
     decision = bool(np.all(opt[np.asarray(scores) > min_score] < threshold))
     return dict(entropy=entropy, calib_albox=calib.astype(np.float32), rel_albox=rel.astype(np.float32),
                 opt_uncert=opt.astype(np.float32), auto_label=decision)
+
+
+def calibrate_class(logits, method, temps=None, tables=None):
+    """CalibrateClass._perform_class_calib without the MC class uncertainty (src/utils_class.py:116-187):
+    -> (entropy [M], probab [M,C]).  ts_*: softmax(logits / T) in the logits' dtype; iso_*: isotonic predict (float64) of
+    the softmax probabilities, renormalised."""
+    logits = np.asarray(logits)
+    if method == "ts_all":
+        prob = stable_softmax(logits / np.float32(np.reshape(temps, -1)[0]))
+    elif method == "ts_percls":
+        prob = stable_softmax(logits / np.asarray(temps, np.float32))
+    elif method in ("iso_all", "iso_percls"):
+        sm = stable_softmax(logits)
+        if method == "iso_all":
+            post = iso_predict(tables[0][0], tables[0][1], sm.flatten()).reshape(sm.shape)
+        else:
+            post = np.stack([iso_predict(tables[i][0], tables[i][1], sm[:, i]) for i in range(logits.shape[-1])], axis=1)
+        prob = post / np.stack([np.sum(post, axis=-1)] * logits.shape[-1], axis=-1)
+    else:
+        raise ValueError("Unknown calibration method")
+    ent = -np.sum(prob * np.nan_to_num(np.log2(np.maximum(prob, 10**-7))), axis=1)
+    return ent, prob

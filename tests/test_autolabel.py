@@ -155,3 +155,55 @@ def test_autolabel_behind_a_sampler_of_another_context():
         np.testing.assert_array_equal(dev["auto_label"].numpy(), host["auto_label"])
         np.testing.assert_allclose(dev["opt_uncert"].numpy(), host["opt_uncert"], rtol=1e-6)
         np.testing.assert_allclose(sig.numpy(), 1.0 / (1.0 + np.exp(-det["logits"].numpy().astype(np.float64))), rtol=1e-5)
+
+
+# ---------------------------------------------------------------------------------------------
+# CalibrateClass (utils_class.py:44-272): the four classification calibrators
+# ---------------------------------------------------------------------------------------------
+def _classcal_golden():
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "classcalib.npz"))
+
+
+def _classcal_tables(g, first, count):
+    off = g["off"]
+    return [(g["tx"][off[t]:off[t + 1]], g["ty"][off[t]:off[t + 1]]) for t in range(first, first + count)]
+
+
+@pytest.mark.parametrize("method", ["ts_all", "ts_percls", "iso_all", "iso_percls"])
+def test_oracle_class_calibration_matches_reference(method):
+    """the oracle against outputs of the reference's own CalibrateClass._perform_class_calib (make_golden_classcalib.py)"""
+    g = _classcal_golden()
+    c = g["logits"].shape[1]
+    temps = g["temp_all"] if method == "ts_all" else g["temps_pc"]
+    tables = _classcal_tables(g, 0, 1) if method == "iso_all" else _classcal_tables(g, 1, c)
+    ent, prob = ar.calibrate_class(g["logits"], method, temps=temps, tables=tables)
+    np.testing.assert_allclose(prob, g["probab_" + method], rtol=1e-6, atol=1e-9)
+    np.testing.assert_allclose(ent, g["entropy_" + method], rtol=1e-6, atol=1e-7)
+
+
+@pytest.mark.gpu
+def test_device_class_calibration_matches_reference():
+    import udal_b200 as u
+    g = _classcal_golden()
+    c = g["logits"].shape[1]
+    tabs = [u.autolabel.IsotonicTable(x, y) for x, y in _classcal_tables(g, 0, 1 + c)]
+    cals = {"ts_all": g["temp_all"], "ts_percls": g["temps_pc"], "iso_all": tabs[0], "iso_percls": tabs[1:]}
+    cc = u.utils_class.CalibrateClass(g["logits"], cals, "iso_percls")
+    for method in u.utils_class.AVAILABLE_CALIB:
+        ent, prob = cc._perform_class_calib(method)
+        np.testing.assert_allclose(prob, g["probab_" + method], rtol=2e-5, atol=1e-7)
+        np.testing.assert_allclose(ent, g["entropy_" + method], rtol=2e-5, atol=2e-6)
+    out = cc.calibrate_class()
+    assert len(out) == 9 and out[0].size == 0          # the reference's selection quirk (strict)
+    np.testing.assert_allclose(out[7], g["probab_iso_percls"], rtol=2e-5, atol=1e-7)
+    loose = u.utils_class.CalibrateClass(g["logits"], cals, "iso_percls", strict_reference=False).calibrate_class()
+    np.testing.assert_allclose(loose[0], g["entropy_iso_percls"], rtol=2e-5, atol=2e-6)
+    # device logits in -> device arrays out; a missing calibrator -> empty arrays
+    eng = u.postprocess._any_engine()
+    dev = u.utils_class.CalibrateClass(eng.ctx.to_device(g["logits"]), {"ts_all": g["temp_all"]}, "ts_all").calibrate_class()
+    np.testing.assert_allclose(dev[1].numpy(), g["probab_ts_all"], rtol=2e-5, atol=1e-7)
+    assert dev[3].size == 0 and dev[5].size == 0
+    with pytest.raises(ValueError):
+        cc._perform_class_calib("bogus")
+    with pytest.raises(NotImplementedError):
+        u.utils_class.CalibrateClass(g["logits"], cals, "ts_all", uncert=[np.ones_like(g["logits"])])

@@ -16,7 +16,7 @@ from . import _lib
 
 _lib.load()  # fail loudly at import time if the CUDA library is missing
 
-from . import anchors, autolabel, bifpn, device, engine, fpn_configs, heads, hparams_config, nms_np, postprocess, scheduler, serving, synthetic, utils, utils_box, utils_extra, wire  # noqa: E402,F401
+from . import anchors, autolabel, bifpn, device, engine, fpn_configs, heads, hparams_config, nms_np, postprocess, scheduler, serving, synthetic, utils, utils_box, utils_class, utils_extra, wire  # noqa: E402,F401
 
 __all__ = ["anchors", "autolabel", "bifpn", "fpn_configs", "device", "engine", "heads", "hparams_config", "nms_np", "postprocess", "synthetic",
-           "scheduler", "serving", "utils", "utils_box", "utils_extra", "wire"]
+           "scheduler", "serving", "utils", "utils_box", "utils_class", "utils_extra", "wire"]

@@ -19,6 +19,7 @@ HEADS_FP32, HEADS_BF16_TC, HEADS_FP16_TC, HEADS_FP32X3_TC = 0, 1, 2, 3
 FEAT_F32, FEAT_F16 = 0, 1
 STAGE_SLOTS = 4
 FUSE_SUM, FUSE_FASTATTN, FUSE_ATTN = 0, 1, 2
+CLASSCAL = {"ts_all": 0, "ts_percls": 1, "iso_all": 2, "iso_percls": 3}
 ACT_NONE, ACT_BN_SWISH, ACT_BN = 0, 1, 2
 HEAD_CLASS, HEAD_BOX = 0, 1
 
@@ -80,6 +81,7 @@ SIGNATURES = {
                                        ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, _VP]),
     "udal_sepconv_bn": (ctypes.c_int, [_VP, _VP, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, _VP, _VP,
                                        _VP, _VP, _VP, ctypes.c_int, _VP]),
+    "udal_calibrate_class": (ctypes.c_int, [_VP, _VP, ctypes.c_longlong, ctypes.c_int, ctypes.c_int, _VP, _VP, _VP, _VP, _VP, _VP]),
     "udal_stage_begin": (ctypes.c_int, [_VP, ctypes.c_int]),
     "udal_stage_h2d": (ctypes.c_int, [_VP, _VP, _VP, ctypes.c_size_t]),
     "udal_stage_end": (ctypes.c_int, [_VP, ctypes.c_int]),

@@ -183,3 +183,90 @@ extern "C" int udal_autolabel(udal_ctx* ctx, const float* boxes, int box_stride,
   UDAL_CHECK_LAUNCH(ctx);
   return UDAL_OK;
 }
+
+
+// ---------------------------------------------------------------------------------------------------------------------
+// CalibrateClass._perform_class_calib without the MC class uncertainty (reference src/utils_class.py:116-187):
+//   ts_all / ts_percls   probab = stable_softmax(logits / T)            (T scalar, or one per class)
+//   iso_all / iso_percls p = stable_softmax(logits); q = iso.predict(p) (one table, or one per class; float64, clipped
+//                        piece-wise linear); probab = q / sum(q)
+//   entropy = -sum(probab * nan_to_num(log2(max(probab, 1e-7))))
+// One thread per detection row.
+// ---------------------------------------------------------------------------------------------------------------------
+namespace {
+
+struct ClassCalParams {
+  const float* logits;   // [rows, C]
+  long long rows;
+  int C, method;
+  const float* temps;    // [1] | [C]
+  const float* tx;       // isotonic knots, tables back to back
+  const float* ty;
+  const int32_t* off;    // [ntables + 1]
+  float* probab;         // [rows, C]
+  float* entropy;        // [rows]
+};
+
+__global__ void class_calibrate_kernel(const ClassCalParams p) {
+  const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= p.rows) return;
+  const float* x = p.logits + r * p.C;
+  float* out = p.probab + r * p.C;
+  const bool ts = p.method == UDAL_CLASSCAL_TS_ALL || p.method == UDAL_CLASSCAL_TS_PERCLS;
+  const bool per = p.method == UDAL_CLASSCAL_TS_PERCLS || p.method == UDAL_CLASSCAL_ISO_PERCLS;
+  // stable softmax of the (temperature-scaled) logits, fp32 like NumPy on float32 inputs
+  float mx = -3.4028234663852886e38f;
+  for (int c = 0; c < p.C; ++c) {
+    const float v = ts ? __fdiv_rn(x[c], p.temps[per ? c : 0]) : x[c];
+    mx = fmaxf(mx, v);
+  }
+  float sum = 0.f;
+  for (int c = 0; c < p.C; ++c) {
+    const float v = ts ? __fdiv_rn(x[c], p.temps[per ? c : 0]) : x[c];
+    const float e = expf(v - mx);
+    out[c] = e;
+    sum += e;
+  }
+  double ent = 0.0;
+  if (ts) {
+    float entf = 0.f;
+    for (int c = 0; c < p.C; ++c) {
+      const float pr = __fdiv_rn(out[c], sum);
+      out[c] = pr;
+      entf += pr * log2f(fmaxf(pr, 1e-7f));
+    }
+    p.entropy[r] = -entf;
+    return;
+  }
+  double qs = 0.0;
+  for (int c = 0; c < p.C; ++c) {
+    const int t = per ? c : 0;
+    const double q = iso_predict(p.tx + p.off[t], p.ty + p.off[t], p.off[t + 1] - p.off[t], (double)__fdiv_rn(out[c], sum));
+    qs += q;
+  }
+  for (int c = 0; c < p.C; ++c) {
+    const int t = per ? c : 0;
+    const double q = iso_predict(p.tx + p.off[t], p.ty + p.off[t], p.off[t + 1] - p.off[t], (double)__fdiv_rn(out[c], sum));
+    const double pr = q / qs;
+    out[c] = (float)pr;
+    ent += pr * log2(fmax(pr, 1e-7));
+  }
+  p.entropy[r] = (float)(-ent);
+}
+
+}  // namespace
+
+extern "C" int udal_calibrate_class(udal_ctx* ctx, const float* logits, long long rows, int C, int method, const float* temps,
+                                    const float* tx, const float* ty, const int32_t* off, float* probab, float* entropy) {
+  UDAL_REQUIRE(ctx && logits && probab && entropy, "NULL argument");
+  UDAL_REQUIRE(rows >= 0 && C >= 1, "udal_calibrate_class: bad sizes");
+  UDAL_REQUIRE(method >= UDAL_CLASSCAL_TS_ALL && method <= UDAL_CLASSCAL_ISO_PERCLS, "Unknown calibration method");
+  const bool ts = method == UDAL_CLASSCAL_TS_ALL || method == UDAL_CLASSCAL_TS_PERCLS;
+  UDAL_REQUIRE(ts ? temps != nullptr : (tx && ty && off), "udal_calibrate_class: calibrator tables missing");
+  UDAL_TRY(udal_join(ctx));
+  if (rows == 0) return UDAL_OK;
+  ClassCalParams p = {logits, rows, C, method, temps, tx, ty, off, probab, entropy};
+  class_calibrate_kernel<<<(unsigned)((rows + 127) / 128), 128, 0, ctx->stream>>>(p);
+  UDAL_CHECK_LAUNCH(ctx);
+  return UDAL_OK;
+}
