@@ -403,6 +403,17 @@ def run_gpu(args, cfg):
         pre = None  # release to the pool first: no allocation inside the timed loop
         pre = eng.decode_moments(cls_bufs, box_bufs, batch)
     decode_ms = ctx.timer_stop() / reps
+    # the same kernel with decode_precision = "fp32" (closed form in fp32; own context on the same GPU, same buffers)
+    eng32 = u.engine.Engine(dict(eng.params, decode_precision="fp32"), eng.cfg.device, "fp32")
+    ctx.sync()
+    pre32 = eng32.decode_moments(cls_bufs, box_bufs, batch)
+    eng32.ctx.sync()
+    eng32.ctx.timer_start()
+    for i in range(reps):
+        pre32 = None
+        pre32 = eng32.decode_moments(cls_bufs, box_bufs, batch)
+    decode32_ms = eng32.ctx.timer_stop() / reps
+    pre32 = None
     ctx.timer_start()
     for i in range(reps):
         eng.nms_v5(pre["boxes"], pre["scores"])
@@ -567,6 +578,10 @@ def run_gpu(args, cfg):
     dec = {"kernel": "decode_moments_kernel<%d>" % eng.T, "what": "decode + MC moments (postprocess.* entry points)",
            "ms": decode_ms, "bound": "hbm", "achieved_GBs": dec_gbs, "frac_of_hbm": dec_gbs / hbm_peak}
     (standalone if fused_run else kernels).append(dec)
+    dec32_gbs = work["decode_bytes"] / (decode32_ms / 1e3) / 1e9
+    standalone.append({"kernel": "decode_moments_f32_kernel", "what": "decode + MC moments, decode_precision=fp32 (closed form in "
+                       "fp32, 1e-4 contract)", "ms": decode32_ms, "bound": "hbm", "achieved_GBs": dec32_gbs,
+                       "frac_of_hbm": dec32_gbs / hbm_peak})
     # dominant kernel = the kernel function with the largest total time inside one step
     totals = {}
     for k in kernels:

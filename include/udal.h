@@ -43,6 +43,11 @@ typedef enum {
 
 /* decode method, reference utils_box.py:105-276 (decode_uncert) */
 enum { UDAL_DECODE_LNORM = 0, UDAL_DECODE_NFLOW = 1, UDAL_DECODE_FALSEDEC = 2 };
+/* arithmetic of the stand-alone decode + MC-moments kernel (udal_decode_moments and the postprocess entry points built on it):
+ * FP64 reproduces the reference's NumPy/TF float64 decode value for value (utils_box.py:105-276); FP32 is the closed form in
+ * fp32 (ex2.approx, series for exp(v) - 1, one-pass shifted variances) - the 1e-4 relative contract of BASELINE.json at the
+ * speed of HBM.  udal_run's fused predict + decode kernels always use the fp32 form. */
+enum { UDAL_DECODE_FP64 = 0, UDAL_DECODE_FP32 = 1 };
 /* NMS method, reference postprocess.py:373-388 */
 enum { UDAL_NMS_HARD = 0, UDAL_NMS_GAUSSIAN = 1 };
 /* head-GEMM arithmetic */
@@ -85,7 +90,8 @@ typedef struct {
   int32_t heads_mode;               /* UDAL_HEADS_* */
   int32_t prefilter_k;              /* global soft-NMS candidate pre-filter (0 = library default) */
   float inv_keep_class, inv_keep_box; /* fp32(1 / (1 - rate)) computed in double by the host, as TF does */
-  int32_t reserved[5];
+  int32_t decode_precision;         /* UDAL_DECODE_FP64 (default 0) | UDAL_DECODE_FP32: arithmetic of the stand-alone K2 kernel */
+  int32_t reserved[4];
 } udal_config;
 
 typedef struct udal_ctx udal_ctx;

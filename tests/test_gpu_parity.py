@@ -406,6 +406,81 @@ def test_postprocess_vs_oracle_baseline_geometries(u, model, size, C, T, batch, 
         np.testing.assert_array_equal(got[4], ref[4])
 
 
+# decode_precision = "fp32": the closed form in fp32 (the arithmetic of udal_run's fused kernels) in the stand-alone K2 kernel.
+# Contract = BASELINE.json's: decoded boxes, variances and scores within 1e-4 relative (boxes: relative to the box side, the
+# scale the error lives on - a corner is a difference of centre and half size); mean logits / classes stay bit-exact.
+F32_CASES = [
+    ("efficientdet-d0", (64, 96), 7, 4, 2, "l-norm", True),
+    ("efficientdet-d0", 512, 10, 1, 1, "l-norm", True),
+    ("efficientdet-d0", 512, 10, 10, 2, "l-norm", True),
+    ("efficientdet-d0", 512, 10, 30, 1, "n-flow", True),
+    ("efficientdet-d0", 512, 10, 10, 1, "falsedec", True),
+    ("efficientdet-d0", 512, 7, 10, 1, "l-norm", False),       # plain decode, 63 logits per pixel (unaligned tiles)
+    ("efficientdet-d0", (384, 1280), 8, 10, 1, "l-norm", True),
+    ("efficientdet-d0", (720, 1280), 10, 20, 1, "l-norm", True),
+    ("efficientdet-d2", 768, 10, 30, 1, "l-norm", True),
+]
+
+
+@pytest.mark.parametrize("stream", [1, 0])   # persistent TMA-staged kernel | per-tile kernel (udal_decode_stream)
+@pytest.mark.parametrize("model,size,C,T,batch,method,la", F32_CASES)
+def test_decode_precision_fp32_vs_oracle(u, model, size, C, T, batch, method, la, stream):
+    switch = ctypes.c_int.in_dll(u._lib.load(), "udal_decode_stream")
+    switch.value = stream
+    try:
+        _check_decode_fp32(u, model, size, C, T, batch, method, la)
+    finally:
+        switch.value = 1
+
+
+def _check_decode_fp32(u, model, size, C, T, batch, method, la):
+    p = u.hparams_config.get_detection_config(
+        model, image_size=size, num_classes=C, enable_softmax=True, loss_attenuation=la,
+        mc_dropout=True, mc_classheadrate=0.05, mc_boxheadrate=0.05, mc_dropoutsamp=T, uncert_adjust_method=method,
+        nms_configs=dict(method="gaussian", max_nms_inputs=0), decode_precision="fp32")
+    cls, box = synth_head_outputs(p, batch, seed=7, la=la)
+    boxes, unc, scores, classes, multi = u.postprocess.extract_uncertainties(copy.deepcopy(p), cls, box)
+    pr = copy.deepcopy(p)
+    pr.pop("decode_precision")
+    rb, runc, rs, rc, rm = ref_np.extract_uncertainties(pr, cls, box)
+    np.testing.assert_array_equal(multi, rm)       # sequential fp32 sum / T: unchanged
+    np.testing.assert_array_equal(classes, rc)
+    np.testing.assert_allclose(scores, rs, rtol=2e-6)
+    side = np.maximum(np.maximum(rb[..., 2] - rb[..., 0], rb[..., 3] - rb[..., 1]), 1.0)[..., None]
+    err = np.abs(boxes.astype(np.float64) - rb) / side
+    assert err.max() < 1e-4, err.max()
+    names = ("mcclass", "albox", "mcbox")
+    for i, (a, b) in enumerate(zip(unc, runc)):
+        if b is None:
+            assert a is None
+            continue
+        if names[i] == "mcbox":  # std of T corners that differ by a fraction of the side
+            e = np.abs(a.astype(np.float64) - b) / np.maximum(b, 1e-4 * side)
+        elif names[i] == "albox" and method == "falsedec":
+            # utils_box.py:186-266 takes sqrt(|dc - dhalf|) of two decoded "variances": no relative bound where they cancel
+            e = np.abs(a.astype(np.float64) - b) / np.maximum(b, 1e-2 * np.sqrt(side))
+        else:
+            e = np.abs(a.astype(np.float64) - b) / np.maximum(np.abs(b), 1e-3)
+        assert e.max() < 1e-4, (names[i], e.max())
+    # through NMS: the detections are those of the oracle up to ties the 1e-4 perturbation can flip
+    scales = np.linspace(1, 2, batch).astype(np.float32)
+    got = u.postprocess.postprocess_global(copy.deepcopy(p), cls, box, scales)
+    ref = ref_np.postprocess_global(copy.deepcopy(pr), cls, box, scales)
+    assert np.all(np.abs(got[3].astype(int) - ref[3].astype(int)) <= 1)
+    matched = total = 0
+    for b in range(batch):
+        n = int(ref[3][b])
+        total += n
+        for j in range(n):
+            d = np.abs(got[0][b, :int(got[3][b])] - ref[0][b, j]).max(-1)
+            k = int(np.argmin(d)) if d.size else -1
+            s = max(ref[0][b, j, 2] - ref[0][b, j, 0], ref[0][b, j, 3] - ref[0][b, j, 1], 1.0)
+            if k >= 0 and d[k] < 2e-4 * s * scales[b] + 1e-4 and got[2][b, k, 0] == ref[2][b, j, 0] \
+                    and abs(got[1][b, k] - ref[1][b, j]) < 1e-5:
+                matched += 1
+    assert matched >= 0.99 * total, (matched, total)
+
+
 def test_device_arrays_in_device_arrays_out_and_dlpack(u):
     import torch
     g = load_golden("post_A_mcla_gauss")

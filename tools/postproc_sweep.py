@@ -22,11 +22,11 @@ N_CLASSES = 10
 SIZE = (512, 512)
 
 
-def params(T, method, max_in):
+def params(T, method, max_in, precision="fp64"):
     p = u.hparams_config.get_detection_config(
         "efficientdet-d0", image_size=SIZE, num_classes=N_CLASSES, enable_softmax=True, loss_attenuation=True,
         mc_dropout=T > 1, mc_classheadrate=0.05 if T > 1 else 0.0, mc_boxheadrate=0.05 if T > 1 else 0.0,
-        mc_dropoutsamp=T)
+        mc_dropoutsamp=T, decode_precision=precision)
     p["nms_configs"] = dict(p["nms_configs"], method=method, max_nms_inputs=max_in)
     return p
 
@@ -85,9 +85,16 @@ def main():
             k3_ms = timed(ctx, lambda: engA.topk(pre["mean_logits"], 5000), args.reps)
             a_ms = timed(ctx, lambda: engA.postprocess_global(cls, box, batch, 0), args.reps)
             del pre
+            # decode_precision = "fp32": the closed form in fp32 (same tile structure, no fp64 issue pressure)
+            eng32 = u.engine.get_engine(params(T, "gaussian", 0, "fp32"))
+            k2f_ms = timed(eng32.ctx, lambda: eng32.decode_moments(cls, box, batch), args.reps)
+            af_ms = timed(eng32.ctx, lambda: eng32.postprocess_global(cls, box, batch, 0), args.reps)
             row = {"B": batch, "T": T, "anchors": N, "classes": C,
                    "K2_decode_moments_ms": k2_ms, "K2_algorithmic_GB": k2_bytes / 1e9,
                    "K2_GBs": k2_bytes / 1e6 / k2_ms, "K2_frac_of_hbm_peak": k2_bytes / 1e6 / k2_ms / peak,
+                   "K2_fp32_decode_moments_ms": k2f_ms, "K2_fp32_GBs": k2_bytes / 1e6 / k2f_ms,
+                   "K2_fp32_frac_of_hbm_peak": k2_bytes / 1e6 / k2f_ms / peak,
+                   "A_fp32_postprocess_global_ms": af_ms,
                    "K3_topk5000_ms": k3_ms, "K3_GBs_one_read": batch * N * C * 4 / 1e6 / k3_ms,
                    "A_postprocess_global_ms": a_ms, "A_us_per_image": a_ms * 1e3 / batch}
             for method in ("gaussian", "hard"):

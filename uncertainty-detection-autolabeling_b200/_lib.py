@@ -41,7 +41,7 @@ class Config(ctypes.Structure):
         ("max_nms_inputs", ctypes.c_int32), ("max_output_size", ctypes.c_int32),
         ("heads_mode", ctypes.c_int32), ("prefilter_k", ctypes.c_int32),
         ("inv_keep_class", ctypes.c_float), ("inv_keep_box", ctypes.c_float),
-        ("reserved", ctypes.c_int32 * 5),
+        ("decode_precision", ctypes.c_int32), ("reserved", ctypes.c_int32 * 4),
     ]
 
 

@@ -116,6 +116,8 @@ int udal_create(const udal_config* cfg, udal_ctx** out) {
   UDAL_REQUIRE(cfg->decode_method >= UDAL_DECODE_LNORM && cfg->decode_method <= UDAL_DECODE_FALSEDEC,
                "decode method %d unsupported (the 'sample' method draws from tfp and is not offered)",
                cfg->decode_method);
+  UDAL_REQUIRE(cfg->decode_precision == UDAL_DECODE_FP64 || cfg->decode_precision == UDAL_DECODE_FP32,
+               "unknown decode_precision %d", cfg->decode_precision);
   UDAL_REQUIRE(cfg->nms_method == UDAL_NMS_HARD || cfg->nms_method == UDAL_NMS_GAUSSIAN,
                "Inference has invalid nms method %d", cfg->nms_method);
   UDAL_REQUIRE(cfg->max_nms_inputs >= 0 && cfg->max_nms_inputs <= 8192, "max_nms_inputs %d outside [0,8192]",

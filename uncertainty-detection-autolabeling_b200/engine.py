@@ -72,7 +72,7 @@ def _key(params, device_id, heads_mode):
     keys = ("image_size", "min_level", "max_level", "num_scales", "aspect_ratios", "anchor_scale",
             "num_classes", "loss_attenuation", "mc_dropout", "mc_dropoutrate", "mc_classheadrate",
             "mc_boxheadrate", "mc_dropoutsamp", "uncert_adjust_method", "fpn_num_filters",
-            "box_class_repeats", "tf_nms_variant", "nms_prefilter_k")
+            "box_class_repeats", "tf_nms_variant", "nms_prefilter_k", "decode_precision")
     d = {k: params.get(k) for k in keys}
     d["nms"] = {k: params["nms_configs"].get(k) for k in
                 ("method", "iou_thresh", "score_thresh", "sigma", "max_nms_inputs", "max_output_size")}
@@ -166,6 +166,12 @@ class Engine:
             raise ValueError("heads_mode must be one of fp32 | fp32x3 | fp16 | bf16, got %r" % (heads_mode,))
         cfg.heads_mode = modes[heads_mode]
         cfg.prefilter_k = int(params.get("nms_prefilter_k", 0) or 0)
+        # arithmetic of the stand-alone decode + moments kernel: "fp64" reproduces the reference's float64 decode value for
+        # value (default), "fp32" is the closed form in fp32 (1e-4 relative contract, HBM bound)
+        prec = params.get("decode_precision", "fp64") or "fp64"
+        if prec not in ("fp64", "fp32"):
+            raise ValueError("decode_precision must be 'fp64' or 'fp32', got %r" % (prec,))
+        cfg.decode_precision = 1 if prec == "fp32" else 0
         self.cfg = cfg
         self.ctx = device.Context(cfg)
         self.lib = self.ctx.lib
