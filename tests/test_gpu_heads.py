@@ -176,7 +176,8 @@ def test_heads_wide_tensor_core_vs_oracle(u, model, size, C, T, batch, la, rc, r
     # features -> detections through udal_run (predict layers + decode_moments + NMS) equals the two-stage path
     scales = np.linspace(1.0, 1.5, batch).astype(np.float32)
     det = sampler.detect(feats, scales, masks=masks)
-    two = u.postprocess.postprocess_global(p, cls, box, scales)
+    # (udal_run decodes 16-bit head outputs with the fp32 closed form - run.cu DecodePrecisionScope - like its fused kernels)
+    two = u.postprocess.postprocess_global(dict(p, decode_precision="fp32"), cls, box, scales)
     for a, b in zip(det, two):
         np.testing.assert_array_equal(a, b)
 

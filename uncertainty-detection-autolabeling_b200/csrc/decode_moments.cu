@@ -772,8 +772,8 @@ struct F32Stat2 {  // F32Stat of two quantities at once
   __device__ __forceinline__ void mean(float t, float& a, float& b) const {
     float sa, sb;
     f2_unpack(sum, sa, sb);
-    a = __fdiv_rn(sa, t);
-    b = __fdiv_rn(sb, t);
+    a = t == 1.f ? sa : __fdiv_rn(sa, t);
+    b = t == 1.f ? sb : __fdiv_rn(sb, t);
   }
   __device__ __forceinline__ void sd(float inv_t, float& a, float& b) const {
     float p1, q1, p2, q2;
@@ -864,7 +864,7 @@ __device__ __forceinline__ void stream_consume(StreamState<EPT2>& S, const float
 }
 
 template <int EPT2>
-__global__ void __launch_bounds__(192, EPT2 <= 5 ? 3 : 2) decode_stream_kernel(const StreamParams sp) {
+__global__ void __maxnreg__(EPT2 <= 5 ? 112 : 168) decode_stream_kernel(const StreamParams sp) {
   const DecodeParams& p = sp.d;
   extern __shared__ __align__(128) float smem_f[];
   const int A = p.A, C = p.C, BC = p.BC;
@@ -932,19 +932,38 @@ __global__ void __launch_bounds__(192, EPT2 <= 5 ? 3 : 2) decode_stream_kernel(c
   const float fTc = (float)Tc, inv_tc = 1.f / fTc, fTb = (float)Tb, inv_tb = 1.f / fTb;
   int s = 0, it = 0;
   uint32_t ph = 0;
-  for (int item = blockIdx.x; item < sp.items; item += gridDim.x, ++it) {
-    const int b = item / sp.tiles, tile = item - b * sp.tiles;
+  // geometry + anchor of this thread for an item; the next item's are fetched one item ahead (the anchor table is the only
+  // global load of the consumers: it must not sit on the critical path of a one-stage item)
+  struct Geo {
+    int b, npx, count, ii;
+    bool live;
+    int64_t anchor0;
+    float4 anc;
+  };
+  auto geo_of = [&](int item) {
+    Geo g;
+    g.b = item / sp.tiles;
+    const int tile = item - g.b * sp.tiles;
     const int l = find_level(p.tile_off, p.geom.num_levels, tile);
     const int hw = p.geom.h[l] * p.geom.w[l];
     const int p0 = (tile - p.tile_off[l]) * kStreamPx;
-    const int npx = min(kStreamPx, hw - p0);
-    const int count = npx * A * C;
-    const int64_t anchor0 = (int64_t)A * (p.geom.pix_off[l] + p0);
-    const bool live = tid < npx * A;
-    const int ii = live ? tid : 0;
+    g.npx = min(kStreamPx, hw - p0);
+    g.count = g.npx * A * C;
+    g.anchor0 = (int64_t)A * (p.geom.pix_off[l] + p0);
+    g.live = tid < g.npx * A;
+    g.ii = g.live ? tid : 0;
+    g.anc = __ldg(reinterpret_cast<const float4*>(p.anchors) + g.anchor0 + g.ii);
+    return g;
+  };
+  Geo nxt = geo_of(blockIdx.x);
+  for (int item = blockIdx.x; item < sp.items; item += gridDim.x, ++it) {
+    const Geo g = nxt;
+    if (item + (int)gridDim.x < sp.items) nxt = geo_of(item + gridDim.x);
+    const int b = g.b, count = g.count, ii = g.ii;
+    const bool live = g.live;
+    const int64_t anchor0 = g.anchor0, n = anchor0 + ii;
+    const float4 anc = g.anc;
     const int box_off = sp.cls_floats + (ii / A) * BC + (ii - (ii / A) * A) * 4;
-    const int64_t n = anchor0 + ii;
-    const float4 anc = __ldg(reinterpret_cast<const float4*>(p.anchors) + n);
     const float say = anc.z - anc.x, sax = anc.w - anc.y;
     const f2_t sa = f2_pack(say, sax), hsa = f2_pack(0.5f * say, 0.5f * sax), saq = f2_pack(say * say, sax * sax);
     const f2_t ca = f2_pack(0.5f * (anc.x + anc.z), 0.5f * (anc.y + anc.w));

@@ -8,6 +8,21 @@ int udal_run_global_fused(udal_ctx* ctx, const float* const* feats, int batch, c
 int udal_heads_sample_fused(udal_ctx* ctx, const float* const* feats, int batch, const uint8_t* keep_masks, uint64_t seed,
                             const udal_prenms_out* pre);
 
+// udal_run with 16-bit tensor-core heads whose predict layers are not fused with K2 (wide towers, class counts without a fused
+// instantiation): the stand-alone decode runs in the arithmetic the fused kernels use (fp32 closed form, HBM bound) whatever
+// decode_precision says - the head outputs carry 16-bit rounding, reproducing the float64 decode digit for digit buys nothing.
+// The fp32 / fp32x3 modes (the 1e-4 contract) follow the configuration.
+namespace {
+struct DecodePrecisionScope {
+  udal_ctx* c;
+  int saved;
+  explicit DecodePrecisionScope(udal_ctx* x) : c(x), saved(x->cfg.decode_precision) {
+    if (c->cfg.heads_mode == UDAL_HEADS_BF16_TC || c->cfg.heads_mode == UDAL_HEADS_FP16_TC) c->cfg.decode_precision = UDAL_DECODE_FP32;
+  }
+  ~DecodePrecisionScope() { c->cfg.decode_precision = saved; }
+};
+}  // namespace
+
 // per-level head outputs in one scratch block, every level starting on a 16-byte boundary (odd channel
 // counts such as 63 = 9 anchors x 7 classes would otherwise misalign the following levels)
 static int head_output_scratch(udal_ctx* ctx, int batch, float** cls, float** box) {
@@ -53,6 +68,7 @@ extern "C" int udal_run_prenms(udal_ctx* ctx, const float* const* feats, int bat
   float* box[UDAL_MAX_LEVELS];
   UDAL_TRY(head_output_scratch(ctx, batch, cls, box));
   UDAL_TRY(udal_heads_sample(ctx, feats, batch, keep_masks, seed, cls, box));
+  DecodePrecisionScope prec(ctx);
   return udal_launch_decode_moments(ctx, cls, box, batch, out);
 }
 
@@ -95,6 +111,7 @@ extern "C" int udal_run(udal_ctx* ctx, const float* const* feats, int batch, con
   float* box[UDAL_MAX_LEVELS];
   UDAL_TRY(head_output_scratch(ctx, batch, cls, box));
   UDAL_TRY(udal_heads_sample(ctx, feats, batch, keep_masks, seed, cls, box));
+  DecodePrecisionScope prec(ctx);
   const int bank = ctx->run_bank;
   if (ctx->post_pending[bank]) {
     UDAL_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_post[bank], 0));

@@ -234,13 +234,15 @@ class Engine:
 
     # ---- kernels ---------------------------------------------------------------------------
     def decode_moments(self, cls, box, batch, want=("mean_logits", "std_logits", "boxes", "albox",
-                                                    "mcbox", "scores", "classes")):
+                                                    "mcbox", "scores", "classes"), out=None):
+        """``out``: the dict a previous call returned - its arrays are written again (no allocation on this call)."""
         n, c = self.N, self.C
+        reuse = out
         out = {}
         st = _lib.PreNmsOut()
         def mk(name, shape, dtype=np.float32, cond=True):
             if name in want and cond:
-                out[name] = self.ctx.empty(shape, dtype)
+                out[name] = reuse[name] if reuse is not None else self.ctx.empty(shape, dtype)
                 setattr(st, name, out[name].ptr)
         mk("mean_logits", (batch, n, c))
         mk("std_logits", (batch, n, c), cond=self.cls_mc)
