@@ -18,6 +18,9 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-fil
 if [ "$2" == "ncu" ]; then
 ncu --set full --clock-control none --import-source on -k regex:"heads_dw|heads_l1|heads_wide|nms_epoch" --launch-skip 20 -c 10 -f \
     -o gpurun_out/prof_$TAG python tools/time_config.py 384 1280 8 10 64 efficientdet-d0 fp16 > gpurun_out/ncu_b_$TAG.log 2>&1; echo rc=$?
+# the stand-alone K2 kernels (fp64 reference arithmetic, fp32 per-tile, fp32 persistent TMA-staged) at configs[3], T = 10, B = 64
+ncu --set full --clock-control none --import-source on -k regex:"decode_moments|decode_stream" --launch-skip 40 -c 6 -f \
+    -o gpurun_out/prof_k2_$TAG python tools/postproc_sweep.py --Ts 10 --batches 64 --reps 1 > gpurun_out/ncu_k2_$TAG.log 2>&1; echo rc=$?
 fi
 # the other BASELINE configs
 timeout 300 python tools/postproc_sweep.py --Ts 1,10,20,30 --out gpurun_out/postproc_sweep_$TAG.json > gpurun_out/postproc_sweep_$TAG.log 2>&1; echo rc=$?

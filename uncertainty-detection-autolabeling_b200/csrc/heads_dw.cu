@@ -504,7 +504,8 @@ struct DfShape {
   static constexpr int BAR = OUT2 + OUT2_BYTES_;       // barriers + tmem slot (256 B)
   static constexpr int BIAS = BAR + 256;               // [NPAD] fp32 predict bias
   static constexpr int QUEUE = BIAS + NPAD * 4;        // item-index ring (IG_QRING ints)
-  static constexpr int EP2 = QUEUE + IG_QRING * 4;     // L2: [2][64] halved BN scale | folded bias of the current level, then [64] keep-scales
+  static constexpr int QUEUEW = QUEUE + IG_QRING * 4;  // decoded items (IG_QRING int4)
+  static constexpr int EP2 = QUEUEW + IG_QRING * 16;   // L2: [2][64] halved BN scale | folded bias of the current level, then [64] keep-scales
   static constexpr int DWW = EP2 + (L2 ? 3 * KF * 4 : 0);   // L2: depthwise weights [9][64] fp16 of the tower layer
   static constexpr int SMEM = DWW + (L2 ? 2 * 9 * KF * 2 : 0) + 1024;   // (tower layer's, then the predict layer's)
   static_assert(STAGES <= 4 && 2 * NPAD <= 256, "layout");
@@ -692,6 +693,7 @@ __global__ void __launch_bounds__(kDfThreads, 1) heads_dwf_kernel(const __grid_c
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + S::BAR + 136);
   float* sBias = reinterpret_cast<float*>(smem + S::BIAS);
   volatile int* sQ = reinterpret_cast<volatile int*>(smem + S::QUEUE);
+  int4* sQW = reinterpret_cast<int4*>(smem + S::QUEUEW);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int T = p.T;
 
@@ -769,7 +771,7 @@ __global__ void __launch_bounds__(kDfThreads, 1) heads_dwf_kernel(const __grid_c
       for (int t = 0; t < T; ++t) {
         if (ig_elect_one()) {
           bar_wait(in_empty + 8 * s, ph ^ 1);
-          if (t == 0) sQ[i & (IG_QRING - 1)] = item;  // published by the arrival on the first sample's full barrier
+          if (t == 0) ig_queue_put(sQ, sQW, i, item, w);  // published by the arrival on the first sample's full barrier
           bar_expect_tx(in_full + 8 * s, S::IN_BYTES);
           asm volatile(
               "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
@@ -1032,7 +1034,7 @@ __global__ void __launch_bounds__(kDfThreads, 1) heads_dwf_kernel(const __grid_c
             done = true;
             break;
           }
-          const IgItem w = ig_item(p, item);
+          const IgItem w = ig_queue_item(sQW, i);
           rows_valid = min(IG_TH, p.H[w.l] - w.ty0);
         }
         dw_build_tile(smem + S::IN + s * DW_IN_STRIDE, smem + S::A + ab * 16384, W, btid, rows_valid);
@@ -1067,7 +1069,7 @@ __global__ void __launch_bounds__(kDfThreads, 1) heads_dwf_kernel(const __grid_c
       __syncwarp();
       const int item = ig_queue_read(sQ, i);
       if (item < 0) break;
-      const IgItem w = ig_item(p, item);
+      const IgItem w = ig_queue_item(sQW, i);
       const int H = p.H[w.l], W = p.W[w.l];
       const int oy = w.ty0 + (m >> 3), ox = w.tx0 + (m & 7);
       const bool ok = oy < H && ox < W;

@@ -196,6 +196,25 @@ __device__ __forceinline__ int ig_claim(int* counter, int items, int lane) {  //
   return v < items ? v : -1;
 }
 __device__ __forceinline__ int ig_queue_read(const volatile int* q, int k) { return q[k & (IG_QRING - 1)]; }
+// The producer also publishes the DECODED item next to its index (a second ring of int4): the level search, the two magic
+// divisions and the constant-bank look-ups of ig_item are ~60 dependent instructions - 10 % of a builder warp's time per
+// tile when every role repeats them (round-2 ncu source view).  Same ordering as the index ring: written before the arrival
+// on the stage's full barrier, read behind it.
+__device__ __forceinline__ void ig_queue_put(volatile int* q, int4* qw, int k, int item, const IgItem& w) {
+  qw[k & (IG_QRING - 1)] = make_int4(w.l, w.nb, w.ty0, w.tx0);
+  q[k & (IG_QRING - 1)] = item;
+}
+__device__ __forceinline__ IgItem ig_queue_item(const int4* qw, int k) {
+  int4 v;
+  asm volatile("ld.volatile.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "r"((uint32_t)__cvta_generic_to_shared(qw + (k & (IG_QRING - 1)))));
+  IgItem it;
+  it.l = v.x;
+  it.nb = v.y;
+  it.ty0 = v.z;
+  it.tx0 = v.w;
+  return it;
+}
 
 __device__ __forceinline__ void ig_group_sync(int g) {  // the 128 threads of epilogue group g
   asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
