@@ -1057,13 +1057,18 @@ int launch_stream(udal_ctx* ctx, StreamParams& sp) {
   cudaFuncAttributes fa;
   UDAL_CUDA(cudaFuncGetAttributes(&fa, decode_stream_kernel<EPT2>));
   int by_regs = 65536 / (fa.numRegs * threads > 0 ? fa.numRegs * ((threads + 31) / 32 * 32) : 1);
-  by_regs = std::max(1, std::min(by_regs, 4));
+  // measured (configs[3], B = 64): two CTAs per SM with a ring of 8 stages are 2 % faster than three with 6 at T >= 10
+  // (0.88 / 0.98 / 0.99 of the HBM peak), three are 6 % faster at T = 1 (one-stage items: the per-item statistics dominate)
+  const int T = sp.d.Tc > sp.d.Tb ? sp.d.Tc : sp.d.Tb;
+  by_regs = std::max(1, std::min(by_regs, T <= 4 ? 3 : 2));
   const size_t fixed = (size_t)2 * sp.cls_floats * 4 + 2 * kStreamMaxStages * 8;
   const size_t per_cta = (size_t)(227 * 1024) / by_regs - 1024;
   UDAL_REQUIRE(per_cta > fixed + 2 * (size_t)sp.stage_floats * 4, "decode_stream_kernel: stage of %d floats does not fit", sp.stage_floats);
   sp.stages = (int)std::min<size_t>(kStreamMaxStages, (per_cta - fixed) / ((size_t)sp.stage_floats * 4));
   const size_t smem = (size_t)sp.stages * sp.stage_floats * 4 + fixed;
   UDAL_CUDA(cudaFuncSetAttribute(decode_stream_kernel<EPT2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  // (without the carve-out hint the driver sizes shared memory for two CTAs of this size, not the three the registers admit)
+  UDAL_CUDA(cudaFuncSetAttribute(decode_stream_kernel<EPT2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   int nb = 0;
   UDAL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, decode_stream_kernel<EPT2>, threads, smem));
   UDAL_REQUIRE(nb >= 1, "decode_stream_kernel does not fit an SM (%zu bytes of shared memory)", smem);
