@@ -38,7 +38,8 @@ namespace {
 constexpr int DW_IN_BYTES = IG_ROWS * IG_BOXW * 128;                 // 23 040: linear halo tile
 constexpr int DW_IN_STRIDE = (DW_IN_BYTES + 1023) / 1024 * 1024;     // 23 552
 constexpr int kDwBuilderWarps = kDwBuilderThreads / 32;              // 4
-constexpr int kDwFirstEpiWarp = 2 + kDwBuilderWarps;                 // 6: (warp & 3) = 2,3,0,1 - every lane quarter per 4 warps
+constexpr int kDwBuilderGroups = 2;                                  // tiles built concurrently (heads_dw_kernel)
+constexpr int kDwFirstEpiWarp = 2 + kDwBuilderGroups * kDwBuilderWarps;   // 10: (warp & 3) = 2,3,0,1 - every lane quarter per 4 warps
 
 // weight image of one pointwise matrix: wimg[n][k] = fp16(w[k][n0 + n]) (n < cout, zero rows past it), K-major, 128B swizzle
 __global__ void dw_weights_kernel(const float* __restrict__ w, int ldw, int n0, int cout, int rows, __half* __restrict__ wimg) {
@@ -58,19 +59,22 @@ __global__ void dw_bias_kernel(const float* __restrict__ bias, int n0, int cout,
 // =====================================================================================================================
 // tower layers (fp16 out) and stand-alone predict layers (fp32 out)
 // =====================================================================================================================
-constexpr int kDwThreads = 64 + kDwBuilderThreads + 256;  // producer, MMA, 4 builder warps, 2 x 4 epilogue warps
+// producer, MMA, 2 x 4 builder warps (two tiles are built concurrently: the builders' latency chain - ~375 instructions per
+// warp at a quarter of a scheduler - is the period of the pipeline), 2 x 4 epilogue warps
+constexpr int kDwThreads = 64 + kDwBuilderGroups * kDwBuilderThreads + 256;
 
 template <int NPAD_, bool PREDICT_>
 struct DwShape {
-  static constexpr int NPAD = NPAD_, NROWS = NPAD_, STAGES = 3;
+  // (the stand-alone predict shapes carry 64-80 KB of fp32 staging: 3 stages and one A buffer per builder group there)
+  static constexpr int NPAD = NPAD_, NROWS = NPAD_, STAGES = PREDICT_ ? 3 : 4, ABUF = PREDICT_ ? 2 : 4;
   static constexpr bool PREDICT = PREDICT_;
   static constexpr int B_BYTES = (NROWS * 128 + 1023) / 1024 * 1024;
   // staging tile of one epilogue group: fp16 [128][64] (16 KB), or fp32 32-channel regions [128][32] (16 KB each, 128B
   // swizzle) plus a dense remainder region [128][NPAD - 64]
   static constexpr int OUT_BYTES = !PREDICT ? 16384 : (NPAD == 64 ? 32768 : 32768 + 128 * (NPAD - 64) * 4);
   static constexpr int SM_B = 0;
-  static constexpr int SM_A = SM_B + B_BYTES;                 // 2 x [128][128 B]
-  static constexpr int SM_OUT = SM_A + 2 * 16384;
+  static constexpr int SM_A = SM_B + B_BYTES;                 // ABUF x [128][128 B]
+  static constexpr int SM_OUT = SM_A + ABUF * 16384;
   static constexpr int SM_IN = SM_OUT + 2 * OUT_BYTES;
   static constexpr int SM_BAR = SM_IN + STAGES * DW_IN_STRIDE;   // barriers (192 B) + 2 x 64 keep-scales (512 B)
   static constexpr int SM_FBS = SM_BAR + 768;
@@ -109,9 +113,9 @@ __global__ void __launch_bounds__(kDwThreads, 1) heads_dw_kernel(const __grid_co
   const uint32_t raw = s32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
   const uint32_t sb = s32(smem);
-  // barriers: in_full[4] @0  in_empty[4] @32  a_full[2] @64  a_empty[2] @80  tfull[2] @96  tempty[2] @112  bfull @128  slot @136
+  // barriers: in_full[4] @0  in_empty[4] @32  a_full[4] @64  tfull[2] @96  tempty[2] @112  bfull @128  slot @136  a_empty[4] @144
   const uint32_t bar0 = sb + S::SM_BAR;
-  const uint32_t in_full = bar0, in_empty = bar0 + 32, a_full = bar0 + 64, a_empty = bar0 + 80, bar_tfull = bar0 + 96,
+  const uint32_t in_full = bar0, in_empty = bar0 + 32, a_full = bar0 + 64, a_empty = bar0 + 144, bar_tfull = bar0 + 96,
                  bar_tempty = bar0 + 112, bar_b = bar0 + 128;
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + S::SM_BAR + 136);
   float* sFb = reinterpret_cast<float*>(smem + S::SM_FBS);
@@ -123,9 +127,11 @@ __global__ void __launch_bounds__(kDwThreads, 1) heads_dw_kernel(const __grid_co
       bar_init(in_full + 8 * i, 1);
       bar_init(in_empty + 8 * i, kDwBuilderWarps);   // one arrival per builder warp
     }
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < S::ABUF; ++i) {
       bar_init(a_full + 8 * i, kDwBuilderWarps);
       bar_init(a_empty + 8 * i, 1);
+    }
+    for (int i = 0; i < 2; ++i) {
       bar_init(bar_tfull + 8 * i, 1);
       bar_init(bar_tempty + 8 * i, 4);               // one arrival per epilogue warp of the group
     }
@@ -167,8 +173,11 @@ __global__ void __launch_bounds__(kDwThreads, 1) heads_dw_kernel(const __grid_co
         bar_wait(in_empty + 8 * s, ph ^ 1);   // stage free (first round passes immediately)
         sQ[k & (IG_QRING - 1)] = item;        // published by the arrival on the stage's full barrier
         if (item < 0) {
-          sQ[(k + 1) & (IG_QRING - 1)] = -1;  // end of the stream, for both epilogue groups
+          sQ[(k + 1) & (IG_QRING - 1)] = -1;  // end of the stream, for both builder / epilogue groups
           bar_arrive(in_full + 8 * s);
+          const int s1 = s + 1 == STAGES ? 0 : s + 1;   // the other builder group waits for the next stage
+          bar_wait(in_empty + 8 * s1, (s1 == 0 ? ph ^ 1 : ph) ^ 1);
+          bar_arrive(in_full + 8 * s1);
         } else {
           bar_expect_tx(in_full + 8 * s, DW_IN_BYTES);
           asm volatile(
@@ -191,9 +200,9 @@ __global__ void __launch_bounds__(kDwThreads, 1) heads_dw_kernel(const __grid_co
     if (lane == 0) bar_wait(bar_b, 0);  // weights resident
     __syncwarp();
     for (int it = 0;; ++it) {
-      const int a = it & 1;
+      const int a = it & 1, ab = it % S::ABUF;
       const uint32_t d_tmem = tmem_base + (uint32_t)(a * NPAD);
-      if (lane == 0) bar_wait(a_full + 8 * a, (it >> 1) & 1);  // the builders' A tile of this item (or the end marker)
+      if (lane == 0) bar_wait(a_full + 8 * ab, (it / S::ABUF) & 1);  // the builders' A tile of this item (or the end marker)
       __syncwarp();
       if (ig_queue_read(sQ, it) < 0) {
         // end of the stream: wake both epilogue groups (their next accumulator "arrives" empty)
@@ -209,26 +218,27 @@ __global__ void __launch_bounds__(kDwThreads, 1) heads_dw_kernel(const __grid_co
       if (ig_elect_one()) {
         bar_wait(bar_tempty + 8 * a, ((it >> 1) & 1) ^ 1);  // accumulator drained by its epilogue group
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint64_t adesc = ig_desc(sb + S::SM_A + a * 16384, 1024, 0);
+        const uint64_t adesc = ig_desc(sb + S::SM_A + ab * 16384, 1024, 0);
         const uint64_t bdesc = ig_desc(sb + S::SM_B, 1024, 0);
 #pragma unroll
         for (int k = 0; k < KF / 16; ++k) ig_mma(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, k ? 1u : 0u);
-        ig_commit(a_empty + 8 * a);     // A buffer reusable once these MMAs retire
+        ig_commit(a_empty + 8 * ab);    // A buffer reusable once these MMAs retire
         ig_commit(bar_tfull + 8 * a);   // accumulator ready
       }
       __syncwarp();
     }
   } else if (warp < kDwFirstEpiWarp) {
     // ===================== builders: depthwise 3x3 (packed fp16) -> A operand =====================
-    const int btid = threadIdx.x - 64;
+    // group gb builds the items i = gb, gb + 2, ..: stage i % STAGES, A buffer i % ABUF
+    const int gb = (warp - 2) >> 2;
+    const int btid = (threadIdx.x - 64) & (kDwBuilderThreads - 1);
     DwWeights W;
     dw_load_weights(p.dw, btid & 7, W);
-    int s = 0, ph = 0;
-    for (int i = 0;; ++i) {
-      const int ab = i & 1;
+    for (int i = gb;; i += kDwBuilderGroups) {
+      const int ab = i % S::ABUF, s = i % STAGES, ph = (i / STAGES) & 1;
       if (lane == 0) {
-        bar_wait(in_full + 8 * s, ph);                    // halo tile landed
-        bar_wait(a_empty + 8 * ab, ((i >> 1) & 1) ^ 1);   // the MMAs of item i-2 are done with this A buffer
+        bar_wait(in_full + 8 * s, ph);                              // halo tile landed
+        bar_wait(a_empty + 8 * ab, ((i / S::ABUF) & 1) ^ 1);        // the MMAs of item i - ABUF are done with this A buffer
       }
       __syncwarp();
       const int item = ig_queue_read(sQ, i);
@@ -243,10 +253,6 @@ __global__ void __launch_bounds__(kDwThreads, 1) heads_dw_kernel(const __grid_co
       if (lane == 0) {
         bar_arrive(a_full + 8 * ab);
         bar_arrive(in_empty + 8 * s);
-      }
-      if (++s == STAGES) {
-        s = 0;
-        ph ^= 1;
       }
     }
   } else {
