@@ -14,6 +14,7 @@
 #include "decode_math.cuh"
 
 #include <algorithm>
+#include <type_traits>
 
 namespace {
 
@@ -784,6 +785,15 @@ struct F32Stat2 {  // F32Stat of two quantities at once
   }
 };
 
+// the same interface for a single sample (no MC axis on either head): the value itself, no statistics - 40 registers less
+struct F32One2 {
+  f2_t sum;
+  template <bool FIRST>
+  __device__ __forceinline__ void add(f2_t x) { sum = x; }
+  __device__ __forceinline__ void mean(float, float& a, float& b) const { f2_unpack(sum, a, b); }
+  __device__ __forceinline__ void sd(float, float& a, float& b) const { a = b = 0.f; }
+};
+
 // exp(v) - 1 for both halves: degree-8 series below 1 (relative truncation < 3e-6), ex2 above
 __device__ __forceinline__ f2_t f2_expm1(f2_t v) {
   f2_t q = f2_fma(v, f2_bcast(1.f / 362880.f), f2_bcast(1.f / 40320.f));
@@ -817,15 +827,16 @@ struct StreamParams {
 };
 
 // consumer state of one item
-template <int EPT2>
+template <int EPT2, bool SINGLE>
 struct StreamState {
-  F32Stat2 st[EPT2];  // logit pairs q = tid + j * consumers
-  F32Stat2 lo, hi;    // (ymin, xmin), (ymax, xmax)
+  typedef typename std::conditional<SINGLE, F32One2, F32Stat2>::type Stat;
+  Stat st[EPT2];      // logit pairs q = tid + j * consumers
+  Stat lo, hi;        // (ymin, xmin), (ymax, xmax)
   f2_t al;            // sum of the aleatoric std (y, x)
 };
 
-template <int EPT2, bool FIRST>
-__device__ __forceinline__ void stream_consume(StreamState<EPT2>& S, const float* __restrict__ sc, const float* __restrict__ sb,
+template <int EPT2, bool FIRST, bool SINGLE>
+__device__ __forceinline__ void stream_consume(StreamState<EPT2, SINGLE>& S, const float* __restrict__ sc, const float* __restrict__ sb,
                                                int tid, int nct, bool do_cls, bool do_box, int la, int sig_off, f2_t sa, f2_t hsa,
                                                f2_t ca, f2_t saq) {
   if (do_cls) {
@@ -863,8 +874,10 @@ __device__ __forceinline__ void stream_consume(StreamState<EPT2>& S, const float
   }
 }
 
-template <int EPT2>
-__global__ void __maxnreg__(EPT2 <= 5 ? 112 : 168) decode_stream_kernel(const StreamParams sp) {
+// SINGLE: one sample on both heads (no MC dropout): the state is the sample itself, 64 registers, five CTAs per SM - the
+// one-stage items of this case are bound by the per-item latency chain (wait, fold, barrier, arg-max, stores), not by HBM
+template <int EPT2, bool SINGLE>
+__global__ void __maxnreg__(SINGLE ? 64 : (EPT2 <= 5 ? 112 : 168)) decode_stream_kernel(const StreamParams sp) {
   const DecodeParams& p = sp.d;
   extern __shared__ __align__(128) float smem_f[];
   const int A = p.A, C = p.C, BC = p.BC;
@@ -967,14 +980,14 @@ __global__ void __maxnreg__(EPT2 <= 5 ? 112 : 168) decode_stream_kernel(const St
     const float say = anc.z - anc.x, sax = anc.w - anc.y;
     const f2_t sa = f2_pack(say, sax), hsa = f2_pack(0.5f * say, 0.5f * sax), saq = f2_pack(say * say, sax * sax);
     const f2_t ca = f2_pack(0.5f * (anc.x + anc.z), 0.5f * (anc.y + anc.w));
-    StreamState<EPT2> S;
+    StreamState<EPT2, SINGLE> S;
     S.al = 0ull;
     for (int t = 0; t < T; ++t) {
       dm_bar_wait(full0 + 8 * s, ph);
       const float* sc = stages + (size_t)s * sp.stage_floats;
       // (a sample index beyond Tc / Tb exists only on the side that has the longer MC axis; t == 0 is valid for both)
-      if (t == 0) stream_consume<EPT2, true>(S, sc, sc + box_off, tid, NCT, true, true, la, 4 * A, sa, hsa, ca, saq);
-      else stream_consume<EPT2, false>(S, sc, sc + box_off, tid, NCT, t < Tc, t < Tb, la, 4 * A, sa, hsa, ca, saq);
+      if (SINGLE || t == 0) stream_consume<EPT2, true, SINGLE>(S, sc, sc + box_off, tid, NCT, true, true, la, 4 * A, sa, hsa, ca, saq);
+      else stream_consume<EPT2, false, SINGLE>(S, sc, sc + box_off, tid, NCT, t < Tc, t < Tb, la, 4 * A, sa, hsa, ca, saq);
       __syncwarp();
       if (lane == 0) dm_bar_arrive(empty0 + 8 * s);
       if (++s == sp.stages) {
@@ -1047,7 +1060,7 @@ __global__ void __maxnreg__(EPT2 <= 5 ? 112 : 168) decode_stream_kernel(const St
   }
 }
 
-template <int EPT2>
+template <int EPT2, bool SINGLE>
 int launch_stream(udal_ctx* ctx, StreamParams& sp) {
   const int threads = sp.consumers + 32;
   int dev = 0, sms = 0;
@@ -1055,25 +1068,25 @@ int launch_stream(udal_ctx* ctx, StreamParams& sp) {
   UDAL_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   // ring depth: as deep as lets the CTAs the register file admits share the SM's shared memory
   cudaFuncAttributes fa;
-  UDAL_CUDA(cudaFuncGetAttributes(&fa, decode_stream_kernel<EPT2>));
+  UDAL_CUDA(cudaFuncGetAttributes(&fa, decode_stream_kernel<EPT2, SINGLE>));
   int by_regs = 65536 / (fa.numRegs * threads > 0 ? fa.numRegs * ((threads + 31) / 32 * 32) : 1);
   // measured (configs[3], B = 64): two CTAs per SM with a ring of 8 stages are 2 % faster than three with 6 at T >= 10
   // (0.88 / 0.98 / 0.99 of the HBM peak), three are 6 % faster at T = 1 (one-stage items: the per-item statistics dominate)
   const int T = sp.d.Tc > sp.d.Tb ? sp.d.Tc : sp.d.Tb;
-  by_regs = std::max(1, std::min(by_regs, T <= 4 ? 3 : 2));
+  by_regs = std::max(1, std::min(by_regs, SINGLE ? 5 : (T <= 4 ? 3 : 2)));
   const size_t fixed = (size_t)2 * sp.cls_floats * 4 + 2 * kStreamMaxStages * 8;
   const size_t per_cta = (size_t)(227 * 1024) / by_regs - 1024;
   UDAL_REQUIRE(per_cta > fixed + 2 * (size_t)sp.stage_floats * 4, "decode_stream_kernel: stage of %d floats does not fit", sp.stage_floats);
   sp.stages = (int)std::min<size_t>(kStreamMaxStages, (per_cta - fixed) / ((size_t)sp.stage_floats * 4));
   const size_t smem = (size_t)sp.stages * sp.stage_floats * 4 + fixed;
-  UDAL_CUDA(cudaFuncSetAttribute(decode_stream_kernel<EPT2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  UDAL_CUDA(cudaFuncSetAttribute(decode_stream_kernel<EPT2, SINGLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   // (without the carve-out hint the driver sizes shared memory for two CTAs of this size, not the three the registers admit)
-  UDAL_CUDA(cudaFuncSetAttribute(decode_stream_kernel<EPT2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  UDAL_CUDA(cudaFuncSetAttribute(decode_stream_kernel<EPT2, SINGLE>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   int nb = 0;
-  UDAL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, decode_stream_kernel<EPT2>, threads, smem));
+  UDAL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, decode_stream_kernel<EPT2, SINGLE>, threads, smem));
   UDAL_REQUIRE(nb >= 1, "decode_stream_kernel does not fit an SM (%zu bytes of shared memory)", smem);
   const int grid = std::min(sp.items, sms * nb);
-  decode_stream_kernel<EPT2><<<grid, threads, smem, ctx->stream>>>(sp);
+  decode_stream_kernel<EPT2, SINGLE><<<grid, threads, smem, ctx->stream>>>(sp);
   UDAL_CHECK_LAUNCH(ctx);
   return UDAL_OK;
 }
@@ -1265,9 +1278,14 @@ int udal_launch_decode_moments(udal_ctx* ctx, const float* const* cls, const flo
     const int pairs = sp.cls_floats / 2;
     const int ept2 = (pairs + sp.consumers - 1) / sp.consumers;
     if (sp.consumers <= 160 && ept2 <= 8 && (size_t)sp.stage_floats * 4 * 2 + (size_t)2 * sp.cls_floats * 4 < 100 * 1024) {
-      if (ept2 <= 4) return launch_stream<4>(ctx, sp);
-      if (ept2 <= 5) return launch_stream<5>(ctx, sp);
-      return launch_stream<8>(ctx, sp);
+      if (p.Tc == 1 && p.Tb == 1) {
+        if (ept2 <= 4) return launch_stream<4, true>(ctx, sp);
+        if (ept2 <= 5) return launch_stream<5, true>(ctx, sp);
+        return launch_stream<8, true>(ctx, sp);
+      }
+      if (ept2 <= 4) return launch_stream<4, false>(ctx, sp);
+      if (ept2 <= 5) return launch_stream<5, false>(ctx, sp);
+      return launch_stream<8, false>(ctx, sp);
     }
   }
   if (ctx->cfg.decode_precision == UDAL_DECODE_FP32) {
