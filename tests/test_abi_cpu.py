@@ -175,6 +175,24 @@ def test_synthetic_generators_match_the_oracle_copy():
         np.testing.assert_array_equal(x, y)
 
 
+def test_decode_precision_is_validated_on_the_host():
+    """params["decode_precision"]: "fp64" (default) | "fp32"; anything else is a ValueError before a context is created,
+    and the key takes part in the engine cache key (a configuration never inherits the other arithmetic's context)."""
+    import udal_b200 as u
+    p = u.hparams_config.get_detection_config("efficientdet-d0", image_size=64, num_classes=7, decode_precision="fp16")
+    with pytest.raises(ValueError, match="decode_precision"):
+        u.engine.Engine(p)
+    a = u.hparams_config.get_detection_config("efficientdet-d0", image_size=64, num_classes=7)
+    b = dict(a, decode_precision="fp32")
+    assert u.engine._key(a, 0, "fp32") != u.engine._key(b, 0, "fp32")
+    assert _lib_config_field("decode_precision")
+
+
+def _lib_config_field(name):
+    import udal_b200 as u
+    return name in [f[0] for f in u._lib.Config._fields_]
+
+
 def test_product_and_tools_do_not_import_the_oracle():
     """oracle/ is test infrastructure: only tests/, __graft_entry__.smoke() and bench.py's CPU baseline legs may use it."""
     import os

@@ -38,8 +38,7 @@ namespace {
 constexpr int DW_IN_BYTES = IG_ROWS * IG_BOXW * 128;                 // 23 040: linear halo tile
 constexpr int DW_IN_STRIDE = (DW_IN_BYTES + 1023) / 1024 * 1024;     // 23 552
 constexpr int kDwBuilderWarps = kDwBuilderThreads / 32;              // 4
-constexpr int kDwBuilderGroups = 2;                                  // tiles built concurrently (heads_dw_kernel)
-constexpr int kDwFirstEpiWarp = 2 + kDwBuilderGroups * kDwBuilderWarps;   // 10: (warp & 3) = 2,3,0,1 - every lane quarter per 4 warps
+// (first epilogue warp of heads_dw_kernel = 2 + GROUPS x 4 = 6 or 10: (warp & 3) = 2,3,0,1 - every TMEM lane quarter per 4 warps)
 
 // weight image of one pointwise matrix: wimg[n][k] = fp16(w[k][n0 + n]) (n < cout, zero rows past it), K-major, 128B swizzle
 __global__ void dw_weights_kernel(const float* __restrict__ w, int ldw, int n0, int cout, int rows, __half* __restrict__ wimg) {
@@ -59,14 +58,18 @@ __global__ void dw_bias_kernel(const float* __restrict__ bias, int n0, int cout,
 // =====================================================================================================================
 // tower layers (fp16 out) and stand-alone predict layers (fp32 out)
 // =====================================================================================================================
-// producer, MMA, 2 x 4 builder warps (two tiles are built concurrently: the builders' latency chain - ~375 instructions per
-// warp at a quarter of a scheduler - is the period of the pipeline), 2 x 4 epilogue warps
-constexpr int kDwThreads = 64 + kDwBuilderGroups * kDwBuilderThreads + 256;
+// threads: producer, MMA, GROUPS x 4 builder warps, 2 x 4 epilogue warps.  Tower layers: GROUPS = 2, two tiles are built
+// concurrently (the builders' latency chain is the period of the pipeline); the stand-alone predict layers keep
+// one group (their 64-80 KB of fp32 staging leave no room for more A buffers / stages, and at 576 threads x 96 registers
+// their epilogue spills: measured 0.50 -> 0.64 ms with two)
 
 template <int NPAD_, bool PREDICT_>
 struct DwShape {
   // (the stand-alone predict shapes carry 64-80 KB of fp32 staging: 3 stages and one A buffer per builder group there)
   static constexpr int NPAD = NPAD_, NROWS = NPAD_, STAGES = PREDICT_ ? 3 : 4, ABUF = PREDICT_ ? 2 : 4;
+  static constexpr int GROUPS = PREDICT_ ? 1 : 2;                          // builder groups
+  static constexpr int THREADS = 64 + GROUPS * kDwBuilderThreads + 256;
+  static constexpr int FIRST_EPI_WARP = 2 + GROUPS * kDwBuilderWarps;
   static constexpr bool PREDICT = PREDICT_;
   static constexpr int B_BYTES = (NROWS * 128 + 1023) / 1024 * 1024;
   // staging tile of one epilogue group: fp16 [128][64] (16 KB), or fp32 32-channel regions [128][32] (16 KB each, 128B
@@ -106,7 +109,7 @@ struct DwMaps {
 };
 
 template <class S>
-__global__ void __launch_bounds__(kDwThreads, 1) heads_dw_kernel(const __grid_constant__ DwMaps maps, const DwParams p) {
+__global__ void __launch_bounds__(S::THREADS, 1) heads_dw_kernel(const __grid_constant__ DwMaps maps, const DwParams p) {
   constexpr int NPAD = S::NPAD, STAGES = S::STAGES;
   constexpr uint32_t kTmemCols = NPAD <= 64 ? 128 : 256;
   extern __shared__ uint8_t smem_raw[];
@@ -146,7 +149,7 @@ __global__ void __launch_bounds__(kDwThreads, 1) heads_dw_kernel(const __grid_co
   }
   // epilogue constants; with swish the 0.5 of x*sigmoid(x) = h*tanh(h) + h, h = x/2, is folded in
   const float half = S::PREDICT ? 1.0f : 0.5f;
-  for (int e = threadIdx.x; e < p.num_levels * NPAD; e += kDwThreads) {
+  for (int e = threadIdx.x; e < p.num_levels * NPAD; e += S::THREADS) {
     const int l = e / NPAD, n = e - l * NPAD;
     sFb[(2 * l) * NPAD + n] = half * __ldg(p.ep_scale[l] + n);
     sFb[(2 * l + 1) * NPAD + n] = half * __ldg(p.ep_bias[l] + n);
@@ -175,9 +178,11 @@ __global__ void __launch_bounds__(kDwThreads, 1) heads_dw_kernel(const __grid_co
         if (item < 0) {
           sQ[(k + 1) & (IG_QRING - 1)] = -1;  // end of the stream, for both builder / epilogue groups
           bar_arrive(in_full + 8 * s);
-          const int s1 = s + 1 == STAGES ? 0 : s + 1;   // the other builder group waits for the next stage
-          bar_wait(in_empty + 8 * s1, (s1 == 0 ? ph ^ 1 : ph) ^ 1);
-          bar_arrive(in_full + 8 * s1);
+          if constexpr (S::GROUPS == 2) {
+            const int s1 = s + 1 == STAGES ? 0 : s + 1;   // the other builder group waits for the next stage
+            bar_wait(in_empty + 8 * s1, (s1 == 0 ? ph ^ 1 : ph) ^ 1);
+            bar_arrive(in_full + 8 * s1);
+          }
         } else {
           bar_expect_tx(in_full + 8 * s, DW_IN_BYTES);
           asm volatile(
@@ -227,14 +232,14 @@ __global__ void __launch_bounds__(kDwThreads, 1) heads_dw_kernel(const __grid_co
       }
       __syncwarp();
     }
-  } else if (warp < kDwFirstEpiWarp) {
+  } else if (warp < S::FIRST_EPI_WARP) {
     // ===================== builders: depthwise 3x3 (packed fp16) -> A operand =====================
     // group gb builds the items i = gb, gb + 2, ..: stage i % STAGES, A buffer i % ABUF
     const int gb = (warp - 2) >> 2;
     const int btid = (threadIdx.x - 64) & (kDwBuilderThreads - 1);
     DwWeights W;
     dw_load_weights(p.dw, btid & 7, W);
-    for (int i = gb;; i += kDwBuilderGroups) {
+    for (int i = gb;; i += S::GROUPS) {
       const int ab = i % S::ABUF, s = i % STAGES, ph = (i / STAGES) & 1;
       if (lane == 0) {
         bar_wait(in_full + 8 * s, ph);                              // halo tile landed
@@ -257,7 +262,7 @@ __global__ void __launch_bounds__(kDwThreads, 1) heads_dw_kernel(const __grid_co
     }
   } else {
     // ===================== epilogue: 2 groups x 4 warps, group g drains accumulator g =====================
-    const int ew = warp - kDwFirstEpiWarp;
+    const int ew = warp - S::FIRST_EPI_WARP;
     const int g = ew >> 2;
     const int q = warp & 3;                 // TMEM lane quarter this warp may access
     const int m = q * 32 + lane;            // GEMM row = pixel (m / 8, m % 8) of the tile
@@ -438,7 +443,7 @@ template <class S>
 int launch_dw(udal_ctx* ctx, const DwMaps& maps, const DwParams& p, int grid) {
   const int smem = S::smem(p.num_levels);
   UDAL_CUDA(cudaFuncSetAttribute(heads_dw_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  heads_dw_kernel<S><<<grid, kDwThreads, smem, ctx->stream>>>(maps, p);
+  heads_dw_kernel<S><<<grid, S::THREADS, smem, ctx->stream>>>(maps, p);
   UDAL_CHECK_LAUNCH(ctx);
   return UDAL_OK;
 }
