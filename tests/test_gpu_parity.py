@@ -433,12 +433,24 @@ def test_decode_precision_fp32_vs_oracle(u, model, size, C, T, batch, method, la
         switch.value = 1
 
 
-def _check_decode_fp32(u, model, size, C, T, batch, method, la):
+@pytest.mark.parametrize("stream", [1, 0])
+@pytest.mark.parametrize("rate_cls,rate_box", [(0.05, 0.0), (0.0, 0.05)])
+def test_decode_precision_fp32_one_head_with_mc(u, rate_cls, rate_box, stream):
+    """MC dropout on one head only: the sample axes of the two inputs differ (T and 1)."""
+    switch = ctypes.c_int.in_dll(u._lib.load(), "udal_decode_stream")
+    switch.value = stream
+    try:
+        _check_decode_fp32(u, "efficientdet-d0", (64, 96), 8, 5, 2, "l-norm", True, rate_cls, rate_box)
+    finally:
+        switch.value = 1
+
+
+def _check_decode_fp32(u, model, size, C, T, batch, method, la, rate_cls=0.05, rate_box=0.05):
     p = u.hparams_config.get_detection_config(
         model, image_size=size, num_classes=C, enable_softmax=True, loss_attenuation=la,
-        mc_dropout=True, mc_classheadrate=0.05, mc_boxheadrate=0.05, mc_dropoutsamp=T, uncert_adjust_method=method,
+        mc_dropout=True, mc_classheadrate=rate_cls, mc_boxheadrate=rate_box, mc_dropoutsamp=T, uncert_adjust_method=method,
         nms_configs=dict(method="gaussian", max_nms_inputs=0), decode_precision="fp32")
-    cls, box = synth_head_outputs(p, batch, seed=7, la=la)
+    cls, box = synth_head_outputs(p, batch, seed=7, la=la, mc_cls=rate_cls > 0, mc_box=rate_box > 0)
     boxes, unc, scores, classes, multi = u.postprocess.extract_uncertainties(copy.deepcopy(p), cls, box)
     pr = copy.deepcopy(p)
     pr.pop("decode_precision")
@@ -467,6 +479,8 @@ def _check_decode_fp32(u, model, size, C, T, batch, method, la):
     got = u.postprocess.postprocess_global(copy.deepcopy(p), cls, box, scales)
     ref = ref_np.postprocess_global(copy.deepcopy(pr), cls, box, scales)
     assert np.all(np.abs(got[3].astype(int) - ref[3].astype(int)) <= 1)
+    gcls = got[2][..., 0] if got[2].ndim == 3 else got[2]     # (no MC on the class head: no logit-std columns)
+    rcls = ref[2][..., 0] if ref[2].ndim == 3 else ref[2]
     matched = total = 0
     for b in range(batch):
         n = int(ref[3][b])
@@ -475,7 +489,7 @@ def _check_decode_fp32(u, model, size, C, T, batch, method, la):
             d = np.abs(got[0][b, :int(got[3][b])] - ref[0][b, j]).max(-1)
             k = int(np.argmin(d)) if d.size else -1
             s = max(ref[0][b, j, 2] - ref[0][b, j, 0], ref[0][b, j, 3] - ref[0][b, j, 1], 1.0)
-            if k >= 0 and d[k] < 2e-4 * s * scales[b] + 1e-4 and got[2][b, k, 0] == ref[2][b, j, 0] \
+            if k >= 0 and d[k] < 2e-4 * s * scales[b] + 1e-4 and gcls[b, k] == rcls[b, j] \
                     and abs(got[1][b, k] - ref[1][b, j]) < 1e-5:
                 matched += 1
     assert matched >= 0.99 * total, (matched, total)
