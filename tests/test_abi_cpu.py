@@ -185,6 +185,9 @@ def test_decode_precision_is_validated_on_the_host():
     a = u.hparams_config.get_detection_config("efficientdet-d0", image_size=64, num_classes=7)
     b = dict(a, decode_precision="fp32")
     assert u.engine._key(a, 0, "fp32") != u.engine._key(b, 0, "fp32")
+    # without the key the arithmetic follows strict_reference (default True -> the reference's float64 decode)
+    assert u.engine.decode_precision(a) == "fp64" and u.engine.decode_precision(dict(a, strict_reference=False)) == "fp32"
+    assert u.engine.decode_precision(dict(a, strict_reference=False, decode_precision="fp64")) == "fp64"
     assert _lib_config_field("decode_precision")
 
 

@@ -68,6 +68,18 @@ def anchor_table(min_level, max_level, num_scales, aspect_ratios, anchor_scale, 
     return np.ascontiguousarray(np.vstack(boxes_all), dtype=np.float32)
 
 
+def decode_precision(params):
+    """Arithmetic of the stand-alone decode + moments kernel: ``params["decode_precision"]`` = "fp64" (the reference's float64
+    decode value for value) | "fp32" (closed form in fp32, 1e-4 contract, HBM bound).  Without the key it follows
+    ``strict_reference`` (default True -> "fp64"; False -> "fp32")."""
+    prec = params.get("decode_precision")
+    if prec is None:
+        prec = "fp64" if params.get("strict_reference", True) else "fp32"
+    if prec not in ("fp64", "fp32"):
+        raise ValueError("decode_precision must be 'fp64' or 'fp32', got %r" % (prec,))
+    return prec
+
+
 def _key(params, device_id, heads_mode):
     keys = ("image_size", "min_level", "max_level", "num_scales", "aspect_ratios", "anchor_scale",
             "num_classes", "loss_attenuation", "mc_dropout", "mc_dropoutrate", "mc_classheadrate",
@@ -77,6 +89,7 @@ def _key(params, device_id, heads_mode):
     d["nms"] = {k: params["nms_configs"].get(k) for k in
                 ("method", "iou_thresh", "score_thresh", "sigma", "max_nms_inputs", "max_output_size")}
     d["device"], d["heads_mode"] = device_id, heads_mode
+    d["decode_precision"] = decode_precision(params)
     return json.dumps(d, sort_keys=True, default=str)
 
 
@@ -166,12 +179,7 @@ class Engine:
             raise ValueError("heads_mode must be one of fp32 | fp32x3 | fp16 | bf16, got %r" % (heads_mode,))
         cfg.heads_mode = modes[heads_mode]
         cfg.prefilter_k = int(params.get("nms_prefilter_k", 0) or 0)
-        # arithmetic of the stand-alone decode + moments kernel: "fp64" reproduces the reference's float64 decode value for
-        # value (default), "fp32" is the closed form in fp32 (1e-4 relative contract, HBM bound)
-        prec = params.get("decode_precision", "fp64") or "fp64"
-        if prec not in ("fp64", "fp32"):
-            raise ValueError("decode_precision must be 'fp64' or 'fp32', got %r" % (prec,))
-        cfg.decode_precision = 1 if prec == "fp32" else 0
+        cfg.decode_precision = 1 if decode_precision(params) == "fp32" else 0
         self.cfg = cfg
         self.ctx = device.Context(cfg)
         self.lib = self.ctx.lib
