@@ -256,6 +256,14 @@ int udal_bifpn_fuse(udal_ctx* ctx, int n, const float* const* in, const int* in_
                     int mode, int per_channel, int pool_avg, int NB, int H, int W, int F, int act, float* out);
 int udal_sepconv_bn(udal_ctx* ctx, const float* in, int NB, int H, int W, int F, int Cout, const float* dw, const float* pw,
                     const float* bias, const float* bn_scale, const float* bn_shift, int act, float* out);
+/* The same separable conv + BN (+ swish) of a 64-channel node (F = Cout = 64: the D0 BiFPN) on the tensor cores, fp32 accurate:
+ * fp32 depthwise on the CUDA cores, the pointwise GEMM as three fp16 tcgen05 passes over (hi, lo) operand pairs (the fp32x3
+ * tower kernel on one map).  udal_sepconv_tc_prepare builds the device tables of one conv once (pointwise hi / lo images,
+ * BN scale | folded bias; freed with the context); udal_sepconv_tc runs it: in / out [NB,H,W,64] fp32, 16-byte aligned,
+ * dw [9][64], act = UDAL_ACT_BN | UDAL_ACT_BN_SWISH. */
+int udal_sepconv_tc_prepare(udal_ctx* ctx, const float* pw, const float* bias, const float* bn_scale, const float* bn_shift,
+                            void** table);
+int udal_sepconv_tc(udal_ctx* ctx, const float* in, int NB, int H, int W, const float* dw, const void* table, int act, float* out);
 
 /* ---- fused post-processing -------------------------------------------------------------- */
 /* postprocess.py:472-621 (postprocess_global), serving variant.  image_scales: device [B] or

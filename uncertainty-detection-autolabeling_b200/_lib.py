@@ -81,6 +81,8 @@ SIGNATURES = {
                                        ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, _VP]),
     "udal_sepconv_bn": (ctypes.c_int, [_VP, _VP, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, _VP, _VP,
                                        _VP, _VP, _VP, ctypes.c_int, _VP]),
+    "udal_sepconv_tc_prepare": (ctypes.c_int, [_VP, _VP, _VP, _VP, _VP, ctypes.POINTER(ctypes.c_void_p)]),
+    "udal_sepconv_tc": (ctypes.c_int, [_VP, _VP, ctypes.c_int, ctypes.c_int, ctypes.c_int, _VP, _VP, ctypes.c_int, _VP]),
     "udal_calibrate_class": (ctypes.c_int, [_VP, _VP, ctypes.c_longlong, ctypes.c_int, ctypes.c_int, _VP, _VP, _VP, _VP, _VP, _VP]),
     "udal_stage_begin": (ctypes.c_int, [_VP, ctypes.c_int]),
     "udal_stage_h2d": (ctypes.c_int, [_VP, _VP, _VP, ctypes.c_size_t]),

@@ -89,9 +89,16 @@ class FPNCells:
                 if len(wsm) != n_in:
                     raise ValueError("one edge weight per input")
             scale, shift = _fold_bn(w["bn"])
-            out.append(dict(resample=res, wsm=wsm, dw=self._dev(np.reshape(w["dw"], (9, self.F))), pw=self._dev(w["pw"]),
-                            b=self._dev(w["b"] if w.get("b") is not None else np.zeros(self.F)),
-                            scale=self._dev(scale), shift=self._dev(shift)))
+            node = dict(resample=res, wsm=wsm, dw=self._dev(np.reshape(w["dw"], (9, self.F))), pw=self._dev(w["pw"]),
+                        b=self._dev(w["b"] if w.get("b") is not None else np.zeros(self.F)),
+                        scale=self._dev(scale), shift=self._dev(shift), tc=None)
+            if self.F == 64:
+                # 64-channel nodes (D0): separable conv on the tensor cores, fp32 accurate (udal_sepconv_tc); tables built once
+                table = ctypes.c_void_p()
+                _lib.check(self.lib.udal_sepconv_tc_prepare(self.ctx.handle, node["pw"].ptr, node["b"].ptr, node["scale"].ptr,
+                                                            node["shift"].ptr, ctypes.byref(table)))
+                node["tc"] = table
+            out.append(node)
         return out
 
     # ---- FNode (efficientdet_keras.py:166-173) --------------------------------------------------
@@ -135,9 +142,12 @@ class FPNCells:
             ins.append(x)
         fused = self._fuse(ins, w["wsm"], nb, th, tw, act=not self.conv_bn_act)
         out = self.ctx.empty((nb, th, tw, self.F))
-        _lib.check(self.lib.udal_sepconv_bn(self.ctx.handle, fused.ptr, nb, th, tw, self.F, self.F, w["dw"].ptr, w["pw"].ptr,
-                                            w["b"].ptr, w["scale"].ptr, w["shift"].ptr,
-                                            _lib.ACT_BN_SWISH if self.conv_bn_act else _lib.ACT_BN, out.ptr))
+        act = _lib.ACT_BN_SWISH if self.conv_bn_act else _lib.ACT_BN
+        if w["tc"] is not None:
+            _lib.check(self.lib.udal_sepconv_tc(self.ctx.handle, fused.ptr, nb, th, tw, w["dw"].ptr, w["tc"], act, out.ptr))
+        else:
+            _lib.check(self.lib.udal_sepconv_bn(self.ctx.handle, fused.ptr, nb, th, tw, self.F, self.F, w["dw"].ptr, w["pw"].ptr,
+                                                w["b"].ptr, w["scale"].ptr, w["shift"].ptr, act, out.ptr))
         return out
 
     def _fuse_raw_pool(self, x, nb, th, tw):

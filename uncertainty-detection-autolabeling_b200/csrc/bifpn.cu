@@ -139,6 +139,98 @@ __global__ void bifpn_fuse_kernel(const FuseParams p) {
   p.out[i] = p.act ? swish_f(acc) : acc;
 }
 
+// The same fusion, four channels per thread (F % 4 == 0, 16-byte aligned maps): 16-byte loads and stores, 32-bit index
+// arithmetic, the edge weights normalised once per thread (w_i / (sum + 0.0001) resp. the softmax) and applied by FMA, swish
+// through ex2 / rcp.  The scalar kernel above divides every value by the weight sum as the reference does (IEEE); this one
+// differs from it by a few ulp per node - the contract of this row is the oracle's 2e-4 - and moves 11x fewer instructions
+// per byte (the scalar kernel: 3.9 ms of an 8.4 ms FPNCells call at D0 1280x384, batch 64; HBM time of its bytes: 0.35 ms).
+__device__ __forceinline__ float4 resample_at4(const float* __restrict__ src, int h, int w, int H, int W, int y, int x, int F,
+                                               int f, int pool_avg) {
+  if (h == H && w == W) return __ldg(reinterpret_cast<const float4*>(src + ((size_t)y * w + x) * F + f));
+  if (h > H && w > W) {
+    const int sy = (h - 1) / H + 1, sx = (w - 1) / W + 1, ky = sy + 1, kx = sx + 1;
+    const int pad_y = max((H - 1) * sy + ky - h, 0) / 2, pad_x = max((W - 1) * sx + kx - w, 0) / 2;
+    const int y0 = y * sy - pad_y, x0 = x * sx - pad_x;
+    float4 best = make_float4(-3.402823466e38f, -3.402823466e38f, -3.402823466e38f, -3.402823466e38f);
+    float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+    int cnt = 0;
+    for (int dy = 0; dy < ky; ++dy) {
+      const int yy = y0 + dy;
+      if (yy < 0 || yy >= h) continue;
+      for (int dx = 0; dx < kx; ++dx) {
+        const int xx = x0 + dx;
+        if (xx < 0 || xx >= w) continue;
+        const float4 v = __ldg(reinterpret_cast<const float4*>(src + ((size_t)yy * w + xx) * F + f));
+        best = make_float4(fmaxf(best.x, v.x), fmaxf(best.y, v.y), fmaxf(best.z, v.z), fmaxf(best.w, v.w));
+        sum = make_float4(sum.x + v.x, sum.y + v.y, sum.z + v.z, sum.w + v.w);
+        ++cnt;
+      }
+    }
+    if (!pool_avg) return best;
+    const float fc = (float)cnt;
+    return make_float4(__fdiv_rn(sum.x, fc), __fdiv_rn(sum.y, fc), __fdiv_rn(sum.z, fc), __fdiv_rn(sum.w, fc));
+  }
+  const float sy = (float)h / (float)H, sx = (float)w / (float)W;
+  const int yy = min((int)floorf((float)y * sy), h - 1), xx = min((int)floorf((float)x * sx), w - 1);
+  return __ldg(reinterpret_cast<const float4*>(src + ((size_t)yy * w + xx) * F + f));
+}
+
+__device__ __forceinline__ float swish_fast(float x) {
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-1.4426950408889634f * x));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.f + e));
+  return x * r;
+}
+
+__global__ void __launch_bounds__(256) bifpn_fuse4_kernel(const FuseParams p) {
+  const int F4 = p.F >> 2;
+  const int px = blockIdx.x * (256 / 16) + (threadIdx.x >> 4);   // 16 threads (64 channels) per pixel and pass
+  const int total_px = p.NB * p.H * p.W;
+  if (px >= total_px) return;
+  const int x = px % p.W;
+  const int r = px / p.W;
+  const int y = r % p.H;
+  const int nb = r / p.H;
+  for (int f4 = threadIdx.x & 15; f4 < F4; f4 += 16) {
+    const int f = 4 * f4;
+    float4 v[3], wn[3];
+    for (int k = 0; k < p.n; ++k) {
+      v[k] = resample_at4(p.in[k] + (size_t)nb * p.h[k] * p.w[k] * p.F, p.h[k], p.w[k], p.H, p.W, y, x, p.F, f, p.pool_avg);
+      if (!p.wsm[k]) wn[k] = make_float4(1.f, 1.f, 1.f, 1.f);
+      else if (p.per_channel) wn[k] = __ldg(reinterpret_cast<const float4*>(p.wsm[k] + f));
+      else {
+        const float w1 = __ldg(p.wsm[k]);
+        wn[k] = make_float4(w1, w1, w1, w1);
+      }
+    }
+    if (p.mode == UDAL_FUSE_FASTATTN) {
+      float4 ws = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int k = 0; k < p.n; ++k) {
+        wn[k] = make_float4(fmaxf(wn[k].x, 0.f), fmaxf(wn[k].y, 0.f), fmaxf(wn[k].z, 0.f), fmaxf(wn[k].w, 0.f));
+        ws = make_float4(ws.x + wn[k].x, ws.y + wn[k].y, ws.z + wn[k].z, ws.w + wn[k].w);
+      }
+      const float4 inv = make_float4(__fdiv_rn(1.f, ws.x + 0.0001f), __fdiv_rn(1.f, ws.y + 0.0001f), __fdiv_rn(1.f, ws.z + 0.0001f),
+                                     __fdiv_rn(1.f, ws.w + 0.0001f));
+      for (int k = 0; k < p.n; ++k) wn[k] = make_float4(wn[k].x * inv.x, wn[k].y * inv.y, wn[k].z * inv.z, wn[k].w * inv.w);
+    } else if (p.mode == UDAL_FUSE_ATTN) {
+      float4 mx = wn[0];
+      for (int k = 1; k < p.n; ++k) mx = make_float4(fmaxf(mx.x, wn[k].x), fmaxf(mx.y, wn[k].y), fmaxf(mx.z, wn[k].z), fmaxf(mx.w, wn[k].w));
+      float4 se = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int k = 0; k < p.n; ++k) {
+        wn[k] = make_float4(expf(wn[k].x - mx.x), expf(wn[k].y - mx.y), expf(wn[k].z - mx.z), expf(wn[k].w - mx.w));
+        se = make_float4(se.x + wn[k].x, se.y + wn[k].y, se.z + wn[k].z, se.w + wn[k].w);
+      }
+      for (int k = 0; k < p.n; ++k)
+        wn[k] = make_float4(__fdiv_rn(wn[k].x, se.x), __fdiv_rn(wn[k].y, se.y), __fdiv_rn(wn[k].z, se.z), __fdiv_rn(wn[k].w, se.w));
+    }
+    float4 acc = make_float4(v[0].x * wn[0].x, v[0].y * wn[0].y, v[0].z * wn[0].z, v[0].w * wn[0].w);
+    for (int k = 1; k < p.n; ++k)
+      acc = make_float4(fmaf(v[k].x, wn[k].x, acc.x), fmaf(v[k].y, wn[k].y, acc.y), fmaf(v[k].z, wn[k].z, acc.z), fmaf(v[k].w, wn[k].w, acc.w));
+    if (p.act) acc = make_float4(swish_fast(acc.x), swish_fast(acc.y), swish_fast(acc.z), swish_fast(acc.w));
+    *reinterpret_cast<float4*>(p.out + (size_t)px * p.F + f) = acc;
+  }
+}
+
 }  // namespace
 
 extern "C" {
@@ -195,7 +287,14 @@ int udal_bifpn_fuse(udal_ctx* ctx, int n, const float* const* in, const int* in_
   p.out = out;
   UDAL_TRY(udal_join(ctx));
   const int64_t total = (int64_t)NB * H * W * F;
-  bifpn_fuse_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(p);
+  bool vec = (F & 3) == 0 && ((uintptr_t)out & 15) == 0 && (int64_t)NB * H * W < (1ll << 31);
+  for (int k = 0; k < n; ++k) vec = vec && ((uintptr_t)in[k] & 15) == 0 && (!p.wsm[k] || !per_channel || ((uintptr_t)p.wsm[k] & 15) == 0);
+  if (vec) {
+    const int64_t pixels = (int64_t)NB * H * W;
+    bifpn_fuse4_kernel<<<(unsigned)((pixels + 15) / 16), 256, 0, ctx->stream>>>(p);
+  } else {
+    bifpn_fuse_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(p);
+  }
   UDAL_CHECK_LAUNCH(ctx);
   return UDAL_OK;
 }

@@ -77,7 +77,7 @@ struct WdParams {
   const void* wimg;                      // bf16 2 atoms x [128 n][64 k], 128B swizzle
   void* out[UDAL_MAX_LEVELS];            // tower: [NB,H,W,128] bf16 (through the tensor maps); predict: [NB,H,W,ch_total] fp32
   int predict, Cout, ch_off, ch_total;   // predict: this launch writes channels [ch_off, ch_off + Cout)
-  int act;                               // fp32-out path (predict = 1): 1 = epilogue scale, bias and an accurate swish (X3 tower layers)
+  int act;                               // fp32-out path (predict = 1): 1 = epilogue scale, bias and an accurate swish (X3 tower layers); 2 = scale and bias (BiFPN)
   int debug;                             // timing experiments only (wrong results): 1 = no depthwise math, 2 = no epilogue math / stores
   int* counter;                          // zeroed work-item counter of this launch (dynamic claiming, heads_umma.cuh)
 };
@@ -431,10 +431,11 @@ __global__ void __launch_bounds__(kWdThreads, 1) heads_wide_kernel(const __grid_
               const float4 g0 = eps[pass * 8 + 2 * u], g1 = eps[pass * 8 + 2 * u + 1];
               const float gs[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
 #pragma unroll
-              for (int e = 0; e < 8; e += 2)
+              for (int e = 0; e < 8; e += 2) {
+                const float a0 = fmaf(__uint_as_float(r[u][e]), gs[e], fb[e]), a1 = fmaf(__uint_as_float(r[u][e + 1]), gs[e + 1], fb[e + 1]);
                 *reinterpret_cast<float2*>(stg + m * WD_STG_STRIDE + u * 8 + e) =
-                    make_float2(wd_swish_accurate(fmaf(__uint_as_float(r[u][e]), gs[e], fb[e])),
-                                wd_swish_accurate(fmaf(__uint_as_float(r[u][e + 1]), gs[e + 1], fb[e + 1])));
+                    p.act == 1 ? make_float2(wd_swish_accurate(a0), wd_swish_accurate(a1)) : make_float2(a0, a1);  // 2: BN only
+              }
             } else {
 #pragma unroll
               for (int e = 0; e < 8; e += 2)
@@ -589,14 +590,18 @@ int udal_heads_wide_prepare(udal_ctx* ctx, int head) {
   return UDAL_OK;
 }
 
+// (num_levels, Hs, Ws, F): the maps this launch covers - the context's pyramid for the heads, one map for a BiFPN node
 template <int CH, bool F32IN, bool FP16, bool X3 = false>
-static int launch_wide_t(udal_ctx* ctx, const void* const* in, int in_nb, int NB, const float* const* in_scale, const float* dw,
-                       const void* wimg, const float* const* ep, int predict, int cout, int ch_off, int ch_total,
-                       void* const* out, int act = 0) {
+static int launch_wide_geom(udal_ctx* ctx, int num_levels, const int* Hs, const int* Ws, int F, const void* const* in, int in_nb, int NB,
+                            const float* const* in_scale, const float* dw, const void* wimg, const float* const* ep, int predict,
+                            int cout, int ch_off, int ch_total, void* const* out, int act = 0) {
   using S = WdShape<CH, F32IN, X3>;
   EncodeTiledFn encode = get_encode();
   UDAL_REQUIRE(encode != nullptr, "cuTensorMapEncodeTiled is not available from this driver");
-  const udal_config& c = ctx->cfg;
+  struct {
+    int num_levels;
+    const int *level_h, *level_w;
+  } c = {num_levels, Hs, Ws};
   WdMaps maps;
   WdParams p;
   memset(&p, 0, sizeof(p));
@@ -604,7 +609,7 @@ static int launch_wide_t(udal_ctx* ctx, const void* const* in, int in_nb, int NB
   p.num_levels = c.num_levels;
   p.NB = NB;
   p.in_nb = in_nb;
-  p.F = c.num_filters;
+  p.F = F;
   p.dw = dw;
   p.wimg = wimg;
   p.predict = predict;
@@ -642,6 +647,15 @@ static int launch_wide_t(udal_ctx* ctx, const void* const* in, int in_nb, int NB
   heads_wide_kernel<CH, F32IN, FP16, X3><<<grid, kWdThreads, S::SMEM, ctx->stream>>>(maps, p);
   UDAL_CHECK_LAUNCH(ctx);
   return UDAL_OK;
+}
+
+template <int CH, bool F32IN, bool FP16, bool X3 = false>
+static int launch_wide_t(udal_ctx* ctx, const void* const* in, int in_nb, int NB, const float* const* in_scale, const float* dw,
+                         const void* wimg, const float* const* ep, int predict, int cout, int ch_off, int ch_total,
+                         void* const* out, int act = 0) {
+  const udal_config& c = ctx->cfg;
+  return launch_wide_geom<CH, F32IN, FP16, X3>(ctx, c.num_levels, c.level_h, c.level_w, c.num_filters, in, in_nb, NB, in_scale, dw,
+                                               wimg, ep, predict, cout, ch_off, ch_total, out, act);
 }
 
 // 16-bit format by the context's heads mode
@@ -911,4 +925,45 @@ int udal_heads_x3_sample(udal_ctx* ctx, const float* const* feats, int batch, co
   UDAL_TRY(run_tower_x3(ctx, UDAL_HEAD_CLASS, feats, batch, scale, cls_out));
   UDAL_TRY(run_tower_x3(ctx, UDAL_HEAD_BOX, feats, batch, scale, box_out));
   return UDAL_OK;
+}
+
+// =====================================================================================================================
+// BiFPN: OpAfterCombine's separable conv + BN of a 64-channel node on the tensor cores, fp32 accurate -
+// the fp32x3 tower kernel on ONE map: fp32 depthwise on the CUDA cores, the pointwise GEMM as three fp16 tcgen05 passes over
+// (hi, lo) operand pairs, epilogue = BN scale | folded bias (act 2), fp32 in and out.  The fp32 CUDA-core kernel it replaces
+// took 3.2 ms of an 8.4 ms FPNCells call (D0 1280x384, batch 64).
+// =====================================================================================================================
+extern "C" int udal_sepconv_tc_prepare(udal_ctx* ctx, const float* pw, const float* bias, const float* bn_scale, const float* bn_shift,
+                                       void** table) {
+  UDAL_REQUIRE(ctx && pw && bias && table, "NULL argument");
+  UDAL_REQUIRE((bn_scale == nullptr) == (bn_shift == nullptr), "udal_sepconv_tc_prepare: BN scale and shift go together");
+  UDAL_CUDA(cudaSetDevice(ctx->cfg.device));
+  UDAL_TRY(udal_join(ctx));
+  // [2][64 n][64 k] fp16 (hi, lo) images, then [2][64] fp32 (scale | folded bias)
+  void* t = nullptr;
+  UDAL_CUDA(cudaMalloc(&t, (size_t)2 * KF * KF * sizeof(__half) + 2 * KF * sizeof(float)));
+  ctx->user_allocs.push_back(t);
+  x3_weights_kernel<<<(KF * KF + 255) / 256, 256, 0, ctx->stream>>>(pw, KF, 0, KF, reinterpret_cast<__half*>(t));
+  UDAL_CHECK_LAUNCH(ctx);
+  float* ep = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(t) + (size_t)2 * KF * KF * sizeof(__half));
+  wide_ep_kernel<<<1, KF, 0, ctx->stream>>>(bias, bn_scale, bn_shift, 0, KF, ep, KF);
+  UDAL_CHECK_LAUNCH(ctx);
+  *table = t;
+  return UDAL_OK;
+}
+
+extern "C" int udal_sepconv_tc(udal_ctx* ctx, const float* in, int NB, int H, int W, const float* dw, const void* table, int act,
+                               float* out) {
+  UDAL_REQUIRE(ctx && in && dw && table && out, "NULL argument");
+  UDAL_REQUIRE(act == UDAL_ACT_BN || act == UDAL_ACT_BN_SWISH, "udal_sepconv_tc: act must be UDAL_ACT_BN or UDAL_ACT_BN_SWISH");
+  UDAL_REQUIRE(NB > 0 && H > 0 && W > 0, "udal_sepconv_tc: bad sizes");
+  UDAL_REQUIRE(((uintptr_t)in & 15) == 0 && ((uintptr_t)out & 15) == 0, "udal_sepconv_tc: maps must be 16-byte aligned");
+  UDAL_CUDA(cudaSetDevice(ctx->cfg.device));
+  UDAL_TRY(udal_join(ctx));
+  UDAL_TRY(udal_work_counters_reset(ctx));   // (stream ordered: behind the previous launch that used the counters)
+  const void* ins[UDAL_MAX_LEVELS] = {in};
+  void* outs[UDAL_MAX_LEVELS] = {out};
+  const float* ep[UDAL_MAX_LEVELS] = {reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(table) + (size_t)2 * KF * KF * sizeof(__half))};
+  return launch_wide_geom<64, true, true, true>(ctx, 1, &H, &W, KF, ins, NB, NB, nullptr, dw, table, ep, 1, KF, 0, KF, outs,
+                                                act == UDAL_ACT_BN_SWISH ? 1 : 2);
 }
