@@ -52,6 +52,65 @@ __global__ void conv1x1_bn_kernel(const float* __restrict__ in, const float* __r
   }
 }
 
+// Register-tiled form for F = 64 (the D0 BiFPN), Cin % 4 == 0, 16-byte aligned maps: block = 128 pixels, thread = 8 pixels x 4
+// outputs (32 accumulators); the input rows go through shared memory in chunks of 32 channels, per 4 channels a thread issues
+// 8 broadcast LDS.128 + 4 LDG.128 (weights, L1 resident) for 128 FMAs (the kernel above: 1 load per FMA).
+constexpr int kC1Px = 128, kC1K = 32;
+__global__ void __launch_bounds__(256) conv1x1_bn64_kernel(const float* __restrict__ in, const float* __restrict__ w,
+                                                          const float* __restrict__ bias, const float* __restrict__ bn_scale,
+                                                          const float* __restrict__ bn_shift, int64_t pixels, int Cin,
+                                                          float* __restrict__ out) {
+  __shared__ __align__(16) float s_in[kC1Px * kC1K];   // [128 px][32 k]
+  const int tid = threadIdx.x, g = tid >> 4, t = tid & 15;   // group of 8 pixels, thread's 4 outputs 4 t ..
+  const int64_t p0 = (int64_t)blockIdx.x * kC1Px;
+  const int npx = (int)min((int64_t)kC1Px, pixels - p0);
+  float4 acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int k0 = 0; k0 < Cin; k0 += kC1K) {
+    const int kn = min(kC1K, Cin - k0);   // multiple of 4
+    __syncthreads();
+    for (int e = tid; e < kC1Px * (kC1K / 4); e += 256) {
+      const int px = e >> 3, k4 = (e & 7) * 4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (px < npx && k4 < kn) v = __ldg(reinterpret_cast<const float4*>(in + (p0 + px) * Cin + k0 + k4));
+      *reinterpret_cast<float4*>(s_in + px * kC1K + k4) = v;
+    }
+    __syncthreads();
+    for (int kk = 0; kk < kn; kk += 4) {
+      float4 wk[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) wk[j] = __ldg(reinterpret_cast<const float4*>(w + (size_t)(k0 + kk + j) * 64) + t);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float4 x = *reinterpret_cast<const float4*>(s_in + (g * 8 + i) * kC1K + kk);
+        const float xv[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          acc[i].x = fmaf(xv[j], wk[j].x, acc[i].x);
+          acc[i].y = fmaf(xv[j], wk[j].y, acc[i].y);
+          acc[i].z = fmaf(xv[j], wk[j].z, acc[i].z);
+          acc[i].w = fmaf(xv[j], wk[j].w, acc[i].w);
+        }
+      }
+    }
+  }
+  const float4 b = bias ? __ldg(reinterpret_cast<const float4*>(bias) + t) : make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (bn_scale) {
+    sc = __ldg(reinterpret_cast<const float4*>(bn_scale) + t);
+    sh = __ldg(reinterpret_cast<const float4*>(bn_shift) + t);
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int px = g * 8 + i;
+    if (px >= npx) continue;
+    float4 v = make_float4(acc[i].x + b.x, acc[i].y + b.y, acc[i].z + b.z, acc[i].w + b.w);
+    if (bn_scale) v = make_float4(fmaf(v.x, sc.x, sh.x), fmaf(v.y, sc.y, sh.y), fmaf(v.z, sc.z, sh.z), fmaf(v.w, sc.w, sh.w));
+    *reinterpret_cast<float4*>(out + (p0 + px) * 64 + 4 * t) = v;
+  }
+}
+
 struct FuseParams {
   int n;                       // inputs (1..3)
   const float* in[3];          // [NB, h_i, w_i, F]
@@ -139,25 +198,34 @@ __global__ void bifpn_fuse_kernel(const FuseParams p) {
   p.out[i] = p.act ? swish_f(acc) : acc;
 }
 
-// The same fusion, four channels per thread (F % 4 == 0, 16-byte aligned maps): 16-byte loads and stores, 32-bit index
-// arithmetic, the edge weights normalised once per thread (w_i / (sum + 0.0001) resp. the softmax) and applied by FMA, swish
-// through ex2 / rcp.  The scalar kernel above divides every value by the weight sum as the reference does (IEEE); this one
-// differs from it by a few ulp per node - the contract of this row is the oracle's 2e-4 - and moves 11x fewer instructions
-// per byte (the scalar kernel: 3.9 ms of an 8.4 ms FPNCells call at D0 1280x384, batch 64; HBM time of its bytes: 0.35 ms).
-__device__ __forceinline__ float4 resample_at4(const float* __restrict__ src, int h, int w, int H, int W, int y, int x, int F,
+// The same fusion, four channels per thread (F % 4 == 0, 16-byte aligned maps): grid = (16-pixel row segments, rows, images)
+// - no index division at all -, the resampling rule of every input resolved on the host (Resample: same / pooling window /
+// nearest scale), 16-byte loads and stores, the edge weights normalised once per thread (w_i / (sum + 0.0001) resp. the
+// softmax) and applied by FMA, swish through ex2 / rcp.  The scalar kernel above divides every value by the weight sum as the
+// reference does (IEEE); this one differs from it by a few ulp per node - the contract of this row is the oracle's 2e-4.
+// (The scalar kernel took 3.9 ms of an 8.4 ms FPNCells call at D0 1280x384, batch 64; HBM time of its bytes: 0.3 ms.)
+struct Resample {
+  int kind;                    // 0 same size, 1 pooling, 2 nearest neighbour
+  int sy, sx, ky, kx, pad_y, pad_x;
+  float fy, fx;                // nearest: (float)h / H, (float)w / W
+};
+struct Fuse4Params {
+  FuseParams f;
+  Resample rs[3];
+};
+
+__device__ __forceinline__ float4 resample_at4(const float* __restrict__ src, const Resample& rs, int h, int w, int y, int x, int F,
                                                int f, int pool_avg) {
-  if (h == H && w == W) return __ldg(reinterpret_cast<const float4*>(src + ((size_t)y * w + x) * F + f));
-  if (h > H && w > W) {
-    const int sy = (h - 1) / H + 1, sx = (w - 1) / W + 1, ky = sy + 1, kx = sx + 1;
-    const int pad_y = max((H - 1) * sy + ky - h, 0) / 2, pad_x = max((W - 1) * sx + kx - w, 0) / 2;
-    const int y0 = y * sy - pad_y, x0 = x * sx - pad_x;
+  if (rs.kind == 0) return __ldg(reinterpret_cast<const float4*>(src + ((size_t)y * w + x) * F + f));
+  if (rs.kind == 1) {
+    const int y0 = y * rs.sy - rs.pad_y, x0 = x * rs.sx - rs.pad_x;
     float4 best = make_float4(-3.402823466e38f, -3.402823466e38f, -3.402823466e38f, -3.402823466e38f);
     float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
     int cnt = 0;
-    for (int dy = 0; dy < ky; ++dy) {
+    for (int dy = 0; dy < rs.ky; ++dy) {
       const int yy = y0 + dy;
       if (yy < 0 || yy >= h) continue;
-      for (int dx = 0; dx < kx; ++dx) {
+      for (int dx = 0; dx < rs.kx; ++dx) {
         const int xx = x0 + dx;
         if (xx < 0 || xx >= w) continue;
         const float4 v = __ldg(reinterpret_cast<const float4*>(src + ((size_t)yy * w + xx) * F + f));
@@ -170,8 +238,7 @@ __device__ __forceinline__ float4 resample_at4(const float* __restrict__ src, in
     const float fc = (float)cnt;
     return make_float4(__fdiv_rn(sum.x, fc), __fdiv_rn(sum.y, fc), __fdiv_rn(sum.z, fc), __fdiv_rn(sum.w, fc));
   }
-  const float sy = (float)h / (float)H, sx = (float)w / (float)W;
-  const int yy = min((int)floorf((float)y * sy), h - 1), xx = min((int)floorf((float)x * sx), w - 1);
+  const int yy = min((int)floorf((float)y * rs.fy), h - 1), xx = min((int)floorf((float)x * rs.fx), w - 1);
   return __ldg(reinterpret_cast<const float4*>(src + ((size_t)yy * w + xx) * F + f));
 }
 
@@ -182,20 +249,18 @@ __device__ __forceinline__ float swish_fast(float x) {
   return x * r;
 }
 
-__global__ void __launch_bounds__(256) bifpn_fuse4_kernel(const FuseParams p) {
+__global__ void __launch_bounds__(256) bifpn_fuse4_kernel(const Fuse4Params q) {
+  const FuseParams& p = q.f;
   const int F4 = p.F >> 2;
-  const int px = blockIdx.x * (256 / 16) + (threadIdx.x >> 4);   // 16 threads (64 channels) per pixel and pass
-  const int total_px = p.NB * p.H * p.W;
-  if (px >= total_px) return;
-  const int x = px % p.W;
-  const int r = px / p.W;
-  const int y = r % p.H;
-  const int nb = r / p.H;
+  const int x = blockIdx.x * 16 + (threadIdx.x >> 4);   // 16 threads (64 channels per pass) per pixel
+  const int y = blockIdx.y, nb = blockIdx.z;
+  if (x >= p.W) return;
+  const size_t px = ((size_t)nb * p.H + y) * p.W + x;
   for (int f4 = threadIdx.x & 15; f4 < F4; f4 += 16) {
     const int f = 4 * f4;
     float4 v[3], wn[3];
     for (int k = 0; k < p.n; ++k) {
-      v[k] = resample_at4(p.in[k] + (size_t)nb * p.h[k] * p.w[k] * p.F, p.h[k], p.w[k], p.H, p.W, y, x, p.F, f, p.pool_avg);
+      v[k] = resample_at4(p.in[k] + (size_t)nb * p.h[k] * p.w[k] * p.F, q.rs[k], p.h[k], p.w[k], y, x, p.F, f, p.pool_avg);
       if (!p.wsm[k]) wn[k] = make_float4(1.f, 1.f, 1.f, 1.f);
       else if (p.per_channel) wn[k] = __ldg(reinterpret_cast<const float4*>(p.wsm[k] + f));
       else {
@@ -227,7 +292,7 @@ __global__ void __launch_bounds__(256) bifpn_fuse4_kernel(const FuseParams p) {
     for (int k = 1; k < p.n; ++k)
       acc = make_float4(fmaf(v[k].x, wn[k].x, acc.x), fmaf(v[k].y, wn[k].y, acc.y), fmaf(v[k].z, wn[k].z, acc.z), fmaf(v[k].w, wn[k].w, acc.w));
     if (p.act) acc = make_float4(swish_fast(acc.x), swish_fast(acc.y), swish_fast(acc.z), swish_fast(acc.w));
-    *reinterpret_cast<float4*>(p.out + (size_t)px * p.F + f) = acc;
+    *reinterpret_cast<float4*>(p.out + px * p.F + f) = acc;
   }
 }
 
@@ -243,6 +308,13 @@ int udal_conv1x1_bn(udal_ctx* ctx, const float* in, int NB, int H, int W, int Ci
   UDAL_REQUIRE((size_t)8 * Cin * sizeof(float) <= 48 * 1024, "udal_conv1x1_bn: %d input channels", Cin);
   UDAL_TRY(udal_join(ctx));
   const int64_t pixels = (int64_t)NB * H * W;
+  const uintptr_t al = (uintptr_t)in | (uintptr_t)w | (uintptr_t)out | (uintptr_t)bias | (uintptr_t)bn_scale | (uintptr_t)bn_shift;
+  if (F == 64 && (Cin & 3) == 0 && (al & 15) == 0) {
+    conv1x1_bn64_kernel<<<(unsigned)((pixels + kC1Px - 1) / kC1Px), 256, 0, ctx->stream>>>(in, w, bias, bn_scale, bn_shift, pixels,
+                                                                                          Cin, out);
+    UDAL_CHECK_LAUNCH(ctx);
+    return UDAL_OK;
+  }
   const int threads = F >= 128 ? 128 : 64;
   conv1x1_bn_kernel<<<(unsigned)((pixels + 7) / 8), threads, (size_t)8 * Cin * sizeof(float), ctx->stream>>>(
       in, w, bias, bn_scale, bn_shift, pixels, Cin, F, out);
@@ -289,9 +361,31 @@ int udal_bifpn_fuse(udal_ctx* ctx, int n, const float* const* in, const int* in_
   const int64_t total = (int64_t)NB * H * W * F;
   bool vec = (F & 3) == 0 && ((uintptr_t)out & 15) == 0 && (int64_t)NB * H * W < (1ll << 31);
   for (int k = 0; k < n; ++k) vec = vec && ((uintptr_t)in[k] & 15) == 0 && (!p.wsm[k] || !per_channel || ((uintptr_t)p.wsm[k] & 15) == 0);
+  vec = vec && H <= 65535 && NB <= 65535;
   if (vec) {
-    const int64_t pixels = (int64_t)NB * H * W;
-    bifpn_fuse4_kernel<<<(unsigned)((pixels + 15) / 16), 256, 0, ctx->stream>>>(p);
+    Fuse4Params q;
+    q.f = p;
+    for (int k = 0; k < n; ++k) {
+      Resample& r = q.rs[k];
+      memset(&r, 0, sizeof(r));
+      const int h = p.h[k], w = p.w[k];
+      if (h == H && w == W) r.kind = 0;
+      else if (h > H && w > W) {
+        r.kind = 1;
+        r.sy = (h - 1) / H + 1;
+        r.sx = (w - 1) / W + 1;
+        r.ky = r.sy + 1;
+        r.kx = r.sx + 1;
+        const int ty = (H - 1) * r.sy + r.ky - h, tx = (W - 1) * r.sx + r.kx - w;
+        r.pad_y = (ty > 0 ? ty : 0) / 2;
+        r.pad_x = (tx > 0 ? tx : 0) / 2;
+      } else {
+        r.kind = 2;
+        r.fy = (float)h / (float)H;
+        r.fx = (float)w / (float)W;
+      }
+    }
+    bifpn_fuse4_kernel<<<dim3((unsigned)((W + 15) / 16), (unsigned)H, (unsigned)NB), 256, 0, ctx->stream>>>(q);
   } else {
     bifpn_fuse_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(p);
   }
