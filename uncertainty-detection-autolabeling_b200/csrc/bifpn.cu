@@ -4,8 +4,8 @@
 // differs, max / average pooling with TF "SAME" padding, nearest-neighbour up-sampling), FNode.fuse_features 86-125
 // (fastattn / attn / sum and their per-channel variants) and OpAfterCombine 176-236 (swish -> separable 3x3 conv ->
 // BN).  The graph itself (which node reads which, fpn_configs.bifpn_config) is host logic and lives in bifpn.py, as it
-// does in the reference.  fp32 throughout on the CUDA cores: this row is a functional producer for the heads, not a
-// tuned kernel set; the separable conv reuses the fp32 tower kernel of heads_fp32.cu.
+// does in the reference.  fp32 in and out; 64-filter nodes run the separable conv on the tensor cores (udal_sepconv_tc,
+// heads_wide.cu: the fp32-accurate fp32x3 tower kernel on one map), other widths the fp32 tower kernel of heads_fp32.cu.
 //
 //   udal_conv1x1_bn   [NB,H,W,Cin] -> [NB,H,W,F]: x @ w + b, then BN (scale, shift) when given
 //   udal_bifpn_fuse   out = act( sum_i weight_i * resample_i(in_i) ), resample_i chosen by the source / target sizes:
