@@ -222,6 +222,24 @@ __device__ __forceinline__ float4 resample_at4(const float* __restrict__ src, co
     float4 best = make_float4(-3.402823466e38f, -3.402823466e38f, -3.402823466e38f, -3.402823466e38f);
     float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
     int cnt = 0;
+    if (rs.ky == 3 && rs.kx == 3) {
+      // stride 2 (every level transition of the pyramid): the nine loads are issued together
+      float4 v[9];
+      bool ok[9];
+#pragma unroll
+      for (int t = 0; t < 9; ++t) {
+        const int yy = y0 + t / 3, xx = x0 + t % 3;
+        ok[t] = yy >= 0 && yy < h && xx >= 0 && xx < w;
+        v[t] = ok[t] ? __ldg(reinterpret_cast<const float4*>(src + ((size_t)yy * w + xx) * F + f)) : best;
+      }
+#pragma unroll
+      for (int t = 0; t < 9; ++t)
+        if (ok[t]) {
+          best = make_float4(fmaxf(best.x, v[t].x), fmaxf(best.y, v[t].y), fmaxf(best.z, v[t].z), fmaxf(best.w, v[t].w));
+          sum = make_float4(sum.x + v[t].x, sum.y + v[t].y, sum.z + v[t].z, sum.w + v[t].w);
+          ++cnt;
+        }
+    } else
     for (int dy = 0; dy < rs.ky; ++dy) {
       const int yy = y0 + dy;
       if (yy < 0 || yy >= h) continue;
