@@ -95,3 +95,28 @@ def test_feature_serving_driver_matches_detect():
     assert len(det) == 5 and det[0].shape == (2, 100, 12) and det[2].shape == (2, 100, 8)
     for a, b in zip(det, ref):
         np.testing.assert_array_equal(a, b)
+
+
+@pytest.mark.gpu
+def test_feature_serving_driver_with_bifpn_on_the_device():
+    """backbone-level maps -> FPNCells -> head sampler inside the driver = the two stages chained by hand"""
+    import udal_b200 as u
+    size, cin, batch = (128, 192), [40, 112, 320, 64, 64], 2
+    p = u.hparams_config.get_detection_config(
+        "efficientdet-d0", image_size=size, num_classes=7, enable_softmax=True, loss_attenuation=True,
+        mc_dropout=True, mc_classheadrate=0.05, mc_boxheadrate=0.05, mc_dropoutsamp=3)
+    nodes = u.fpn_configs.bifpn_config(3, 7)["nodes"]
+    wf = u.synthetic.init_bifpn_weights(64, 3, cin, nodes, seed=5)
+    wh = heads_ref.init_head_weights(64, 3, 5, 9, 7, True, seed=3, randomize_bn=True)
+    eng = u.engine.get_engine(p)
+    sizes = [(16, 24), (8, 12), (4, 6), (2, 3), (1, 2)]
+    assert [tuple(x) for x in eng.level_hw] == sizes
+    rng = np.random.default_rng(2)
+    feats = [rng.normal(size=(batch, h, w, c)).astype(np.float32) for (h, w), c in zip(sizes, cin)]
+    scales = np.float32([1.0, 1.5])
+    drv = u.serving.FeatureServingDriver(p, wh, lambda images: (feats, scales), bifpn_weights=wf)
+    det = drv.serve([None] * batch)
+    fpn = u.bifpn.FPNCells(p, wf)(feats)
+    ref = u.heads.HeadSampler(p, wh).detect(fpn, scales, seed=1)
+    for a, b in zip(det, ref):
+        np.testing.assert_array_equal(a, b)

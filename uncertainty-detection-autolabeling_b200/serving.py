@@ -11,7 +11,7 @@ valid_len, logits), but computes it with the head sampler from BiFPN feature map
 """
 import numpy as np
 
-from . import heads
+from . import device, heads
 
 
 def _find(variables, *suffixes):
@@ -70,16 +70,26 @@ def weights_from_variables(variables, params):
 
 class FeatureServingDriver:
     """``serve(image_arrays)`` like infer_lib.ServingDriver: ``features_fn(image_arrays)`` must return
-    ``(fpn_feats, image_scales)`` - the 5 BiFPN maps [B,H_l,W_l,F] (host or device arrays) and the per-image
-    scale factors of ``DetectionInputProcessor`` (infer_lib.py:238-254)."""
+    ``(feats, image_scales)`` - the per-image scale factors of ``DetectionInputProcessor`` (infer_lib.py:238-254) and
+    either the 5 BiFPN maps [B,H_l,W_l,F] or, when ``bifpn_weights`` is given (``bifpn.weights_from_variables``), the
+    backbone-level maps the first FPN cell reads (levels 3..5 + the resample_p6 / p7 outputs): ``FPNCells`` then runs on the
+    device and its outputs feed the head sampler without leaving the GPU (efficientdet_keras.py:979-1050 from ``fpn_cells`` on).
+    Host or device arrays."""
 
-    def __init__(self, params, weights, features_fn, device_id=None, heads_mode=None):
+    def __init__(self, params, weights, features_fn, device_id=None, heads_mode=None, bifpn_weights=None):
         self.params = params
         self.features_fn = features_fn
         self.sampler = heads.HeadSampler(params, weights, device_id, heads_mode)
+        self.fpn = None
+        if bifpn_weights is not None:
+            from . import bifpn
+            self.fpn = bifpn.FPNCells(params, bifpn_weights, device_id)
         self._seed = 0
 
     def serve(self, image_arrays):
         feats, scales = self.features_fn(image_arrays)
+        if self.fpn is not None:
+            feats = self.fpn([x if device.is_device_array(x) else self.fpn.ctx.to_device(np.ascontiguousarray(x, np.float32))
+                              for x in feats])
         self._seed += 1
         return self.sampler.detect(feats, scales, seed=self._seed)
