@@ -222,24 +222,6 @@ __device__ __forceinline__ float4 resample_at4(const float* __restrict__ src, co
     float4 best = make_float4(-3.402823466e38f, -3.402823466e38f, -3.402823466e38f, -3.402823466e38f);
     float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
     int cnt = 0;
-    if (rs.ky == 3 && rs.kx == 3) {
-      // stride 2 (every level transition of the pyramid): the nine loads are issued together
-      float4 v[9];
-      bool ok[9];
-#pragma unroll
-      for (int t = 0; t < 9; ++t) {
-        const int yy = y0 + t / 3, xx = x0 + t % 3;
-        ok[t] = yy >= 0 && yy < h && xx >= 0 && xx < w;
-        v[t] = ok[t] ? __ldg(reinterpret_cast<const float4*>(src + ((size_t)yy * w + xx) * F + f)) : best;
-      }
-#pragma unroll
-      for (int t = 0; t < 9; ++t)
-        if (ok[t]) {
-          best = make_float4(fmaxf(best.x, v[t].x), fmaxf(best.y, v[t].y), fmaxf(best.z, v[t].z), fmaxf(best.w, v[t].w));
-          sum = make_float4(sum.x + v[t].x, sum.y + v[t].y, sum.z + v[t].z, sum.w + v[t].w);
-          ++cnt;
-        }
-    } else
     for (int dy = 0; dy < rs.ky; ++dy) {
       const int yy = y0 + dy;
       if (yy < 0 || yy >= h) continue;
@@ -267,7 +249,7 @@ __device__ __forceinline__ float swish_fast(float x) {
   return x * r;
 }
 
-__global__ void __launch_bounds__(256) bifpn_fuse4_kernel(const Fuse4Params q) {
+__global__ void __launch_bounds__(256, 4) bifpn_fuse4_kernel(const Fuse4Params q) {
   const FuseParams& p = q.f;
   const int F4 = p.F >> 2;
   const int x = blockIdx.x * 16 + (threadIdx.x >> 4);   // 16 threads (64 channels per pass) per pixel
@@ -277,7 +259,9 @@ __global__ void __launch_bounds__(256) bifpn_fuse4_kernel(const Fuse4Params q) {
   for (int f4 = threadIdx.x & 15; f4 < F4; f4 += 16) {
     const int f = 4 * f4;
     float4 v[3], wn[3];
-    for (int k = 0; k < p.n; ++k) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      if (k >= p.n) break;
       v[k] = resample_at4(p.in[k] + (size_t)nb * p.h[k] * p.w[k] * p.F, q.rs[k], p.h[k], p.w[k], y, x, p.F, f, p.pool_avg);
       if (!p.wsm[k]) wn[k] = make_float4(1.f, 1.f, 1.f, 1.f);
       else if (p.per_channel) wn[k] = __ldg(reinterpret_cast<const float4*>(p.wsm[k] + f));
@@ -288,27 +272,37 @@ __global__ void __launch_bounds__(256) bifpn_fuse4_kernel(const Fuse4Params q) {
     }
     if (p.mode == UDAL_FUSE_FASTATTN) {
       float4 ws = make_float4(0.f, 0.f, 0.f, 0.f);
-      for (int k = 0; k < p.n; ++k) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        if (k >= p.n) break;
         wn[k] = make_float4(fmaxf(wn[k].x, 0.f), fmaxf(wn[k].y, 0.f), fmaxf(wn[k].z, 0.f), fmaxf(wn[k].w, 0.f));
         ws = make_float4(ws.x + wn[k].x, ws.y + wn[k].y, ws.z + wn[k].z, ws.w + wn[k].w);
       }
       const float4 inv = make_float4(__fdiv_rn(1.f, ws.x + 0.0001f), __fdiv_rn(1.f, ws.y + 0.0001f), __fdiv_rn(1.f, ws.z + 0.0001f),
                                      __fdiv_rn(1.f, ws.w + 0.0001f));
-      for (int k = 0; k < p.n; ++k) wn[k] = make_float4(wn[k].x * inv.x, wn[k].y * inv.y, wn[k].z * inv.z, wn[k].w * inv.w);
+#pragma unroll
+      for (int k = 0; k < 3; ++k)
+        if (k < p.n) wn[k] = make_float4(wn[k].x * inv.x, wn[k].y * inv.y, wn[k].z * inv.z, wn[k].w * inv.w);
     } else if (p.mode == UDAL_FUSE_ATTN) {
       float4 mx = wn[0];
-      for (int k = 1; k < p.n; ++k) mx = make_float4(fmaxf(mx.x, wn[k].x), fmaxf(mx.y, wn[k].y), fmaxf(mx.z, wn[k].z), fmaxf(mx.w, wn[k].w));
+#pragma unroll
+      for (int k = 1; k < 3; ++k)
+        if (k < p.n) mx = make_float4(fmaxf(mx.x, wn[k].x), fmaxf(mx.y, wn[k].y), fmaxf(mx.z, wn[k].z), fmaxf(mx.w, wn[k].w));
       float4 se = make_float4(0.f, 0.f, 0.f, 0.f);
-      for (int k = 0; k < p.n; ++k) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        if (k >= p.n) break;
         wn[k] = make_float4(expf(wn[k].x - mx.x), expf(wn[k].y - mx.y), expf(wn[k].z - mx.z), expf(wn[k].w - mx.w));
         se = make_float4(se.x + wn[k].x, se.y + wn[k].y, se.z + wn[k].z, se.w + wn[k].w);
       }
-      for (int k = 0; k < p.n; ++k)
-        wn[k] = make_float4(__fdiv_rn(wn[k].x, se.x), __fdiv_rn(wn[k].y, se.y), __fdiv_rn(wn[k].z, se.z), __fdiv_rn(wn[k].w, se.w));
+#pragma unroll
+      for (int k = 0; k < 3; ++k)
+        if (k < p.n) wn[k] = make_float4(__fdiv_rn(wn[k].x, se.x), __fdiv_rn(wn[k].y, se.y), __fdiv_rn(wn[k].z, se.z), __fdiv_rn(wn[k].w, se.w));
     }
     float4 acc = make_float4(v[0].x * wn[0].x, v[0].y * wn[0].y, v[0].z * wn[0].z, v[0].w * wn[0].w);
-    for (int k = 1; k < p.n; ++k)
-      acc = make_float4(fmaf(v[k].x, wn[k].x, acc.x), fmaf(v[k].y, wn[k].y, acc.y), fmaf(v[k].z, wn[k].z, acc.z), fmaf(v[k].w, wn[k].w, acc.w));
+#pragma unroll
+    for (int k = 1; k < 3; ++k)
+      if (k < p.n) acc = make_float4(fmaf(v[k].x, wn[k].x, acc.x), fmaf(v[k].y, wn[k].y, acc.y), fmaf(v[k].z, wn[k].z, acc.z), fmaf(v[k].w, wn[k].w, acc.w));
     if (p.act) acc = make_float4(swish_fast(acc.x), swish_fast(acc.y), swish_fast(acc.z), swish_fast(acc.w));
     *reinterpret_cast<float4*>(p.out + px * p.F + f) = acc;
   }
