@@ -60,104 +60,6 @@ __device__ __forceinline__ void moments_reg(const float (&v)[TMAX], int T, float
   sd = __fsqrt_rn(__fdiv_rn(s, fT));
 }
 
-// decode one (anchor, sample).  t = (ty,tx,th,tw), sg = sigma (std) or unused.
-struct Decoded {
-  float box[4];
-  float sd[4];
-};
-
-__device__ __forceinline__ Decoded decode_la(const float4 a, const float4 t, const float4 sg, int method) {
-  // utils_box.py:125-160 / 186-266, fp64
-  const double a0 = a.x, a1 = a.y, a2 = a.z, a3 = a.w;
-  const double yca = __dmul_rn(__dadd_rn(a0, a2), 0.5);
-  const double xca = __dmul_rn(__dadd_rn(a1, a3), 0.5);
-  const double ha = __dsub_rn(a2, a0);
-  const double wa = __dsub_rn(a3, a1);
-  const double ty = t.x, tx = t.y, th = t.z, tw = t.w;
-  const double vy = __dmul_rn((double)sg.x, (double)sg.x);
-  const double vx = __dmul_rn((double)sg.y, (double)sg.y);
-  const double vh = __dmul_rn((double)sg.z, (double)sg.z);
-  const double vw = __dmul_rn((double)sg.w, (double)sg.w);
-  const double yc = __dadd_rn(__dmul_rn(ty, ha), yca);
-  const double xc = __dadd_rn(__dmul_rn(tx, wa), xca);
-  Decoded r;
-  if (method == UDAL_DECODE_FALSEDEC) {
-    const double w = __dmul_rn(exp(tw), wa);
-    const double h = __dmul_rn(exp(th), ha);
-    const double hh = __dmul_rn(h, 0.5), hw = __dmul_rn(w, 0.5);
-    r.box[0] = (float)__dsub_rn(yc, hh);
-    r.box[1] = (float)__dsub_rn(xc, hw);
-    r.box[2] = (float)__dadd_rn(yc, hh);
-    r.box[3] = (float)__dadd_rn(xc, hw);
-    const double dw = __dmul_rn(exp(vw), wa);
-    const double dh = __dmul_rn(exp(vh), ha);
-    const double dyc = __dadd_rn(__dmul_rn(vy, ha), yca);
-    const double dxc = __dadd_rn(__dmul_rn(vx, wa), xca);
-    const double dhh = __dmul_rn(dh, 0.5), dhw = __dmul_rn(dw, 0.5);
-    r.sd[0] = (float)sqrt(fabs(__dsub_rn(dyc, dhh)));
-    r.sd[1] = (float)sqrt(fabs(__dsub_rn(dxc, dhw)));
-    r.sd[2] = (float)sqrt(__dadd_rn(dyc, dhh));
-    r.sd[3] = (float)sqrt(__dadd_rn(dxc, dhw));
-    return r;
-  }
-  // l-norm (and n-flow, whose tfp closed forms are the same expressions)
-  const double ew = exp(__dadd_rn(tw, __dmul_rn(vw, 0.5)));
-  const double eh = exp(__dadd_rn(th, __dmul_rn(vh, 0.5)));
-  const double w = __dmul_rn(ew, wa);
-  const double h = __dmul_rn(eh, ha);
-  const double hh = __dmul_rn(h, 0.5), hw = __dmul_rn(w, 0.5);
-  r.box[0] = (float)__dsub_rn(yc, hh);
-  r.box[1] = (float)__dsub_rn(xc, hw);
-  r.box[2] = (float)__dadd_rn(yc, hh);
-  r.box[3] = (float)__dadd_rn(xc, hw);
-  double dw, dh, dyc, dxc;
-  if (method == UDAL_DECODE_NFLOW) {
-    // tfp: Normal->Scale->Shift stddev = |scale * sd|; LogNormal variance -> Scale
-    const double sy = sqrt(vy), sx = sqrt(vx), sh = sqrt(vh), sw = sqrt(vw);
-    const double q = fabs(__dmul_rn(ha, sy)), p = fabs(__dmul_rn(wa, sx));
-    dyc = __dmul_rn(q, q);
-    dxc = __dmul_rn(p, p);
-    const double sh2 = __dmul_rn(sh, sh), sw2 = __dmul_rn(sw, sw);
-    const double lh = __dmul_rn(__dsub_rn(exp(sh2), 1.0), exp(__dadd_rn(__dmul_rn(2.0, th), sh2)));
-    const double lw = __dmul_rn(__dsub_rn(exp(sw2), 1.0), exp(__dadd_rn(__dmul_rn(2.0, tw), sw2)));
-    const double qh = fabs(__dmul_rn(ha, sqrt(lh))), qw = fabs(__dmul_rn(wa, sqrt(lw)));
-    dh = __dmul_rn(qh, qh);
-    dw = __dmul_rn(qw, qw);
-  } else {
-    dw = __dmul_rn(__dmul_rn(__dsub_rn(exp(vw), 1.0), exp(__dadd_rn(__dmul_rn(2.0, tw), vw))),
-                   __dmul_rn(wa, wa));
-    dh = __dmul_rn(__dmul_rn(__dsub_rn(exp(vh), 1.0), exp(__dadd_rn(__dmul_rn(2.0, th), vh))),
-                   __dmul_rn(ha, ha));
-    dyc = __dmul_rn(vy, __dmul_rn(ha, ha));
-    dxc = __dmul_rn(vx, __dmul_rn(wa, wa));
-  }
-  const float sdy = (float)sqrt(__dadd_rn(dyc, __dmul_rn(dh, 0.25)));
-  const float sdx = (float)sqrt(__dadd_rn(dxc, __dmul_rn(dw, 0.25)));
-  r.sd[0] = sdy;
-  r.sd[1] = sdx;
-  r.sd[2] = sdy;
-  r.sd[3] = sdx;
-  return r;
-}
-
-__device__ __forceinline__ void decode_plain(const float4 a, const float4 t, float (&box)[4]) {
-  // anchors.py:41-75, fp32
-  const float yca = __fmul_rn(__fadd_rn(a.x, a.z), 0.5f);
-  const float xca = __fmul_rn(__fadd_rn(a.y, a.w), 0.5f);
-  const float ha = __fsub_rn(a.z, a.x);
-  const float wa = __fsub_rn(a.w, a.y);
-  // fp32 exp of the reference (Eigen / NumPy, < 1 ulp): the correctly rounded value is the closest match
-  const float w = __fmul_rn((float)exp((double)t.w), wa);
-  const float h = __fmul_rn((float)exp((double)t.z), ha);
-  const float yc = __fadd_rn(__fmul_rn(t.x, ha), yca);
-  const float xc = __fadd_rn(__fmul_rn(t.y, wa), xca);
-  const float hh = __fmul_rn(h, 0.5f), hw = __fmul_rn(w, 0.5f);
-  box[0] = __fsub_rn(yc, hh);
-  box[1] = __fsub_rn(xc, hw);
-  box[2] = __fadd_rn(yc, hh);
-  box[3] = __fadd_rn(xc, hw);
-}
-
 __device__ __forceinline__ int find_level(const int* off, int nl, int v) {
   int l = 0;
 #pragma unroll
@@ -1122,8 +1024,14 @@ struct GatherParams {
   udal_prenms_topk_out out;
 };
 
-// decode + moments on the k gathered (anchor, class) rows of each image
+// decode + moments on the k gathered (anchor, class) rows of each image.  F32: decode_precision fp32 (closed form in fp32);
+// otherwise the per-axis fp64 decode of the dense kernel (exp / sqrt through fast_math64.cuh: the same values, a third of
+// the instructions of the libm calls this kernel used to make - it was fp64-instruction bound: 189 us for 64 x 5000 rows, T = 10)
+template <bool F32>
 __global__ void __launch_bounds__(kThreads) decode_gather_kernel(const GatherParams p) {
+  __shared__ double smem_tbl[64];
+  if (threadIdx.x < 64) smem_tbl[threadIdx.x] = kExp2Table[threadIdx.x];
+  __syncthreads();
   const int b = blockIdx.y;
   const int j = blockIdx.x * kThreads + threadIdx.x;
   if (j >= p.k) return;
@@ -1145,16 +1053,22 @@ __global__ void __launch_bounds__(kThreads) decode_gather_kernel(const GatherPar
     for (int t = 0; t < T; ++t) {
       const float4 tt = __ldg(reinterpret_cast<const float4*>(bb + (size_t)t * t_stride));
       float d[4];
-      if (p.la) {
-        const float4 sg = __ldg(reinterpret_cast<const float4*>(bb + (size_t)t * t_stride + 4 * p.A));
-        const Decoded dd = decode_la(anc, tt, sg, p.method);
-        for (int q = 0; q < 4; ++q) {
-          d[q] = dd.box[q];
-          if (pass == 0) al[q] = t == 0 ? dd.sd[q] : __fadd_rn(al[q], dd.sd[q]);
-        }
+      float4 sg = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (p.la) sg = __ldg(reinterpret_cast<const float4*>(bb + (size_t)t * t_stride + 4 * p.A));
+      float sd[4] = {0.f, 0.f, 0.f, 0.f};
+      if (F32) {
+        const float say = anc.z - anc.x, sax = anc.w - anc.y;
+        f32_decode_axis(p.method, p.la, say, 0.5f * (anc.x + anc.z), say * say, tt.x, tt.z, sg.x, sg.z, d[0], d[2], sd[0], sd[2]);
+        f32_decode_axis(p.method, p.la, sax, 0.5f * (anc.y + anc.w), sax * sax, tt.y, tt.w, sg.y, sg.w, d[1], d[3], sd[1], sd[3]);
+      } else if (p.la) {
+        decode_axis_la(p.method, smem_tbl, anc.x, anc.z, tt.x, tt.z, sg.x, sg.z, d[0], d[2], sd[0], sd[2]);
+        decode_axis_la(p.method, smem_tbl, anc.y, anc.w, tt.y, tt.w, sg.y, sg.w, d[1], d[3], sd[1], sd[3]);
       } else {
-        decode_plain(anc, tt, d);
+        decode_axis_plain(anc.x, anc.z, tt.x, tt.z, d[0], d[2]);
+        decode_axis_plain(anc.y, anc.w, tt.y, tt.w, d[1], d[3]);
       }
+      if (p.la && pass == 0)
+        for (int q = 0; q < 4; ++q) al[q] = t == 0 ? sd[q] : __fadd_rn(al[q], sd[q]);
       for (int q = 0; q < 4; ++q) {
         if (pass == 0) {
           sum[q] = t == 0 ? d[q] : __fadd_rn(sum[q], d[q]);
@@ -1184,7 +1098,7 @@ __global__ void __launch_bounds__(kThreads) decode_gather_kernel(const GatherPar
     v.w = __fsqrt_rn(__fdiv_rn(ss[3], (float)T));
     reinterpret_cast<float4*>(p.out.mcbox)[o] = v;
   }
-  if (p.out.scores) p.out.scores[o] = sigmoid_ref(p.topk_val[o]);
+  if (p.out.scores) p.out.scores[o] = F32 ? __frcp_rn(1.f + f32_exp(-p.topk_val[o])) : sigmoid_ref(p.topk_val[o]);
   if (p.out.classes) p.out.classes[o] = c;
   if (p.out.mcclass && p.std_logits) p.out.mcclass[o] = p.std_logits[(size_t)b * p.N * p.C + flat];
 }
@@ -1381,7 +1295,8 @@ int udal_launch_decode_gather(udal_ctx* ctx, const float* const* box, int batch,
   p.std_logits = std_logits;
   p.out = *out;
   dim3 grid((k + kThreads - 1) / kThreads, batch);
-  decode_gather_kernel<<<grid, kThreads, 0, ctx->stream>>>(p);
+  if (ctx->cfg.decode_precision == UDAL_DECODE_FP32) decode_gather_kernel<true><<<grid, kThreads, 0, ctx->stream>>>(p);
+  else decode_gather_kernel<false><<<grid, kThreads, 0, ctx->stream>>>(p);
   UDAL_CHECK_LAUNCH(ctx);
   return UDAL_OK;
 }
