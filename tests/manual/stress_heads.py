@@ -1,5 +1,6 @@
-"""Development helper: bf16 head sampler vs the CPU oracle over geometries that make the persistent
-implicit-GEMM kernels loop many times per CTA (the pytest cases keep the oracle cost small)."""
+"""Development helper: tensor-core head sampler (python tests/manual/stress_heads.py [bf16 | fp16]) vs the CPU oracle over
+geometries that make the persistent kernels loop many times per CTA, three repetitions each - identical errors across the
+repetitions = no race (the pytest cases keep the oracle cost small)."""
 import sys
 import time
 
@@ -9,6 +10,7 @@ sys.path.insert(0, ".")
 import udal_b200 as u
 from oracle import heads_ref
 
+MODE = sys.argv[1] if len(sys.argv) > 1 else "fp16"
 CASES = [  # size, C, T, batch
     ((384, 1280), 8, 10, 1),
     ((384, 1280), 8, 7, 1),
@@ -22,7 +24,7 @@ worst_all = 0.0
 for size, C, T, batch in CASES:
     p = u.hparams_config.get_detection_config(
         "efficientdet-d0", image_size=size, num_classes=C, enable_softmax=True, loss_attenuation=True,
-        mc_dropout=True, mc_classheadrate=0.05, mc_boxheadrate=0.05, mc_dropoutsamp=T, heads_mode="bf16")
+        mc_dropout=True, mc_classheadrate=0.05, mc_boxheadrate=0.05, mc_dropoutsamp=T, heads_mode=MODE)
     eng = u.engine.get_engine(p)
     L = len(eng.level_hw)
     w = heads_ref.init_head_weights(eng.F, eng.R, L, eng.A, C, True, seed=9, randomize_bn=True)
