@@ -50,6 +50,7 @@ struct NmsParams {
   float* sel_scores;   // [S,max_out]
   int32_t* valid;      // [S]
   int32_t* flag;       // [S] 1 = truncated run not provably exact (nullable)
+  int only_marked;     // 1: only the segments the per-segment epoch kernel left (valid[s] == -1, nms_cta.cu)
   // soft-mode re-insertion set; a segment's slice starts at its candidate offset
   float* r_score;
   int32_t* r_rank;
@@ -104,6 +105,7 @@ __global__ void __launch_bounds__((STAGED ? 1 : kWarpsPerBlock) * 32) nms_v5_sor
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int s = blockIdx.x * WPB + warp;
   if (s >= p.segments) return;
+  if (p.only_marked && p.valid[s] != -1) return;   // (warp-uniform; no block barrier follows)
   float4* sel_box = smem_boxes + (size_t)warp * p.max_out;
   float4* s_box = smem_boxes + (size_t)WPB * p.max_out;                    // [kStageCap]
   float* s_score = reinterpret_cast<float*>(s_box + kStageCap);            // [kStageCap]
@@ -489,6 +491,13 @@ int udal_nms_sorted(udal_ctx* ctx, const float* boxes, const float* scores, cons
   p.sel_scores = sel_scores;
   p.valid = valid;
   p.flag = flag;
+  if (cand_idx && seg_start && seg_count && !next_score && !flag) {
+    // per-class segments: one cooperative CTA per segment (nms_cta.cu); what it leaves (valid = -1) runs below
+    int handled = 0;
+    UDAL_TRY(udal_nms_epoch_segments(ctx, boxes, scores, cand_idx, seg_start, seg_count, segments, segs_per_image, img_stride, sel_row,
+                                     sel_rank, sel_scores, valid, &handled));
+    p.only_marked = handled;
+  }
   if (p.soft) {
     char* scr;
     const size_t per = (size_t)total_cand;

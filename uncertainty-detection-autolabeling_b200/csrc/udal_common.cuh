@@ -240,6 +240,9 @@ int udal_nms_full(udal_ctx* ctx, const float* boxes, const float* scores, int se
                   const int32_t* flag, int32_t* sel_row, float* sel_scores, int32_t* valid);
 int udal_nms_prefilter_k(const udal_ctx* ctx, int n);
 extern int udal_nms_cta;
+int udal_nms_epoch_segments(udal_ctx* ctx, const float* boxes, const float* scores, const int32_t* cand_idx, const int32_t* seg_start,
+                            const int32_t* seg_count, int segments, int segs_per_image, int64_t img_stride, int32_t* sel_row,
+                            int32_t* sel_rank, float* sel_scores, int32_t* valid, int* handled);
 int udal_nms_epoch(udal_ctx* ctx, const float* boxes, const float* scores, int segments, int n, int32_t* sel_idx,
                    float* sel_scores, int32_t* valid);
 // top-K pre-filter of a global NMS (scratch of the context's current bank) and the selection that consumes it
