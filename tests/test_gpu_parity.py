@@ -332,7 +332,17 @@ def test_postprocess_global_vs_oracle_random(u, C, T, batch, size, method):
 
 @pytest.mark.parametrize("C,T,batch,k,method", [(7, 10, 2, 500, "gaussian"), (10, 3, 1, 5000, "hard"),
                                                 (90, 2, 1, 2000, "gaussian")])
-def test_postprocess_per_class_vs_oracle_random(u, C, T, batch, k, method):
+@pytest.mark.parametrize("seg", [1, 0])   # soft NMS of a few segments: one CTA per segment (nms_cta.cu) | one warp (nms.cu)
+def test_postprocess_per_class_vs_oracle_random(u, C, T, batch, k, method, seg):
+    switch = ctypes.c_int.in_dll(u._lib.load(), "udal_nms_seg")
+    switch.value = seg
+    try:
+        _per_class_vs_oracle_random(u, C, T, batch, k, method)
+    finally:
+        switch.value = 1
+
+
+def _per_class_vs_oracle_random(u, C, T, batch, k, method):
     p = u.hparams_config.get_detection_config(
         "efficientdet-d0", image_size=(64, 96), num_classes=C, enable_softmax=True, loss_attenuation=True,
         mc_dropout=True, mc_classheadrate=0.05, mc_boxheadrate=0.05, mc_dropoutsamp=T,
