@@ -249,6 +249,39 @@ __device__ __forceinline__ float swish_fast(float x) {
   return x * r;
 }
 
+// normalised edge weights of a node with scalar weights (the reference default): one division per thread, not four
+__device__ __forceinline__ void fuse_weights_scalar(const FuseParams& p, float (&wn)[3]) {
+#pragma unroll
+  for (int k = 0; k < 3; ++k) wn[k] = (k < p.n && p.wsm[k]) ? __ldg(p.wsm[k]) : 1.f;
+  if (p.mode == UDAL_FUSE_FASTATTN) {
+    float ws = 0.f;
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+      if (k < p.n) {
+        wn[k] = fmaxf(wn[k], 0.f);
+        ws += wn[k];
+      }
+    const float inv = __fdiv_rn(1.f, ws + 0.0001f);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) wn[k] *= inv;
+  } else if (p.mode == UDAL_FUSE_ATTN) {
+    float mx = wn[0];
+#pragma unroll
+    for (int k = 1; k < 3; ++k)
+      if (k < p.n) mx = fmaxf(mx, wn[k]);
+    float se = 0.f;
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+      if (k < p.n) {
+        wn[k] = expf(wn[k] - mx);
+        se += wn[k];
+      }
+    const float inv = __fdiv_rn(1.f, se);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) wn[k] *= inv;
+  }
+}
+
 __global__ void __launch_bounds__(256, 4) bifpn_fuse4_kernel(const Fuse4Params q) {
   const FuseParams& p = q.f;
   const int F4 = p.F >> 2;
@@ -256,6 +289,8 @@ __global__ void __launch_bounds__(256, 4) bifpn_fuse4_kernel(const Fuse4Params q
   const int y = blockIdx.y, nb = blockIdx.z;
   if (x >= p.W) return;
   const size_t px = ((size_t)nb * p.H + y) * p.W + x;
+  float ws[3] = {1.f, 1.f, 1.f};
+  if (!p.per_channel) fuse_weights_scalar(p, ws);
   for (int f4 = threadIdx.x & 15; f4 < F4; f4 += 16) {
     const int f = 4 * f4;
     float4 v[3], wn[3];
@@ -263,41 +298,41 @@ __global__ void __launch_bounds__(256, 4) bifpn_fuse4_kernel(const Fuse4Params q
     for (int k = 0; k < 3; ++k) {
       if (k >= p.n) break;
       v[k] = resample_at4(p.in[k] + (size_t)nb * p.h[k] * p.w[k] * p.F, q.rs[k], p.h[k], p.w[k], y, x, p.F, f, p.pool_avg);
-      if (!p.wsm[k]) wn[k] = make_float4(1.f, 1.f, 1.f, 1.f);
-      else if (p.per_channel) wn[k] = __ldg(reinterpret_cast<const float4*>(p.wsm[k] + f));
-      else {
-        const float w1 = __ldg(p.wsm[k]);
-        wn[k] = make_float4(w1, w1, w1, w1);
-      }
+      wn[k] = make_float4(ws[k], ws[k], ws[k], ws[k]);
     }
-    if (p.mode == UDAL_FUSE_FASTATTN) {
-      float4 ws = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-      for (int k = 0; k < 3; ++k) {
-        if (k >= p.n) break;
-        wn[k] = make_float4(fmaxf(wn[k].x, 0.f), fmaxf(wn[k].y, 0.f), fmaxf(wn[k].z, 0.f), fmaxf(wn[k].w, 0.f));
-        ws = make_float4(ws.x + wn[k].x, ws.y + wn[k].y, ws.z + wn[k].z, ws.w + wn[k].w);
-      }
-      const float4 inv = make_float4(__fdiv_rn(1.f, ws.x + 0.0001f), __fdiv_rn(1.f, ws.y + 0.0001f), __fdiv_rn(1.f, ws.z + 0.0001f),
-                                     __fdiv_rn(1.f, ws.w + 0.0001f));
+    if (p.per_channel) {
 #pragma unroll
       for (int k = 0; k < 3; ++k)
-        if (k < p.n) wn[k] = make_float4(wn[k].x * inv.x, wn[k].y * inv.y, wn[k].z * inv.z, wn[k].w * inv.w);
-    } else if (p.mode == UDAL_FUSE_ATTN) {
-      float4 mx = wn[0];
+        if (k < p.n) wn[k] = p.wsm[k] ? __ldg(reinterpret_cast<const float4*>(p.wsm[k] + f)) : make_float4(1.f, 1.f, 1.f, 1.f);
+      if (p.mode == UDAL_FUSE_FASTATTN) {
+        float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-      for (int k = 1; k < 3; ++k)
-        if (k < p.n) mx = make_float4(fmaxf(mx.x, wn[k].x), fmaxf(mx.y, wn[k].y), fmaxf(mx.z, wn[k].z), fmaxf(mx.w, wn[k].w));
-      float4 se = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int k = 0; k < 3; ++k) {
+          if (k >= p.n) break;
+          wn[k] = make_float4(fmaxf(wn[k].x, 0.f), fmaxf(wn[k].y, 0.f), fmaxf(wn[k].z, 0.f), fmaxf(wn[k].w, 0.f));
+          sum = make_float4(sum.x + wn[k].x, sum.y + wn[k].y, sum.z + wn[k].z, sum.w + wn[k].w);
+        }
+        const float4 inv = make_float4(__fdiv_rn(1.f, sum.x + 0.0001f), __fdiv_rn(1.f, sum.y + 0.0001f), __fdiv_rn(1.f, sum.z + 0.0001f),
+                                       __fdiv_rn(1.f, sum.w + 0.0001f));
 #pragma unroll
-      for (int k = 0; k < 3; ++k) {
-        if (k >= p.n) break;
-        wn[k] = make_float4(expf(wn[k].x - mx.x), expf(wn[k].y - mx.y), expf(wn[k].z - mx.z), expf(wn[k].w - mx.w));
-        se = make_float4(se.x + wn[k].x, se.y + wn[k].y, se.z + wn[k].z, se.w + wn[k].w);
+        for (int k = 0; k < 3; ++k)
+          if (k < p.n) wn[k] = make_float4(wn[k].x * inv.x, wn[k].y * inv.y, wn[k].z * inv.z, wn[k].w * inv.w);
+      } else if (p.mode == UDAL_FUSE_ATTN) {
+        float4 mx = wn[0];
+#pragma unroll
+        for (int k = 1; k < 3; ++k)
+          if (k < p.n) mx = make_float4(fmaxf(mx.x, wn[k].x), fmaxf(mx.y, wn[k].y), fmaxf(mx.z, wn[k].z), fmaxf(mx.w, wn[k].w));
+        float4 se = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          if (k >= p.n) break;
+          wn[k] = make_float4(expf(wn[k].x - mx.x), expf(wn[k].y - mx.y), expf(wn[k].z - mx.z), expf(wn[k].w - mx.w));
+          se = make_float4(se.x + wn[k].x, se.y + wn[k].y, se.z + wn[k].z, se.w + wn[k].w);
+        }
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+          if (k < p.n) wn[k] = make_float4(__fdiv_rn(wn[k].x, se.x), __fdiv_rn(wn[k].y, se.y), __fdiv_rn(wn[k].z, se.z), __fdiv_rn(wn[k].w, se.w));
       }
-#pragma unroll
-      for (int k = 0; k < 3; ++k)
-        if (k < p.n) wn[k] = make_float4(__fdiv_rn(wn[k].x, se.x), __fdiv_rn(wn[k].y, se.y), __fdiv_rn(wn[k].z, se.z), __fdiv_rn(wn[k].w, se.w));
     }
     float4 acc = make_float4(v[0].x * wn[0].x, v[0].y * wn[0].y, v[0].z * wn[0].z, v[0].w * wn[0].w);
 #pragma unroll
